@@ -1,0 +1,261 @@
+"""`tf`-shaped adapter so the reference's call sites keep working with `import ...compat as tf`.
+
+Covers exactly what scripts/train_script.py:99-203 and rllab/sampler/base.py:113-154,216,234 use on this path:
+
+    placeholder, uint8/float32, image.convert_image_dtype, subtract, multiply, variable_scope,
+    Session().run(fetches, feed_dict), train.AdamOptimizer(lr).minimize(loss, var_list=...),
+    train.Saver().save/restore, global_variables_initializer, get_collection, GraphKeys, ConfigProto.
+
+`Session.run` does what TF's executor did: find the smallest forward level that produces every fetch
+(`input_z` alone runs only the source encoder — the pruning base.py:234 relies on), copy the fed batch host ->
+device through pinned memory, launch, and copy the fetched values back as numpy arrays.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .models import Fetch, _ContextModel
+from .network import FWD_ALL
+
+uint8 = torch.uint8
+float32 = torch.float32
+
+_scope_stack: List[str] = []
+
+
+@contextlib.contextmanager
+def variable_scope(name: str):
+    _scope_stack.append(name)
+    try:
+        yield name
+    finally:
+        _scope_stack.pop()
+
+
+def current_scope() -> str:
+    return "".join(s + "/" for s in _scope_stack)
+
+
+class Placeholder:
+    """tf.placeholder: a typed shape plus the (only) preprocessing chain the reference applies to it."""
+
+    def __init__(self, dtype, shape, name=None, chain=(), root=None):
+        self.dtype, self.shape, self.name = dtype, tuple(int(s) for s in shape), name
+        self.chain = tuple(chain)
+        self.root = root or self
+        if root is None:
+            self.consumers: List[_ContextModel] = []
+
+    def _derive(self, op):
+        return Placeholder(self.dtype, self.shape, self.name, self.chain + (op,), self.root)
+
+    def _register_consumer(self, model):
+        norm = (("convert_image_dtype",), ("subtract", 0.5), ("multiply", 2.0))
+        if self.root.dtype == torch.uint8:
+            if self.chain != norm:
+                raise _lib.CtxError("a uint8 placeholder must be normalised exactly as base.py:117-119 "
+                                    "(convert_image_dtype, subtract 0.5, multiply 2.0); got %r" % (self.chain,))
+        elif self.chain:
+            raise _lib.CtxError("float placeholders are consumed as-is (train_script.py:118)")
+        self.root.consumers.append(model)
+
+
+def placeholder(dtype, shape=(), name=None) -> Placeholder:
+    return Placeholder(dtype, shape, name)
+
+
+class image:                                                      # noqa: N801  (mirrors tf.image)
+    @staticmethod
+    def convert_image_dtype(x: Placeholder, dtype=float32) -> Placeholder:
+        return x._derive(("convert_image_dtype",))
+
+
+def subtract(x: Placeholder, v: float) -> Placeholder:
+    return x._derive(("subtract", float(v)))
+
+
+def multiply(x: Placeholder, v: float) -> Placeholder:
+    return x._derive(("multiply", float(v)))
+
+
+class GraphKeys:
+    TRAINABLE_VARIABLES = "trainable_variables"
+
+
+_models: List[_ContextModel] = []
+
+
+def get_collection(key, scope: str = "") -> List[str]:
+    out = []
+    for m in _models:
+        out += [v for v in m.trainable_variables() if v.startswith(scope)]
+    return out
+
+
+def global_variables_initializer():
+    return None
+
+
+class ConfigProto:
+    def __init__(self, **kw):
+        class _G:
+            allow_growth = True
+        self.gpu_options = _G()
+
+
+class _Minimize:
+    def __init__(self, opt: "_Adam", loss: Fetch):
+        self.opt, self.loss = opt, loss
+
+
+class _Adam:
+    def __init__(self, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta1, beta2, epsilon
+
+    def minimize(self, loss: Fetch, var_list=None) -> _Minimize:
+        if not isinstance(loss, Fetch) or loss.name != "loss":
+            raise _lib.CtxError("minimize() supports the model's .loss (train_script.py:128)")
+        return _Minimize(self, loss)
+
+
+class _Saver:
+    """tf.train.Saver stand-in: a .npz keyed by the TF variable names."""
+
+    def __init__(self, var_list=None):
+        pass
+
+    @staticmethod
+    def _path(p):
+        return p if p.endswith(".npz") else p + ".npz"
+
+    def save(self, sess, path):
+        sd = {}
+        for m in _models:
+            for k, v in m.net.state_dict().items():
+                sd[m.scope + k] = v
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        np.savez(self._path(path), **sd)
+        return path
+
+    def restore(self, sess, path):
+        sd = dict(np.load(self._path(path)))
+        for m in _models:
+            m.net.load_state_dict(sd, prefix=m.scope)
+
+
+class train:                                                      # noqa: N801  (mirrors tf.train)
+    AdamOptimizer = _Adam
+    Saver = _Saver
+
+
+def register_model(model: _ContextModel):
+    """Called by build_model(); makes the model visible to Saver / get_collection."""
+    if model not in _models:
+        _models.append(model)
+
+
+def reset_default_graph():
+    _models.clear()
+
+
+def build_model(model: _ContextModel, image: Placeholder, **kw):
+    """`with tf.variable_scope("contextmodel"): model.build(image)` (train_script.py:119-121) in one call."""
+    model.build(image, scope=current_scope(), **kw)
+    register_model(model)
+    return model
+
+
+class Session:
+    def __init__(self, config=None):
+        self._pinned: Dict[Any, torch.Tensor] = {}
+
+    def _stage(self, ph: Placeholder, value) -> torch.Tensor:
+        """Host value -> pinned staging buffer -> device (non_blocking), as one [3,B,H,W,C] tensor."""
+        if torch.is_tensor(value) and value.is_cuda:
+            return value
+        arr = np.asarray(value)
+        want = np.uint8 if ph.root.dtype == torch.uint8 else np.float32
+        key = (id(ph.root), arr.shape, want)
+        pin = self._pinned.get(key)
+        if pin is None:
+            pin = torch.empty(arr.shape, dtype=torch.uint8 if want is np.uint8 else torch.float32).pin_memory()
+            self._pinned[key] = pin
+        np.copyto(pin.numpy(), arr, casting="unsafe")            # f64 -> f32 cast happens here (train_script feed)
+        return pin.to("cuda", non_blocking=True)
+
+    def run(self, fetches, feed_dict: Optional[dict] = None):
+        single = not isinstance(fetches, (list, tuple))
+        flist = [fetches] if single else list(fetches)
+        # a normalised-image placeholder may itself be fetched (base.py:234 fetches self.image_trans)
+        flist = [Fetch(f.root.consumers[0], "image_trans") if isinstance(f, Placeholder) and f.root.consumers else f
+                 for f in flist]
+        feed_dict = feed_dict or {}
+        models: List[_ContextModel] = []
+        for f in flist:
+            m = f.loss.model if isinstance(f, _Minimize) else getattr(f, "model", None)
+            if m is not None and m not in models:
+                models.append(m)
+        lr_value = None
+        for k, v in feed_dict.items():
+            if isinstance(k, Placeholder) and k.shape == ():
+                lr_value = float(v)
+        results: Dict[int, Any] = {}
+        for m in models:
+            register_model(m)
+            root = m.placeholder.root if isinstance(m.placeholder, Placeholder) else None
+            if root is not None:
+                fed = [v for k, v in feed_dict.items() if isinstance(k, Placeholder) and k.root is root]
+                if not fed:
+                    raise _lib.CtxError("no value fed for the model's image placeholder")
+                m.net.set_input(self._stage(m.placeholder, fed[0]))
+            mine = [f for f in flist if (f.loss.model if isinstance(f, _Minimize) else getattr(f, "model", None)) is m]
+            mins = [f for f in mine if isinstance(f, _Minimize)]
+            level = max([FWD_ALL] if mins else [f.level for f in mine])
+            if mins:
+                opt = mins[0].opt
+                lr = opt.lr
+                if isinstance(lr, Placeholder):
+                    if lr_value is None:
+                        raise _lib.CtxError("learning-rate placeholder was not fed")
+                    lr = lr_value
+                m.net.zero_grad()
+                m.net.forward(FWD_ALL)
+                # fetched values must be those of the pre-update graph, like TF: read them before Adam
+                for f in mine:
+                    if isinstance(f, Fetch):
+                        results[id(f)] = m.net.fetch(f.name).detach().clone()
+                    elif isinstance(f, NNErr):
+                        results[id(f)] = m.net.nn_err(f.nlen)
+                m.net.backward()
+                m.net.adam_step(float(lr), opt.b1, opt.b2, opt.eps)
+            else:
+                m.net.forward(max(level, 1))
+                for f in mine:
+                    results[id(f)] = m.net.nn_err(f.nlen) if isinstance(f, NNErr) else m.net.fetch(f.name)
+        out = []
+        for f in flist:
+            if isinstance(f, _Minimize):
+                out.append(None)
+            elif isinstance(f, NNErr):
+                out.append(results[id(f)])
+            else:
+                v = results[id(f)].detach().cpu().numpy()
+                out.append(v.item() if v.ndim == 0 else v)
+        return out[0] if single else out
+
+    def close(self):
+        self._pinned.clear()
+
+
+class NNErr:
+    """Handle for the trainer's nearest-neighbour frame-index error (train_script.py:148)."""
+
+    def __init__(self, model: _ContextModel, nlen: int):
+        self.model, self.nlen, self.level = model, int(nlen), FWD_ALL
+        self.name = "nn_err"

@@ -1,0 +1,145 @@
+// C-ABI entry points for the GEMM-shaped ops + library-wide helpers (errors, device info).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ctx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return CTX_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached_dev = -1;
+  static int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+static int check_geom(const ctx_conv_geom* g, const char* who) {
+  CTX_REQUIRE(g != nullptr, "%s: null geometry", who);
+  CTX_REQUIRE(g->N >= 0 && g->H > 0 && g->W > 0 && g->P > 0 && g->Q > 0 && g->kh > 0 && g->kw > 0 && g->stride > 0 &&
+                  g->pad_h >= 0 && g->pad_w >= 0,
+              "%s: bad geometry N=%d H=%d W=%d P=%d Q=%d k=%dx%d stride=%d pad=%d,%d", who, g->N, g->H, g->W, g->P,
+              g->Q, g->kh, g->kw, g->stride, g->pad_h, g->pad_w);
+  // every small-grid pixel must map inside the padded big grid (SAME geometry)
+  CTX_REQUIRE((g->P - 1) * g->stride - g->pad_h < g->H && (g->Q - 1) * g->stride - g->pad_w < g->W,
+              "%s: small grid %dx%d does not fit big grid %dx%d at stride %d", who, g->P, g->Q, g->H, g->W, g->stride);
+  return CTX_OK;
+}
+
+}  // namespace ctx
+
+using namespace ctx;
+
+extern "C" int ctx_version(void) { return CTX_B200_VERSION; }
+
+extern "C" const char* ctx_last_error(void) { return g_err; }
+
+extern "C" int ctx_device_info(int32_t* sms, int32_t* major, int32_t* minor) {
+  int dev = 0;
+  CTX_CUDA(cudaGetDevice(&dev));
+  int a = 0, b = 0, c = 0;
+  CTX_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+  CTX_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+  CTX_CUDA(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sms) *sms = a;
+  if (major) *major = b;
+  if (minor) *minor = c;
+  return CTX_OK;
+}
+
+extern "C" int ctx_tc_available(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (major == 10 && tc_compiled()) ? 1 : 0;
+}
+
+extern "C" int ctx_conv2d_fprop(const float* x, int32_t C, const float* w, float* y, int32_t Co,
+                                const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream) {
+  int rc = check_geom(g, "conv2d_fprop");
+  if (rc) return rc;
+  CTX_REQUIRE(x && w && y && C > 0 && Co > 0, "conv2d_fprop: null pointer or bad channel count");
+  if (g->N == 0) return CTX_OK;
+  Epi e = make_epi(epi);
+  if (impl != CTX_IMPL_SIMT) {
+    int ok = tc_conv2d_fprop_eligible(C, Co, *g);
+    if (ok && ctx_tc_available()) return tc_conv2d_fprop(x, C, w, y, Co, *g, e, (cudaStream_t)stream);
+    if (impl == CTX_IMPL_TC) { set_error("conv2d_fprop: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+  }
+  return simt_conv2d_fprop(x, C, w, y, Co, *g, e, (cudaStream_t)stream);
+}
+
+extern "C" int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t x2_batch,
+                                    const float* w, float* y, int32_t Cn, const ctx_conv_geom* g,
+                                    const ctx_epilogue* epi, int32_t impl, void* stream) {
+  int rc = check_geom(g, "conv2d_transpose");
+  if (rc) return rc;
+  CTX_REQUIRE(x1 && w && y && C1 > 0 && Cn > 0 && C2 >= 0, "conv2d_transpose: null pointer or bad channel count");
+  CTX_REQUIRE((C2 == 0) == (x2 == nullptr), "conv2d_transpose: x2 and C2 must both be set or both be empty");
+  CTX_REQUIRE(C2 == 0 || x2_batch > 0, "conv2d_transpose: x2_batch must be positive");
+  if (g->N == 0) return CTX_OK;
+  Epi e = make_epi(epi);
+  if (impl != CTX_IMPL_SIMT) {
+    int ok = tc_conv2d_transpose_eligible(C1, C2, x2_batch, Cn, *g);
+    if (ok && ctx_tc_available())
+      return tc_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, (cudaStream_t)stream);
+    if (impl == CTX_IMPL_TC) { set_error("conv2d_transpose: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+  }
+  return simt_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, (cudaStream_t)stream);
+}
+
+extern "C" int ctx_conv2d_wgrad(const float* big, int32_t Ca, const float* small1, int32_t Cb1, const float* small2,
+                                int32_t Cb2, int32_t small2_batch, float* dw, const ctx_conv_geom* g, int32_t impl,
+                                void* stream) {
+  int rc = check_geom(g, "conv2d_wgrad");
+  if (rc) return rc;
+  CTX_REQUIRE(big && small1 && dw && Ca > 0 && Cb1 > 0 && Cb2 >= 0, "conv2d_wgrad: null pointer or bad channel count");
+  CTX_REQUIRE((Cb2 == 0) == (small2 == nullptr), "conv2d_wgrad: small2 and Cb2 must both be set or both be empty");
+  CTX_REQUIRE(Cb2 == 0 || small2_batch > 0, "conv2d_wgrad: small2_batch must be positive");
+  if (g->N == 0) return CTX_OK;
+  if (impl != CTX_IMPL_SIMT) {
+    int ok = tc_conv2d_wgrad_eligible(Ca, Cb1, Cb2, small2_batch, *g);
+    if (ok && ctx_tc_available())
+      return tc_conv2d_wgrad(big, Ca, small1, Cb1, small2, Cb2, small2_batch, dw, *g, (cudaStream_t)stream);
+    if (impl == CTX_IMPL_TC) { set_error("conv2d_wgrad: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+  }
+  return simt_conv2d_wgrad(big, Ca, small1, Cb1, small2, Cb2, small2_batch, dw, *g, (cudaStream_t)stream);
+}
+
+extern "C" int ctx_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
+                        const float* B, int32_t ldb, float* C, int32_t ldc, const ctx_epilogue* epi, int32_t impl,
+                        void* stream) {
+  CTX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
+  CTX_REQUIRE(A && B && C, "gemm: null pointer");
+  CTX_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm: leading dimension too small");
+  if (M == 0 || N == 0) return CTX_OK;
+  Epi e = make_epi(epi);
+  if (impl != CTX_IMPL_SIMT) {
+    int ok = tc_gemm_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
+    if (ok && ctx_tc_available())
+      return tc_gemm(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
+    if (impl == CTX_IMPL_TC) { set_error("gemm: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+  }
+  return simt_gemm(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
+}

@@ -1,0 +1,477 @@
+// HBM-bound pointwise and reduction kernels of the hot path: image normalisation, lrelu', bias gradients,
+// the three losses (+ their gradients), skip-gradient split, fused Adam, TF32 operand preparation, nn_err and
+// the two reward distances.  All are grid-stride, 128-bit vectorised where the layout allows, with
+// warp-shuffle + one atomic per block for reductions.
+#include "common.cuh"
+
+namespace ctx {
+
+static inline int grid_for(int64_t work_items, int block, int per_sm = 8) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 1;
+  int64_t g = cdiv(work_items, block);
+  int64_t cap = (int64_t)sms * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+
+// ---- u8 -> [-1,1] ------------------------------------------------------------------------------------------
+__global__ void u8_normalize_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const float inv = 1.0f / 255.0f;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n / 4;
+  if ((((uintptr_t)x) & 3) == 0 && (((uintptr_t)y) & 15) == 0) {
+    for (int64_t j = i; j < n4; j += stride) {
+      uchar4 u = reinterpret_cast<const uchar4*>(x)[j];
+      float4 o;
+      // three separate fp32 roundings, exactly as the TF graph (no FMA contraction)
+      o.x = __fmul_rn(__fsub_rn(__fmul_rn((float)u.x, inv), 0.5f), 2.0f);
+      o.y = __fmul_rn(__fsub_rn(__fmul_rn((float)u.y, inv), 0.5f), 2.0f);
+      o.z = __fmul_rn(__fsub_rn(__fmul_rn((float)u.z, inv), 0.5f), 2.0f);
+      o.w = __fmul_rn(__fsub_rn(__fmul_rn((float)u.w, inv), 0.5f), 2.0f);
+      reinterpret_cast<float4*>(y)[j] = o;
+    }
+    for (int64_t j = n4 * 4 + i; j < n; j += stride)
+      y[j] = __fmul_rn(__fsub_rn(__fmul_rn((float)x[j], inv), 0.5f), 2.0f);
+  } else {
+    for (int64_t j = i; j < n; j += stride)
+      y[j] = __fmul_rn(__fsub_rn(__fmul_rn((float)x[j], inv), 0.5f), 2.0f);
+  }
+}
+
+// ---- lrelu backward ------------------------------------------------------------------------------------------
+__global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yref, float* out,
+                                 int64_t n, float slope, int accumulate) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = dy[i] * (yref[i] >= 0.f ? 1.f : slope);
+    if (accumulate) v += out[i];
+    out[i] = v;
+  }
+}
+
+// ---- bias gradient: column sums of dy[M, C] --------------------------------------------------------------------
+// block = 32 x 8 threads: threadIdx.x walks 32 consecutive columns (coalesced), threadIdx.y strides rows.
+__global__ void bias_grad_kernel(const float* __restrict__ dy, int64_t M, int C, int ldy, float* db,
+                                 int64_t rows_per_block) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += dy[r * ldy + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
+    atomicAdd(db + c, t);
+  }
+}
+
+// ---- pixel reconstruction losses + gradient ------------------------------------------------------------------------
+__global__ void l2_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                               const float* __restrict__ resid, int64_t per_pass, const float* __restrict__ weight,
+                               float* loss, float* __restrict__ dpred) {
+  // blockIdx.y = decoder pass g; elements of one pass are [B*per_img] and line up with tgt / resid
+  const int g = blockIdx.y;
+  const float wg = weight ? weight[g] : 1.f;
+  const float* pg = pred + (int64_t)g * per_pass;
+  float* dg = dpred ? dpred + (int64_t)g * per_pass : nullptr;
+  float s = 0.f;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < per_pass; i += stride) {
+    float d = pg[i] + (resid ? resid[i] : 0.f) - tgt[i];
+    s += d * d;
+    if (dg) dg[i] = wg * d;
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(loss + g, 0.5f * s);
+}
+
+// ---- feature alignment loss + gradient --------------------------------------------------------------------------------
+__global__ void mse_scaled_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                  int64_t rows, int F, float scale_inv, float gcoef, float* loss, float* da,
+                                  int ldda, float* db, int lddb, int accumulate) {
+  const int64_t n = rows * F;
+  float s = 0.f;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int64_t r = i / F;
+    const int c = (int)(i - r * F);
+    const float d = a[r * lda + c] - b[r * ldb + c];
+    s += d * d;
+    const float gv = gcoef * d;
+    if (da) { float* q = da + r * ldda + c; *q = accumulate ? *q + gv : gv; }
+    if (db) { float* q = db + r * lddb + c; *q = accumulate ? *q - gv : -gv; }
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, scale_inv * s);
+}
+
+// ---- decoder-level data-gradient split ------------------------------------------------------------------------------
+__global__ void split_skip_grad_kernel(const float* __restrict__ dcat, int G, int64_t B, int64_t pix, int C1, int C2,
+                                       const float* __restrict__ state_ref, const float* __restrict__ skip_ref,
+                                       float slope, float* __restrict__ dstate, float* dskip, int accumulate_skip) {
+  const int Ct = C1 + C2;
+  const int64_t n_state = (int64_t)G * B * pix * C1;
+  const int64_t n_skip = B * pix * C2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < n_state; j += stride) {
+    const int64_t row = j / C1;
+    const int c = (int)(j - row * C1);
+    float v = dcat[row * Ct + c];
+    if (state_ref) v *= (state_ref[j] >= 0.f ? 1.f : slope);
+    dstate[j] = v;
+  }
+  for (int64_t j = i; j < n_skip; j += stride) {
+    const int64_t row = j / C2;                         // row in [0, B*pix)
+    const int c = (int)(j - row * C2);
+    float v = 0.f;
+    for (int g = 0; g < G; ++g) v += dcat[((int64_t)g * B * pix + row) * Ct + C1 + c];
+    if (skip_ref) v *= (skip_ref[j] >= 0.f ? 1.f : slope);
+    dskip[j] = accumulate_skip ? dskip[j] + v : v;
+  }
+}
+
+__global__ void add_bcast_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                 int64_t n, int64_t nb) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = a[i] + b[i % nb];
+}
+
+// ---- fused TF-Adam ----------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps,
+                            float gscale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n / 4;
+  const float ob1 = 1.f - b1, ob2 = 1.f - b2;
+  for (int64_t j = i; j < n4; j += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[j];
+    float4 gg = reinterpret_cast<const float4*>(g)[j];
+    float4 mm = reinterpret_cast<float4*>(m)[j];
+    float4 vv = reinterpret_cast<float4*>(v)[j];
+#define CTX_ADAM1(c)                                               \
+    {                                                              \
+      float gr = gg.c * gscale;                                    \
+      mm.c = b1 * mm.c + ob1 * gr;                                 \
+      vv.c = b2 * vv.c + ob2 * gr * gr;                            \
+      pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);                   \
+    }
+    CTX_ADAM1(x) CTX_ADAM1(y) CTX_ADAM1(z) CTX_ADAM1(w)
+#undef CTX_ADAM1
+    reinterpret_cast<float4*>(p)[j] = pp;
+    reinterpret_cast<float4*>(m)[j] = mm;
+    reinterpret_cast<float4*>(v)[j] = vv;
+  }
+  for (int64_t j = n4 * 4 + i; j < n; j += stride) {
+    float gr = g[j] * gscale;
+    float mm = b1 * m[j] + ob1 * gr;
+    float vv = b2 * v[j] + ob2 * gr * gr;
+    m[j] = mm; v[j] = vv;
+    p[j] -= lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
+// ---- TF32 operand preparation --------------------------------------------------------------------------------------
+__global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = round_tf32(x[i]);
+}
+
+// out[b][c][r] = in[b][r][c]; 32x32 smem tile, block (32, 8)
+__global__ void transpose_round_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                       int do_round) {
+  __shared__ float tile[32][33];
+  const int64_t boff = (int64_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[boff + (int64_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) {
+      float v = tile[threadIdx.x][j];
+      out[boff + (int64_t)c * rows + r] = do_round ? round_tf32(v) : v;
+    }
+  }
+}
+
+// ---- nn_err -------------------------------------------------------------------------------------------------------
+// dist[a, b] = mean_i (tgt[a,i] - out[b,i])^2 ; one block per (a, b) pair, direct form (no ||a||^2-2ab trick,
+// so rounding behaves like the reference's reduce_mean of squared differences).
+__global__ void nn_dist_kernel(const float* __restrict__ tgt, const float* __restrict__ out, int B, int64_t per_img,
+                               float* __restrict__ dist) {
+  const int a = blockIdx.x, b = blockIdx.y;
+  const float* ta = tgt + (int64_t)a * per_img;
+  const float* ob = out + (int64_t)b * per_img;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < per_img; i += blockDim.x) {
+    float d = ta[i] - ob[i];
+    s = fmaf(d, d, s);
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) dist[(int64_t)a * B + b] = s / (float)per_img;
+}
+
+// idx[b] = first argmin_a dist[a,b];  err = sum_b |idx[b] - b % nlen|   (single block)
+__global__ void nn_argmin_kernel(const float* __restrict__ dist, int B, int nlen, int64_t* __restrict__ idx,
+                                 int64_t* __restrict__ err) {
+  __shared__ unsigned long long total;
+  if (threadIdx.x == 0) total = 0ull;
+  __syncthreads();
+  unsigned long long local = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float best = dist[b];
+    int bi = 0;
+    for (int a = 1; a < B; ++a) {
+      float d = dist[(int64_t)a * B + b];
+      if (d < best) { best = d; bi = a; }
+    }
+    idx[b] = bi;
+    int diff = bi - (b % nlen);
+    local += (unsigned long long)(diff < 0 ? -diff : diff);
+  }
+  atomicAdd(&total, local);
+  __syncthreads();
+  if (threadIdx.x == 0) *err = (int64_t)total;
+}
+
+// ---- rewards ---------------------------------------------------------------------------------------------------------
+// one block per (path, frame j)
+__global__ void reward_ours_kernel(const float* __restrict__ z, const float* __restrict__ x,
+                                   const float* __restrict__ means, const float* __restrict__ mean_imgs, int T, int F,
+                                   int64_t per_img, float scale, float fw, float iw, double* rewards,
+                                   int64_t rew_stride, float* cost) {
+  const int p = blockIdx.y, j = blockIdx.x;
+  const int64_t row = (int64_t)p * T + j;
+  float sf = 0.f, si = 0.f;
+  if (fw != 0.f) {
+    const float* zz = z + row * F;
+    const float* mm = means + (int64_t)j * F;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) { float d = mm[k] - zz[k]; sf = fmaf(d, d, sf); }
+  }
+  if (iw != 0.f) {
+    const float* xx = x + row * per_img;
+    const float* mi = mean_imgs + (int64_t)j * per_img;
+    for (int64_t k = threadIdx.x; k < per_img; k += blockDim.x) { float d = mi[k] - xx[k]; si = fmaf(d, d, si); }
+  }
+  sf = block_sum(sf);
+  si = block_sum(si);
+  if (threadIdx.x == 0) {
+    float c = fw * sf + iw * (scale * si);
+    if (cost) cost[row] = c;
+    if (rewards) rewards[(int64_t)p * rew_stride + 2 * j + 1] -= (double)c * (double)(j * j);
+  }
+}
+
+__global__ void reward_inception_kernel(const float* __restrict__ feat, const float* __restrict__ means,
+                                        const float* __restrict__ stdv, int T, int64_t per_frame, double* rewards,
+                                        int64_t rew_stride, float* cost) {
+  const int p = blockIdx.y, j = blockIdx.x;
+  const int64_t row = (int64_t)p * T + j;
+  const float* f = feat + row * per_frame;
+  const float* mu = means + (int64_t)j * per_frame;
+  const float* sd = stdv + (int64_t)j * per_frame;
+  float s = 0.f;
+  for (int64_t k = threadIdx.x; k < per_frame; k += blockDim.x) {
+    float sdv = sd[k];
+    float d = (sdv == 0.f) ? 0.f : (mu[k] - f[k]);
+    s += d * d / (sdv + 1e-5f);
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) {
+    float m = s / (float)per_frame;
+    if (cost) cost[row] = m;
+    if (rewards) rewards[(int64_t)p * rew_stride + 2 * j + 1] -= (double)m * (double)(j * j);
+  }
+}
+
+}  // namespace ctx
+
+// ==== C-ABI ============================================================================================================
+using namespace ctx;
+
+extern "C" int ctx_u8_normalize(const uint8_t* x, float* y, int64_t n, void* stream) {
+  CTX_REQUIRE(x && y && n >= 0, "u8_normalize: bad arguments");
+  if (n == 0) return CTX_OK;
+  u8_normalize_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  CTX_LAUNCH_CHECK("u8_normalize");
+  return CTX_OK;
+}
+
+extern "C" int ctx_lrelu_bwd(const float* dy, const float* y_ref, float* out, int64_t n, float slope,
+                             int32_t accumulate, void* stream) {
+  CTX_REQUIRE(dy && y_ref && out && n >= 0, "lrelu_bwd: bad arguments");
+  if (n == 0) return CTX_OK;
+  lrelu_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y_ref, out, n, slope, accumulate);
+  CTX_LAUNCH_CHECK("lrelu_bwd");
+  return CTX_OK;
+}
+
+extern "C" int ctx_bias_grad(const float* dy, int64_t M, int32_t C, int32_t ldy, float* db, void* stream) {
+  CTX_REQUIRE(dy && db && M >= 0 && C > 0 && ldy >= C, "bias_grad: bad arguments");
+  if (M == 0) return CTX_OK;
+  int sms = sm_count();
+  if (sms <= 0) return cuda_fail(cudaErrorNoDevice, "bias_grad");
+  int gx = (int)cdiv(C, 32);
+  int64_t want_y = cdiv((int64_t)sms * 4, gx);
+  int64_t rows_per_block = cdiv(M, want_y);
+  if (rows_per_block < 64) rows_per_block = 64;
+  int gy = (int)cdiv(M, rows_per_block);
+  bias_grad_kernel<<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, M, C, ldy, db, rows_per_block);
+  CTX_LAUNCH_CHECK("bias_grad");
+  return CTX_OK;
+}
+
+extern "C" int ctx_l2_loss_fwd_bwd(const float* pred, const float* tgt, const float* resid, int32_t G, int64_t B,
+                                   int64_t per_img, const float* weight, float* loss, float* dpred, void* stream) {
+  CTX_REQUIRE(pred && tgt && loss && G > 0 && B >= 0 && per_img > 0, "l2_loss: bad arguments");
+  if (B == 0) return CTX_OK;
+  int64_t per_pass = B * per_img;
+  int gx = grid_for(per_pass, 256, 4);
+  l2_loss_kernel<<<dim3(gx, G), 256, 0, (cudaStream_t)stream>>>(pred, tgt, resid, per_pass, weight, loss, dpred);
+  CTX_LAUNCH_CHECK("l2_loss");
+  return CTX_OK;
+}
+
+extern "C" int ctx_mse_scaled_fwd_bwd(const float* a, int32_t lda, const float* b, int32_t ldb, int64_t rows,
+                                      int32_t F, float scale, float inv_count, float grad_weight, float* loss,
+                                      float* da, int32_t ldda, float* db, int32_t lddb, int32_t accumulate,
+                                      void* stream) {
+  CTX_REQUIRE(a && b && rows >= 0 && F > 0, "mse_scaled: bad arguments");
+  if (rows == 0) return CTX_OK;
+  mse_scaled_kernel<<<grid_for(rows * F, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      a, lda, b, ldb, rows, F, scale * inv_count, grad_weight * 2.f * scale * inv_count, loss, da, ldda, db, lddb,
+      accumulate);
+  CTX_LAUNCH_CHECK("mse_scaled");
+  return CTX_OK;
+}
+
+extern "C" int ctx_split_skip_grad(const float* dcat, int32_t G, int64_t B, int64_t pix, int32_t C1, int32_t C2,
+                                   const float* state_ref, const float* skip_ref, float slope, float* dstate,
+                                   float* dskip, int32_t accumulate_skip, void* stream) {
+  CTX_REQUIRE(dcat && dstate && dskip && G > 0 && C1 > 0 && C2 > 0, "split_skip_grad: bad arguments");
+  if (B == 0 || pix == 0) return CTX_OK;
+  int64_t n = (int64_t)G * B * pix * C1;
+  split_skip_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      dcat, G, B, pix, C1, C2, state_ref, skip_ref, slope, dstate, dskip, accumulate_skip);
+  CTX_LAUNCH_CHECK("split_skip_grad");
+  return CTX_OK;
+}
+
+extern "C" int ctx_add_bcast(const float* a, const float* b, float* out, int64_t rows, int64_t b_rows, int64_t C,
+                             void* stream) {
+  CTX_REQUIRE(a && b && out && rows >= 0 && b_rows > 0 && C > 0, "add_bcast: bad arguments");
+  if (rows == 0) return CTX_OK;
+  add_bcast_kernel<<<grid_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, rows * C, b_rows * C);
+  CTX_LAUNCH_CHECK("add_bcast");
+  return CTX_OK;
+}
+
+extern "C" int ctx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1,
+                             float b2, float eps, float grad_scale, void* stream) {
+  CTX_REQUIRE(p && g && m && v && n >= 0, "adam_step: bad arguments");
+  CTX_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                  ((uintptr_t)v % 16 == 0), "adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return CTX_OK;
+  adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, b1, b2, eps,
+                                                                            grad_scale);
+  CTX_LAUNCH_CHECK("adam_step");
+  return CTX_OK;
+}
+
+extern "C" int ctx_round_tf32(const float* x, float* y, int64_t n, void* stream) {
+  CTX_REQUIRE(x && y && n >= 0, "round_tf32: bad arguments");
+  if (n == 0) return CTX_OK;
+  round_tf32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  CTX_LAUNCH_CHECK("round_tf32");
+  return CTX_OK;
+}
+
+extern "C" int ctx_transpose_round(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols,
+                                   int32_t do_round, void* stream) {
+  CTX_REQUIRE(in && out && batch > 0 && rows > 0 && cols > 0, "transpose_round: bad arguments");
+  CTX_REQUIRE(batch <= 65535 && cdiv(rows, 32) <= 65535, "transpose_round: grid too large");
+  dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), (unsigned)batch);
+  transpose_round_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, rows, cols, do_round);
+  CTX_LAUNCH_CHECK("transpose_round");
+  return CTX_OK;
+}
+
+extern "C" int ctx_nn_err(const float* tgt, const float* out, int32_t B, int64_t per_img, int32_t nlen,
+                          float* dist_ws, int64_t* idx, int64_t* err, void* stream) {
+  CTX_REQUIRE(tgt && out && dist_ws && idx && err && B > 0 && per_img > 0 && nlen > 0, "nn_err: bad arguments");
+  CTX_REQUIRE(B <= 65535, "nn_err: batch too large");
+  nn_dist_kernel<<<dim3(B, B), 128, 0, (cudaStream_t)stream>>>(tgt, out, B, per_img, dist_ws);
+  CTX_LAUNCH_CHECK("nn_dist");
+  nn_argmin_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dist_ws, B, nlen, idx, err);
+  CTX_LAUNCH_CHECK("nn_argmin");
+  return CTX_OK;
+}
+
+extern "C" int ctx_reward_ours(const float* z, const float* x, const float* means, const float* mean_imgs,
+                               int32_t paths, int32_t T, int32_t F, int64_t per_img, float scale,
+                               float feat_weight, float img_weight, double* rewards, int64_t rew_stride,
+                               float* cost, void* stream) {
+  CTX_REQUIRE(paths >= 0 && T > 0 && F > 0 && per_img > 0, "reward_ours: bad arguments");
+  CTX_REQUIRE((feat_weight == 0.f || (z && means)) && (img_weight == 0.f || (x && mean_imgs)),
+              "reward_ours: null input for an enabled term");
+  CTX_REQUIRE(rewards || cost, "reward_ours: no output requested");
+  CTX_REQUIRE(!rewards || rew_stride >= 2 * (int64_t)T, "reward_ours: rew_stride must cover indices 2j+1");
+  CTX_REQUIRE(paths <= 65535, "reward_ours: too many paths per call");
+  if (paths == 0) return CTX_OK;
+  reward_ours_kernel<<<dim3(T, paths), 256, 0, (cudaStream_t)stream>>>(
+      z, x, means, mean_imgs, T, F, per_img, scale, feat_weight, img_weight, rewards, rew_stride, cost);
+  CTX_LAUNCH_CHECK("reward_ours");
+  return CTX_OK;
+}
+
+extern "C" int ctx_reward_inception(const float* feat, const float* means, const float* std, int32_t paths,
+                                    int32_t T, int64_t per_frame, double* rewards, int64_t rew_stride, float* cost,
+                                    void* stream) {
+  CTX_REQUIRE(feat && means && std && paths >= 0 && T > 0 && per_frame > 0, "reward_inception: bad arguments");
+  CTX_REQUIRE(rewards || cost, "reward_inception: no output requested");
+  CTX_REQUIRE(!rewards || rew_stride >= 2 * (int64_t)T, "reward_inception: rew_stride must cover indices 2j+1");
+  CTX_REQUIRE(paths <= 65535, "reward_inception: too many paths per call");
+  if (paths == 0) return CTX_OK;
+  reward_inception_kernel<<<dim3(T, paths), 256, 0, (cudaStream_t)stream>>>(feat, means, std, T, per_frame, rewards,
+                                                                            rew_stride, cost);
+  CTX_LAUNCH_CHECK("reward_inception");
+  return CTX_OK;
+}

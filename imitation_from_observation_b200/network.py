@@ -1,0 +1,487 @@
+"""Graph executor for the context-translation network: explicit forward, backward and TF-Adam over flat buffers.
+
+This is the B200 replacement for "TF builds a graph, sess.run executes a pruned subgraph": the graph is static
+(SURVEY.md §3.4), so forward and backward are written out once, every activation / gradient lives in a
+pre-allocated HBM buffer, and each node is one call into libctx_b200.so on the current CUDA stream.
+
+Design points:
+  * frames that share encoder weights are stacked on the batch axis and run as one launch
+    ([src; tgt] through scope "conv" — arm_shaping.py:1290-1307; the two decoder passes [trans_z; tgt_z]
+    through scope "deconv" — :1314-1343), so shared weights are read once and their gradients are one wgrad;
+  * tf.concat([h, skip], 3) (:1323-1329) is never materialised: the transposed-conv kernel takes two sources;
+  * lrelu' is fused into the epilogue of the kernel that produces each data gradient;
+  * parameters, gradients and Adam moments are three flat fp32 buffers with identical layout (ordered so that
+    gradients complete front-to-back during backward -> bucketed all-reduce), one fused Adam launch.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import IMPL_AUTO, IMPL_SIMT
+from .spec import NetSpec
+
+FWD_SRC, FWD_TRANS, FWD_ALL = 1, 2, 3
+_ALIGN = 64          # floats; every parameter starts on a 256-byte boundary (TMA / 128-bit access friendly)
+
+
+def _numel(shape) -> int:
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
+class ContextNet:
+    """One network instance bound to a device, a per-rank batch size and a precision mode.
+
+    precision = "fp32": every GEMM-shaped op uses the exact-fp32 SIMT kernels.
+    precision = "tf32": tcgen05 kernels (TF32 operands rounded to nearest, fp32 accumulate) wherever the shape
+                        qualifies, SIMT elsewhere.
+    """
+
+    def __init__(self, spec: NetSpec, batch: int, device="cuda", precision: str = "tf32", seed: int = 0,
+                 global_batch: Optional[int] = None, ablation_type: str = "None", params_from: "ContextNet" = None):
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        _lib.load()                                   # fail loudly if the extension is missing
+        self.spec = spec
+        self.B = int(batch)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CtxError("ContextNet needs a CUDA device: the B200 path has no CPU fallback")
+        self.precision = precision
+        self.impl = IMPL_SIMT if precision == "fp32" else IMPL_AUTO
+        self.round = precision == "tf32"
+        self.global_batch = int(global_batch) if global_batch else self.B
+        self.ablation_type = ablation_type
+        self._w_recon = {"None": (1.0, 1.0), "L2": (1.0, 1.0), "L2L3": (1.0, 0.0), "L1": (0.0, 1.0)}[ablation_type]
+        self._w_sim = {"None": 1.0, "L2": 0.0, "L2L3": 0.0, "L1": 1.0}[ablation_type]
+        self.step_count = 0
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+        # ---- flat parameter / gradient / moment buffers -----------------------------------------------------
+        self.shapes = spec.param_shapes()
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for name, shp in self.shapes.items():
+            self.offsets[name] = off
+            off += -(-_numel(shp) // _ALIGN) * _ALIGN
+        self.flat_size = off
+        if params_from is not None:
+            if params_from.spec.param_shapes() != self.shapes:
+                raise ValueError("params_from has a different architecture")
+            self.flat_p = params_from.flat_p
+        else:
+            self.flat_p = torch.zeros(off, device=self.device, dtype=torch.float32)
+        self.flat_g = None
+        self.flat_m = None
+        self.flat_v = None
+        self.P = {n: self._view(self.flat_p, n) for n in self.shapes}
+        self.G: Dict[str, torch.Tensor] = {}
+        if params_from is None:
+            self.init_params(seed)
+        self.ctx_scope = "conv_context" if spec.separate_ctx_encoder else "conv"
+        self.sizes = [(spec.height, spec.width)] + spec.enc_sizes()
+        self.chans = spec.enc_channels()
+        self.F = spec.featsize
+        self.flat = spec.flat_dim()
+        self.dec = spec.dec_layers()
+        self._level = 0
+
+    # ---- buffers ------------------------------------------------------------------------------------------------
+    def _view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        o = self.offsets[name]
+        shp = self.shapes[name]
+        return flat[o:o + _numel(shp)].view(shp)
+
+    def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+            self._bufs[name] = t
+        return t
+
+    def _ensure_grads(self):
+        if self.flat_g is None:
+            self.flat_g = torch.zeros(self.flat_size, device=self.device, dtype=torch.float32)
+            self.G = {n: self._view(self.flat_g, n) for n in self.shapes}
+
+    def _ensure_moments(self):
+        if self.flat_m is None:
+            self.flat_m = torch.zeros(self.flat_size, device=self.device, dtype=torch.float32)
+            self.flat_v = torch.zeros(self.flat_size, device=self.device, dtype=torch.float32)
+
+    # ---- parameters ---------------------------------------------------------------------------------------------
+    def init_params(self, seed: int = 0):
+        """arm_shaping.py:25-29,52-55,67-79: conv truncated_normal(0.02), deconv/linear random_normal(0.02),
+        biases 0.  (Host-side torch RNG; initialisation is not on the hot path.)"""
+        g = torch.Generator().manual_seed(seed)
+        for name, shp in self.shapes.items():
+            if name.endswith("biases") or name.endswith("bias"):
+                t = torch.zeros(shp)
+            else:
+                t = torch.randn(shp, generator=g) * 0.02
+                if "_conv/w" in name:
+                    for _ in range(8):
+                        bad = t.abs() > 0.04
+                        if not bad.any():
+                            break
+                        t = torch.where(bad, torch.randn(shp, generator=g) * 0.02, t)
+                    t = t.clamp(-0.04, 0.04)
+            self.P[name].copy_(t.to(self.device))
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        """TF-checkpoint-keyed parameters (SURVEY.md §8b 'Checkpoint keys')."""
+        return {n: self.P[n].detach().cpu().numpy().copy() for n in self.shapes}
+
+    def load_state_dict(self, sd: Dict[str, "np.ndarray | torch.Tensor"], prefix: str = ""):
+        for n in self.shapes:
+            key = prefix + n
+            if key not in sd:
+                raise KeyError("missing parameter %s" % key)
+            v = sd[key]
+            v = torch.as_tensor(np.asarray(v)) if not torch.is_tensor(v) else v
+            if tuple(v.shape) != tuple(self.shapes[n]):
+                raise ValueError("parameter %s has shape %s, expected %s" % (key, tuple(v.shape), self.shapes[n]))
+            self.P[n].copy_(v.to(device=self.device, dtype=torch.float32))
+
+    # ---- inputs ---------------------------------------------------------------------------------------------------
+    def _input_buffers(self):
+        """xe: frames through scope "conv" ([src; tgt] and, for a shared encoder, [src; tgt; ctx]); xc: ctx frames."""
+        B, (H, W), C = self.B, self.sizes[0], self.chans[0]
+        n_e = 2 * B if self.spec.separate_ctx_encoder else 3 * B
+        xe = self._buf("xe", (n_e, H, W, C))
+        xc = self._buf("xc", (B, H, W, C)) if self.spec.separate_ctx_encoder else xe[2 * B:]
+        return xe, xc
+
+    def set_input(self, image: torch.Tensor):
+        """image [3,B,H,W,C] (0 = src, 1 = ctx, 2 = tgt — arm_shaping.py:1278-1280), uint8 or fp32, on the device.
+        uint8 is normalised on the fly (base.py:117-119)."""
+        B = self.B
+        if tuple(image.shape) != (3, B) + self.sizes[0] + (self.chans[0],):
+            raise _lib.CtxError("input must be [3,%d,%d,%d,%d], got %s"
+                                % ((B,) + self.sizes[0] + (self.chans[0],) + (tuple(image.shape),)))
+        xe, xc = self._input_buffers()
+        dst = (xe[:B], xc, xe[B:2 * B])
+        for r in range(3):
+            if image.dtype == torch.uint8:
+                ops.u8_normalize(image[r].contiguous(), out=dst[r])
+            else:
+                dst[r].copy_(image[r])
+
+    # ---- forward pieces (also the functional enc1 / enc2 / translate / dec surface) ------------------------------
+    def encode_convs(self, scope: str, x: torch.Tensor, outs: Sequence[torch.Tensor]):
+        """4 x (conv5x5/3x3 SAME + bias + lrelu) — arm_shaping.py:1283-1286."""
+        h = x
+        for j in range(4):
+            ops.conv2d(h, self.P["%s/h%d_conv/w" % (scope, j)], self.P["%s/h%d_conv/biases" % (scope, j)],
+                       stride=self.spec.strides[j], act=True, out=outs[j], round_tf32=self.round, impl=self.impl)
+            h = outs[j]
+
+    def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, bias=None, act=False, act_ref=None,
+              accumulate=False, round_=None):
+        epi = _lib.Epilogue(None if bias is None else bias.data_ptr(), act_ref, ops.LRELU_SLOPE, int(act),
+                            int(accumulate), int(self.round if round_ is None else round_))
+        ops.gemm_raw(tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, epi, self.impl)
+
+    def _fwd_encoder(self, scope: str, x: torch.Tensor, hs: List[torch.Tensor], h4: torch.Tensor):
+        n = x.shape[0]
+        self.encode_convs(scope, x, hs)
+        self._gemm(False, False, n, self.F, self.flat, hs[3].data_ptr(), self.flat,
+                   self.P[scope + "/h4_lin/Matrix"].data_ptr(), self.F, h4.data_ptr(), self.F,
+                   bias=self.P[scope + "/h4_lin/bias"], act=True)
+
+    def _fwd_hz(self, scope: str, h4_rows: torch.Tensor, out_ptr: int, ldo: int, act: bool):
+        self._gemm(False, False, h4_rows.shape[0], self.F, self.F, h4_rows.data_ptr(), self.F,
+                   self.P[scope + "/hz_lin/Matrix"].data_ptr(), self.F, out_ptr, ldo,
+                   bias=self.P[scope + "/hz_lin/bias"], act=act)
+
+    def _enc_buffers(self, n_rows: int, tag: str):
+        hs = [self._buf("%s_h%d" % (tag, j), (n_rows,) + self.sizes[j + 1] + (self.chans[j + 1],)) for j in range(4)]
+        h4 = self._buf("%s_h4" % tag, (n_rows, self.F))
+        return hs, h4
+
+    def forward(self, level: int = FWD_ALL):
+        """Run the graph up to `level`:
+             FWD_SRC   — source encoder only (`input_z`; the reward path, base.py:232-235)
+             FWD_TRANS — + context encoder, translator, decoder on trans_z (`translated_z`, `out`; base.py:216)
+             FWD_ALL   — + target encoder, decoder on tgt_z, the three losses (training, train_script.py:163)
+        """
+        sp, B, F = self.spec, self.B, self.F
+        xe, xc = self._input_buffers()
+        n_e = xe.shape[0]
+        e_hs, e_h4 = self._enc_buffers(n_e, "e")
+        cat = self._buf("cat", (B, 2 * F))
+        z2 = self._buf("z2", (2 * B, F))
+        f4 = 4  # bytes per float
+
+        if level == FWD_ALL:
+            rows = n_e                                   # [src; tgt] (+ ctx when the encoder is shared)
+        elif level == FWD_TRANS and not sp.separate_ctx_encoder:
+            rows = None                                  # src rows and ctx rows, two launches
+        else:
+            rows = B
+        if rows is not None:
+            self._fwd_encoder("conv", xe[:rows], [h[:rows] for h in e_hs], e_h4[:rows])
+        else:
+            self._fwd_encoder("conv", xe[:B], [h[:B] for h in e_hs], e_h4[:B])
+            self._fwd_encoder("conv", xe[2 * B:], [h[2 * B:] for h in e_hs], e_h4[2 * B:])
+        self._fwd_hz("conv", e_h4[:B], cat.data_ptr(), 2 * F, act=True)                    # src z -> cat[:, :F]
+        if level >= FWD_TRANS:
+            if sp.separate_ctx_encoder:
+                c_hs, c_h4 = self._enc_buffers(B, "c")
+                self._fwd_encoder("conv_context", xc, c_hs, c_h4)
+            else:
+                c_hs, c_h4 = [h[2 * B:] for h in e_hs], e_h4[2 * B:]
+            self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
+            th0 = self._buf("th0", (B, F))
+            self._gemm(False, False, B, F, 2 * F, cat.data_ptr(), 2 * F,
+                       self.P["translate/trans_h0/Matrix"].data_ptr(), F, th0.data_ptr(), F,
+                       bias=self.P["translate/trans_h0/bias"], act=True)
+            self._gemm(False, False, B, F, F, th0.data_ptr(), F, self.P["translate/trans_z/Matrix"].data_ptr(), F,
+                       z2.data_ptr(), F, bias=self.P["translate/trans_z/bias"], act=False)      # trans_z -> z2[:B]
+            nd = B
+            if level == FWD_ALL:
+                self._fwd_hz("conv", e_h4[B:2 * B], z2.data_ptr() + B * F * f4, F, act=True)  # tgt z -> z2[B:]
+                nd = 2 * B
+            d = self._dec_buffers()
+            self._fwd_decoder(z2[:nd], [c[:B] for c in c_hs], [t[:nd] for t in d])
+            if level == FWD_ALL:
+                self._fwd_losses(d[4], xe[B:2 * B], xc)
+        self._level = level
+
+    def _dec_buffers(self):
+        B = self.B
+        d = [self._buf("d0", (2 * B,) + self.sizes[4] + (self.chans[4],))]
+        for i, L in enumerate(self.dec):
+            d.append(self._buf("d%d" % (i + 1), (2 * B,) + tuple(L["out_hw"]) + (L["c_out"],)))
+        return d
+
+    def _fwd_decoder(self, z: torch.Tensor, skips: Sequence[torch.Tensor], d: Sequence[torch.Tensor]):
+        """arm_shaping.py:1314-1329 for all stacked passes at once; skips = ctx (h0,h1,h2,h3), batch B."""
+        n = z.shape[0]
+        self._gemm(False, False, n, self.flat, self.F, z.data_ptr(), self.F,
+                   self.P["deconv/d_h0_lin/Matrix"].data_ptr(), self.flat, d[0].data_ptr(), self.flat,
+                   bias=self.P["deconv/d_h0_lin/bias"], act=True)
+        for i, L in enumerate(self.dec):
+            last = i == 3
+            ops.conv2d_transpose(d[i], self.P["deconv/%s/w" % L["name"]], L["out_hw"],
+                                 bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2=skips[3 - i],
+                                 act=not last, out=d[i + 1], round_tf32=self.round and not last, impl=self.impl)
+
+    def _fwd_losses(self, d4: torch.Tensor, tgt: torch.Tensor, ctx: torch.Tensor):
+        B, F = self.B, self.F
+        losses = self._buf("losses", (4,))
+        losses.zero_()
+        g_d4 = self._buf("g_d4", tuple(d4.shape))
+        w = self._bufs.get("w_recon")
+        if w is None:
+            w = self._bufs["w_recon"] = torch.tensor(self._w_recon, device=self.device, dtype=torch.float32)
+        ops.l2_loss_fwd_bwd(d4, tgt, losses[0:2], dpred=g_d4, resid=ctx if self.spec.residual_out else None,
+                            weight=w)
+        z2 = self._bufs["z2"]
+        ops.mse_scaled_fwd_bwd(z2[:B], z2[B:], 1e3, 1.0 / (B * F), loss=losses[2:3])      # reported: local mean
+
+    # ---- backward -----------------------------------------------------------------------------------------------------
+    def zero_grad(self):
+        self._ensure_grads()
+        self.flat_g.zero_()
+
+    def backward(self, on_stage=None):
+        """Gradient of the (ablated) loss w.r.t. every parameter, accumulated into the flat gradient buffer.
+        `on_stage(scope)` is called as soon as all gradients of a parameter scope ("deconv", "translate", "conv",
+        "conv_context" — the order of the flat buffer) are enqueued, so a bucketed all-reduce can start early."""
+        if self._level != FWD_ALL:
+            raise _lib.CtxError("backward() needs forward(FWD_ALL) first")
+        self._ensure_grads()
+        sp, B, F, flat = self.spec, self.B, self.F, self.flat
+        P, G, bufs = self.P, self.G, self._bufs
+        f4 = 4
+        xe, xc = self._input_buffers()
+        n_e = xe.shape[0]
+        e_hs, e_h4 = self._enc_buffers(n_e, "e")
+        if sp.separate_ctx_encoder:
+            c_hs, c_h4 = self._enc_buffers(B, "c")
+        else:
+            c_hs, c_h4 = [h[2 * B:] for h in e_hs], e_h4[2 * B:]
+        d = self._dec_buffers()
+        cat, z2, th0 = bufs["cat"], bufs["z2"], bufs["th0"]
+
+        # gradient buffers of the encoder activations (pre-activation gradients, i.e. lrelu' already applied)
+        ge_hs = [self._buf("g_e_h%d" % j, tuple(e_hs[j].shape)) for j in range(4)]
+        ge_h4 = self._buf("g_e_h4", tuple(e_h4.shape))
+        if sp.separate_ctx_encoder:
+            gc_hs = [self._buf("g_c_h%d" % j, tuple(c_hs[j].shape)) for j in range(4)]
+            gc_h4 = self._buf("g_c_h4", tuple(c_h4.shape))
+        else:
+            gc_hs, gc_h4 = [g[2 * B:] for g in ge_hs], ge_h4[2 * B:]
+
+        # ---- decoder: d_h4 .. d_h1 -------------------------------------------------------------------------------
+        g_out = bufs["g_d4"]                              # d loss / d d4 (written by the loss kernel)
+        for i in (3, 2, 1, 0):
+            L = self.dec[i]
+            wname = "deconv/%s/w" % L["name"]
+            state, skip = d[i], c_hs[3 - i]
+            # filter gradient: big = g_out [2B, out_hw, Cout], small = [state ‖ skip]
+            ops.conv2d_wgrad(g_out, state, L["k"], L["stride"], small2=skip, dw=G[wname], impl=self.impl)
+            ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+            # data gradient of the concatenated input = SAME conv of g_out with the [kh,kw,Cout,Cin] filter as HWIO
+            dcat = self._buf("dcat%d" % i, (2 * B,) + tuple(L["in_hw"]) + (L["c_state"] + L["c_skip"],))
+            ops.conv2d(g_out, P[wname], None, stride=L["stride"], act=False, out=dcat, impl=self.impl)
+            g_state = self._buf("g_d%d" % i, tuple(state.shape))
+            ops.split_skip_grad(dcat, 2, B, L["c_state"], L["c_skip"], g_state, gc_hs[3 - i],
+                                state_ref=state, skip_ref=skip, accumulate_skip=False)
+            g_out = g_state
+        # ---- d_h0_lin ------------------------------------------------------------------------------------------------
+        g_d0 = g_out                                       # [2B, flat], lrelu' applied
+        Wd0 = P["deconv/d_h0_lin/Matrix"]
+        self._gemm(True, False, F, flat, 2 * B, z2.data_ptr(), F, g_d0.data_ptr(), flat,
+                   G["deconv/d_h0_lin/Matrix"].data_ptr(), flat, accumulate=True, round_=False)
+        ops.bias_grad(g_d0, G["deconv/d_h0_lin/bias"])
+        g_z2 = self._buf("g_z2", (2 * B, F))
+        self._gemm(False, True, 2 * B, F, flat, g_d0.data_ptr(), flat, Wd0.data_ptr(), flat, g_z2.data_ptr(), F)
+        if on_stage:
+            on_stage("deconv")
+        # ---- feature-alignment loss gradient (mean over the GLOBAL batch so DP ranks sum correctly) ---------------
+        if self._w_sim != 0.0:
+            ops.mse_scaled_fwd_bwd(z2[:B], z2[B:], 1e3, 1.0 / (self.global_batch * F), da=g_z2[:B], db=g_z2[B:],
+                                   grad_weight=self._w_sim, accumulate=True)
+        g_transz = g_z2[:B]                                # trans_z is linear
+        g_tz = g_z2[B:]
+        ops.lrelu_bwd(g_tz, z2[B:], out=g_tz)              # tgt_z = lrelu(hz_lin(.))
+        # ---- translator -------------------------------------------------------------------------------------------------
+        self._gemm(True, False, F, F, B, th0.data_ptr(), F, g_transz.data_ptr(), F,
+                   G["translate/trans_z/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+        ops.bias_grad(g_transz, G["translate/trans_z/bias"])
+        g_th0 = self._buf("g_th0", (B, F))
+        self._gemm(False, True, B, F, F, g_transz.data_ptr(), F, P["translate/trans_z/Matrix"].data_ptr(), F,
+                   g_th0.data_ptr(), F, act_ref=th0.data_ptr())
+        self._gemm(True, False, 2 * F, F, B, cat.data_ptr(), 2 * F, g_th0.data_ptr(), F,
+                   G["translate/trans_h0/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+        ops.bias_grad(g_th0, G["translate/trans_h0/bias"])
+        g_cat = self._buf("g_cat", (B, 2 * F))
+        Wt0 = P["translate/trans_h0/Matrix"]               # [2F, F]
+        # src half: masked by lrelu'(src_z); ctx half: masked only if the ctx hz_lin has an lrelu
+        self._gemm(False, True, B, F, F, g_th0.data_ptr(), F, Wt0.data_ptr(), F, g_cat.data_ptr(), 2 * F,
+                   act_ref=cat.data_ptr())
+        self._gemm(False, True, B, F, F, g_th0.data_ptr(), F, Wt0.data_ptr() + F * F * f4, F,
+                   g_cat.data_ptr() + F * f4, 2 * F,
+                   act_ref=(cat.data_ptr() + F * f4) if sp.ctx_hz_lrelu else None)
+        if on_stage:
+            on_stage("translate")
+        # ---- hz_lin of the three roles -> gradient w.r.t. h4 (lrelu' fused) -------------------------------------------
+        def hz_backward(scope, g_ptr, ldg, h4_rows, gh4_rows):
+            n = h4_rows.shape[0]
+            self._gemm(True, False, F, F, n, h4_rows.data_ptr(), F, g_ptr, ldg,
+                       G[scope + "/hz_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+            check = _lib.check
+            check(_lib.load().ctx_bias_grad(g_ptr, n, F, ldg, G[scope + "/hz_lin/bias"].data_ptr(), ops._stream()),
+                  "ctx_bias_grad")
+            self._gemm(False, True, n, F, F, g_ptr, ldg, P[scope + "/hz_lin/Matrix"].data_ptr(), F,
+                       gh4_rows.data_ptr(), F, act_ref=h4_rows.data_ptr())
+
+        hz_backward("conv", g_cat.data_ptr(), 2 * F, e_h4[:B], ge_h4[:B])                     # src
+        hz_backward("conv", g_tz.data_ptr(), F, e_h4[B:2 * B], ge_h4[B:2 * B])               # tgt
+        hz_backward(self.ctx_scope, g_cat.data_ptr() + F * f4, 2 * F, c_h4, gc_h4)           # ctx
+
+        # ---- encoders: h4_lin then the four convs --------------------------------------------------------------------------
+        def encoder_backward(scope, x, hs, h4, g_hs, g_h4, groups):
+            """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate."""
+            n = x.shape[0]
+            self._gemm(True, False, flat, F, n, hs[3].data_ptr(), flat, g_h4.data_ptr(), F,
+                       G[scope + "/h4_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+            ops.bias_grad(g_h4, G[scope + "/h4_lin/bias"])
+            for (r0, nr, acc) in groups:
+                self._gemm(False, True, nr, flat, F, g_h4[r0:r0 + nr].data_ptr(), F,
+                           P[scope + "/h4_lin/Matrix"].data_ptr(), F, g_hs[3][r0:r0 + nr].data_ptr(), flat,
+                           act_ref=hs[3][r0:r0 + nr].data_ptr(), accumulate=acc)
+            for j in (3, 2, 1, 0):
+                wname = "%s/h%d_conv/w" % (scope, j)
+                src = hs[j - 1] if j > 0 else x
+                ops.conv2d_wgrad(src, g_hs[j], sp.kernels[j], sp.strides[j], dw=G[wname], impl=self.impl)
+                ops.bias_grad(g_hs[j], G["%s/h%d_conv/biases" % (scope, j)])
+                if j > 0:
+                    for (r0, nr, acc) in groups:
+                        ops.conv2d_transpose(g_hs[j][r0:r0 + nr], P[wname], self.sizes[j], stride=sp.strides[j],
+                                             out=g_hs[j - 1][r0:r0 + nr], act_ref=hs[j - 1][r0:r0 + nr],
+                                             accumulate=acc, round_tf32=self.round, impl=self.impl)
+
+        if sp.separate_ctx_encoder:
+            encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False)])
+            if on_stage:
+                on_stage("conv")
+            encoder_backward("conv_context", xc, c_hs, c_h4, gc_hs, gc_h4, [(0, B, True)])
+            if on_stage:
+                on_stage("conv_context")
+        else:
+            encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False), (2 * B, B, True)])
+            if on_stage:
+                on_stage("conv")
+
+    # ---- optimiser -------------------------------------------------------------------------------------------------------
+    def adam_step(self, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+        """tf.train.AdamOptimizer (train_script.py:128), one fused launch over the flat buffers."""
+        self._ensure_moments()
+        self.step_count += 1
+        t = self.step_count
+        lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr_t, b1, b2, eps)
+
+    def train_step(self, lr: float = 1e-4, allreduce=None):
+        """forward + backward + (optional bucketed gradient all-reduce) + Adam: one `sess.run(optimizer, ...)`.
+        `allreduce` is a parallel.BucketedAllReduce (or anything with stage_done(scope) / finish())."""
+        self.zero_grad()
+        self.forward(FWD_ALL)
+        if allreduce is not None:
+            self.backward(on_stage=allreduce.stage_done)
+            allreduce.finish()
+        else:
+            self.backward()
+        self.adam_step(lr)
+
+    # ---- fetches -----------------------------------------------------------------------------------------------------------
+    def fetch(self, name: str) -> torch.Tensor:
+        """Device tensor for a reference attribute name (arm_shaping.py:1296,1312,1349-1354)."""
+        B, F, bufs = self.B, self.F, self._bufs
+        need = {"input_z": FWD_SRC, "translated_z": FWD_TRANS, "out": FWD_TRANS}.get(name, FWD_ALL)
+        if self._level < need:
+            raise _lib.CtxError("fetch(%r) needs forward(level>=%d)" % (name, need))
+        if name == "input_z":
+            return bufs["cat"][:, :F]
+        if name == "ctx_z":
+            return bufs["cat"][:, F:]
+        if name == "translated_z":
+            return bufs["z2"][:B]
+        if name == "target_z":
+            return bufs["z2"][B:]
+        if name in ("out", "out2"):
+            d4 = bufs["d4"]
+            rows = d4[:B] if name == "out" else d4[B:]
+            if self.spec.residual_out:
+                _, xc = self._input_buffers()
+                return ops.add_bcast(rows.contiguous(), xc.contiguous())
+            return rows
+        if name == "recon1":
+            return bufs["losses"][0]
+        if name == "recon2":
+            return bufs["losses"][1]
+        if name == "simloss":
+            return bufs["losses"][2]
+        if name == "loss":
+            l = bufs["losses"]
+            return self._w_recon[0] * l[0] + self._w_recon[1] * l[1] + self._w_sim * l[2]
+        if name == "image_trans":
+            xe, xc = self._input_buffers()
+            return torch.stack([xe[:B], xc, xe[B:2 * B]])
+        raise KeyError(name)
+
+    def nn_err(self, nlen: int) -> int:
+        """scripts/train_script.py:148 on the current batch (integer)."""
+        xe, _ = self._input_buffers()
+        err, _ = ops.nn_err(xe[self.B:2 * self.B].contiguous(), self.fetch("out").contiguous(), nlen)
+        return int(err.item())

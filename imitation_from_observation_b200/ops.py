@@ -1,0 +1,270 @@
+"""Tensor-level operator API over the C-ABI: one Python function per reference TF op call site.
+
+Every function takes/returns CUDA ``torch.Tensor``s (fp32, contiguous NHWC) — torch is only the container and
+the stream provider; all arithmetic happens in libctx_b200.so.  There is no CPU path: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvGeom, Epilogue, IMPL_AUTO, IMPL_SIMT, IMPL_TC, check
+from .spec import same_out, same_pad
+
+LRELU_SLOPE = 0.2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> int:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.CtxError("%s must be a CUDA tensor (the B200 path has no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise _lib.CtxError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.CtxError("%s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def _opt(t: Optional[torch.Tensor], name: str) -> Optional[int]:
+    return None if t is None else _req(t, name)
+
+
+def make_epilogue(bias=None, act: bool = False, act_ref=None, accumulate: bool = False, round_tf32: bool = False,
+                  slope: float = LRELU_SLOPE) -> Epilogue:
+    return Epilogue(_opt(bias, "bias"), _opt(act_ref, "act_ref"), float(slope), int(act), int(accumulate),
+                    int(round_tf32))
+
+
+def conv_geom(n: int, big_hw: Tuple[int, int], k: int, stride: int) -> ConvGeom:
+    """SAME geometry for a (transposed) conv whose big grid is ``big_hw``."""
+    H, W = big_hw
+    return ConvGeom(n, H, W, same_out(H, stride), same_out(W, stride), k, k, stride,
+                    same_pad(H, k, stride)[0], same_pad(W, k, stride)[0])
+
+
+def device_info():
+    lib = _lib.load()
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib.ctx_device_info(C.byref(a), C.byref(b), C.byref(c)), "ctx_device_info")
+    return a.value, b.value, c.value
+
+
+def tc_available() -> bool:
+    return bool(_lib.load().ctx_tc_available())
+
+
+# ---- convolutions ----------------------------------------------------------------------------------------------
+def conv2d(x, w, bias=None, stride: int = 2, act: bool = False, out=None, act_ref=None, accumulate=False,
+           round_tf32=False, impl=IMPL_AUTO):
+    """tf.nn.conv2d(SAME) + bias_add (+ lrelu) — arm_shaping.py:21-32.  x [N,H,W,C], w [kh,kw,C,Co] (HWIO)."""
+    N, H, W_, Cin = x.shape
+    kh, kw, Cw, Co = w.shape
+    if Cw != Cin or kh != kw:
+        raise _lib.CtxError("conv2d: filter %s does not match input %s" % (tuple(w.shape), tuple(x.shape)))
+    g = conv_geom(N, (H, W_), kh, stride)
+    if out is None:
+        out = torch.empty((N, g.P, g.Q, Co), device=x.device, dtype=torch.float32)
+    epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
+    check(_lib.load().ctx_conv2d_fprop(_req(x, "x"), Cin, _req(w, "w"), _req(out, "out"), Co, C.byref(g),
+                                       C.byref(epi), impl, _stream()), "ctx_conv2d_fprop")
+    return out
+
+
+def conv2d_transpose(x1, w, out_hw, bias=None, stride: int = 2, x2=None, act: bool = False, out=None, act_ref=None,
+                     accumulate=False, round_tf32=False, impl=IMPL_AUTO):
+    """tf.nn.conv2d_transpose(SAME) + bias_add (+ lrelu) over concat([x1, x2], 3) — arm_shaping.py:62-85,1323-1329.
+    x1 [N,P,Q,C1]; x2 [N2,P,Q,C2] is read at image n % N2; w [kh,kw,Cn,C1+C2]."""
+    N, P, Q, C1 = x1.shape
+    kh, kw, Cn, Ck = w.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    if Ck != C1 + C2 or kh != kw:
+        raise _lib.CtxError("conv2d_transpose: filter %s does not match inputs" % (tuple(w.shape),))
+    g = conv_geom(N, tuple(out_hw), kh, stride)
+    if (g.P, g.Q) != (P, Q):
+        raise _lib.CtxError("conv2d_transpose: output %s inconsistent with input grid %s at stride %d"
+                            % (tuple(out_hw), (P, Q), stride))
+    if x2 is not None and tuple(x2.shape[1:3]) != (P, Q):
+        raise _lib.CtxError("conv2d_transpose: skip grid mismatch")
+    if out is None:
+        out = torch.empty((N, g.H, g.W, Cn), device=x1.device, dtype=torch.float32)
+    epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
+    check(_lib.load().ctx_conv2d_transpose(_req(x1, "x1"), C1, _opt(x2, "x2"), C2, 0 if x2 is None else x2.shape[0],
+                                           _req(w, "w"), _req(out, "out"), Cn, C.byref(g), C.byref(epi), impl,
+                                           _stream()), "ctx_conv2d_transpose")
+    return out
+
+
+def conv2d_wgrad(big, small1, k: int, stride: int, small2=None, dw=None, impl=IMPL_AUTO):
+    """dw[k,k,Ca,Cb1+Cb2] += sum_pixels big[shifted] (x) [small1 ‖ small2].  big [N,H,W,Ca], small* [.,P,Q,Cb*]."""
+    N, H, W_, Ca = big.shape
+    Cb1 = small1.shape[3]
+    Cb2 = 0 if small2 is None else small2.shape[3]
+    g = conv_geom(N, (H, W_), k, stride)
+    if tuple(small1.shape[:3]) != (N, g.P, g.Q):
+        raise _lib.CtxError("conv2d_wgrad: small grid %s does not match geometry (%d,%d,%d)"
+                            % (tuple(small1.shape), N, g.P, g.Q))
+    if dw is None:
+        dw = torch.zeros((k, k, Ca, Cb1 + Cb2), device=big.device, dtype=torch.float32)
+    check(_lib.load().ctx_conv2d_wgrad(_req(big, "big"), Ca, _req(small1, "small1"), Cb1, _opt(small2, "small2"), Cb2,
+                                       0 if small2 is None else small2.shape[0], _req(dw, "dw"), C.byref(g), impl,
+                                       _stream()), "ctx_conv2d_wgrad")
+    return dw
+
+
+# ---- dense -------------------------------------------------------------------------------------------------------
+def gemm_raw(tA: bool, tB: bool, M: int, N: int, K: int, A_ptr: int, lda: int, B_ptr: int, ldb: int, C_ptr: int,
+             ldc: int, epi: Optional[Epilogue] = None, impl=IMPL_AUTO):
+    check(_lib.load().ctx_gemm(int(tA), int(tB), M, N, K, A_ptr, lda, B_ptr, ldb, C_ptr, ldc,
+                               C.byref(epi) if epi is not None else None, impl, _stream()), "ctx_gemm")
+
+
+def _mat(t: torch.Tensor, name: str):
+    """(ptr, rows, cols, ld) of a 2-D row-major view with unit column stride (column slices allowed)."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise _lib.CtxError("%s must be a 2-D fp32 CUDA matrix with unit column stride" % name)
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return t.data_ptr(), t.shape[0], t.shape[1], ld
+
+
+def gemm(A, B, out=None, transA=False, transB=False, bias=None, act=False, act_ref=None, accumulate=False,
+         round_tf32=False, impl=IMPL_AUTO):
+    """C = opA(A) @ opB(B) with the fused epilogue (tf.matmul + bias, arm_shaping.py:48-59, and its gradients).
+    A, B, out may be row-slices / column-slices of larger row-major matrices."""
+    pa, ar, ac, lda = _mat(A, "A")
+    pb, br, bc, ldb = _mat(B, "B")
+    M, K = (ac, ar) if transA else (ar, ac)
+    K2, N = (bc, br) if transB else (br, bc)
+    if K != K2:
+        raise _lib.CtxError("gemm: inner dimensions differ (%d vs %d)" % (K, K2))
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    pc, cr, cc, ldc = _mat(out, "out")
+    if (cr, cc) != (M, N):
+        raise _lib.CtxError("gemm: out has shape %s, expected %s" % ((cr, cc), (M, N)))
+    if act_ref is not None and (not act_ref.is_contiguous() or ldc != N):
+        raise _lib.CtxError("gemm: act_ref requires a dense output")
+    epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
+    gemm_raw(transA, transB, M, N, K, pa, lda, pb, ldb, pc, ldc, epi, impl)
+    return out
+
+
+# ---- pointwise / reductions -----------------------------------------------------------------------------------------
+def u8_normalize(x_u8, out=None):
+    """convert_image_dtype, -0.5, *2 — base.py:117-119."""
+    p = _req(x_u8, "x", torch.uint8)
+    if out is None:
+        out = torch.empty(x_u8.shape, device=x_u8.device, dtype=torch.float32)
+    check(_lib.load().ctx_u8_normalize(p, _req(out, "out"), x_u8.numel(), _stream()), "ctx_u8_normalize")
+    return out
+
+
+def lrelu_bwd(dy, y_ref, out=None, accumulate=False, slope=LRELU_SLOPE):
+    if out is None:
+        out = torch.empty_like(dy)
+    check(_lib.load().ctx_lrelu_bwd(_req(dy, "dy"), _req(y_ref, "y_ref"), _req(out, "out"), dy.numel(), slope,
+                                    int(accumulate), _stream()), "ctx_lrelu_bwd")
+    return out
+
+
+def bias_grad(dy2d, db):
+    """db[C] += column sums of dy (any leading shape, last dim C, dense)."""
+    Cc = dy2d.shape[-1]
+    M = dy2d.numel() // Cc
+    check(_lib.load().ctx_bias_grad(_req(dy2d, "dy"), M, Cc, Cc, _req(db, "db"), _stream()), "ctx_bias_grad")
+    return db
+
+
+def l2_loss_fwd_bwd(pred, tgt, loss, dpred=None, resid=None, weight=None):
+    """loss[g] += 0.5*sum (pred_g + resid - tgt)^2 ; dpred = weight[g]*(pred_g + resid - tgt)."""
+    B = tgt.shape[0]
+    G = pred.shape[0] // B
+    per_img = tgt.numel() // B
+    check(_lib.load().ctx_l2_loss_fwd_bwd(_req(pred, "pred"), _req(tgt, "tgt"), _opt(resid, "resid"), G, B, per_img,
+                                          _opt(weight, "weight"), _req(loss, "loss"), _opt(dpred, "dpred"), _stream()),
+          "ctx_l2_loss_fwd_bwd")
+
+
+def mse_scaled_fwd_bwd(a, b, scale, inv_count, loss=None, da=None, db=None, grad_weight=1.0, accumulate=False):
+    pa, rows, F, lda = _mat(a, "a")
+    pb, _, _, ldb = _mat(b, "b")
+    pda, ldda = (None, 0) if da is None else (_mat(da, "da")[0], _mat(da, "da")[3])
+    pdb, lddb = (None, 0) if db is None else (_mat(db, "db")[0], _mat(db, "db")[3])
+    check(_lib.load().ctx_mse_scaled_fwd_bwd(pa, lda, pb, ldb, rows, F, scale, inv_count, grad_weight,
+                                             _opt(loss, "loss"), pda, ldda, pdb, lddb, int(accumulate), _stream()),
+          "ctx_mse_scaled_fwd_bwd")
+
+
+def split_skip_grad(dcat, G, B, C1, C2, dstate, dskip, state_ref=None, skip_ref=None, accumulate_skip=False,
+                    slope=LRELU_SLOPE):
+    pix = dcat.numel() // (G * B * (C1 + C2))
+    check(_lib.load().ctx_split_skip_grad(_req(dcat, "dcat"), G, B, pix, C1, C2, _opt(state_ref, "state_ref"),
+                                          _opt(skip_ref, "skip_ref"), slope, _req(dstate, "dstate"),
+                                          _req(dskip, "dskip"), int(accumulate_skip), _stream()),
+          "ctx_split_skip_grad")
+
+
+def add_bcast(a, b, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    Cc = a.numel() // a.shape[0]
+    check(_lib.load().ctx_add_bcast(_req(a, "a"), _req(b, "b"), _req(out, "out"), a.shape[0], b.shape[0], Cc,
+                                    _stream()), "ctx_add_bcast")
+    return out
+
+
+def adam_step(p, g, m, v, lr_t, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+    check(_lib.load().ctx_adam_step(_req(p, "p"), _req(g, "g"), _req(m, "m"), _req(v, "v"), p.numel(), lr_t, b1, b2,
+                                    eps, grad_scale, _stream()), "ctx_adam_step")
+
+
+def round_tf32(x, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().ctx_round_tf32(_req(x, "x"), _req(out, "out"), x.numel(), _stream()), "ctx_round_tf32")
+    return out
+
+
+def transpose_round(x, batch, rows, cols, out=None, round_tf32_=True):
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().ctx_transpose_round(_req(x, "x"), _req(out, "out"), batch, rows, cols, int(round_tf32_),
+                                          _stream()), "ctx_transpose_round")
+    return out
+
+
+def nn_err(tgt, out, nlen: int):
+    """scripts/train_script.py:148.  Returns (err int64[1], idx int64[B]) device tensors."""
+    B = tgt.shape[0]
+    per_img = tgt.numel() // B
+    dist = torch.empty((B, B), device=tgt.device, dtype=torch.float32)
+    idx = torch.empty((B,), device=tgt.device, dtype=torch.int64)
+    err = torch.zeros((1,), device=tgt.device, dtype=torch.int64)
+    check(_lib.load().ctx_nn_err(_req(tgt, "tgt"), _req(out, "out"), B, per_img, nlen, dist.data_ptr(),
+                                 idx.data_ptr(), err.data_ptr(), _stream()), "ctx_nn_err")
+    return err, idx
+
+
+def reward_ours(z, x, means, mean_imgs, paths: int, T: int, scale: float, rewards=None, cost=None,
+                feat_weight=1.0, img_weight=1.0):
+    """rllab/sampler/base.py:243-257 batched over paths.  rewards: float64 [paths, >=2T] updated in place."""
+    F = means.shape[-1]
+    per_img = mean_imgs.numel() // T
+    rs = 0 if rewards is None else rewards.stride(0)
+    check(_lib.load().ctx_reward_ours(_opt(z, "z"), _opt(x, "x"), _req(means, "means"), _req(mean_imgs, "mean_imgs"),
+                                      paths, T, F, per_img, scale, feat_weight, img_weight,
+                                      None if rewards is None else _req(rewards, "rewards", torch.float64), rs,
+                                      _opt(cost, "cost"), _stream()), "ctx_reward_ours")
+
+
+def reward_inception(feat, means, std, paths: int, T: int, rewards=None, cost=None):
+    per = means.numel() // T
+    rs = 0 if rewards is None else rewards.stride(0)
+    check(_lib.load().ctx_reward_inception(_req(feat, "feat"), _req(means, "means"), _req(std, "std"), paths, T, per,
+                                           None if rewards is None else _req(rewards, "rewards", torch.float64), rs,
+                                           _opt(cost, "cost"), _stream()), "ctx_reward_inception")

@@ -1,0 +1,142 @@
+"""Reward featurizer: the model-dependent part of ``BaseSampler.initialize`` / ``process_samples``
+(rllab/sampler/base.py:57-156, 166-257), batched for B200.
+
+The reference issues one ``sess.run`` per trajectory per viewpoint with B=25 (250 tiny launches per TRPO
+iteration).  Here all trajectories of an iteration are stacked into one uint8 batch, copied to
+the device once, pushed through the source encoder in one launch per layer, and reduced to rewards by one
+distance kernel that writes straight into the float64 reward array:
+
+    cost[p,j]   = sum_k (means[vp][j,k] - z[p,j,k])^2 + scale * sum_hwc (imgs[vp][j] - x[p,j])^2   (base.py:243-245)
+    rewards[p][2j+1] -= cost[p,j] * j^2                                                            (base.py:256-257)
+
+Everything downstream of the rewards (GAE, baselines, logging; base.py:259-395) is generic rllab bookkeeping
+and stays in the caller.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .models import ContextAEReal, ContextSkipNew, _ContextModel
+
+KWARG_KEYS = ("mode", "mode2", "scale", "nvp", "imsize", "name", "modelname", "modeldata", "meanfile", "layer",
+              "experttheano", "ablation_type", "vp", "angle", "goal", "object", "geoms")     # SURVEY.md §5 "Config"
+
+
+class RewardFeaturizer:
+    """Holds the restored model plus the expert statistics; `process_paths` is the per-iteration hot call."""
+
+    T = 25                                  # frames per trajectory: self.batch_size = 25 (base.py:115)
+
+    def __init__(self, mode: str = "ours", name: str = "push", imsize=(48, 48), nvp: int = 1, scale: float = 1.0,
+                 modelname: Optional[str] = None, modeldata: Optional[str] = None, ablation_type: str = "None",
+                 precision: str = "tf32", model: Optional[_ContextModel] = None, device="cuda", **unused_kwargs):
+        if not mode.startswith("ours") or mode == "oursinception":
+            raise _lib.CtxError("RewardFeaturizer covers mode='ours' (base.py:192-257); inception modes need the "
+                                "InceptionV3 front-end, which is outside this hot path's first scope")
+        if ablation_type not in ("None", "nofeat", "noimage"):
+            raise _lib.CtxError("ablation_type %r is broken in the reference (base.py:250-252 uses an undefined "
+                                "image_recon) and is not provided" % ablation_type)
+        self.mode, self.name, self.imsize, self.nvp, self.scale = mode, name, tuple(imsize), int(nvp), float(scale)
+        self.modelname, self.modeldata, self.ablation_type = modelname, modeldata, ablation_type
+        self.precision, self.device = precision, device
+        self.model = model
+        self.means: List[torch.Tensor] = []
+        self.imgs: List[torch.Tensor] = []
+        self.initialized = False
+
+    # -- base.py:113-154 ---------------------------------------------------------------------------------------------
+    def initialize(self):
+        if self.model is None:
+            if self.name in ("real", "sweep"):
+                self.model = ContextAEReal()                                   # base.py:134-135
+            elif self.name in ("push", "reach", "strike", "throw"):
+                self.model = ContextSkipNew()                                  # base.py:136-137
+            else:
+                raise _lib.CtxError("unknown task name %r" % self.name)
+            shape = (3, self.T) + self.imsize + (3,)
+            self.model.build(torch.empty(shape, dtype=torch.uint8, device="meta"), device=self.device,
+                             precision=self.precision)
+            if self.modelname:
+                sd = dict(np.load(self.modelname if self.modelname.endswith(".npz") else self.modelname + ".npz"))
+                prefix = "contextmodel/" if any(k.startswith("contextmodel/") for k in sd) else ""
+                self.model.net.load_state_dict(sd, prefix=prefix)
+        self.initialized = True
+
+    # -- base.py:195-223: expert statistics, once per process ----------------------------------------------------------
+    def compute_expert_means(self, validdata: np.ndarray, contexts: Sequence[np.ndarray], chunk_videos: int = 64):
+        """validdata [nlen, N, H, W, 3] float in [-1,1] (the trainer's vdata .npy); contexts[vp] = first frame of the
+        agent's first trajectory (uint8 [H,W,3]).  Sets self.means[vp] [T,F] and self.imgs[vp] [T,H,W,3]."""
+        if not self.initialized:
+            self.initialize()
+        skip = 2 if self.name in ("real", "sweep") else 1                      # base.py:208-210
+        demo = ((validdata[::skip] + 1) * 127.5).astype(np.uint8)             # base.py:214, [T, N, H, W, 3]
+        if demo.shape[0] != self.T:
+            raise _lib.CtxError("demos have %d frames after skip, expected %d" % (demo.shape[0], self.T))
+        N = demo.shape[1]
+        m = self.model
+        self.means, self.imgs = [], []
+        for vp in range(self.nvp):
+            ctx = torch.as_tensor(np.ascontiguousarray(contexts[vp])).to(self.device)[None]   # [1,H,W,3] u8
+            z_ctx, skips = m.enc2(ctx)
+            sum_z = torch.zeros((self.T, m.net.F), device=self.device, dtype=torch.float64)
+            sum_img = torch.zeros((self.T,) + self.imsize + (3,), device=self.device, dtype=torch.float64)
+            for v0 in range(0, N, chunk_videos):
+                vids = demo[:, v0:v0 + chunk_videos]                             # [T, n, H, W, 3]
+                n = vids.shape[1]
+                frames = torch.as_tensor(np.ascontiguousarray(vids.transpose(1, 0, 2, 3, 4))).to(self.device)
+                frames = frames.reshape((n * self.T,) + self.imsize + (3,))
+                z_src = m.enc1(frames)
+                tz = m.translate(z_src, z_ctx.expand(n * self.T, -1))
+                out = m.dec(tz, skips, ctx_frames=ctx)
+                sum_z += tz.view(n, self.T, -1).sum(0, dtype=torch.float64)
+                sum_img += out.view((n, self.T) + self.imsize + (3,)).sum(0, dtype=torch.float64)
+            self.means.append((sum_z / N).float().contiguous())
+            self.imgs.append((sum_img / N).float().contiguous())
+
+    # -- base.py:232-257: the hot loop ---------------------------------------------------------------------------------
+    def process_paths(self, paths: List[dict]) -> np.ndarray:
+        """Subtract the feature/pixel distance from every path's rewards, in place; returns the costs [paths,T]."""
+        if not self.initialized:
+            self.initialize()
+        if not self.means:
+            raise _lib.CtxError("expert statistics missing: call compute_expert_means() first (base.py:195-223)")
+        P = len(paths)
+        if P == 0:
+            return np.zeros((0, self.T), np.float32)
+        H, W = self.imsize
+        L = max(len(p["rewards"]) for p in paths)
+        if L < 2 * self.T:
+            raise _lib.CtxError("rewards must have at least %d entries (index 2j+1, j<25)" % (2 * self.T))
+        # gather host side: frames [nvp, P, T, H, W, 3] uint8 and rewards [P, L] float64, pinned for async copies
+        frames = torch.empty((self.nvp, P, self.T, H, W, 3), dtype=torch.uint8).pin_memory()
+        rewards = torch.zeros((P, L), dtype=torch.float64).pin_memory()
+        fr_np, rw_np = frames.numpy(), rewards.numpy()
+        for i, path in enumerate(paths):
+            imgs = [im for im in path["env_infos"]["imgs"] if im is not None]          # base.py:193
+            if len(imgs) != self.T:
+                raise _lib.CtxError("path %d has %d frames, expected %d" % (i, len(imgs), self.T))
+            arr = np.asarray(imgs)                                                       # [T, nvp, H, W, 3]
+            for vp in range(self.nvp):
+                fr_np[vp, i] = arr[:, vp]
+            rw_np[i, :len(path["rewards"])] = path["rewards"]
+        d_frames = frames.to(self.device, non_blocking=True)
+        d_rewards = rewards.to(self.device, non_blocking=True)
+        d_cost = torch.zeros((P, self.T), device=self.device, dtype=torch.float32)
+        fw = 0.0 if self.ablation_type == "nofeat" else 1.0
+        iw = 0.0 if self.ablation_type == "noimage" else 1.0
+        total = torch.zeros((P, self.T), device=self.device, dtype=torch.float32)
+        for vp in range(self.nvp):
+            u8 = d_frames[vp].reshape((P * self.T, H, W, 3))
+            x = ops.u8_normalize(u8)                                                     # image_trans[0]
+            z = self.model.enc1(x)                                                       # input_z, base.py:234
+            ops.reward_ours(z, x, self.means[vp], self.imgs[vp], P, self.T, self.scale, rewards=d_rewards,
+                            cost=d_cost, feat_weight=fw, img_weight=iw)
+            total += d_cost
+        out_rewards = d_rewards.cpu().numpy()
+        for i, path in enumerate(paths):
+            path["rewards"][:] = out_rewards[i, :len(path["rewards"])]
+        return total.cpu().numpy()

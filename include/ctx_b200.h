@@ -1,0 +1,190 @@
+/* ctx_b200.h — C-ABI of libctx_b200.so: the context-translation encoder/decoder hot path on B200 (sm_100a).
+ *
+ * The reference (wyndwarrior/imitation_from_observation) has no FFI: its boundary for this path is a Python
+ * graph object evaluated with sess.run.  Every dense op of that graph is a TensorFlow call
+ * site; each entry point below replaces one of those call sites (cited per function, paths relative to the
+ * reference root).  The Python host (imitation_from_observation_b200/) binds these with ctypes; the binding a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All tensors are dense fp32 (unless stated), NHWC, in DEVICE memory owned by the caller.  The library
+ *    allocates nothing persistent and keeps no state except the per-thread last-error string.
+ *  - Every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately:
+ *    0 = ok, negative = error (message via ctx_last_error()).  No internal synchronisation.
+ *  - Preconditions (shape limits, alignment for the tensor-core path) are checked and reported, never UB.
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point fails with CTX_ERR_CUDA.
+ *  - Gradient outputs documented "+=" ACCUMULATE into caller-zeroed buffers (split-K partial sums are
+ *    reduced with fp32 atomics), so a flat gradient buffer is zeroed once per step.
+ */
+#ifndef CTX_B200_H_
+#define CTX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTX_B200_VERSION 100
+
+enum {
+  CTX_OK = 0,
+  CTX_ERR_ARG = -1,      /* bad shape / null pointer / unsupported combination */
+  CTX_ERR_CUDA = -2,     /* CUDA runtime error (launch failure, no device)      */
+  CTX_ERR_UNSUPPORTED = -3
+};
+
+/* Which implementation a GEMM-shaped entry point uses. */
+enum {
+  CTX_IMPL_AUTO = 0,     /* tcgen05 tensor-core kernel when the shape qualifies, else the SIMT kernel */
+  CTX_IMPL_SIMT = 1,     /* fp32 CUDA-core kernel (exact fp32 products)                               */
+  CTX_IMPL_TC = 2        /* force tcgen05 (TF32 operands, fp32 accumulate); error if shape not eligible */
+};
+
+/* Geometry of one SAME conv / transposed conv.  "big" is the conv input (= transposed-conv output) grid,
+ * "small" the conv output (= transposed-conv input) grid:  P = ceil(H/stride), pad_* = TF SAME low pads. */
+typedef struct ctx_conv_geom {
+  int32_t N;             /* images                                                         */
+  int32_t H, W;          /* big grid                                                       */
+  int32_t P, Q;          /* small grid                                                     */
+  int32_t kh, kw;
+  int32_t stride;
+  int32_t pad_h, pad_w;  /* rows/cols of zero padding above / left of the big grid         */
+} ctx_conv_geom;
+
+/* Fused epilogue of every GEMM-shaped kernel; applied per output element v (flat index i, column n):
+ *   v += bias[n]                      if bias
+ *   v  = max(v, slope*v)              if act == 1                 (lrelu, arm_shaping.py:18-19)
+ *   v *= (act_ref[i] >= 0 ? 1:slope)  if act_ref                  (lrelu' in backward, from the saved output)
+ *   v += out[i]                       if accumulate
+ *   v  = round_to_tf32(v)             if round_tf32               (so the next tcgen05 consumer is unbiased)
+ */
+typedef struct ctx_epilogue {
+  const float* bias;
+  const float* act_ref;
+  float slope;
+  int32_t act;
+  int32_t accumulate;
+  int32_t round_tf32;
+} ctx_epilogue;
+
+int ctx_version(void);
+const char* ctx_last_error(void);
+/* sm count, compute capability; CTX_ERR_CUDA without a device. */
+int ctx_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* 1 if the tcgen05 path can run on the current device (sm_100). */
+int ctx_tc_available(void);
+
+/* ---- convolutions ------------------------------------------------------------------------------------- */
+
+/* y[N,P,Q,Co] = epi( sum_{r,s,c} x[n, p*st+r-pad_h, q*st+s-pad_w, c] * w[r,s,c,co] )
+ * Replaces tf.nn.conv2d(SAME)+bias_add (+lrelu) — gym/envs/mujoco/arm_shaping.py:21-32 — and is the
+ * data-gradient of conv2d_transpose (x = dY of the deconv, w = its [kh,kw,Cout,Cin] filter read as HWIO). */
+int ctx_conv2d_fprop(const float* x, int32_t C, const float* w, float* y, int32_t Co,
+                     const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream);
+
+/* y[N,H,W,Cn] = epi( sum_{p,q,r,s,k : p*st+r-pad_h == h, q*st+s-pad_w == w} x[n,p,q,k] * w[r,s,cn,k] )
+ * with x the channel concatenation [x1 (C1 ch, batch N) ‖ x2 (C2 ch, batch x2_batch, image n % x2_batch)];
+ * x2 may be NULL (C2 = 0).  w is [kh,kw,Cn,C1+C2].
+ * Replaces tf.nn.conv2d_transpose(SAME)+bias_add over tf.concat([h, skip], 3) — arm_shaping.py:62-85,
+ * 1323-1329 (the concat is never materialised) — and is the data-gradient of conv2d (x1 = dY, w = HWIO). */
+int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t x2_batch,
+                         const float* w, float* y, int32_t Cn,
+                         const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream);
+
+/* dw[kh,kw,Ca,Cb1+Cb2] += sum_{n,p,q} big[n, p*st+r-pad_h, q*st+s-pad_w, a] * small[n,p,q,b]
+ * with small = [small1 (Cb1 ch) ‖ small2 (Cb2 ch, batch small2_batch, image n % small2_batch)].
+ * Filter gradient of conv2d (big = x, small = dY -> HWIO) and of conv2d_transpose (big = dY, small = x ->
+ * [kh,kw,Cout,Cin]); the autodiff the reference gets from AdamOptimizer.minimize (scripts/train_script.py:128). */
+int ctx_conv2d_wgrad(const float* big, int32_t Ca, const float* small1, int32_t Cb1,
+                     const float* small2, int32_t Cb2, int32_t small2_batch,
+                     float* dw, const ctx_conv_geom* g, int32_t impl, void* stream);
+
+/* ---- dense layers --------------------------------------------------------------------------------------- */
+
+/* C[M,N] = epi( opA(A) * opB(B) ), row-major with leading dimensions (elements).
+ * transA = 0: A is [M,K] (lda >= K); 1: A is stored [K,M] (lda >= M).  transB likewise for [K,N] / [N,K].
+ * Replaces tf.matmul(x, Matrix) + bias — arm_shaping.py:48-59 — and its two gradient GEMMs. */
+int ctx_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
+             const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+             const ctx_epilogue* epi, int32_t impl, void* stream);
+
+/* ---- pointwise / reductions ------------------------------------------------------------------------------ */
+
+/* y = (float(x) * (1/255) - 0.5) * 2 in fp32 — rllab/sampler/base.py:117-119, scripts/train_script.py:102-104. */
+int ctx_u8_normalize(const uint8_t* x, float* y, int64_t n, void* stream);
+
+/* out (+)= dy * (y_ref >= 0 ? 1 : slope) — derivative of arm_shaping.py:18-19 from the saved output. */
+int ctx_lrelu_bwd(const float* dy, const float* y_ref, float* out, int64_t n, float slope, int32_t accumulate,
+                  void* stream);
+
+/* db[C] += column sums of dy[M,C] (ld = ldy) — gradient of tf.nn.bias_add (arm_shaping.py:30,80). */
+int ctx_bias_grad(const float* dy, int64_t M, int32_t C, int32_t ldy, float* db, void* stream);
+
+/* Pixel reconstruction losses, arm_shaping.py:1352-1353 (tf.nn.l2_loss = sum(t^2)/2), and their gradient.
+ * pred is [G*B, per_img] (G decoder passes stacked on the batch axis), tgt is [B, per_img] (image b % B),
+ * resid optional [B, per_img] added to pred first (ContextAEInception2 residual output, :1890-1891).
+ * loss[g] += 0.5 * sum_{b,i} (pred[g*B+b,i] + resid[b,i] - tgt[b,i])^2 ;  dpred = weight[g] * (pred+resid-tgt)
+ * (weight[g] in {0,1} selects the terms of the ablated loss, ablations_code/ablations.py:175-182). */
+int ctx_l2_loss_fwd_bwd(const float* pred, const float* tgt, const float* resid, int32_t G, int64_t B,
+                        int64_t per_img, const float* weight, float* loss, float* dpred, void* stream);
+
+/* Feature-alignment loss, arm_shaping.py:1345:  loss += scale * inv_count * sum (a-b)^2 ;
+ * da (+)= grad_weight * 2*scale*inv_count*(a-b) ; db (+)= -that.  inv_count = 1/(global_batch*F) so that
+ * data-parallel ranks sum to the global mean.  a,b,da,db are [rows, F] with leading dimensions. */
+int ctx_mse_scaled_fwd_bwd(const float* a, int32_t lda, const float* b, int32_t ldb, int64_t rows, int32_t F,
+                           float scale, float inv_count, float grad_weight, float* loss,
+                           float* da, int32_t ldda, float* db, int32_t lddb, int32_t accumulate,
+                           void* stream);
+
+/* Split the data-gradient of a decoder level, dcat [G*B, pix, C1+C2], into
+ *   dstate[G*B, pix, C1] = dcat[..., :C1] * lrelu'(state_ref)           (state_ref may be NULL: no mask)
+ *   dskip [B,   pix, C2] (+)= (sum_g dcat[g*B+b, pix, C1:]) * lrelu'(skip_ref)
+ * — the gradient of tf.concat([h, skip], 3) (arm_shaping.py:1323-1329) with the skip shared by G passes. */
+int ctx_split_skip_grad(const float* dcat, int32_t G, int64_t B, int64_t pix, int32_t C1, int32_t C2,
+                        const float* state_ref, const float* skip_ref, float slope,
+                        float* dstate, float* dskip, int32_t accumulate_skip, void* stream);
+
+/* out[rows, C] = a[rows, C] + b[rows % b_rows, C]   (residual output of ContextAEInception2). */
+int ctx_add_bcast(const float* a, const float* b, float* out, int64_t rows, int64_t b_rows, int64_t C,
+                  void* stream);
+
+/* TF-style Adam on flat buffers (scripts/train_script.py:128; epsilon outside the bias correction):
+ *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr_t * m / (sqrt(v) + eps)
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  grad_scale multiplies g first (1.0 normally). */
+int ctx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
+                  float eps, float grad_scale, void* stream);
+
+/* y = round_to_nearest_tf32(x) (keeps fp32 storage) — operand preparation for the tcgen05 path. */
+int ctx_round_tf32(const float* x, float* y, int64_t n, void* stream);
+
+/* out[c, r] = round_tf32?(in[r, c]) for a [rows, cols] matrix, `batch` matrices back to back. */
+int ctx_transpose_round(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols,
+                        int32_t round_tf32, void* stream);
+
+/* nn_err — scripts/train_script.py:148 (integer, bit-exact):
+ *   idx[b] = argmin_a mean_i (tgt[a,i] - out[b,i])^2  (first minimum);  err = sum_b |idx[b] - (b % nlen)|.
+ * dist_ws is a caller-provided [B,B] fp32 workspace; idx is [B] int64; err one int64. */
+int ctx_nn_err(const float* tgt, const float* out, int32_t B, int64_t per_img, int32_t nlen,
+               float* dist_ws, int64_t* idx, int64_t* err, void* stream);
+
+/* Feature-distance reward — rllab/sampler/base.py:243-257 — for `paths` trajectories of T frames each:
+ *   cost[p,j] = sum_k (means[j,k]-z[p*T+j,k])^2 + scale * sum_i (mean_imgs[j,i]-x[p*T+j,i])^2
+ *   rewards[p*rew_stride + 2j+1] -= (double)cost[p,j] * j*j       (rewards are float64, like path['rewards'])
+ * feat_weight / img_weight in {0,1} implement ablation_type nofeat / noimage (base.py:246-249).
+ * cost (optional, may be NULL) receives the fp32 costs [paths, T]. */
+int ctx_reward_ours(const float* z, const float* x, const float* means, const float* mean_imgs,
+                    int32_t paths, int32_t T, int32_t F, int64_t per_img, float scale,
+                    float feat_weight, float img_weight, double* rewards, int64_t rew_stride, float* cost,
+                    void* stream);
+
+/* Inception-feature reward — rllab/sampler/base.py:184-189:
+ *   d = means[j,i]-feat[p*T+j,i]; d = 0 where std == 0; m[p,j] = mean_i d^2/(std[j,i]+1e-5);
+ *   rewards[p*rew_stride + 2j+1] -= (double)m[p,j] * j*j */
+int ctx_reward_inception(const float* feat, const float* means, const float* std, int32_t paths, int32_t T,
+                         int64_t per_frame, double* rewards, int64_t rew_stride, float* cost, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTX_B200_H_ */

@@ -1,0 +1,271 @@
+"""GPU parity tests of the whole path: graph forward/backward/Adam against the committed golden vectors and the
+CPU oracle, the reference-facing surfaces (Session.run, ModelTrainer, RewardFeaturizer), and size-independent
+properties at BASELINE.json's full sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, rel_err
+from imitation_from_observation_b200 import _lib, compat as tf, ops, spec as S, synthetic
+from imitation_from_observation_b200.models import ContextAEInception2, ContextAEReal, ContextSkipNew
+from imitation_from_observation_b200.network import FWD_ALL, FWD_SRC, FWD_TRANS, ContextNet
+from imitation_from_observation_b200.sampler import RewardFeaturizer
+from imitation_from_observation_b200.trainer import ModelTrainer
+from oracle import gen_golden, tf_semantics as O
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "tf32": 1e-3}          # north_star: 1e-3 relative fp32; the exact-fp32 path is held tighter
+
+
+def run_net(spec, B, P, image, precision, **kw):
+    net = ContextNet(spec, B, precision=precision, **kw)
+    net.load_state_dict(P)
+    net.set_input(image.cuda())
+    net.zero_grad()
+    net.forward(FWD_ALL)
+    net.backward()
+    torch.cuda.synchronize()
+    return net
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))))
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_golden_forward_backward(path, precision):
+    name = os.path.basename(path)[:-4]
+    spec, B = gen_golden.CASES[name]
+    d = np.load(path)
+    P = {k[6:]: d[k] for k in d.files if k.startswith("param:")}
+    net = run_net(spec, B, P, torch.from_numpy(d["image"]), precision)
+    tol = TOL[precision]
+    for k in ("input_z", "translated_z", "target_z", "ctx_z", "out", "out2", "simloss", "recon1", "recon2", "loss"):
+        assert rel_err(net.fetch(k).cpu(), d["out:" + k]) < tol, k
+    for k in spec.param_shapes():
+        assert rel_err(net.G[k].cpu(), d["grad:" + k]) < tol, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_context_skip_new_64x64_b32_vs_oracle(precision):
+    """BASELINE.json configs[0]: 64x64x3, batch 32, full-size network, loss and every gradient vs the fp32 oracle."""
+    spec, B = S.context_skip_new(64, 64), 32
+    P = O.init_params(spec, seed=0)
+    gen = torch.Generator().manual_seed(1)
+    for k in P:
+        if k.endswith("bias") or k.endswith("biases"):
+            P[k] = torch.randn(P[k].shape, generator=gen) * 0.01
+    bank = synthetic.video_bank(25, 16, 64, 64)
+    image = torch.from_numpy(synthetic.trainer_batch(synthetic.to_float(bank), B, 25, 16,
+                                                     np.random.RandomState(0))).float()
+    ref, G = O.loss_and_grads(spec, P, image)
+    net = run_net(spec, B, P, image, precision)
+    tol = TOL[precision]
+    for k in ("input_z", "translated_z", "out", "out2", "simloss", "recon1", "recon2", "loss"):
+        assert rel_err(net.fetch(k).cpu(), ref[k]) < tol, k
+    for k in spec.param_shapes():
+        assert rel_err(net.G[k].cpu(), G[k]) < tol, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_reference_faithful_48x48_and_real_36x64(precision):
+    tol = TOL[precision]
+    for spec, B in ((S.context_skip_new(48, 48), 10), (S.context_ae_real(36, 64), 10)):
+        P = O.init_params(spec, seed=2)
+        image = torch.rand((3, B, spec.height, spec.width, 3), generator=torch.Generator().manual_seed(3)) * 2 - 1
+        ref, G = O.loss_and_grads(spec, P, image)
+        net = run_net(spec, B, P, image, precision)
+        for k in ("translated_z", "out", "out2", "loss"):
+            assert rel_err(net.fetch(k).cpu(), ref[k]) < tol, (spec.name, k)
+        for k in spec.param_shapes():
+            assert rel_err(net.G[k].cpu(), G[k]) < tol, (spec.name, k)
+
+
+def test_forward_levels_prune_like_tf():
+    """input_z needs only the source encoder; translated_z/out need no target encoder (base.py:216,234)."""
+    spec, B = gen_golden.CASES["skipnew_16x16"]
+    d = np.load(os.path.join(GOLDEN_DIR, "skipnew_16x16.npz"))
+    P = {k[6:]: d[k] for k in d.files if k.startswith("param:")}
+    net = ContextNet(spec, B, precision="fp32")
+    net.load_state_dict(P)
+    net.set_input(torch.from_numpy(d["image"]).cuda())
+    net.forward(FWD_SRC)
+    assert rel_err(net.fetch("input_z").cpu(), d["out:input_z"]) < 1e-4
+    with pytest.raises(_lib.CtxError):
+        net.fetch("out")
+    net.forward(FWD_TRANS)
+    assert rel_err(net.fetch("out").cpu(), d["out:out"]) < 1e-4
+    assert rel_err(net.fetch("translated_z").cpu(), d["out:translated_z"]) < 1e-4
+    with pytest.raises(_lib.CtxError):
+        net.backward()
+
+
+def test_adam_training_steps_match_oracle():
+    spec, B = gen_golden.CASES["skipnew_16x16"]
+    P = {k: v.clone() for k, v in gen_golden.golden_params(spec, 4).items()}
+    image = torch.rand((3, B, 16, 16, 3), generator=torch.Generator().manual_seed(5)) * 2 - 1
+    net = ContextNet(spec, B, precision="fp32")
+    net.load_state_dict(P)
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    for t in (1, 2, 3):
+        _, G = O.loss_and_grads(spec, P, image)
+        O.tf_adam_step(P, G, M, V, t, 1e-3)
+        net.set_input(image.cuda())
+        net.train_step(1e-3)
+    sd = net.state_dict()
+    for k in P:
+        assert rel_err(sd[k], P[k]) < 1e-4, k
+
+
+def test_ablation_losses():
+    spec, B = gen_golden.CASES["skipnew_16x16"]
+    P = gen_golden.golden_params(spec, 6)
+    image = torch.rand((3, B, 16, 16, 3), generator=torch.Generator().manual_seed(7)) * 2 - 1
+    for ab in ("L2", "L2L3", "L1"):
+        ref, G = O.loss_and_grads(spec, P, image, ablation_type=ab)
+        net = run_net(spec, B, P, image, "fp32", ablation_type=ab)
+        assert rel_err(net.fetch("loss").cpu(), O.ablation_loss(ref, ab)) < 1e-4
+        for k in ("deconv/d_h2/w", "conv/h2_conv/w", "translate/trans_z/Matrix", "conv_context/h1_conv/w"):
+            assert rel_err(net.G[k].cpu(), G[k]) < 1e-4, (ab, k)
+
+
+def test_session_run_like_base_py():
+    """The call pattern of rllab/sampler/base.py:113-154,216,234 through the tf-shaped adapter, uint8 feed."""
+    tf.reset_default_graph()
+    B, idim = 5, (16, 16)
+    tfinput = tf.placeholder(tf.uint8, (3, B) + idim + (3,), name="x")
+    image_trans = tf.image.convert_image_dtype(tfinput, dtype=tf.float32)
+    image_trans = tf.subtract(image_trans, 0.5)
+    image_trans = tf.multiply(image_trans, 2.0)
+    autodc = ContextSkipNew(df_dim=4, gf_dim=4, featsize=16)
+    autodc.build(image_trans, precision="fp32")
+    sess = tf.Session(config=tf.ConfigProto())
+    P = gen_golden.golden_params(autodc.spec, 8)
+    autodc.net.load_state_dict(P)
+    rs = np.random.RandomState(0)
+    frames = rs.randint(0, 256, size=(3, B) + idim + (3,)).astype(np.uint8)
+    feats, img_t = sess.run([autodc.input_z, image_trans], {tfinput: [frames[0], frames[1], frames[2]]})
+    x = O.normalize_u8(torch.from_numpy(frames))
+    ref = O.forward(autodc.spec, P, x)
+    assert np.array_equal(img_t, x.numpy())
+    assert rel_err(feats, ref["input_z"]) < 1e-4
+    tz, out = sess.run([autodc.translated_z, autodc.out], {tfinput: frames})
+    assert rel_err(tz, ref["translated_z"]) < 1e-4 and rel_err(out, ref["out"]) < 1e-4
+    saver = tf.train.Saver()
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        saver.save(sess, os.path.join(td, "m"))
+        autodc.net.flat_p.zero_()
+        saver.restore(sess, os.path.join(td, "m"))
+    assert rel_err(sess.run(autodc.input_z, {tfinput: frames}), ref["input_z"]) < 1e-4
+
+
+def test_model_trainer_loop_runs_and_learns():
+    logs = []
+    tr = ModelTrainer(idims=(16, 16), nvideos=12, ntrain=8, batch_size=10, model="ContextSkipNew", nitr=42,
+                      save_every=1000, nlen=5, nskip=1, rescale=True, inception=False, strides=None, kernels=None,
+                      filters=None, precision="fp32", log=logs.append)
+    tr.model = lambda: ContextSkipNew(df_dim=8, gf_dim=8, featsize=32)
+    allloss, validloss = tr.train()
+    assert len(allloss) == 10 and len(validloss) == 1 and all(np.isfinite(allloss))
+    assert allloss[-1] < allloss[0]
+    assert all(isinstance(h["NNErr"], int) for h in tr.history)
+
+
+def test_reward_featurizer_matches_reference_loop():
+    """process_paths (batched) == the reference's per-path loop (base.py:232-257) evaluated with the oracle."""
+    H = W = 16
+    T = RewardFeaturizer.T
+    model = ContextSkipNew(df_dim=4, gf_dim=4, featsize=16)
+    model.build(torch.empty((3, T, H, W, 3), device="meta"), precision="fp32")
+    P = gen_golden.golden_params(model.spec, 9)
+    model.net.load_state_dict(P)
+    feat = RewardFeaturizer(mode="ours", name="push", imsize=(H, W), nvp=1, scale=0.5, model=model)
+    bank = synthetic.video_bank(T, 6, H, W, seed=3)
+    validdata = synthetic.to_float(bank)
+    rs = np.random.RandomState(1)
+    paths = []
+    for p in range(4):
+        imgs = []
+        for t in range(2 * T):
+            imgs.append(rs.randint(0, 256, size=(1, H, W, 3)).astype(np.uint8) if t % 2 == 1 else None)
+        paths.append({"env_infos": {"imgs": imgs}, "rewards": rs.randn(2 * T)})
+    context = [im for im in paths[0]["env_infos"]["imgs"] if im is not None][0][0]
+    feat.compute_expert_means(validdata, [context])
+    # oracle: expert means exactly as base.py:195-223
+    tfe, tim = [], []
+    ctx25 = np.stack([context] * T)
+    for i in range(validdata.shape[1]):
+        inp = ((validdata[:, i] + 1) * 127.5).astype(np.uint8)
+        x = O.normalize_u8(torch.from_numpy(np.stack([inp, ctx25, ctx25])))
+        r = O.forward(model.spec, P, x)
+        tfe.append(r["translated_z"].numpy())
+        tim.append(r["out"].numpy())
+    means, mimgs = np.mean(tfe, axis=0), np.mean(tim, axis=0)
+    assert rel_err(feat.means[0].cpu(), means) < 1e-4 and rel_err(feat.imgs[0].cpu(), mimgs) < 1e-4
+    expected = []
+    for path in paths:
+        cur = np.stack([im[0] for im in path["env_infos"]["imgs"] if im is not None])
+        x = O.normalize_u8(torch.from_numpy(cur))
+        z = O.encode(model.spec, P, "conv", x, True)[5].numpy()
+        expected.append(O.reward_ours(z, x.numpy(), means, mimgs, 0.5, path["rewards"]))
+    feat.process_paths(paths)
+    for path, exp in zip(paths, expected):
+        assert np.allclose(path["rewards"], exp, rtol=2e-4, atol=1e-5 * np.abs(exp).max())
+
+
+def test_functional_enc_dec_surface():
+    model = ContextAEInception2([1, 2, 1, 2], [3, 3, 3, 3], [8, 8, 4, 4], featsize=16)
+    spec, B = gen_golden.CASES["incep2_6x6"]
+    d = np.load(os.path.join(GOLDEN_DIR, "incep2_6x6.npz"))
+    model.build(torch.empty((3, B, 6, 6, 8), device="meta"), precision="fp32")
+    model.net.load_state_dict({k[6:]: d[k] for k in d.files if k.startswith("param:")})
+    img = torch.from_numpy(d["image"]).cuda()
+    z_src = model.enc1(img[0])
+    z_ctx, skips = model.enc2(img[1])
+    tz = model.translate(z_src, z_ctx)
+    out = model.dec(tz, skips, ctx_frames=img[1])
+    assert rel_err(z_src.cpu(), d["out:input_z"]) < 1e-4 and rel_err(tz.cpu(), d["out:translated_z"]) < 1e-4
+    assert rel_err(out.cpu(), d["out:out"]) < 1e-4
+    res = model.forward(img[0], img[1], img[2])
+    assert rel_err(res["out2"].cpu(), d["out:out2"]) < 1e-4 and rel_err(res["loss"].cpu(), d["out:loss"]) < 1e-4
+
+
+# ---- size-independent properties at BASELINE.json's full sizes (no oracle: it would take minutes) ------------------
+def test_full_size_b256_properties():
+    """configs[1]: 64x64x3, B=256.  (1) conv / conv_transpose adjointness on the largest layers; (2) the gradient is
+    linear in the loss weights: grad(L2) == grad(L2L3) + [grad(L1) - sim part]; here simply grad(None)-grad(L2)
+    equals the pure simloss gradient, which is zero for decoder parameters; (3) a training step lowers the loss."""
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn((512, 32, 32, 64), generator=gen).cuda()
+    w = (torch.randn((5, 5, 64, 128), generator=gen) * 0.02).cuda()
+    y = ops.conv2d(x, w, None, stride=2)
+    dy = torch.randn(tuple(y.shape), generator=gen).cuda()
+    xt = ops.conv2d_transpose(dy, w, (32, 32), stride=2)
+    lhs, rhs = float((y.double() * dy.double()).sum()), float((x.double() * xt.double()).sum())
+    assert abs(lhs - rhs) < 2e-3 * abs(lhs)
+    spec, B = S.context_skip_new(64, 64), 256
+    bank = synthetic.to_float(synthetic.video_bank(25, 32, 64, 64))
+    image = torch.from_numpy(synthetic.trainer_batch(bank, B, 25, 32, np.random.RandomState(0))).float().cuda()
+    nets = {}
+    for ab in ("None", "L2"):
+        n = ContextNet(spec, B, precision="tf32", ablation_type=ab, seed=0)
+        n.set_input(image)
+        n.zero_grad()
+        n.forward(FWD_ALL)
+        n.backward()
+        nets[ab] = n
+    torch.cuda.synchronize()
+    for k in ("deconv/d_h1/w", "deconv/d_h4/w", "deconv/d_h0_lin/bias"):
+        a, b = nets["None"].G[k], nets["L2"].G[k]
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()) + 1e-12, k
+    assert float((nets["None"].G["translate/trans_z/Matrix"] - nets["L2"].G["translate/trans_z/Matrix"]).abs().max()) > 0
+    assert all(bool(torch.isfinite(nets["None"].G[k]).all()) for k in spec.param_shapes())
+    n = nets["None"]
+    l0 = float(n.fetch("loss"))
+    for _ in range(3):
+        n.set_input(image)
+        n.train_step(1e-4)
+    n.forward(FWD_ALL)
+    assert float(n.fetch("loss")) < l0

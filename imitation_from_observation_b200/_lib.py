@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_i
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctx_b200.so")
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC3, IMPL_FAST = 0, 1, 2, 3, 4
 
 
 class CtxError(RuntimeError):
@@ -35,6 +35,7 @@ SIGNATURES = {
     "ctx_last_error": (c_char_p, []),
     "ctx_device_info": (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "ctx_tc_available": (c_int32, []),
+    "ctx_launch_count": (c_int64, []),
     "ctx_conv2d_fprop": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, POINTER(ConvGeom),
                                    POINTER(Epilogue), c_int32, c_void_p]),
     "ctx_conv2d_transpose": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,

@@ -190,6 +190,8 @@ class Session:
         return pin.to("cuda", non_blocking=True)
 
     def run(self, fetches, feed_dict: Optional[dict] = None):
+        if fetches is None:                                   # sess.run(tf.global_variables_initializer())
+            return None
         single = not isinstance(fetches, (list, tuple))
         flist = [fetches] if single else list(fetches)
         # a normalised-image placeholder may itself be fetched (base.py:234 fetches self.image_trans)

@@ -18,6 +18,21 @@ int cuda_fail(cudaError_t e, const char* what) {
   return CTX_ERR_CUDA;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+// impl -> (use tensor cores?, passes, error if not eligible?)
+struct ImplChoice { bool tc; int passes; bool force; };
+static ImplChoice impl_choice(int impl) {
+  switch (impl) {
+    case CTX_IMPL_SIMT: return {false, 0, false};
+    case CTX_IMPL_TC: return {true, 1, true};
+    case CTX_IMPL_TC3: return {true, 3, true};
+    case CTX_IMPL_FAST: return {true, 1, false};
+    default: return {true, 3, false};          // CTX_IMPL_AUTO
+  }
+}
+
 int sm_count() {
   static int cached_dev = -1;
   static int cached = 0;
@@ -65,6 +80,8 @@ extern "C" int ctx_device_info(int32_t* sms, int32_t* major, int32_t* minor) {
   return CTX_OK;
 }
 
+extern "C" int64_t ctx_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 extern "C" int ctx_tc_available(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -82,10 +99,11 @@ extern "C" int ctx_conv2d_fprop(const float* x, int32_t C, const float* w, float
   CTX_REQUIRE(x && w && y && C > 0 && Co > 0, "conv2d_fprop: null pointer or bad channel count");
   if (g->N == 0) return CTX_OK;
   Epi e = make_epi(epi);
-  if (impl != CTX_IMPL_SIMT) {
+  const ImplChoice ic = impl_choice(impl);
+  if (ic.tc) {
     int ok = tc_conv2d_fprop_eligible(C, Co, *g);
-    if (ok && ctx_tc_available()) return tc_conv2d_fprop(x, C, w, y, Co, *g, e, (cudaStream_t)stream);
-    if (impl == CTX_IMPL_TC) { set_error("conv2d_fprop: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+    if (ok && ctx_tc_available()) return tc_conv2d_fprop(x, C, w, y, Co, *g, e, ic.passes, (cudaStream_t)stream);
+    if (ic.force) { set_error("conv2d_fprop: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
   return simt_conv2d_fprop(x, C, w, y, Co, *g, e, (cudaStream_t)stream);
 }
@@ -100,11 +118,12 @@ extern "C" int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2
   CTX_REQUIRE(C2 == 0 || x2_batch > 0, "conv2d_transpose: x2_batch must be positive");
   if (g->N == 0) return CTX_OK;
   Epi e = make_epi(epi);
-  if (impl != CTX_IMPL_SIMT) {
+  const ImplChoice ic = impl_choice(impl);
+  if (ic.tc) {
     int ok = tc_conv2d_transpose_eligible(C1, C2, x2_batch, Cn, *g);
     if (ok && ctx_tc_available())
-      return tc_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, (cudaStream_t)stream);
-    if (impl == CTX_IMPL_TC) { set_error("conv2d_transpose: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+      return tc_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, ic.passes, (cudaStream_t)stream);
+    if (ic.force) { set_error("conv2d_transpose: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
   return simt_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, (cudaStream_t)stream);
 }
@@ -118,11 +137,12 @@ extern "C" int ctx_conv2d_wgrad(const float* big, int32_t Ca, const float* small
   CTX_REQUIRE((Cb2 == 0) == (small2 == nullptr), "conv2d_wgrad: small2 and Cb2 must both be set or both be empty");
   CTX_REQUIRE(Cb2 == 0 || small2_batch > 0, "conv2d_wgrad: small2_batch must be positive");
   if (g->N == 0) return CTX_OK;
-  if (impl != CTX_IMPL_SIMT) {
+  const ImplChoice ic = impl_choice(impl);
+  if (ic.tc) {
     int ok = tc_conv2d_wgrad_eligible(Ca, Cb1, Cb2, small2_batch, *g);
     if (ok && ctx_tc_available())
-      return tc_conv2d_wgrad(big, Ca, small1, Cb1, small2, Cb2, small2_batch, dw, *g, (cudaStream_t)stream);
-    if (impl == CTX_IMPL_TC) { set_error("conv2d_wgrad: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+      return tc_conv2d_wgrad(big, Ca, small1, Cb1, small2, Cb2, small2_batch, dw, *g, ic.passes, (cudaStream_t)stream);
+    if (ic.force) { set_error("conv2d_wgrad: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
   return simt_conv2d_wgrad(big, Ca, small1, Cb1, small2, Cb2, small2_batch, dw, *g, (cudaStream_t)stream);
 }
@@ -135,11 +155,12 @@ extern "C" int ctx_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, in
   CTX_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm: leading dimension too small");
   if (M == 0 || N == 0) return CTX_OK;
   Epi e = make_epi(epi);
-  if (impl != CTX_IMPL_SIMT) {
+  const ImplChoice ic = impl_choice(impl);
+  if (ic.tc) {
     int ok = tc_gemm_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
     if (ok && ctx_tc_available())
-      return tc_gemm(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
-    if (impl == CTX_IMPL_TC) { set_error("gemm: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
+      return tc_gemm(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ic.passes, (cudaStream_t)stream);
+    if (ic.force) { set_error("gemm: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
   return simt_gemm(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
 }

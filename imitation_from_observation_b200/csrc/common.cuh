@@ -30,7 +30,10 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                               \
     cudaError_t e__ = cudaGetLastError();                            \
     if (e__ != cudaSuccess) return ::ctx::cuda_fail(e__, name);      \
+    ::ctx::count_launch();                                           \
   } while (0)
+
+void count_launch();   // every successful kernel launch of this library (ctx_launch_count)
 
 int sm_count();   // cached; <=0 when no device
 

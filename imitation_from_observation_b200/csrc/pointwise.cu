@@ -177,6 +177,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
+  // TF's ApplyAdam functor, term for term (fp32 scalars):  m += (g - m)*(1 - b1);  v += (g*g - v)*(1 - b2);
+  // var -= (m*alpha) / (sqrt(v) + eps)
   const float ob1 = 1.f - b1, ob2 = 1.f - b2;
   for (int64_t j = i; j < n4; j += stride) {
     float4 pp = reinterpret_cast<float4*>(p)[j];
@@ -186,9 +188,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 #define CTX_ADAM1(c)                                               \
     {                                                              \
       float gr = gg.c * gscale;                                    \
-      mm.c = b1 * mm.c + ob1 * gr;                                 \
-      vv.c = b2 * vv.c + ob2 * gr * gr;                            \
-      pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);                   \
+      mm.c = __fadd_rn(mm.c, __fmul_rn(__fsub_rn(gr, mm.c), ob1));                  \
+      vv.c = __fadd_rn(vv.c, __fmul_rn(__fsub_rn(__fmul_rn(gr, gr), vv.c), ob2));   \
+      pp.c = __fsub_rn(pp.c, __fdiv_rn(__fmul_rn(mm.c, lr_t), __fadd_rn(__fsqrt_rn(vv.c), eps)));  \
     }
     CTX_ADAM1(x) CTX_ADAM1(y) CTX_ADAM1(z) CTX_ADAM1(w)
 #undef CTX_ADAM1
@@ -198,10 +200,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
   for (int64_t j = n4 * 4 + i; j < n; j += stride) {
     float gr = g[j] * gscale;
-    float mm = b1 * m[j] + ob1 * gr;
-    float vv = b2 * v[j] + ob2 * gr * gr;
+    float mm = __fadd_rn(m[j], __fmul_rn(__fsub_rn(gr, m[j]), ob1));
+    float vv = __fadd_rn(v[j], __fmul_rn(__fsub_rn(__fmul_rn(gr, gr), v[j]), ob2));
     m[j] = mm; v[j] = vv;
-    p[j] -= lr_t * mm / (sqrtf(vv) + eps);
+    p[j] = __fsub_rn(p[j], __fdiv_rn(__fmul_rn(mm, lr_t), __fadd_rn(__fsqrt_rn(vv), eps)));
   }
 }
 
@@ -328,8 +330,9 @@ __global__ void reward_inception_kernel(const float* __restrict__ feat, const fl
 using namespace ctx;
 
 extern "C" int ctx_u8_normalize(const uint8_t* x, float* y, int64_t n, void* stream) {
-  CTX_REQUIRE(x && y && n >= 0, "u8_normalize: bad arguments");
+  CTX_REQUIRE(n >= 0, "u8_normalize: negative size");
   if (n == 0) return CTX_OK;
+  CTX_REQUIRE(x && y, "u8_normalize: null pointer");
   u8_normalize_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
   CTX_LAUNCH_CHECK("u8_normalize");
   return CTX_OK;

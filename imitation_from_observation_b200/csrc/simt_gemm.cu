@@ -327,6 +327,7 @@ static int launch_simt(const Prob& p, int max_splits, cudaStream_t stream, const
     kern<<<grid, 256, 0, stream>>>(p, kper);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, name);
+    count_launch();
     return CTX_OK;
   };
   if (p.N <= 16) return run(simt_gemm_kernel<Prob, 128, 16, 8, 1>, 128, 16);

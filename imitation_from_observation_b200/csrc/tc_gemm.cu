@@ -1,14 +1,882 @@
-// tcgen05 path — placeholder until the tensor-core kernels land: nothing is eligible, so CTX_IMPL_AUTO uses
-// the SIMT kernels and CTX_IMPL_TC reports CTX_ERR_UNSUPPORTED.
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a: conv fprop, transposed conv (per stride phase), conv
+// filter gradient and dense GEMM, all through ONE warp-specialised kernel.
+//
+//   D[128 x BN] (+)= A[128 x K] * B[BN x K]^T        fp32 accumulate in TMEM, operands TF32
+//
+// * Operands are staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle) — im2col is never
+//   materialised: an A tile of a convolution is ONE 4-D TMA box {32 channels, BQ cols, BP rows, NB images} taken
+//   at the filter tap's (dh, dw) offset; out-of-range coordinates are zero-filled by the TMA unit, which is
+//   exactly TF SAME padding.  Stride-2 convolutions read through four "parity views" of the input
+//   (base + (hp*W+wp)*C, strides doubled), so every tap is again a dense box.
+// * The channel concatenation of a decoder level ([state ‖ skip], arm_shaping.py:1323-1329) is two K segments
+//   with two tensor maps — it never exists in memory.
+// * Filter gradients use MN-major operands (pixels are the K dimension): the same pixel boxes, four 32-channel
+//   atoms per 128-row tile; split-K over pixel blocks, reduced with vector fp32 atomics.
+// * Precision (SURVEY.md §7 "hard parts"): passes == 1 is plain TF32 (operands must already be
+//   rounded to TF32 by the producer's epilogue).  passes == 3 is the fp32-faithful split
+//   a*b ~= hi(a)*hi(b) + hi(a)*lo(b) + lo(a)*hi(b): four "splitter" warps turn each landed fp32 tile into a
+//   (hi, lo) pair in shared memory (elementwise, so it is layout-agnostic), and the MMA warp issues three
+//   tcgen05.mma per K step.  Error per product ~2^-21, i.e. fp32-grade — needed because lrelu's derivative is
+//   discontinuous and single-pass TF32 flips ~3e-4 of the masks (measured).
+//
+// Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = splitters during the main loop, then the epilogue (TMEM -> registers -> fused bias / lrelu /
+// lrelu' / accumulate / TF32 rounding -> global, or vector atomics for split-K).
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <string.h>
 #include "kernels.h"
+
 namespace ctx {
-bool tc_compiled() { return false; }
-int tc_conv2d_fprop_eligible(int, int, const ctx_conv_geom&) { return 0; }
-int tc_conv2d_fprop(const float*, int, const float*, float*, int, const ctx_conv_geom&, const Epi&, cudaStream_t) { return CTX_ERR_UNSUPPORTED; }
-int tc_conv2d_transpose_eligible(int, int, int, int, const ctx_conv_geom&) { return 0; }
-int tc_conv2d_transpose(const float*, int, const float*, int, int, const float*, float*, int, const ctx_conv_geom&, const Epi&, cudaStream_t) { return CTX_ERR_UNSUPPORTED; }
-int tc_conv2d_wgrad_eligible(int, int, int, int, const ctx_conv_geom&) { return 0; }
-int tc_conv2d_wgrad(const float*, int, const float*, int, const float*, int, int, float*, const ctx_conv_geom&, cudaStream_t) { return CTX_ERR_UNSUPPORTED; }
-int tc_gemm_eligible(int, int, int, int, int, const float*, int, const float*, int, const float*, int) { return 0; }
-int tc_gemm(int, int, int, int, int, const float*, int, const float*, int, float*, int, const Epi&, cudaStream_t) { return CTX_ERR_UNSUPPORTED; }
+
+// ------------------------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------------------------
+enum { A_PIX = 0, A_MN = 1 };     // A operand: K-major pixel boxes | MN-major (4 atoms of 32 channels)
+enum { B_K = 0, B_MN = 1 };       // B operand: K-major 2-D rows | MN-major 2-D (BN/32 atoms)
+
+constexpr int kMaxSeg = 64;
+constexpr int kMaxMapsA = 8;
+constexpr int kThreads = 192;
+
+struct Seg {                       // one K segment = one filter tap of one source tensor
+  int16_t dh, dw;                  // pixel offset of the A box
+  uint8_t mapA;                    // which tensor map
+  uint8_t wrap;                    // source 2: image index taken modulo a_wrap
+  uint16_t nblk;                   // number of 32-wide K blocks in this segment
+  int32_t bk0;                     // B: K coordinate of the segment's first block
+  int32_t br0;                     // B (K-major only): row offset added to the tile's n0
+};
+
+struct TcParams {
+  CUtensorMap mapA[kMaxMapsA];
+  CUtensorMap mapB[2];
+  Seg seg[kMaxSeg];
+  int32_t nseg;
+  int32_t a_mode, b_mode;
+  int32_t passes;                  // 1 | 3
+  int32_t write_hi;                // passes==3: also overwrite the raw tile with rna(hi) (else rely on HW truncation)
+  int32_t BN;                      // 64 | 128 | 256
+  int32_t stages;
+  int32_t total_kblocks;           // whole K loop (all splits)
+  int32_t kblocks_per_split;
+  // row grid of the A/D tile: rows r -> (dn, dp, dq)
+  int32_t NG, PG, QG;              // grid extents (images, rows, cols); A_MN: NG = M, PG = QG = 1
+  int32_t BP, NB;                  // tile = NB images x BP rows x QG cols  (== 128 rows), or 32 for A_MN k-blocks
+  int32_t tiles_per_img;           // PG / BP when NB == 1, else 1
+  int32_t a_wrap;                  // batch of the wrapped source
+  // A_MN: K blocks are 32-pixel boxes of this pixel grid (images x kPG x kQG), kNB images x kBP rows each
+  int32_t kPG, kQG, kBP, kNB, k_tiles_per_img;
+  // A_MN (wgrad): per-atom tap decode
+  int32_t Ca;                      // channels per tap on the M axis
+  int32_t M;                       // valid rows of D
+  int32_t N;                       // valid cols of D
+  // B_MN second source (wgrad over [small1 ‖ small2])
+  int32_t Cb1;                     // columns < Cb1 come from mapB[0], the rest from mapB[1] (pixel rows wrapped)
+  // output
+  float* out;
+  int64_t sN, sP, sQ, obase;       // element strides of D rows over (n, p, q)
+  int32_t atomic_out;
+  Epi epi;
+  int32_t* err_flag;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// device helpers (raw PTX; names follow the PTX ISA)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost lease) — after ~2 s it records the
+// barrier id and traps, which surfaces as a launch failure on the host.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* err_flag, int id) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, 0x1000 + id);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp gets row (lane_base + t), columns col .. col+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SM100 "version 1").
+//   K-major : SWIZZLE_128B (16-byte chunks): rows of 128 B (32 tf32 along K), 8-row groups SBO = 1024 B apart;
+//             LBO unused.
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (32-byte chunks; TMA's SWIZZLE_128B_ATOM_32B):
+//             atoms of [4 k-rows x 128 B (32 elements along M/N)]; the next 4 k-rows are SBO = 512 B further,
+//             the next 32-element MN atom LBO bytes further.  One K=8 MMA therefore spans two k-groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61; // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kATileBytes = 128 * 128;          // 128 rows (or 4 atoms x 32 rows) x 128 B
+
+__global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t b_tile_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t raw_bytes = kATileBytes + b_tile_bytes;            // fp32 tiles as landed by TMA
+  const uint32_t stage_bytes = raw_bytes * (p.passes == 3 ? 2u : 1u);   // [A | B | A_lo | B_lo]
+  const int S = p.stages;
+
+  __shared__ __align__(8) uint64_t bars[3 * 8 + 1];                 // full[S], ready[S], empty[S], acc_full
+  __shared__ uint32_t tmem_slot;
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto ready_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[16 + s]); };
+  const uint32_t acc_bar = smem_u32(&bars[24]);
+
+  // this CTA's K range (split-K over blockIdx.z)
+  const int kb_begin = blockIdx.z * p.kblocks_per_split;
+  const int kb_end = min(p.total_kblocks, kb_begin + p.kblocks_per_split);
+  const int nkb = kb_end - kb_begin;
+  // tile origin on the row grid
+  const int tile_m = blockIdx.x;
+  int n0, p0;
+  if (p.NB > 1 || p.tiles_per_img == 1) { n0 = tile_m * p.NB; p0 = 0; }
+  else { n0 = tile_m / p.tiles_per_img; p0 = (tile_m - n0 * p.tiles_per_img) * p.BP; }
+  const int ncol0 = blockIdx.y * p.BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    // 3-pass mode keeps two accumulators: D1 = hi*hi, D2 = the two cross terms.  The tensor core truncates when
+    // it adds into a running fp32 sum (measured: error grows linearly with the number of accumulations), so the
+    // small terms must not ride on the big sum; D1 + D2 is formed once, in the epilogue, with a rounded fp32 add.
+    uint32_t ncols = (uint32_t)p.BN * (p.passes == 3 ? 2u : 1u);
+    if (ncols < 32u) ncols = 32u;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      // =============================== TMA producer (one lane) =================================================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        if (p.a_mode == A_PIX) {
+          // enumerate (segment, channel block) pairs; skip to kb_begin
+          int kb = 0;
+          for (int sg = 0; sg < p.nseg && kb < kb_end; ++sg) {
+            const Seg s = p.seg[sg];
+            if (kb + s.nblk <= kb_begin) { kb += s.nblk; continue; }
+            for (int cb = 0; cb < s.nblk && kb < kb_end; ++cb, ++kb) {
+              if (kb < kb_begin) continue;
+              mbar_wait(empty_bar(stage), phase ^ 1, p.err_flag, 1);
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              const uint32_t sb = sa + kATileBytes;
+              mbar_arrive_expect_tx(full_bar(stage), raw_bytes);
+              const int nimg = s.wrap ? (n0 % p.a_wrap) : n0;
+              tma_load_4d(sa, &p.mapA[s.mapA], full_bar(stage), cb * 32, s.dw, p0 + s.dh, nimg);
+              if (p.b_mode == B_K) {
+                tma_load_2d(sb, &p.mapB[0], full_bar(stage), s.bk0 + cb * 32, s.br0 + ncol0);
+              } else {
+                for (int a = 0; a < p.BN / 32; ++a)
+                  tma_load_2d(sb + a * 4096, &p.mapB[0], full_bar(stage), ncol0 + a * 32, s.bk0 + cb * 32);
+              }
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          // A_MN: K blocks are 32-pixel boxes; the 128 tile rows are 4 atoms (tap, 32 channels)
+          const int m0 = tile_m * 128;
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
+            int kn0, kp0;
+            if (p.kNB > 1 || p.k_tiles_per_img == 1) { kn0 = kb * p.kNB; kp0 = 0; }
+            else { kn0 = kb / p.k_tiles_per_img; kp0 = (kb - kn0 * p.k_tiles_per_img) * p.kBP; }
+            mbar_wait(empty_bar(stage), phase ^ 1, p.err_flag, 2);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint32_t sb = sa + kATileBytes;
+            int natomA = 0;
+            for (int j = 0; j < 4; ++j) natomA += (m0 + 32 * j < p.M) ? 1 : 0;
+            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)natomA * 4096u + b_tile_bytes);
+            for (int j = 0; j < 4; ++j) {
+              const int m = m0 + 32 * j;
+              if (m >= p.M) break;
+              const int tap = m / p.Ca, a0 = m - tap * p.Ca;
+              const Seg s = p.seg[tap];
+              tma_load_4d(sa + j * 4096, &p.mapA[s.mapA], full_bar(stage), a0, s.dw, kp0 + s.dh, kn0);
+            }
+            const int prow = (kn0 * p.kPG + kp0) * p.kQG;               // first pixel row of this K block
+            for (int a = 0; a < p.BN / 32; ++a) {
+              const int n = ncol0 + a * 32;
+              if (n < p.Cb1 || p.N <= p.Cb1) {       // (columns past N are zero-filled by the TMA unit)
+                tma_load_2d(sb + a * 4096, &p.mapB[0], full_bar(stage), n, prow);
+              } else {
+                const int prow2 = ((kn0 % p.a_wrap) * p.kPG + kp0) * p.kQG;
+                tma_load_2d(sb + a * 4096, &p.mapB[1], full_bar(stage), n - p.Cb1, prow2);
+              }
+            }
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // =============================== MMA issuer (one lane) ===================================================
+      if (lane == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.a_mode == A_MN ? 1u : 0u) << 15) |
+                               ((p.b_mode == B_MN ? 1u : 0u) << 16) | ((uint32_t)(p.BN >> 3) << 17) |
+                               ((128u >> 4) << 24);
+        const bool amn = p.a_mode == A_MN, bmn = p.b_mode == B_MN;
+        const uint32_t a_lbo = amn ? 4096u : 16u, a_sbo = amn ? 512u : 1024u, a_step = amn ? 1024u : 32u;
+        const uint32_t b_lbo = bmn ? 4096u : 16u, b_sbo = bmn ? 512u : 1024u, b_step = bmn ? 1024u : 32u;
+        const uint32_t a_lt = amn ? 1u : 2u, b_lt = bmn ? 1u : 2u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(p.passes == 3 ? ready_bar(stage) : full_bar(stage), phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_desc(sa + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t bd = make_desc(sb + ks * b_step, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_base, ad, bd, idesc, (i | ks) ? 1u : 0u);
+            if (p.passes == 3) {
+              const uint64_t ad_lo = make_desc(sa + raw_bytes + ks * a_step, a_lbo, a_sbo, a_lt);
+              const uint64_t bd_lo = make_desc(sb + raw_bytes + ks * b_step, b_lbo, b_sbo, b_lt);
+              umma_tf32(tmem_base + (uint32_t)p.BN, ad, bd_lo, idesc, (i | ks) ? 1u : 0u);
+              umma_tf32(tmem_base + (uint32_t)p.BN, ad_lo, bd, idesc, 1u);
+            }
+          }
+          umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(acc_bar);                      // accumulator complete
+      }
+    } else if (p.passes == 3) {
+      // =============================== splitters: fp32 tile -> (hi, lo) =======================================
+      const int t = threadIdx.x - 64;              // 0..127
+      const int nchunk = (int)(raw_bytes >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full_bar(stage), phase, p.err_flag, 4);
+        const uint32_t base = smem_base + stage * stage_bytes;
+        for (int c = t; c < nchunk; c += 128) {
+          const uint32_t addr = base + ((uint32_t)c << 4);
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+          float4 h, l;
+          if (p.write_hi) {
+            h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
+          } else {
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          }
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + raw_bytes), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+          if (p.write_hi)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+        }
+        fence_async_smem();                        // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(ready_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  // ================================= epilogue: warps 2..5 ======================================================
+  if (warp >= 2) {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                   // tile row
+    if (nkb > 0) {
+      mbar_wait(acc_bar, 0, p.err_flag, 5);
+      tc_fence_after();
+    }
+    // row -> (n, p, q) -> output offset
+    const int per_img = p.BP * p.QG;
+    const int dn = r / per_img, rem = r - dn * per_img;
+    const int dp = rem / p.QG, dq = rem - dp * p.QG;
+    const int gn = n0 + dn, gp = p0 + dp;
+    const bool row_ok = gn < p.NG && gp < p.PG && (nkb > 0 || !p.atomic_out);
+    const int64_t roff = p.obase + (int64_t)gn * p.sN + (int64_t)gp * p.sP + (int64_t)dq * p.sQ;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t v[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (p.passes == 3) {
+          uint32_t v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (!row_ok) continue;
+      const int col = ncol0 + c0;
+      if (col >= p.N) continue;
+      float* optr = p.out + roff + col;
+      if (p.atomic_out) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (col + j + 3 < p.N) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (col + j + e < p.N) atomicAdd(optr + j + e, __uint_as_float(v[j + e]));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (col + j + 3 < p.N) {
+            float4 o;
+            float* oo = reinterpret_cast<float*>(&o);
+            float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), ref = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.epi.accumulate) prev = *reinterpret_cast<const float4*>(optr + j);
+            if (p.epi.act_ref) ref = __ldg(reinterpret_cast<const float4*>(p.epi.act_ref + roff + col + j));
+            const float* pp = reinterpret_cast<const float*>(&prev);
+            const float* rr = reinterpret_cast<const float*>(&ref);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(v[j + e]);
+              if (p.epi.bias) x += __ldg(p.epi.bias + col + j + e);
+              if (p.epi.act) x = fmaxf(x, p.epi.slope * x);
+              if (p.epi.act_ref) x *= (rr[e] >= 0.f ? 1.f : p.epi.slope);
+              if (p.epi.accumulate) x += pp[e];
+              if (p.epi.round) x = round_tf32(x);
+              oo[e] = x;
+            }
+            *reinterpret_cast<float4*>(optr + j) = o;
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (col + j + e < p.N)
+                optr[j + e] = p.epi.apply(__uint_as_float(v[j + e]), col + j + e, roff + col + j + e, p.out);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    uint32_t ncols = (uint32_t)p.BN * (p.passes == 3 ? 2u : 1u);
+    if (ncols < 32u) ncols = 32u;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// fp32 tensor map, rank <= 4, zero fill; 128-byte swizzle of 16-byte chunks (K-major operand tiles) or of
+// 32-byte chunks (mn_major: the only layout tcgen05 accepts for MN-major 32-bit operands).  dims/box innermost first; strides in ELEMENTS for
+// dims 1..rank-1.
+static int make_map(CUtensorMap* out, const float* base, int rank, const int64_t* dims, const int64_t* strides,
+                    const int* box, bool mn_major = false) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return CTX_ERR_CUDA; }
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (dims[i] <= 0 || box[i] <= 0 || box[i] > 256) { set_error("tensor map: bad dim/box %d: %lld/%d", i, (long long)dims[i], box[i]); return CTX_ERR_ARG; }
+  }
+  for (int i = 1; i < rank; ++i) {
+    gs[i - 1] = (cuuint64_t)strides[i] * 4u;
+    if (gs[i - 1] % 16 != 0) { set_error("tensor map: stride %d (%lld elements) is not 16-byte aligned", i, (long long)strides[i]); return CTX_ERR_ARG; }
+  }
+  if (((uintptr_t)base & 15) != 0) { set_error("tensor map: base pointer is not 16-byte aligned"); return CTX_ERR_ARG; }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return CTX_ERR_CUDA; }
+  return CTX_OK;
+}
+
+bool tc_compiled() { return true; }
+
+// Tile a (P x Q) pixel grid into boxes of exactly `rows` pixels: full-width rows, either BP rows of one image
+// or NB whole images.
+static bool tile_grid(int P, int Q, int rows, int* BP, int* NB, int* tiles_per_img) {
+  if (Q <= 0 || P <= 0 || Q > rows || rows % Q != 0) return false;
+  const int per_img = P * Q;
+  if (per_img >= rows) {
+    const int bp = rows / Q;
+    if (P % bp != 0) return false;
+    *BP = bp; *NB = 1; *tiles_per_img = P / bp;
+  } else {
+    if (rows % per_img != 0) return false;
+    *BP = P; *NB = rows / per_img; *tiles_per_img = 1;
+  }
+  return true;
+}
+
+static int pick_bn(int N) { return N >= 256 ? 256 : (N >= 128 ? 128 : 64); }
+
+static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, const char* name) {
+  const int sms = sm_count();
+  if (sms <= 0) return cuda_fail(cudaErrorNoDevice, name);
+  const uint32_t raw = kATileBytes + (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = raw * (p.passes == 3 ? 2u : 1u);
+  static int max_dyn = 0;
+  if (max_dyn == 0) {
+    cudaFuncAttributes fa;
+    CTX_CUDA(cudaFuncGetAttributes(&fa, tc_igemm_kernel));
+    int dev = 0, optin = 0;
+    CTX_CUDA(cudaGetDevice(&dev));
+    CTX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int dyn = optin - (int)fa.sharedSizeBytes;
+    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    max_dyn = dyn;
+  }
+  int stages = (int)(((uint32_t)max_dyn - 1024u) / stage_bytes);      // 1024: alignment slack
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("%s: tile does not fit shared memory", name); return CTX_ERR_ARG; }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  p.err_flag = nullptr;
+  const int n_tiles = (int)cdiv(p.N, p.BN);
+  if (n_tiles > 65535 || splits > 65535) { set_error("%s: grid too large", name); return CTX_ERR_ARG; }
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  tc_igemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  CTX_LAUNCH_CHECK(name);
+  count_launch();
+  return CTX_OK;
+}
+
+static void fill_common(TcParams& p, int passes, const Epi& epi) {
+  memset(&p, 0, sizeof(p));
+  p.passes = passes;
+  p.write_hi = 1;
+  p.epi = epi;
+  p.a_wrap = 1;
+  p.Cb1 = 1 << 30;
+}
+
+static bool aligned16(const void* ptr) { return ((uintptr_t)ptr & 15) == 0; }
+
+// ---- conv fprop ------------------------------------------------------------------------------------------------
+int tc_conv2d_fprop_eligible(int C, int Co, const ctx_conv_geom& g) {
+  int bp, nb, tpi;
+  if (C % 32 != 0 || Co % 32 != 0) return 0;
+  if (g.stride != 1 && g.stride != 2) return 0;
+  if (g.kh * g.kw > kMaxSeg) return 0;
+  if (!tile_grid(g.P, g.Q, 128, &bp, &nb, &tpi)) return 0;
+  return 1;
+}
+
+// Tensor maps of a (possibly stride-2) NHWC tensor read at conv-tap offsets.  For stride 2, map[hp*2+wp] is the
+// parity view x[n, 2*h2+hp, 2*w2+wp, c]; a tap r (relative to the output pixel: r' = r - pad) reads parity
+// hp = r' & 1 at row offset (r' - hp) / 2.
+static int make_tap_maps(CUtensorMap* maps, const float* x, int C, int N, int H, int W, int stride, int box_q,
+                         int box_p, int box_n, bool mn_major) {
+  if (stride == 1) {
+    int64_t dims[4] = {C, W, H, N}, str[4] = {1, C, (int64_t)W * C, (int64_t)H * W * C};
+    int box[4] = {32, box_q, box_p, box_n};
+    return make_map(&maps[0], x, 4, dims, str, box, mn_major);
+  }
+  for (int hp = 0; hp < 2; ++hp)
+    for (int wp = 0; wp < 2; ++wp) {
+      const int Hh = (H - hp + 1) / 2, Wh = (W - wp + 1) / 2;
+      if (Hh <= 0 || Wh <= 0) { memset(&maps[hp * 2 + wp], 0, sizeof(CUtensorMap)); continue; }
+      int64_t dims[4] = {C, Wh, Hh, N}, str[4] = {1, 2 * (int64_t)C, 2 * (int64_t)W * C, (int64_t)H * W * C};
+      int box[4] = {32, box_q, box_p, box_n};
+      int rc = make_map(&maps[hp * 2 + wp], x + ((int64_t)hp * W + wp) * C, 4, dims, str, box, mn_major);
+      if (rc) return rc;
+    }
+  return CTX_OK;
+}
+
+static void tap_seg(Seg& s, int r, int sx, const ctx_conv_geom& g) {
+  const int rr = r - g.pad_h, ss = sx - g.pad_w;
+  if (g.stride == 1) { s.mapA = 0; s.dh = (int16_t)rr; s.dw = (int16_t)ss; return; }
+  const int hp = rr & 1, wp = ss & 1;                 // two's complement: correct for negatives
+  s.mapA = (uint8_t)(hp * 2 + wp);
+  s.dh = (int16_t)((rr - hp) / 2);
+  s.dw = (int16_t)((ss - wp) / 2);
+}
+
+int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, const ctx_conv_geom& g,
+                    const Epi& epi, int passes, cudaStream_t stream) {
+  TcParams p;
+  fill_common(p, passes, epi);
+  int tpi;
+  if (!tile_grid(g.P, g.Q, 128, &p.BP, &p.NB, &tpi)) return CTX_ERR_UNSUPPORTED;
+  CTX_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), "conv2d_fprop(tc): pointers must be 16-byte aligned");
+  p.tiles_per_img = tpi;
+  p.a_mode = A_PIX; p.b_mode = B_MN;
+  p.BN = pick_bn(Co);
+  p.NG = g.N; p.PG = g.P; p.QG = g.Q;
+  p.M = g.N * g.P * g.Q; p.N = Co;
+  int rc = make_tap_maps(p.mapA, x, C, g.N, g.H, g.W, g.stride, g.Q, p.BP, p.NB, false);
+  if (rc) return rc;
+  {
+    int64_t dims[2] = {Co, (int64_t)g.kh * g.kw * C}, str[2] = {1, Co};
+    int box[2] = {32, 32};
+    rc = make_map(&p.mapB[0], w, 2, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.nseg = g.kh * g.kw;
+  for (int r = 0; r < g.kh; ++r)
+    for (int s = 0; s < g.kw; ++s) {
+      Seg& sg = p.seg[r * g.kw + s];
+      tap_seg(sg, r, s, g);
+      sg.wrap = 0; sg.nblk = (uint16_t)(C / 32); sg.bk0 = (r * g.kw + s) * C; sg.br0 = 0;
+    }
+  p.total_kblocks = p.nseg * (C / 32);
+  p.kblocks_per_split = p.total_kblocks;
+  p.out = y;
+  p.sN = (int64_t)g.P * g.Q * Co; p.sP = (int64_t)g.Q * Co; p.sQ = Co; p.obase = 0;
+  p.atomic_out = 0;
+  const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
+  return launch_tc(p, m_tiles, 1, stream, "tc_conv2d_fprop");
+}
+
+// ---- transposed conv (one launch per stride phase) ---------------------------------------------------------------
+static void phase_geom(const ctx_conv_geom& g, int ph, int pw, int* Hp, int* Wp, int* r0, int* s0, int* nr, int* ns,
+                       int* dh0, int* dw0) {
+  const int st = g.stride;
+  *Hp = g.H > ph ? (g.H - ph + st - 1) / st : 0;
+  *Wp = g.W > pw ? (g.W - pw + st - 1) / st : 0;
+  *r0 = (ph + g.pad_h) % st; *s0 = (pw + g.pad_w) % st;
+  *nr = *r0 < g.kh ? (g.kh - *r0 + st - 1) / st : 0;
+  *ns = *s0 < g.kw ? (g.kw - *s0 + st - 1) / st : 0;
+  *dh0 = (ph + g.pad_h - *r0) / st; *dw0 = (pw + g.pad_w - *s0) / st;
+}
+
+int tc_conv2d_transpose_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g) {
+  if (C1 % 32 != 0 || C2 % 32 != 0 || Cn % 4 != 0 || Cn < 32) return 0;
+  if (g.stride != 1 && g.stride != 2) return 0;
+  for (int ph = 0; ph < g.stride; ++ph)
+    for (int pw = 0; pw < g.stride; ++pw) {
+      int Hp, Wp, r0, s0, nr, ns, dh0, dw0, bp, nb, tpi;
+      phase_geom(g, ph, pw, &Hp, &Wp, &r0, &s0, &nr, &ns, &dh0, &dw0);
+      if (Hp == 0 || Wp == 0) continue;
+      if (!tile_grid(Hp, Wp, 128, &bp, &nb, &tpi)) return 0;
+      if (C2 > 0 && nb > 1 && x2_batch % nb != 0) return 0;
+      if (nr * ns * 2 > kMaxSeg) return 0;
+    }
+  return 1;
+}
+
+int tc_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2_batch, const float* w, float* y,
+                        int Cn, const ctx_conv_geom& g, const Epi& epi, int passes, cudaStream_t stream) {
+  CTX_REQUIRE(aligned16(x1) && aligned16(w) && aligned16(y) && (x2 == nullptr || aligned16(x2)),
+              "conv2d_transpose(tc): pointers must be 16-byte aligned");
+  const int st = g.stride, Ck = C1 + C2;
+  for (int ph = 0; ph < st; ++ph)
+    for (int pw = 0; pw < st; ++pw) {
+      int Hp, Wp, r0, s0, nr, ns, dh0, dw0, tpi;
+      phase_geom(g, ph, pw, &Hp, &Wp, &r0, &s0, &nr, &ns, &dh0, &dw0);
+      if (Hp == 0 || Wp == 0) continue;
+      TcParams p;
+      fill_common(p, passes, epi);
+      if (!tile_grid(Hp, Wp, 128, &p.BP, &p.NB, &tpi)) return CTX_ERR_UNSUPPORTED;
+      p.tiles_per_img = tpi;
+      p.a_mode = A_PIX; p.b_mode = B_K;
+      p.BN = pick_bn(Cn);
+      p.NG = g.N; p.PG = Hp; p.QG = Wp;
+      p.M = g.N * Hp * Wp; p.N = Cn;
+      p.a_wrap = x2_batch > 0 ? x2_batch : 1;
+      {
+        int64_t dims[4] = {C1, g.Q, g.P, g.N}, str[4] = {1, C1, (int64_t)g.Q * C1, (int64_t)g.P * g.Q * C1};
+        int box[4] = {32, Wp, p.BP, p.NB};
+        int rc = make_map(&p.mapA[0], x1, 4, dims, str, box);
+        if (rc) return rc;
+      }
+      if (C2 > 0) {
+        int64_t dims[4] = {C2, g.Q, g.P, x2_batch}, str[4] = {1, C2, (int64_t)g.Q * C2, (int64_t)g.P * g.Q * C2};
+        int box[4] = {32, Wp, p.BP, p.NB};
+        int rc = make_map(&p.mapA[1], x2, 4, dims, str, box);
+        if (rc) return rc;
+      }
+      {
+        int64_t dims[2] = {Ck, (int64_t)g.kh * g.kw * Cn}, str[2] = {1, Ck};
+        int box[2] = {32, p.BN};
+        int rc = make_map(&p.mapB[0], w, 2, dims, str, box);
+        if (rc) return rc;
+      }
+      int nseg = 0, kblocks = 0;
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < ns; ++j) {
+          const int tap = (r0 + st * i) * g.kw + (s0 + st * j);
+          for (int src = 0; src < (C2 > 0 ? 2 : 1); ++src) {
+            Seg& sg = p.seg[nseg++];
+            sg.mapA = (uint8_t)src; sg.wrap = (uint8_t)src;
+            sg.dh = (int16_t)(dh0 - i); sg.dw = (int16_t)(dw0 - j);
+            sg.nblk = (uint16_t)((src ? C2 : C1) / 32);
+            sg.bk0 = src ? C1 : 0; sg.br0 = tap * Cn;
+            kblocks += sg.nblk;
+          }
+        }
+      p.nseg = nseg;
+      p.total_kblocks = kblocks;
+      p.kblocks_per_split = kblocks;
+      p.out = y;
+      p.obase = ((int64_t)ph * g.W + pw) * Cn;
+      p.sN = (int64_t)g.H * g.W * Cn; p.sP = (int64_t)st * g.W * Cn; p.sQ = (int64_t)st * Cn;
+      p.atomic_out = 0;
+      const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
+      int rc = launch_tc(p, m_tiles, 1, stream, "tc_conv2d_transpose");
+      if (rc) return rc;
+    }
+  return CTX_OK;
+}
+
+// ---- conv filter gradient ------------------------------------------------------------------------------------------
+int tc_conv2d_wgrad_eligible(int Ca, int Cb1, int Cb2, int s2_batch, const ctx_conv_geom& g) {
+  int bp, nb, tpi;
+  if (Ca % 32 != 0 || Cb1 % 32 != 0 || Cb2 % 32 != 0) return 0;
+  if (g.stride != 1 && g.stride != 2) return 0;
+  if (g.kh * g.kw > kMaxSeg) return 0;
+  if (!tile_grid(g.P, g.Q, 32, &bp, &nb, &tpi)) return 0;
+  if (Cb2 > 0 && nb > 1 && s2_batch % nb != 0) return 0;
+  return 1;
+}
+
+static int pick_splits(int tiles, int kblocks, int min_per_split) {
+  const int sms = sm_count();
+  int want = (int)cdiv(2 * (int64_t)sms, tiles);
+  int maxs = kblocks / min_per_split;
+  if (maxs < 1) maxs = 1;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  return want;
+}
+
+int tc_conv2d_wgrad(const float* big, int Ca, const float* s1, int Cb1, const float* s2, int Cb2, int s2_batch,
+                    float* dw, const ctx_conv_geom& g, int passes, cudaStream_t stream) {
+  CTX_REQUIRE(aligned16(big) && aligned16(s1) && aligned16(dw) && (s2 == nullptr || aligned16(s2)),
+              "conv2d_wgrad(tc): pointers must be 16-byte aligned");
+  TcParams p;
+  fill_common(p, passes, make_epi(nullptr));
+  int tpi;
+  if (!tile_grid(g.P, g.Q, 32, &p.kBP, &p.kNB, &tpi)) return CTX_ERR_UNSUPPORTED;
+  p.k_tiles_per_img = tpi;
+  p.a_mode = A_MN; p.b_mode = B_MN;
+  const int N = Cb1 + Cb2;
+  p.BN = pick_bn(N);
+  p.kPG = g.P; p.kQG = g.Q;
+  p.Ca = Ca; p.M = g.kh * g.kw * Ca; p.N = N;
+  p.Cb1 = Cb1; p.a_wrap = s2_batch > 0 ? s2_batch : 1;
+  int rc = make_tap_maps(p.mapA, big, Ca, g.N, g.H, g.W, g.stride, g.Q, p.kBP, p.kNB, true);
+  if (rc) return rc;
+  {
+    int64_t dims[2] = {Cb1, (int64_t)g.N * g.P * g.Q}, str[2] = {1, Cb1};
+    int box[2] = {32, 32};
+    rc = make_map(&p.mapB[0], s1, 2, dims, str, box, true);
+    if (rc) return rc;
+  }
+  if (Cb2 > 0) {
+    int64_t dims[2] = {Cb2, (int64_t)s2_batch * g.P * g.Q}, str[2] = {1, Cb2};
+    int box[2] = {32, 32};
+    rc = make_map(&p.mapB[1], s2, 2, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.nseg = g.kh * g.kw;
+  for (int r = 0; r < g.kh; ++r)
+    for (int s = 0; s < g.kw; ++s) tap_seg(p.seg[r * g.kw + s], r, s, g);
+  p.total_kblocks = p.kNB > 1 ? (int)cdiv(g.N, p.kNB) : g.N * tpi;
+  // epilogue row grid: rows are dw rows
+  const int m_tiles = (int)cdiv(p.M, 128);
+  const int n_tiles = (int)cdiv(N, p.BN);
+  const int splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8);
+  p.kblocks_per_split = (int)cdiv(p.total_kblocks, splits);
+  const int real_splits = (int)cdiv(p.total_kblocks, p.kblocks_per_split);
+  p.out = dw;
+  p.atomic_out = 1;
+  // D rows are addressed linearly: a 128-"image" tile of 1x1 grids
+  p.NG = p.M; p.PG = 1; p.QG = 1; p.BP = 1; p.NB = 128; p.tiles_per_img = 1;
+  p.sN = N; p.sP = 0; p.sQ = 0; p.obase = 0;
+  return launch_tc(p, m_tiles, real_splits, stream, "tc_conv2d_wgrad");
+}
+
+// ---- dense GEMM ------------------------------------------------------------------------------------------------------
+int tc_gemm_eligible(int tA, int tB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                     const float* C, int ldc) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return 0;
+  if (lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0 || N % 4 != 0 || K % 4 != 0) return 0;
+  if (N < 32) return 0;
+  if (tA && tB) return 0;                          // MN-major A with K-major B is not wired up (unused by the graph)
+  if (tA && (M % 32 != 0)) return 0;
+  if (!tB && (N % 32 != 0)) return 0;
+  return 1;
+}
+
+int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            const Epi& epi, int passes, cudaStream_t stream) {
+  TcParams p;
+  fill_common(p, passes, epi);
+  p.BN = pick_bn(N);
+  p.M = M; p.N = N;
+  const bool plain_accumulate = epi.accumulate && !epi.bias && !epi.act && !epi.act_ref && !epi.round;
+  int rc;
+  if (!tA) {
+    // A [M,K] row-major: K-major rows; tile = 128 consecutive rows ("images"), one 1x1 pixel each
+    p.a_mode = A_PIX;
+    int64_t dims[4] = {K, 1, 1, M}, str[4] = {1, lda, lda, lda};
+    int box[4] = {32, 1, 1, 128};
+    rc = make_map(&p.mapA[0], A, 4, dims, str, box);
+    if (rc) return rc;
+    p.nseg = 1;
+    Seg& sg = p.seg[0];
+    sg.mapA = 0; sg.wrap = 0; sg.dh = 0; sg.dw = 0; sg.nblk = (uint16_t)cdiv(K, 32); sg.bk0 = 0; sg.br0 = 0;
+    CTX_REQUIRE(cdiv(K, 32) < 65536, "gemm(tc): K too large");
+    p.total_kblocks = (int)cdiv(K, 32);
+  } else {
+    // A stored [K,M]: MN-major; K blocks are 32 consecutive rows of the stored matrix
+    p.a_mode = A_MN;
+    p.Ca = M; p.kPG = 1; p.kQG = 1; p.kBP = 1; p.kNB = 32; p.k_tiles_per_img = 1;
+    int64_t dims[4] = {M, 1, 1, K}, str[4] = {1, lda, lda, lda};
+    int box[4] = {32, 1, 1, 32};
+    rc = make_map(&p.mapA[0], A, 4, dims, str, box, true);
+    if (rc) return rc;
+    p.nseg = 1;
+    Seg& sg = p.seg[0];
+    sg.mapA = 0; sg.wrap = 0; sg.dh = 0; sg.dw = 0; sg.nblk = 0; sg.bk0 = 0; sg.br0 = 0;
+    p.total_kblocks = (int)cdiv(K, 32);
+  }
+  if (!tB) {
+    p.b_mode = B_MN;                                 // B [K,N] row-major
+    int64_t dims[2] = {N, K}, str[2] = {1, ldb};
+    int box[2] = {32, 32};
+    rc = make_map(&p.mapB[0], B, 2, dims, str, box, true);
+  } else {
+    p.b_mode = B_K;                                  // B stored [N,K]
+    int64_t dims[2] = {K, N}, str[2] = {1, ldb};
+    int box[2] = {32, p.BN};
+    rc = make_map(&p.mapB[0], B, 2, dims, str, box);
+  }
+  if (rc) return rc;
+  const int m_tiles = (int)cdiv(M, 128), n_tiles = (int)cdiv(N, p.BN);
+  int splits = 1;
+  if (plain_accumulate) splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8);
+  p.kblocks_per_split = (int)cdiv(p.total_kblocks, splits);
+  splits = (int)cdiv(p.total_kblocks, p.kblocks_per_split);
+  p.atomic_out = (plain_accumulate && splits > 1) ? 1 : 0;
+  if (p.atomic_out) p.epi.accumulate = 0;
+  p.out = C;
+  // D (and a K-major A) rows are matrix rows: a 128-"image" tile of 1x1 grids
+  p.NG = M; p.PG = 1; p.QG = 1; p.BP = 1; p.NB = 128; p.tiles_per_img = 1;
+  p.sN = ldc; p.sP = 0; p.sQ = 0; p.obase = 0;
+  return launch_tc(p, m_tiles, splits, stream, "tc_gemm");
+}
+
+}  // namespace ctx

@@ -342,7 +342,7 @@ class ContextNet:
         Wd0 = P["deconv/d_h0_lin/Matrix"]
         self._gemm(True, False, F, flat, 2 * B, z2.data_ptr(), F, g_d0.data_ptr(), flat,
                    G["deconv/d_h0_lin/Matrix"].data_ptr(), flat, accumulate=True, round_=False)
-        ops.bias_grad(g_d0, G["deconv/d_h0_lin/bias"])
+        ops.bias_grad(g_d0.view(2 * B, flat), G["deconv/d_h0_lin/bias"])
         g_z2 = self._buf("g_z2", (2 * B, F))
         self._gemm(False, True, 2 * B, F, flat, g_d0.data_ptr(), flat, Wd0.data_ptr(), flat, g_z2.data_ptr(), F)
         if on_stage:
@@ -448,7 +448,8 @@ class ContextNet:
     def fetch(self, name: str) -> torch.Tensor:
         """Device tensor for a reference attribute name (arm_shaping.py:1296,1312,1349-1354)."""
         B, F, bufs = self.B, self.F, self._bufs
-        need = {"input_z": FWD_SRC, "translated_z": FWD_TRANS, "out": FWD_TRANS}.get(name, FWD_ALL)
+        need = {"input_z": FWD_SRC, "translated_z": FWD_TRANS, "out": FWD_TRANS, "ctx_z": FWD_TRANS,
+                "image_trans": 0}.get(name, FWD_ALL)
         if self._level < need:
             raise _lib.CtxError("fetch(%r) needs forward(level>=%d)" % (name, need))
         if name == "input_z":

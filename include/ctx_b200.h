@@ -36,9 +36,13 @@ enum {
 
 /* Which implementation a GEMM-shaped entry point uses. */
 enum {
-  CTX_IMPL_AUTO = 0,     /* tcgen05 tensor-core kernel when the shape qualifies, else the SIMT kernel */
-  CTX_IMPL_SIMT = 1,     /* fp32 CUDA-core kernel (exact fp32 products)                               */
-  CTX_IMPL_TC = 2        /* force tcgen05 (TF32 operands, fp32 accumulate); error if shape not eligible */
+  CTX_IMPL_AUTO = 0,     /* tcgen05 kernel, 3-pass TF32 split (fp32-faithful, ~2^-21 per product) when the  */
+                         /* shape qualifies, else the SIMT kernel                                            */
+  CTX_IMPL_SIMT = 1,     /* fp32 CUDA-core kernel (exact fp32 products)                                      */
+  CTX_IMPL_TC = 2,       /* force tcgen05, single-pass TF32 (operands must be TF32-rounded); error if the    */
+                         /* shape is not eligible                                                            */
+  CTX_IMPL_TC3 = 3,      /* force tcgen05, 3-pass split; error if the shape is not eligible                  */
+  CTX_IMPL_FAST = 4      /* single-pass TF32 when the shape qualifies, else SIMT                             */
 };
 
 /* Geometry of one SAME conv / transposed conv.  "big" is the conv input (= transposed-conv output) grid,
@@ -74,6 +78,8 @@ const char* ctx_last_error(void);
 int ctx_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* 1 if the tcgen05 path can run on the current device (sm_100). */
 int ctx_tc_available(void);
+/* Number of kernels this library has launched in this process (all streams); bench.py's "gpu_launches". */
+int64_t ctx_launch_count(void);
 
 /* ---- convolutions ------------------------------------------------------------------------------------- */
 

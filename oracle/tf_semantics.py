@@ -216,12 +216,22 @@ def loss_and_grads(spec, P: Dict[str, torch.Tensor], image: torch.Tensor, ablati
 # optimiser, metrics, rewards
 # ------------------------------------------------------------------------------------------------------------
 def tf_adam_step(P, G, M, V, t: int, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
-    """tf.train.AdamOptimizer (scripts/train_script.py:128): epsilon is *outside* the bias correction."""
+    """tf.train.AdamOptimizer (scripts/train_script.py:128): epsilon is *outside* the bias correction.
+    Restated term for term from TF's published ApplyAdam functor (tensorflow/core/kernels/training_ops.cc, TF 1.x;
+    TensorFlow is a third-party dependency absent from /root/reference):
+        alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+        m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2);  var -= (m * alpha) / (sqrt(v) + epsilon)
+    with every scalar held in the tensors' dtype (so for fp32, 1 - beta2 is the fp32 value 0.00100004673)."""
     lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
     for k in P:
-        M[k].mul_(b1).add_(G[k], alpha=1 - b1)
-        V[k].mul_(b2).addcmul_(G[k], G[k], value=1 - b2)
-        P[k].sub_(lr_t * M[k] / (V[k].sqrt() + eps))
+        dt = P[k].dtype
+        one = torch.ones((), dtype=dt)
+        ob1 = one - torch.tensor(b1, dtype=dt)
+        ob2 = one - torch.tensor(b2, dtype=dt)
+        alpha = torch.tensor(lr_t, dtype=dt)
+        M[k].add_((G[k] - M[k]) * ob1)
+        V[k].add_((G[k] * G[k] - V[k]) * ob2)
+        P[k].sub_((M[k] * alpha) / (V[k].sqrt() + torch.tensor(eps, dtype=dt)))
 
 
 def nn_err(tgt: torch.Tensor, out: torch.Tensor, nlen: int) -> int:

@@ -7,15 +7,17 @@ import torch
 
 from conftest import rel_err
 from imitation_from_observation_b200 import _lib, ops
-from imitation_from_observation_b200._lib import IMPL_AUTO, IMPL_SIMT
+from imitation_from_observation_b200._lib import IMPL_AUTO, IMPL_FAST, IMPL_SIMT
 from oracle import tf_semantics as O
 
 pytestmark = pytest.mark.gpu
-FP32_TOL, TF32_TOL = 2e-5, 1e-3
+# exact-fp32 SIMT and the 3-pass TF32 split (IMPL_AUTO) are both held to fp32 grade; the single-pass TF32 mode
+# (IMPL_FAST) is fed unrounded operands here, so it sees the hardware's truncation (2^-10 per operand)
+FP32_TOL, TF32_TOL = 2e-5, 3e-3
 
 
 def _impls():
-    return [(IMPL_SIMT, FP32_TOL), (IMPL_AUTO, TF32_TOL)]
+    return [(IMPL_SIMT, FP32_TOL), (IMPL_AUTO, FP32_TOL), (IMPL_FAST, TF32_TOL)]
 
 
 def g(seed):
@@ -276,7 +278,7 @@ def test_errors_are_reported_not_ub():
     with pytest.raises(_lib.CtxError):
         ops.conv2d(x.cpu(), torch.zeros((5, 5, 4, 8)).cuda())      # CPU tensor: no fallback
     with pytest.raises(_lib.CtxError):
-        ops.conv2d_transpose(x, torch.zeros((5, 5, 8, 4)).cuda(), (15, 16))   # inconsistent output_shape
+        ops.conv2d_transpose(x, torch.zeros((5, 5, 8, 4)).cuda(), (17, 16))   # inconsistent output_shape
     with pytest.raises(_lib.CtxError):
         ops.gemm(torch.zeros((4, 5)).cuda(), torch.zeros((6, 7)).cuda())
     empty = ops.conv2d(torch.zeros((0, 8, 8, 4)).cuda(), torch.zeros((5, 5, 4, 8)).cuda())

@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one full training step (forward + backward + TF-Adam) of ContextSkipNew on
+64x64x3 frames, B = 256 triples per GPU  (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W                 # ours (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the restated reference on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic frames.  `value` = input frames per second
+(1 triple = src + ctx + tgt frame = 3 input frames, 2 frames reconstructed), whole job over all ranks, with the
+batch already resident in HBM.  `e2e` is the same metric through the reference-facing call
+(`compat.Session.run([optimizer, loss], feed_dict)`, i.e. what scripts/train_script.py:163 does) with the batch
+in HOST memory: host->device copy and the loss read-back are inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec fwd+bwd+Adam, ContextSkipNew 64x64x3, B=256 triples per GPU"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md 'clocks line')."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)) if power else None)
+        return out
+
+
+def make_batches(spec, B, n, seed):
+    """n distinct [3,B,H,W,C] float32 trainer batches drawn as scripts/train_script.py:154-159 does."""
+    from imitation_from_observation_b200 import synthetic
+    bank = synthetic.to_float(synthetic.video_bank(25, 48, spec.height, spec.width, seed=1234 + seed)).astype(np.float32)
+    rng = np.random.RandomState(seed)
+    return [synthetic.trainer_batch(bank, B, 25, 48, rng) for _ in range(n)]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the restated reference (oracle/tf_semantics.py, PyTorch CPU fp32) on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(spec, sample_B, steps, warmup, threads, budget_s=None):
+    """Mean seconds per (fwd + bwd + TF-Adam) step of the restated reference on `sample_B` triples.  With
+    `budget_s`, sample_B is first reduced (by a 4-triple calibration step) so that warmup+steps fit the budget.
+    Returns (seconds per step, triples per step actually used)."""
+    import torch
+    from oracle import tf_semantics as O
+    torch.set_num_threads(threads)
+    P = O.init_params(spec, seed=0)
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+
+    def one(batch, t):
+        t0 = time.perf_counter()
+        _, G = O.loss_and_grads(spec, P, batch)
+        O.tf_adam_step(P, G, M, V, t, 1e-4)
+        return time.perf_counter() - t0
+
+    cal = torch.from_numpy(make_batches(spec, 4, 1, 0)[0])
+    one(cal, 1)                                    # first call pays one-off library set-up
+    t4 = one(cal, 2)
+    if budget_s is not None:
+        per_triple = max(t4 / 4.0, 1e-6)           # upper bound: Adam's fixed cost is folded in
+        fit = int(budget_s / ((warmup + steps) * per_triple))
+        sample_B = max(4, min(sample_B, fit))
+    batches = [torch.from_numpy(b) for b in make_batches(spec, sample_B, 2, 0)]
+    times = []
+    for it in range(warmup + steps):
+        dt = one(batches[it % 2], it + 3)
+        if it >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), sample_B
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from imitation_from_observation_b200 import spec as S
+    spec = S.context_skip_new(64, 64)
+    threads = os.cpu_count() or 1
+    t, sample_B = cpu_reference_step_time(spec, args.ref_batch, args.steps, args.warmup, threads, budget_s=150.0)
+    value = 3.0 * sample_B / t
+    sample = "%d-triple slice of the B=256 batch per step (fwd+bwd+Adam), PyTorch-CPU fp32 restatement" % sample_B
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="ContextSkipNew 64x64x3 train step; reference arm runs %d triples per step on "
+                                     "the host cores" % sample_B, triples_per_step=sample_B),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ours
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from imitation_from_observation_b200 import _lib, compat as tf, ops, parallel, spec as S
+    from imitation_from_observation_b200.models import ContextSkipNew
+    from imitation_from_observation_b200.network import FWD_ALL
+
+    rank, world, local = parallel.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback on the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    B = args.batch
+    spec = S.context_skip_new(64, 64)
+    peaks = load_peaks()
+
+    # the reference-facing object graph (train_script.py:118-129)
+    tf.reset_default_graph()
+    tfinput = tf.placeholder(tf.float32, (3, B, 64, 64, 3), name="x")
+    model = ContextSkipNew()
+    with tf.variable_scope("contextmodel"):
+        tf.build_model(model, tfinput, precision=args.precision, seed=0, global_batch=B * world, device=dev)
+    net = model.net
+    if world > 1:
+        net.attach_allreduce()
+    lr_ph = tf.placeholder(tf.float32, shape=[])
+    optimizer = tf.train.AdamOptimizer(lr_ph).minimize(model.loss)
+    sess = tf.Session()
+
+    nb = 4
+    host = [torch.from_numpy(b).pin_memory() for b in make_batches(spec, B, nb, seed=rank)]
+    devb = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        net.set_input(devb[i % nb])
+        net.train_step(1e-4)
+
+    def step_e2e(i):
+        _, loss = sess.run([optimizer, model.loss], {tfinput: host[i % nb], lr_ph: 1e-4})
+        return loss
+
+    # ---- device-resident timing --------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = ops.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_step = ms_total / args.steps
+    value = 3.0 * B * world / (ms_step * 1e-3)
+
+    # ---- end to end through Session.run with host batches -------------------------------------------------------
+    for i in range(max(2, args.warmup // 2)):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    last_loss = None
+    for i in range(args.steps):
+        last_loss = step_e2e(i)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = 3.0 * B * world / (float(ms2.item()) / args.steps * 1e-3)
+    h2d = int(host[0].numel() * host[0].element_size())
+
+    # ---- roofline of the dominant kernel (tc_igemm_kernel), timed per launch with events on the launch stream ---
+    roofline, breakdown = None, None
+    if rank == 0:
+        ops.PROFILE = []
+        net.set_input(devb[0])
+        net.zero_grad()
+        net.forward(FWD_ALL)
+        net.backward()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for kind, impl, flops, a, b in prof:
+            key = {1: "simt", 2: "tc", 3: "tc"}.get(impl, "simt")
+            t = a.elapsed_time(b) * 1e-3
+            d = agg.setdefault(key, dict(flops=0.0, s=0.0, calls=0))
+            d["flops"] += flops; d["s"] += t; d["calls"] += 1
+            d2 = agg.setdefault(key + ":" + kind, dict(flops=0.0, s=0.0, calls=0))
+            d2["flops"] += flops; d2["s"] += t; d2["calls"] += 1
+        breakdown = {k: dict(tflops=v["flops"] / max(v["s"], 1e-12) / 1e12, ms=v["s"] * 1e3, calls=v["calls"])
+                     for k, v in sorted(agg.items())}
+        dom = "tc" if "tc" in agg and agg["tc"]["s"] >= agg.get("simt", dict(s=0))["s"] * 0.5 else "simt"
+        if dom in agg:
+            ach = agg[dom]["flops"] / agg[dom]["s"] / 1e12
+            passes = 3 if args.precision == "tf32x3" else 1
+            if dom == "tc":
+                peak = peaks["bf16_tflops_sustained"] / 2.0
+                basis = ("TF32 dense = %s bf16 sustained %.1f TFLOP/s / 2" % (peaks["source"], peaks["bf16_tflops_sustained"]))
+            else:
+                peak, basis = 80.0, "nominal fp32 CUDA-core peak (no measured figure)"
+            roofline = dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                            kernel="tc_igemm_kernel" if dom == "tc" else "simt_gemm_kernel", peak_basis=basis,
+                            tensor_passes=passes if dom == "tc" else 0,
+                            frac_of_issued_tensor_flops=(ach * passes / peak) if dom == "tc" else None,
+                            share_of_step=agg[dom]["s"] * 1e3 / ms_step)
+
+    # ---- CPU baseline: the restated reference on this box's host cores, bounded sample ---------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t, sb = cpu_reference_step_time(spec, args.ref_batch, 1, 0, threads, budget_s=25.0)
+        cpu = dict(value=3.0 * sb / t, unit=UNIT, cores=threads, kind="port", ms_per_step=1e3 * t,
+                   sample="one (fwd+bwd+Adam) step on %d of the %d triples after a 4-triple warm-up, PyTorch-CPU fp32 "
+                          "restatement of the TF graph (oracle/tf_semantics.py)" % (sb, B))
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32 (tensor-core operands tf32, %s)" % ("3-pass split" if args.precision == "tf32x3" else
+                                                                   "exact fp32 SIMT" if args.precision == "fp32" else "single pass"),
+                    data="synthetic",
+                    config=dict(workload="ContextSkipNew 64x64x3, %d triples/GPU (BASELINE configs[1]): fwd+bwd+TF-Adam" % B,
+                                triples_per_gpu=B, global_triples=B * world, precision=args.precision,
+                                parallelism="dp%d" % world, params=spec.num_params(),
+                                l2="working set per step (params+grads+moments 0.76 GB, activations ~1.3 GB) exceeds L2; "
+                                   "%d distinct input batches rotate" % nb),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                             api="compat.Session.run([optimizer, loss], feed_dict) with a pinned host batch",
+                             last_loss=float(last_loss)),
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, kernel_breakdown=breakdown,
+                    gflop_per_step=3 * 2.0 * spec.fwd_macs_per_triple() * B / 1e9,
+                    step_tflops=3 * 2.0 * spec.fwd_macs_per_triple() * B * world / (ms_step * 1e-3) / 1e12)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=256, help="triples per GPU")
+    ap.add_argument("--ref-batch", type=int, default=256, help="max triples per step of the CPU reference (reduced to fit the time budget)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

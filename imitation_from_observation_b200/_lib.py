@@ -36,6 +36,7 @@ SIGNATURES = {
     "ctx_device_info": (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "ctx_tc_available": (c_int32, []),
     "ctx_launch_count": (c_int64, []),
+    "ctx_last_impl": (c_int32, []),
     "ctx_conv2d_fprop": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, POINTER(ConvGeom),
                                    POINTER(Epilogue), c_int32, c_void_p]),
     "ctx_conv2d_transpose": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,

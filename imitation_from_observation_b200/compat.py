@@ -179,6 +179,9 @@ class Session:
         """Host value -> pinned staging buffer -> device (non_blocking), as one [3,B,H,W,C] tensor."""
         if torch.is_tensor(value) and value.is_cuda:
             return value
+        want_t = torch.uint8 if ph.root.dtype == torch.uint8 else torch.float32
+        if torch.is_tensor(value) and value.dtype == want_t and value.is_contiguous() and value.is_pinned():
+            return value.to("cuda", non_blocking=True)                # caller already staged it in pinned memory
         arr = np.asarray(value)
         want = np.uint8 if ph.root.dtype == torch.uint8 else np.float32
         key = (id(ph.root), arr.shape, want)
@@ -234,8 +237,7 @@ class Session:
                         results[id(f)] = m.net.fetch(f.name).detach().clone()
                     elif isinstance(f, NNErr):
                         results[id(f)] = m.net.nn_err(f.nlen)
-                m.net.backward()
-                m.net.adam_step(float(lr), opt.b1, opt.b2, opt.eps)
+                m.net.apply_gradients(float(lr), opt.b1, opt.b2, opt.eps)
             else:
                 m.net.forward(max(level, 1))
                 for f in mine:

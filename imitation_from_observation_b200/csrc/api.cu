@@ -19,6 +19,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static unsigned long long g_launches = 0;
+static thread_local int g_last_impl = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 // impl -> (use tensor cores?, passes, error if not eligible?)
@@ -80,6 +81,8 @@ extern "C" int ctx_device_info(int32_t* sms, int32_t* major, int32_t* minor) {
   return CTX_OK;
 }
 
+extern "C" int ctx_last_impl(void) { return g_last_impl; }
+
 extern "C" int64_t ctx_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int ctx_tc_available(void) {
@@ -96,15 +99,17 @@ extern "C" int ctx_conv2d_fprop(const float* x, int32_t C, const float* w, float
                                 const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream) {
   int rc = check_geom(g, "conv2d_fprop");
   if (rc) return rc;
-  CTX_REQUIRE(x && w && y && C > 0 && Co > 0, "conv2d_fprop: null pointer or bad channel count");
+  CTX_REQUIRE(C > 0 && Co > 0, "conv2d_fprop: bad channel count");
   if (g->N == 0) return CTX_OK;
+  CTX_REQUIRE(x && w && y, "conv2d_fprop: null pointer");
   Epi e = make_epi(epi);
   const ImplChoice ic = impl_choice(impl);
   if (ic.tc) {
     int ok = tc_conv2d_fprop_eligible(C, Co, *g);
-    if (ok && ctx_tc_available()) return tc_conv2d_fprop(x, C, w, y, Co, *g, e, ic.passes, (cudaStream_t)stream);
+    if (ok && ctx_tc_available()) { g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC; return tc_conv2d_fprop(x, C, w, y, Co, *g, e, ic.passes, (cudaStream_t)stream); }
     if (ic.force) { set_error("conv2d_fprop: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
+  g_last_impl = CTX_IMPL_SIMT;
   return simt_conv2d_fprop(x, C, w, y, Co, *g, e, (cudaStream_t)stream);
 }
 
@@ -113,7 +118,9 @@ extern "C" int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2
                                     const ctx_epilogue* epi, int32_t impl, void* stream) {
   int rc = check_geom(g, "conv2d_transpose");
   if (rc) return rc;
-  CTX_REQUIRE(x1 && w && y && C1 > 0 && Cn > 0 && C2 >= 0, "conv2d_transpose: null pointer or bad channel count");
+  CTX_REQUIRE(C1 > 0 && Cn > 0 && C2 >= 0, "conv2d_transpose: bad channel count");
+  if (g->N == 0) return CTX_OK;
+  CTX_REQUIRE(x1 && w && y, "conv2d_transpose: null pointer");
   CTX_REQUIRE((C2 == 0) == (x2 == nullptr), "conv2d_transpose: x2 and C2 must both be set or both be empty");
   CTX_REQUIRE(C2 == 0 || x2_batch > 0, "conv2d_transpose: x2_batch must be positive");
   if (g->N == 0) return CTX_OK;
@@ -121,10 +128,13 @@ extern "C" int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2
   const ImplChoice ic = impl_choice(impl);
   if (ic.tc) {
     int ok = tc_conv2d_transpose_eligible(C1, C2, x2_batch, Cn, *g);
-    if (ok && ctx_tc_available())
+    if (ok && ctx_tc_available()) {
+      g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC;
       return tc_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, ic.passes, (cudaStream_t)stream);
+    }
     if (ic.force) { set_error("conv2d_transpose: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
+  g_last_impl = CTX_IMPL_SIMT;
   return simt_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, (cudaStream_t)stream);
 }
 
@@ -133,17 +143,22 @@ extern "C" int ctx_conv2d_wgrad(const float* big, int32_t Ca, const float* small
                                 void* stream) {
   int rc = check_geom(g, "conv2d_wgrad");
   if (rc) return rc;
-  CTX_REQUIRE(big && small1 && dw && Ca > 0 && Cb1 > 0 && Cb2 >= 0, "conv2d_wgrad: null pointer or bad channel count");
+  CTX_REQUIRE(Ca > 0 && Cb1 > 0 && Cb2 >= 0, "conv2d_wgrad: bad channel count");
+  if (g->N == 0) return CTX_OK;
+  CTX_REQUIRE(big && small1 && dw, "conv2d_wgrad: null pointer");
   CTX_REQUIRE((Cb2 == 0) == (small2 == nullptr), "conv2d_wgrad: small2 and Cb2 must both be set or both be empty");
   CTX_REQUIRE(Cb2 == 0 || small2_batch > 0, "conv2d_wgrad: small2_batch must be positive");
   if (g->N == 0) return CTX_OK;
   const ImplChoice ic = impl_choice(impl);
   if (ic.tc) {
     int ok = tc_conv2d_wgrad_eligible(Ca, Cb1, Cb2, small2_batch, *g);
-    if (ok && ctx_tc_available())
+    if (ok && ctx_tc_available()) {
+      g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC;
       return tc_conv2d_wgrad(big, Ca, small1, Cb1, small2, Cb2, small2_batch, dw, *g, ic.passes, (cudaStream_t)stream);
+    }
     if (ic.force) { set_error("conv2d_wgrad: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
+  g_last_impl = CTX_IMPL_SIMT;
   return simt_conv2d_wgrad(big, Ca, small1, Cb1, small2, Cb2, small2_batch, dw, *g, (cudaStream_t)stream);
 }
 
@@ -158,9 +173,12 @@ extern "C" int ctx_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, in
   const ImplChoice ic = impl_choice(impl);
   if (ic.tc) {
     int ok = tc_gemm_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
-    if (ok && ctx_tc_available())
+    if (ok && ctx_tc_available()) {
+      g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC;
       return tc_gemm(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ic.passes, (cudaStream_t)stream);
+    }
     if (ic.force) { set_error("gemm: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
+  g_last_impl = CTX_IMPL_SIMT;
   return simt_gemm(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
 }

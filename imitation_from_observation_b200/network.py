@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from ._lib import IMPL_AUTO, IMPL_SIMT
+from ._lib import IMPL_AUTO, IMPL_FAST, IMPL_SIMT
 from .spec import NetSpec
 
 FWD_SRC, FWD_TRANS, FWD_ALL = 1, 2, 3
@@ -39,15 +39,19 @@ def _numel(shape) -> int:
 class ContextNet:
     """One network instance bound to a device, a per-rank batch size and a precision mode.
 
+    precision = "tf32x3" (default): tcgen05 kernels with the 3-pass TF32 split (hi*hi + hi*lo + lo*hi, fp32
+                        accumulate; ~2^-21 per product, i.e. fp32-faithful) wherever the shape qualifies, the exact
+                        fp32 SIMT kernels elsewhere.  This is the parity mode.
     precision = "fp32": every GEMM-shaped op uses the exact-fp32 SIMT kernels.
-    precision = "tf32": tcgen05 kernels (TF32 operands rounded to nearest, fp32 accumulate) wherever the shape
-                        qualifies, SIMT elsewhere.
+    precision = "tf32": single-pass TF32 (operands rounded to nearest by the producing epilogue) wherever the
+                        shape qualifies.  Fast mode: forward outputs stay within ~1e-3, but lrelu masks flip for
+                        ~3e-4 of the units, so gradients only agree in aggregate (relative L2 ~1e-2).
     """
 
-    def __init__(self, spec: NetSpec, batch: int, device="cuda", precision: str = "tf32", seed: int = 0,
+    def __init__(self, spec: NetSpec, batch: int, device="cuda", precision: str = "tf32x3", seed: int = 0,
                  global_batch: Optional[int] = None, ablation_type: str = "None", params_from: "ContextNet" = None):
-        if precision not in ("fp32", "tf32"):
-            raise ValueError("precision must be 'fp32' or 'tf32'")
+        if precision not in ("fp32", "tf32x3", "tf32"):
+            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32'")
         _lib.load()                                   # fail loudly if the extension is missing
         self.spec = spec
         self.B = int(batch)
@@ -55,13 +59,14 @@ class ContextNet:
         if self.device.type != "cuda":
             raise _lib.CtxError("ContextNet needs a CUDA device: the B200 path has no CPU fallback")
         self.precision = precision
-        self.impl = IMPL_SIMT if precision == "fp32" else IMPL_AUTO
+        self.impl = {"fp32": IMPL_SIMT, "tf32x3": IMPL_AUTO, "tf32": IMPL_FAST}[precision]
         self.round = precision == "tf32"
         self.global_batch = int(global_batch) if global_batch else self.B
         self.ablation_type = ablation_type
         self._w_recon = {"None": (1.0, 1.0), "L2": (1.0, 1.0), "L2L3": (1.0, 0.0), "L1": (0.0, 1.0)}[ablation_type]
         self._w_sim = {"None": 1.0, "L2": 0.0, "L2L3": 0.0, "L1": 1.0}[ablation_type]
         self.step_count = 0
+        self.allreduce = None          # parallel.BucketedAllReduce when data-parallel (attach_allreduce)
         self._bufs: Dict[str, torch.Tensor] = {}
 
         # ---- flat parameter / gradient / moment buffers -----------------------------------------------------
@@ -432,17 +437,32 @@ class ContextNet:
         lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
         ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr_t, b1, b2, eps)
 
+    def attach_allreduce(self, group=None):
+        """Data parallelism: after this, every optimiser step sum-all-reduces the flat gradient (bucketed, launched
+        from backward's stage callbacks) before Adam.  Build the net with global_batch = world * batch."""
+        from . import parallel
+        self._ensure_grads()
+        self.allreduce = parallel.BucketedAllReduce(self.flat_g, parallel.scope_ranges(self.offsets, self.flat_size),
+                                                    group=group)
+        return self.allreduce
+
+    def apply_gradients(self, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+        """backward (+ bucketed gradient all-reduce when data-parallel) + Adam; forward(FWD_ALL) must have run."""
+        if self.allreduce is not None:
+            self.backward(on_stage=self.allreduce.stage_done)
+            self.allreduce.finish()
+        else:
+            self.backward()
+        self.adam_step(lr, b1, b2, eps)
+
     def train_step(self, lr: float = 1e-4, allreduce=None):
         """forward + backward + (optional bucketed gradient all-reduce) + Adam: one `sess.run(optimizer, ...)`.
         `allreduce` is a parallel.BucketedAllReduce (or anything with stage_done(scope) / finish())."""
+        if allreduce is not None:
+            self.allreduce = allreduce
         self.zero_grad()
         self.forward(FWD_ALL)
-        if allreduce is not None:
-            self.backward(on_stage=allreduce.stage_done)
-            allreduce.finish()
-        else:
-            self.backward()
-        self.adam_step(lr)
+        self.apply_gradients(lr)
 
     # ---- fetches -----------------------------------------------------------------------------------------------------------
     def fetch(self, name: str) -> torch.Tensor:

@@ -16,6 +16,28 @@ from .spec import same_out, same_pad
 
 LRELU_SLOPE = 0.2
 
+# ---- optional per-call profiling (bench.py's roofline leg) -------------------------------------------------------
+# When PROFILE is a list, every GEMM-shaped call appends (kind, impl, flops, start_event, end_event); the events
+# are recorded on the stream the kernels are launched on (torch's current stream).
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("kind", "flops", "e0")
+
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+        self.e0 = None
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def done(self):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.kind, int(_lib.load().ctx_last_impl()), self.flops, self.e0, e1))
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -48,6 +70,11 @@ def conv_geom(n: int, big_hw: Tuple[int, int], k: int, stride: int) -> ConvGeom:
                     same_pad(H, k, stride)[0], same_pad(W, k, stride)[0])
 
 
+def launch_count() -> int:
+    """Kernels launched by libctx_b200.so in this process so far."""
+    return int(_lib.load().ctx_launch_count())
+
+
 def device_info():
     lib = _lib.load()
     a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
@@ -71,8 +98,10 @@ def conv2d(x, w, bias=None, stride: int = 2, act: bool = False, out=None, act_re
     if out is None:
         out = torch.empty((N, g.P, g.Q, Co), device=x.device, dtype=torch.float32)
     epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * kh * kw * Cin)
     check(_lib.load().ctx_conv2d_fprop(_req(x, "x"), Cin, _req(w, "w"), _req(out, "out"), Co, C.byref(g),
                                        C.byref(epi), impl, _stream()), "ctx_conv2d_fprop")
+    pr.done()
     return out
 
 
@@ -94,9 +123,11 @@ def conv2d_transpose(x1, w, out_hw, bias=None, stride: int = 2, x2=None, act: bo
     if out is None:
         out = torch.empty((N, g.H, g.W, Cn), device=x1.device, dtype=torch.float32)
     epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * kh * kw * Ck)
     check(_lib.load().ctx_conv2d_transpose(_req(x1, "x1"), C1, _opt(x2, "x2"), C2, 0 if x2 is None else x2.shape[0],
                                            _req(w, "w"), _req(out, "out"), Cn, C.byref(g), C.byref(epi), impl,
                                            _stream()), "ctx_conv2d_transpose")
+    pr.done()
     return out
 
 
@@ -111,17 +142,21 @@ def conv2d_wgrad(big, small1, k: int, stride: int, small2=None, dw=None, impl=IM
                             % (tuple(small1.shape), N, g.P, g.Q))
     if dw is None:
         dw = torch.zeros((k, k, Ca, Cb1 + Cb2), device=big.device, dtype=torch.float32)
+    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Ca)
     check(_lib.load().ctx_conv2d_wgrad(_req(big, "big"), Ca, _req(small1, "small1"), Cb1, _opt(small2, "small2"), Cb2,
                                        0 if small2 is None else small2.shape[0], _req(dw, "dw"), C.byref(g), impl,
                                        _stream()), "ctx_conv2d_wgrad")
+    pr.done()
     return dw
 
 
 # ---- dense -------------------------------------------------------------------------------------------------------
 def gemm_raw(tA: bool, tB: bool, M: int, N: int, K: int, A_ptr: int, lda: int, B_ptr: int, ldb: int, C_ptr: int,
              ldc: int, epi: Optional[Epilogue] = None, impl=IMPL_AUTO):
+    pr = _Prof("gemm", 2.0 * M * N * K)
     check(_lib.load().ctx_gemm(int(tA), int(tB), M, N, K, A_ptr, lda, B_ptr, ldb, C_ptr, ldc,
                                C.byref(epi) if epi is not None else None, impl, _stream()), "ctx_gemm")
+    pr.done()
 
 
 def _mat(t: torch.Tensor, name: str):

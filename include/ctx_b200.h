@@ -80,6 +80,8 @@ int ctx_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 int ctx_tc_available(void);
 /* Number of kernels this library has launched in this process (all streams); bench.py's "gpu_launches". */
 int64_t ctx_launch_count(void);
+/* Which implementation the last GEMM-shaped call of this thread used: CTX_IMPL_SIMT / CTX_IMPL_TC / CTX_IMPL_TC3. */
+int ctx_last_impl(void);
 
 /* ---- convolutions ------------------------------------------------------------------------------------- */
 

@@ -57,11 +57,14 @@ struct TcParams {
   int32_t nseg;
   int32_t a_mode, b_mode;
   int32_t passes;                  // 1 | 3
-  int32_t write_hi;                // passes==3: also overwrite the raw tile with rna(hi) (else rely on HW truncation)
   int32_t BN;                      // 64 | 128 | 256
-  int32_t stages;
+  int32_t raw_slots, lo_slots;     // ring depths: fp32 tiles landed by TMA | their lo parts (3-pass only)
   int32_t total_kblocks;           // whole K loop (all splits)
   int32_t kblocks_per_split;
+  // stride phases of a transposed conv merged into one launch (blockIdx.z = phase; no split-K then)
+  int32_t nphase;
+  int32_t ph_seg0[4], ph_nseg[4], ph_kblocks[4];
+  int64_t ph_obase[4];
   // row grid of the A/D tile: rows r -> (dn, dp, dq)
   int32_t NG, PG, QG;              // grid extents (images, rows, cols); A_MN: NG = M, PG = QG = 1
   int32_t BP, NB;                  // tile = NB images x BP rows x QG cols  (== 128 rows), or 32 for A_MN k-blocks
@@ -194,19 +197,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
 
   const uint32_t b_tile_bytes = (uint32_t)p.BN * 128u;
   const uint32_t raw_bytes = kATileBytes + b_tile_bytes;            // fp32 tiles as landed by TMA
-  const uint32_t stage_bytes = raw_bytes * (p.passes == 3 ? 2u : 1u);   // [A | B | A_lo | B_lo]
-  const int S = p.stages;
+  // smem: [raw ring: R x (A | B)] [lo ring: L x (A_lo | B_lo)].  The raw ring is deep (it hides the TMA latency),
+  // the lo ring only bridges splitter -> tensor core.
+  const int R = p.raw_slots, L = p.lo_slots;
+  const uint32_t lo_base = smem_base + (uint32_t)R * raw_bytes;
 
-  __shared__ __align__(8) uint64_t bars[3 * 8 + 1];                 // full[S], ready[S], empty[S], acc_full
+  __shared__ __align__(8) uint64_t bars[8 + 4 + 8 + 4 + 1];        // full[R], ready[L], raw_empty[R], lo_empty[L], acc
   __shared__ uint32_t tmem_slot;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto ready_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
-  auto empty_bar = [&](int s) { return smem_u32(&bars[16 + s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[12 + s]); };
+  auto lo_empty_bar = [&](int s) { return smem_u32(&bars[20 + s]); };
   const uint32_t acc_bar = smem_u32(&bars[24]);
 
-  // this CTA's K range (split-K over blockIdx.z)
-  const int kb_begin = blockIdx.z * p.kblocks_per_split;
-  const int kb_end = min(p.total_kblocks, kb_begin + p.kblocks_per_split);
+  // this CTA's K range: split-K over blockIdx.z, or (merged transposed-conv phases) the whole K of phase z
+  int kb_begin, kb_end, seg0 = 0, nseg = p.nseg;
+  int64_t obase = p.obase;
+  if (p.nphase > 1) {
+    const int z = blockIdx.z;
+    seg0 = p.ph_seg0[z]; nseg = p.ph_nseg[z]; obase = p.ph_obase[z];
+    kb_begin = 0; kb_end = p.ph_kblocks[z];
+  } else {
+    kb_begin = blockIdx.z * p.kblocks_per_split;
+    kb_end = min(p.total_kblocks, kb_begin + p.kblocks_per_split);
+  }
   const int nkb = kb_end - kb_begin;
   // tile origin on the row grid
   const int tile_m = blockIdx.x;
@@ -216,10 +230,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   const int ncol0 = blockIdx.y * p.BN;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < R; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(ready_bar(s), 128);
       mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < L; ++s) {
+      mbar_init(ready_bar(s), 128);
+      mbar_init(lo_empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -249,13 +266,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         if (p.a_mode == A_PIX) {
           // enumerate (segment, channel block) pairs; skip to kb_begin
           int kb = 0;
-          for (int sg = 0; sg < p.nseg && kb < kb_end; ++sg) {
-            const Seg s = p.seg[sg];
+          for (int sg = 0; sg < nseg && kb < kb_end; ++sg) {
+            const Seg s = p.seg[seg0 + sg];
             if (kb + s.nblk <= kb_begin) { kb += s.nblk; continue; }
             for (int cb = 0; cb < s.nblk && kb < kb_end; ++cb, ++kb) {
               if (kb < kb_begin) continue;
               mbar_wait(empty_bar(stage), phase ^ 1, p.err_flag, 1);
-              const uint32_t sa = smem_base + stage * stage_bytes;
+              const uint32_t sa = smem_base + stage * raw_bytes;
               const uint32_t sb = sa + kATileBytes;
               mbar_arrive_expect_tx(full_bar(stage), raw_bytes);
               const int nimg = s.wrap ? (n0 % p.a_wrap) : n0;
@@ -266,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
                 for (int a = 0; a < p.BN / 32; ++a)
                   tma_load_2d(sb + a * 4096, &p.mapB[0], full_bar(stage), ncol0 + a * 32, s.bk0 + cb * 32);
               }
-              if (++stage == S) { stage = 0; phase ^= 1; }
+              if (++stage == R) { stage = 0; phase ^= 1; }
             }
           }
         } else {
@@ -277,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             if (p.kNB > 1 || p.k_tiles_per_img == 1) { kn0 = kb * p.kNB; kp0 = 0; }
             else { kn0 = kb / p.k_tiles_per_img; kp0 = (kb - kn0 * p.k_tiles_per_img) * p.kBP; }
             mbar_wait(empty_bar(stage), phase ^ 1, p.err_flag, 2);
-            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint32_t sa = smem_base + stage * raw_bytes;
             const uint32_t sb = sa + kATileBytes;
             int natomA = 0;
             for (int j = 0; j < 4; ++j) natomA += (m0 + 32 * j < p.M) ? 1 : 0;
@@ -299,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
                 tma_load_2d(sb + a * 4096, &p.mapB[1], full_bar(stage), n - p.Cb1, prow2);
               }
             }
-            if (++stage == S) { stage = 0; phase ^= 1; }
+            if (++stage == R) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -313,27 +330,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         const uint32_t a_lbo = amn ? 4096u : 16u, a_sbo = amn ? 512u : 1024u, a_step = amn ? 1024u : 32u;
         const uint32_t b_lbo = bmn ? 4096u : 16u, b_sbo = bmn ? 512u : 1024u, b_step = bmn ? 1024u : 32u;
         const uint32_t a_lt = amn ? 1u : 2u, b_lt = bmn ? 1u : 2u;
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, lst = 0;
+        uint32_t phase = 0, lphase = 0;
         for (int i = 0; i < nkb; ++i) {
-          mbar_wait(p.passes == 3 ? ready_bar(stage) : full_bar(stage), phase, p.err_flag, 3);
+          if (p.passes == 3) mbar_wait(ready_bar(lst), lphase, p.err_flag, 3);
+          else mbar_wait(full_bar(stage), phase, p.err_flag, 3);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sa = smem_base + stage * raw_bytes;
           const uint32_t sb = sa + kATileBytes;
+          const uint32_t la = lo_base + lst * raw_bytes;
+          const uint32_t lb = la + kATileBytes;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ad = make_desc(sa + ks * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t bd = make_desc(sb + ks * b_step, b_lbo, b_sbo, b_lt);
             umma_tf32(tmem_base, ad, bd, idesc, (i | ks) ? 1u : 0u);
             if (p.passes == 3) {
-              const uint64_t ad_lo = make_desc(sa + raw_bytes + ks * a_step, a_lbo, a_sbo, a_lt);
-              const uint64_t bd_lo = make_desc(sb + raw_bytes + ks * b_step, b_lbo, b_sbo, b_lt);
+              const uint64_t ad_lo = make_desc(la + ks * a_step, a_lbo, a_sbo, a_lt);
+              const uint64_t bd_lo = make_desc(lb + ks * b_step, b_lbo, b_sbo, b_lt);
               umma_tf32(tmem_base + (uint32_t)p.BN, ad, bd_lo, idesc, (i | ks) ? 1u : 0u);
               umma_tf32(tmem_base + (uint32_t)p.BN, ad_lo, bd, idesc, 1u);
             }
           }
-          umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          umma_commit(empty_bar(stage));          // frees the raw slot once these MMAs have read it
+          if (++stage == R) { stage = 0; phase ^= 1; }
+          if (p.passes == 3) {
+            umma_commit(lo_empty_bar(lst));       // ... and the lo slot
+            if (++lst == L) { lst = 0; lphase ^= 1; }
+          }
         }
         umma_commit(acc_bar);                      // accumulator complete
       }
@@ -341,32 +365,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       // =============================== splitters: fp32 tile -> (hi, lo) =======================================
       const int t = threadIdx.x - 64;              // 0..127
       const int nchunk = (int)(raw_bytes >> 4);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, lst = 0;
+      uint32_t phase = 0, lphase = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(full_bar(stage), phase, p.err_flag, 4);
-        const uint32_t base = smem_base + stage * stage_bytes;
-        for (int c = t; c < nchunk; c += 128) {
-          const uint32_t addr = base + ((uint32_t)c << 4);
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-          float4 h, l;
-          if (p.write_hi) {
-            h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
-          } else {
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        mbar_wait(lo_empty_bar(lst), lphase ^ 1, p.err_flag, 6);
+        const uint32_t base = smem_base + stage * raw_bytes;
+        const uint32_t lbase = lo_base + lst * raw_bytes;
+        // batches of 8 chunks per thread: all loads first (8 LDS.128 in flight), then mask / subtract / store —
+        // inline asm statements are never reordered by the compiler, so the batching has to be explicit
+        for (int c0 = t; c0 < nchunk; c0 += 8 * 128) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 128;
+            if (c < nchunk)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(base + ((uint32_t)c << 4)));
           }
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + raw_bytes), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-          if (p.write_hi)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 128;
+            if (c < nchunk) {
+              const uint32_t off = (uint32_t)c << 4;
+              // the tensor core reads an fp32 word as TF32 by ignoring its low 13 bits (verified on B200:
+              // tools/tc_check.py "trunc"), so the raw tile already IS the hi part; lo = x - trunc(x) is exact
+              float4 l;
+              l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u);
+              l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u);
+              l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u);
+              l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lbase + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+            }
+          }
         }
         fence_async_smem();                        // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(ready_bar(stage));
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        mbar_arrive(ready_bar(lst));
+        if (++stage == R) { stage = 0; phase ^= 1; }
+        if (++lst == L) { lst = 0; lphase ^= 1; }
       }
     }
   }
@@ -385,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     const int dp = rem / p.QG, dq = rem - dp * p.QG;
     const int gn = n0 + dn, gp = p0 + dp;
     const bool row_ok = gn < p.NG && gp < p.PG && (nkb > 0 || !p.atomic_out);
-    const int64_t roff = p.obase + (int64_t)gn * p.sN + (int64_t)gp * p.sP + (int64_t)dq * p.sQ;
+    const int64_t roff = obase + (int64_t)gn * p.sN + (int64_t)gp * p.sP + (int64_t)dq * p.sQ;
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t v[32];
       if (nkb > 0) {
@@ -527,13 +563,19 @@ static bool tile_grid(int P, int Q, int rows, int* BP, int* NB, int* tiles_per_i
   return true;
 }
 
-static int pick_bn(int N) { return N >= 256 ? 256 : (N >= 128 ? 128 : 64); }
+// N tile: 128 for the 3-pass mode (with a 5-deep raw ring it is the best-balanced 1-CTA shape: tensor 768, splitter
+// ~512, TMA ~42 B/cycle per k-block), 256 for single-pass; halved while the grid would not fill the SMs.
+static int pick_bn(int N, int64_t m_tiles, int passes) {
+  int bn = passes == 3 ? 128 : 256;
+  const int sms = sm_count();
+  while (bn > 64 && (N <= bn / 2 || m_tiles * cdiv(N, bn) < sms)) bn /= 2;
+  return bn;
+}
 
 static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, const char* name) {
   const int sms = sm_count();
   if (sms <= 0) return cuda_fail(cudaErrorNoDevice, name);
   const uint32_t raw = kATileBytes + (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = raw * (p.passes == 3 ? 2u : 1u);
   static int max_dyn = 0;
   if (max_dyn == 0) {
     cudaFuncAttributes fa;
@@ -545,25 +587,25 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
     CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     max_dyn = dyn;
   }
-  int stages = (int)(((uint32_t)max_dyn - 1024u) / stage_bytes);      // 1024: alignment slack
-  if (stages > 8) stages = 8;
-  if (stages < 2) { set_error("%s: tile does not fit shared memory", name); return CTX_ERR_ARG; }
-  p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const int slots = (int)(((uint32_t)max_dyn - 1024u) / raw);          // 1024: alignment slack
+  p.lo_slots = p.passes == 3 ? 2 : 0;
+  p.raw_slots = slots - p.lo_slots;
+  if (p.raw_slots > 8) p.raw_slots = 8;
+  if (p.raw_slots < 2) { set_error("%s: tile does not fit shared memory", name); return CTX_ERR_ARG; }
+  const size_t smem = (size_t)(p.raw_slots + p.lo_slots) * raw + 1024;
   p.err_flag = nullptr;
   const int n_tiles = (int)cdiv(p.N, p.BN);
   if (n_tiles > 65535 || splits > 65535) { set_error("%s: grid too large", name); return CTX_ERR_ARG; }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
   tc_igemm_kernel<<<grid, kThreads, smem, stream>>>(p);
   CTX_LAUNCH_CHECK(name);
-  count_launch();
   return CTX_OK;
 }
 
 static void fill_common(TcParams& p, int passes, const Epi& epi) {
   memset(&p, 0, sizeof(p));
   p.passes = passes;
-  p.write_hi = 1;
+  p.nphase = 1;
   p.epi = epi;
   p.a_wrap = 1;
   p.Cb1 = 1 << 30;
@@ -621,7 +663,8 @@ int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, con
   CTX_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), "conv2d_fprop(tc): pointers must be 16-byte aligned");
   p.tiles_per_img = tpi;
   p.a_mode = A_PIX; p.b_mode = B_MN;
-  p.BN = pick_bn(Co);
+  const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
+  p.BN = pick_bn(Co, m_tiles, passes);
   p.NG = g.N; p.PG = g.P; p.QG = g.Q;
   p.M = g.N * g.P * g.Q; p.N = Co;
   int rc = make_tap_maps(p.mapA, x, C, g.N, g.H, g.W, g.stride, g.Q, p.BP, p.NB, false);
@@ -644,7 +687,6 @@ int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, con
   p.out = y;
   p.sN = (int64_t)g.P * g.Q * Co; p.sP = (int64_t)g.Q * Co; p.sQ = Co; p.obase = 0;
   p.atomic_out = 0;
-  const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
   return launch_tc(p, m_tiles, 1, stream, "tc_conv2d_fprop");
 }
 
@@ -680,62 +722,99 @@ int tc_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2
   CTX_REQUIRE(aligned16(x1) && aligned16(w) && aligned16(y) && (x2 == nullptr || aligned16(x2)),
               "conv2d_transpose(tc): pointers must be 16-byte aligned");
   const int st = g.stride, Ck = C1 + C2;
+  // Collect the stride phases.  Phases with identical tile geometry (always the case for even sizes) are merged
+  // into ONE launch, blockIdx.z = phase, heaviest phase first (it has the most filter taps).
+  struct Ph { int ph, pw, Hp, Wp, r0, s0, nr, ns, dh0, dw0, BP, NB, tpi, taps; };
+  Ph phs[4];
+  int nph = 0;
   for (int ph = 0; ph < st; ++ph)
     for (int pw = 0; pw < st; ++pw) {
-      int Hp, Wp, r0, s0, nr, ns, dh0, dw0, tpi;
-      phase_geom(g, ph, pw, &Hp, &Wp, &r0, &s0, &nr, &ns, &dh0, &dw0);
-      if (Hp == 0 || Wp == 0) continue;
-      TcParams p;
-      fill_common(p, passes, epi);
-      if (!tile_grid(Hp, Wp, 128, &p.BP, &p.NB, &tpi)) return CTX_ERR_UNSUPPORTED;
-      p.tiles_per_img = tpi;
-      p.a_mode = A_PIX; p.b_mode = B_K;
-      p.BN = pick_bn(Cn);
-      p.NG = g.N; p.PG = Hp; p.QG = Wp;
-      p.M = g.N * Hp * Wp; p.N = Cn;
-      p.a_wrap = x2_batch > 0 ? x2_batch : 1;
-      {
-        int64_t dims[4] = {C1, g.Q, g.P, g.N}, str[4] = {1, C1, (int64_t)g.Q * C1, (int64_t)g.P * g.Q * C1};
-        int box[4] = {32, Wp, p.BP, p.NB};
-        int rc = make_map(&p.mapA[0], x1, 4, dims, str, box);
-        if (rc) return rc;
-      }
-      if (C2 > 0) {
-        int64_t dims[4] = {C2, g.Q, g.P, x2_batch}, str[4] = {1, C2, (int64_t)g.Q * C2, (int64_t)g.P * g.Q * C2};
-        int box[4] = {32, Wp, p.BP, p.NB};
-        int rc = make_map(&p.mapA[1], x2, 4, dims, str, box);
-        if (rc) return rc;
-      }
-      {
-        int64_t dims[2] = {Ck, (int64_t)g.kh * g.kw * Cn}, str[2] = {1, Ck};
-        int box[2] = {32, p.BN};
-        int rc = make_map(&p.mapB[0], w, 2, dims, str, box);
-        if (rc) return rc;
-      }
-      int nseg = 0, kblocks = 0;
-      for (int i = 0; i < nr; ++i)
-        for (int j = 0; j < ns; ++j) {
-          const int tap = (r0 + st * i) * g.kw + (s0 + st * j);
-          for (int src = 0; src < (C2 > 0 ? 2 : 1); ++src) {
-            Seg& sg = p.seg[nseg++];
-            sg.mapA = (uint8_t)src; sg.wrap = (uint8_t)src;
-            sg.dh = (int16_t)(dh0 - i); sg.dw = (int16_t)(dw0 - j);
-            sg.nblk = (uint16_t)((src ? C2 : C1) / 32);
-            sg.bk0 = src ? C1 : 0; sg.br0 = tap * Cn;
-            kblocks += sg.nblk;
-          }
+      Ph q;
+      q.ph = ph; q.pw = pw;
+      phase_geom(g, ph, pw, &q.Hp, &q.Wp, &q.r0, &q.s0, &q.nr, &q.ns, &q.dh0, &q.dw0);
+      if (q.Hp == 0 || q.Wp == 0) continue;
+      if (!tile_grid(q.Hp, q.Wp, 128, &q.BP, &q.NB, &q.tpi)) return CTX_ERR_UNSUPPORTED;
+      q.taps = q.nr * q.ns;
+      phs[nph++] = q;
+    }
+  for (int i = 1; i < nph; ++i)                         // insertion sort, descending taps
+    for (int j = i; j > 0 && phs[j].taps > phs[j - 1].taps; --j) { Ph t = phs[j]; phs[j] = phs[j - 1]; phs[j - 1] = t; }
+  bool same = nph > 1;
+  int total_segs = 0;
+  for (int i = 0; i < nph; ++i) {
+    same = same && phs[i].Hp == phs[0].Hp && phs[i].Wp == phs[0].Wp;
+    total_segs += phs[i].taps * (C2 > 0 ? 2 : 1);
+  }
+  same = same && total_segs <= kMaxSeg;
+
+  auto fill_phase_segs = [&](TcParams& p, const Ph& q, int seg0, int* kblocks) {
+    int nseg = 0;
+    *kblocks = 0;
+    for (int i = 0; i < q.nr; ++i)
+      for (int j = 0; j < q.ns; ++j) {
+        const int tap = (q.r0 + st * i) * g.kw + (q.s0 + st * j);
+        for (int src = 0; src < (C2 > 0 ? 2 : 1); ++src) {
+          Seg& sg = p.seg[seg0 + nseg++];
+          sg.mapA = (uint8_t)src; sg.wrap = (uint8_t)src;
+          sg.dh = (int16_t)(q.dh0 - i); sg.dw = (int16_t)(q.dw0 - j);
+          sg.nblk = (uint16_t)((src ? C2 : C1) / 32);
+          sg.bk0 = src ? C1 : 0; sg.br0 = tap * Cn;
+          *kblocks += sg.nblk;
         }
-      p.nseg = nseg;
-      p.total_kblocks = kblocks;
-      p.kblocks_per_split = kblocks;
-      p.out = y;
-      p.obase = ((int64_t)ph * g.W + pw) * Cn;
-      p.sN = (int64_t)g.H * g.W * Cn; p.sP = (int64_t)st * g.W * Cn; p.sQ = (int64_t)st * Cn;
-      p.atomic_out = 0;
-      const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
-      int rc = launch_tc(p, m_tiles, 1, stream, "tc_conv2d_transpose");
+      }
+    return nseg;
+  };
+
+  for (int first = 0; first < nph; first += (same ? nph : 1)) {
+    const Ph& q0 = phs[first];
+    const int count = same ? nph : 1;
+    TcParams p;
+    fill_common(p, passes, epi);
+    p.BP = q0.BP; p.NB = q0.NB; p.tiles_per_img = q0.tpi;
+    p.a_mode = A_PIX; p.b_mode = B_K;
+    const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * q0.tpi;
+    p.BN = pick_bn(Cn, (int64_t)m_tiles * count, passes);
+    p.NG = g.N; p.PG = q0.Hp; p.QG = q0.Wp;
+    p.M = g.N * q0.Hp * q0.Wp; p.N = Cn;
+    p.a_wrap = x2_batch > 0 ? x2_batch : 1;
+    {
+      int64_t dims[4] = {C1, g.Q, g.P, g.N}, str[4] = {1, C1, (int64_t)g.Q * C1, (int64_t)g.P * g.Q * C1};
+      int box[4] = {32, q0.Wp, p.BP, p.NB};
+      int rc = make_map(&p.mapA[0], x1, 4, dims, str, box);
       if (rc) return rc;
     }
+    if (C2 > 0) {
+      int64_t dims[4] = {C2, g.Q, g.P, x2_batch}, str[4] = {1, C2, (int64_t)g.Q * C2, (int64_t)g.P * g.Q * C2};
+      int box[4] = {32, q0.Wp, p.BP, p.NB};
+      int rc = make_map(&p.mapA[1], x2, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    {
+      int64_t dims[2] = {Ck, (int64_t)g.kh * g.kw * Cn}, str[2] = {1, Ck};
+      int box[2] = {32, p.BN};
+      int rc = make_map(&p.mapB[0], w, 2, dims, str, box);
+      if (rc) return rc;
+    }
+    int seg0 = 0;
+    for (int i = 0; i < count; ++i) {
+      const Ph& q = phs[first + i];
+      int kblocks = 0;
+      const int nseg = fill_phase_segs(p, q, seg0, &kblocks);
+      p.ph_seg0[i] = seg0; p.ph_nseg[i] = nseg; p.ph_kblocks[i] = kblocks;
+      p.ph_obase[i] = ((int64_t)q.ph * g.W + q.pw) * Cn;
+      seg0 += nseg;
+    }
+    p.nphase = count;
+    p.nseg = p.ph_nseg[0];
+    p.total_kblocks = p.ph_kblocks[0];
+    p.kblocks_per_split = p.ph_kblocks[0];
+    p.obase = p.ph_obase[0];
+    p.out = y;
+    p.sN = (int64_t)g.H * g.W * Cn; p.sP = (int64_t)st * g.W * Cn; p.sQ = (int64_t)st * Cn;
+    p.atomic_out = 0;
+    int rc = launch_tc(p, m_tiles, count, stream, "tc_conv2d_transpose");
+    if (rc) return rc;
+  }
   return CTX_OK;
 }
 
@@ -771,7 +850,7 @@ int tc_conv2d_wgrad(const float* big, int Ca, const float* s1, int Cb1, const fl
   p.k_tiles_per_img = tpi;
   p.a_mode = A_MN; p.b_mode = B_MN;
   const int N = Cb1 + Cb2;
-  p.BN = pick_bn(N);
+  p.BN = pick_bn(N, 1 << 20, passes);           // split-K fills the machine, so take the widest tile
   p.kPG = g.P; p.kQG = g.Q;
   p.Ca = Ca; p.M = g.kh * g.kw * Ca; p.N = N;
   p.Cb1 = Cb1; p.a_wrap = s2_batch > 0 ? s2_batch : 1;
@@ -824,9 +903,11 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
             const Epi& epi, int passes, cudaStream_t stream) {
   TcParams p;
   fill_common(p, passes, epi);
-  p.BN = pick_bn(N);
-  p.M = M; p.N = N;
   const bool plain_accumulate = epi.accumulate && !epi.bias && !epi.act && !epi.act_ref && !epi.round;
+  const int m_tiles = (int)cdiv(M, 128);
+  // split-K (plain accumulation only) fills the machine by itself; otherwise narrow the N tile on small grids
+  p.BN = pick_bn(N, plain_accumulate ? (1 << 20) : m_tiles, passes);
+  p.M = M; p.N = N;
   int rc;
   if (!tA) {
     // A [M,K] row-major: K-major rows; tile = 128 consecutive rows ("images"), one 1x1 pixel each
@@ -865,7 +946,7 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
     rc = make_map(&p.mapB[0], B, 2, dims, str, box);
   }
   if (rc) return rc;
-  const int m_tiles = (int)cdiv(M, 128), n_tiles = (int)cdiv(N, p.BN);
+  const int n_tiles = (int)cdiv(N, p.BN);
   int splits = 1;
   if (plain_accumulate) splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8);
   p.kblocks_per_split = (int)cdiv(p.total_kblocks, splits);

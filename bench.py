@@ -269,7 +269,7 @@ def run_ours(args):
         dom = "tc" if "tc" in agg and agg["tc"]["s"] >= agg.get("simt", dict(s=0))["s"] * 0.5 else "simt"
         if dom in agg:
             ach = agg[dom]["flops"] / agg[dom]["s"] / 1e12
-            passes = 3 if args.precision == "tf32x3" else 1
+            passes = {"tf32x3": 3.0, "mixed": 5.0 / 3.0, "tf32": 1.0}.get(args.precision, 0.0)   # mean MMAs per product
             if dom == "tc":
                 peak = peaks["bf16_tflops_sustained"] / 2.0
                 basis = ("TF32 dense = %s bf16 sustained %.1f TFLOP/s / 2" % (peaks["source"], peaks["bf16_tflops_sustained"]))
@@ -293,8 +293,11 @@ def run_ours(args):
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32 (tensor-core operands tf32, %s)" % ("3-pass split" if args.precision == "tf32x3" else
-                                                                   "exact fp32 SIMT" if args.precision == "fp32" else "single pass"),
+                    dtype="f32 (%s)" % {"tf32x3": "tensor-core operands tf32, 3-pass split, fp32 accumulate",
+                                        "mixed": "tensor-core operands tf32: 3-pass split forward, single pass backward; "
+                                                 "fp32 accumulate",
+                                        "tf32": "tensor-core operands tf32, single pass, fp32 accumulate",
+                                        "fp32": "exact fp32 SIMT"}[args.precision],
                     data="synthetic",
                     config=dict(workload="ContextSkipNew 64x64x3, %d triples/GPU (BASELINE configs[1]): fwd+bwd+TF-Adam" % B,
                                 triples_per_gpu=B, global_triples=B * world, precision=args.precision,
@@ -319,7 +322,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "tf32x3", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=256, help="triples per GPU")
     ap.add_argument("--ref-batch", type=int, default=256, help="max triples per step of the CPU reference (reduced to fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -53,10 +53,11 @@ SIGNATURES = {
     "ctx_mse_scaled_fwd_bwd": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_float, c_float,
                                          c_float, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     "ctx_split_skip_grad": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p,
-                                      c_float, c_void_p, c_void_p, c_int32, c_void_p]),
+                                      c_float, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "ctx_add_bcast": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "ctx_im2col": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, POINTER(ConvGeom), c_int32, c_void_p]),
     "ctx_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
-                                c_float, c_void_p]),
+                                c_float, c_void_p, c_void_p]),
     "ctx_round_tf32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ctx_transpose_round": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ctx_nn_err": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -132,6 +132,14 @@ extern "C" int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2
       g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC;
       return tc_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, ic.passes, (cudaStream_t)stream);
     }
+    // few output channels (the last decoder layer, Cn = 3): one GEMM over (tap, channel) columns + scatter epilogue
+    if (!ok && ctx_tc_available() && !e.act && !e.act_ref && !e.round &&
+        tc_conv2d_transpose_scatter_eligible(C1, C2, x2_batch, Cn, *g)) {
+      g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC;
+      rc = bias_init(y, e.bias, (int64_t)g->N * g->H * g->W * Cn, Cn, e.accumulate, (cudaStream_t)stream);
+      if (rc) return rc;
+      return tc_conv2d_transpose_scatter(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, ic.passes, (cudaStream_t)stream);
+    }
     if (ic.force) { set_error("conv2d_transpose: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
   g_last_impl = CTX_IMPL_SIMT;

@@ -22,6 +22,9 @@ int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, con
 int tc_conv2d_transpose_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g);
 int tc_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2_batch, const float* w,
                         float* y, int Cn, const ctx_conv_geom& g, const Epi& epi, int passes, cudaStream_t stream);
+int tc_conv2d_transpose_scatter_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g);
+int tc_conv2d_transpose_scatter(const float* x1, int C1, const float* x2, int C2, int x2_batch, const float* w,
+                                float* y, int Cn, const ctx_conv_geom& g, int passes, cudaStream_t stream);
 int tc_conv2d_wgrad_eligible(int Ca, int Cb1, int Cb2, int s2_batch, const ctx_conv_geom& g);
 int tc_conv2d_wgrad(const float* big, int Ca, const float* s1, int Cb1, const float* s2, int Cb2, int s2_batch,
                     float* dw, const ctx_conv_geom& g, int passes, cudaStream_t stream);
@@ -29,5 +32,8 @@ int tc_gemm_eligible(int tA, int tB, int M, int N, int K, const float* A, int ld
                      const float* C, int ldc);
 int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, const Epi& epi, int passes, cudaStream_t stream);
+
+// pointwise.cu
+int bias_init(float* y, const float* bias, int64_t n, int C, int accumulate, cudaStream_t stream);
 
 }  // namespace ctx

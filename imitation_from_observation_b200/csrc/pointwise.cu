@@ -140,7 +140,8 @@ __global__ void mse_scaled_kernel(const float* __restrict__ a, int lda, const fl
 // ---- decoder-level data-gradient split ------------------------------------------------------------------------------
 __global__ void split_skip_grad_kernel(const float* __restrict__ dcat, int G, int64_t B, int64_t pix, int C1, int C2,
                                        const float* __restrict__ state_ref, const float* __restrict__ skip_ref,
-                                       float slope, float* __restrict__ dstate, float* dskip, int accumulate_skip) {
+                                       float slope, float* __restrict__ dstate, float* dskip, int accumulate_skip,
+                                       int rnd) {
   const int Ct = C1 + C2;
   const int64_t n_state = (int64_t)G * B * pix * C1;
   const int64_t n_skip = B * pix * C2;
@@ -151,7 +152,7 @@ __global__ void split_skip_grad_kernel(const float* __restrict__ dcat, int G, in
     const int c = (int)(j - row * C1);
     float v = dcat[row * Ct + c];
     if (state_ref) v *= (state_ref[j] >= 0.f ? 1.f : slope);
-    dstate[j] = v;
+    dstate[j] = rnd ? round_tf32(v) : v;
   }
   for (int64_t j = i; j < n_skip; j += stride) {
     const int64_t row = j / C2;                         // row in [0, B*pix)
@@ -159,7 +160,54 @@ __global__ void split_skip_grad_kernel(const float* __restrict__ dcat, int G, in
     float v = 0.f;
     for (int g = 0; g < G; ++g) v += dcat[((int64_t)g * B * pix + row) * Ct + C1 + c];
     if (skip_ref) v *= (skip_ref[j] >= 0.f ? 1.f : slope);
-    dskip[j] = accumulate_skip ? dskip[j] + v : v;
+    v = accumulate_skip ? dskip[j] + v : v;
+    dskip[j] = rnd ? round_tf32(v) : v;
+  }
+}
+
+// 128-bit version (C1 % 4 == 0, C2 % 4 == 0): one thread per float4 of a concatenated row; the G passes of a row are
+// handled by the same thread, so every byte of dcat is read exactly once.
+__global__ void split_skip_grad_vec_kernel(const float4* __restrict__ dcat, int G, int64_t rows, int C1q, int C2q,
+                                           const float4* __restrict__ state_ref, const float4* __restrict__ skip_ref,
+                                           float slope, float4* __restrict__ dstate, float4* dskip,
+                                           int accumulate_skip, int rnd, FastDiv divCt) {
+  const int Ctq = C1q + C2q;
+  const int64_t total = rows * Ctq;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int64_t row;
+    int c;
+    if (total < (1ll << 31)) { int r32; divCt.divmod((int)i, r32, c); row = r32; }
+    else { row = i / Ctq; c = (int)(i - row * Ctq); }
+    if (c < C1q) {
+      for (int g = 0; g < G; ++g) {
+        const int64_t r = (int64_t)g * rows + row;
+        float4 v = dcat[r * Ctq + c];
+        if (state_ref) {
+          const float4 a = state_ref[r * C1q + c];
+          v.x *= (a.x >= 0.f ? 1.f : slope); v.y *= (a.y >= 0.f ? 1.f : slope);
+          v.z *= (a.z >= 0.f ? 1.f : slope); v.w *= (a.w >= 0.f ? 1.f : slope);
+        }
+        if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+        dstate[r * C1q + c] = v;
+      }
+    } else {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < G; ++g) {
+        const float4 t = dcat[((int64_t)g * rows + row) * Ctq + c];
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      const int64_t j = row * C2q + (c - C1q);
+      if (skip_ref) {
+        const float4 a = skip_ref[j];
+        v.x *= (a.x >= 0.f ? 1.f : slope); v.y *= (a.y >= 0.f ? 1.f : slope);
+        v.z *= (a.z >= 0.f ? 1.f : slope); v.w *= (a.w >= 0.f ? 1.f : slope);
+      }
+      if (accumulate_skip) { const float4 o = dskip[j]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+      dskip[j] = v;
+    }
   }
 }
 
@@ -170,10 +218,60 @@ __global__ void add_bcast_kernel(const float* __restrict__ a, const float* __res
   for (; i < n; i += stride) out[i] = a[i] + b[i % nb];
 }
 
+// ---- y = (accumulate ? y : 0) + bias[c]: initialises the output of the scatter-epilogue transposed conv -----------
+__global__ void bias_init_kernel(float* __restrict__ y, const float* __restrict__ bias, int64_t n, int C,
+                                 int accumulate) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = accumulate ? y[i] : 0.f;
+    if (bias) v += __ldg(bias + (int)(i % C));
+    y[i] = v;
+  }
+}
+
+int bias_init(float* y, const float* bias, int64_t n, int C, int accumulate, cudaStream_t stream) {
+  if (accumulate && !bias) return CTX_OK;
+  bias_init_kernel<<<grid_for(n, 256), 256, 0, stream>>>(y, bias, n, C, accumulate);
+  CTX_LAUNCH_CHECK("bias_init");
+  return CTX_OK;
+}
+
+// ---- patch matrix of a SAME conv over a few-channel NHWC tensor (C*kh*kw <= ld) ------------------------------------
+// out[(n,p,q), (r*kw+s)*C + c] = x[n, p*st+r-pad_h, q*st+s-pad_w, c]  (0 outside the image and in columns >= kh*kw*C).
+// One thread per output element, column index fastest: stores are fully coalesced, loads hit L1/L2 (every input
+// element is read kh*kw/st^2 times from cache, once from HBM).
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int ld, int C, int H,
+                              int W, int kw, int K, int st, int padh, int padw, int rnd, FastDiv divLd,
+                              FastDiv divC, FastDiv divKw, FastDiv divQ, FastDiv divP) {
+  constexpr int R = 32;                                     // rows per block
+  const int row0 = blockIdx.x * R;
+  const int nrow = min(R, rows - row0);
+  const int total = nrow * ld;
+  float* o = out + (int64_t)row0 * ld;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int j, k;
+    divLd.divmod(e, j, k);
+    float v = 0.f;
+    if (k < K) {
+      int tap, c, r, s, t, q, n, pp;
+      divC.divmod(k, tap, c);
+      divKw.divmod(tap, r, s);
+      divQ.divmod(row0 + j, t, q);
+      divP.divmod(t, n, pp);
+      const int h = pp * st + r - padh, w = q * st + s - padw;
+      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+        v = __ldg(x + (((int64_t)n * H + h) * W + w) * C + c);
+      if (rnd) v = round_tf32(v);
+    }
+    o[e] = v;
+  }
+}
+
 // ---- fused TF-Adam ----------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps,
-                            float gscale) {
+                            float gscale, float* __restrict__ p_tf32) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
@@ -197,6 +295,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     reinterpret_cast<float4*>(p)[j] = pp;
     reinterpret_cast<float4*>(m)[j] = mm;
     reinterpret_cast<float4*>(v)[j] = vv;
+    if (p_tf32)
+      reinterpret_cast<float4*>(p_tf32)[j] =
+          make_float4(round_tf32(pp.x), round_tf32(pp.y), round_tf32(pp.z), round_tf32(pp.w));
   }
   for (int64_t j = n4 * 4 + i; j < n; j += stride) {
     float gr = g[j] * gscale;
@@ -204,6 +305,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     float vv = __fadd_rn(v[j], __fmul_rn(__fsub_rn(__fmul_rn(gr, gr), v[j]), ob2));
     m[j] = mm; v[j] = vv;
     p[j] = __fsub_rn(p[j], __fdiv_rn(__fmul_rn(mm, lr_t), __fadd_rn(__fsqrt_rn(vv), eps)));
+    if (p_tf32) p_tf32[j] = round_tf32(p[j]);
   }
 }
 
@@ -388,12 +490,22 @@ extern "C" int ctx_mse_scaled_fwd_bwd(const float* a, int32_t lda, const float* 
 
 extern "C" int ctx_split_skip_grad(const float* dcat, int32_t G, int64_t B, int64_t pix, int32_t C1, int32_t C2,
                                    const float* state_ref, const float* skip_ref, float slope, float* dstate,
-                                   float* dskip, int32_t accumulate_skip, void* stream) {
+                                   float* dskip, int32_t accumulate_skip, int32_t round_tf32, void* stream) {
   CTX_REQUIRE(dcat && dstate && dskip && G > 0 && C1 > 0 && C2 > 0, "split_skip_grad: bad arguments");
   if (B == 0 || pix == 0) return CTX_OK;
-  int64_t n = (int64_t)G * B * pix * C1;
-  split_skip_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      dcat, G, B, pix, C1, C2, state_ref, skip_ref, slope, dstate, dskip, accumulate_skip);
+  auto al = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  if (C1 % 4 == 0 && C2 % 4 == 0 && al(dcat) && al(dstate) && al(dskip) && al(state_ref) && al(skip_ref)) {
+    const int64_t rows = B * pix;
+    const int Ctq = (C1 + C2) / 4;
+    split_skip_grad_vec_kernel<<<grid_for(rows * Ctq, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dcat), G, rows, C1 / 4, C2 / 4, reinterpret_cast<const float4*>(state_ref),
+        reinterpret_cast<const float4*>(skip_ref), slope, reinterpret_cast<float4*>(dstate),
+        reinterpret_cast<float4*>(dskip), accumulate_skip, round_tf32, FastDiv(Ctq));
+  } else {
+    int64_t n = (int64_t)G * B * pix * C1;
+    split_skip_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        dcat, G, B, pix, C1, C2, state_ref, skip_ref, slope, dstate, dskip, accumulate_skip, round_tf32);
+  }
   CTX_LAUNCH_CHECK("split_skip_grad");
   return CTX_OK;
 }
@@ -407,14 +519,31 @@ extern "C" int ctx_add_bcast(const float* a, const float* b, float* out, int64_t
   return CTX_OK;
 }
 
+extern "C" int ctx_im2col(const float* x, int32_t C, float* out, int32_t ld, const ctx_conv_geom* g,
+                          int32_t round_tf32, void* stream) {
+  CTX_REQUIRE(g != nullptr && x && out, "im2col: null pointer");
+  CTX_REQUIRE(C > 0 && g->kh > 0 && g->kw > 0 && g->stride > 0 && ld >= g->kh * g->kw * C,
+              "im2col: ld (%d) must be >= kh*kw*C (%d)", ld, g->kh * g->kw * C);
+  const int64_t rows = (int64_t)g->N * g->P * g->Q;
+  if (rows == 0) return CTX_OK;
+  CTX_REQUIRE(rows < (1ll << 31) - 64 && ld <= 4096, "im2col: too many rows (%lld) or ld too large", (long long)rows);
+  im2col_kernel<<<(unsigned)cdiv(rows, 32), 256, 0, (cudaStream_t)stream>>>(
+      x, out, (int)rows, ld, C, g->H, g->W, g->kw, g->kh * g->kw * C, g->stride, g->pad_h, g->pad_w, round_tf32,
+      FastDiv(ld),
+      FastDiv(C), FastDiv(g->kw), FastDiv(g->Q), FastDiv(g->P));
+  CTX_LAUNCH_CHECK("im2col");
+  return CTX_OK;
+}
+
 extern "C" int ctx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1,
-                             float b2, float eps, float grad_scale, void* stream) {
+                             float b2, float eps, float grad_scale, float* p_tf32, void* stream) {
   CTX_REQUIRE(p && g && m && v && n >= 0, "adam_step: bad arguments");
   CTX_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
-                  ((uintptr_t)v % 16 == 0), "adam_step: buffers must be 16-byte aligned");
+                  ((uintptr_t)v % 16 == 0) && ((uintptr_t)p_tf32 % 16 == 0),
+              "adam_step: buffers must be 16-byte aligned");
   if (n == 0) return CTX_OK;
   adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, b1, b2, eps,
-                                                                            grad_scale);
+                                                                            grad_scale, p_tf32);
   CTX_LAUNCH_CHECK("adam_step");
   return CTX_OK;
 }

@@ -82,6 +82,9 @@ struct TcParams {
   float* out;
   int64_t sN, sP, sQ, obase;       // element strides of D rows over (n, p, q)
   int32_t atomic_out;
+  // scatter epilogue (transposed conv with few output channels computed as ONE pixel x (tap, channel) GEMM):
+  // column j = tap*sc_Cn + co of row (n, p, q) is added to out[n, p*sc_st + r - sc_padh, q*sc_st + s - sc_padw, co]
+  int32_t scatter, sc_kw, sc_Cn, sc_st, sc_padh, sc_padw, sc_H, sc_W;
   Epi epi;
   int32_t* err_flag;
 };
@@ -189,6 +192,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kATileBytes = 128 * 128;          // 128 rows (or 4 atoms x 32 rows) x 128 B
 
+// TMEM columns to allocate: one accumulator (two in 3-pass mode) of BN columns, rounded up to a power of two >= 32
+__host__ __device__ __forceinline__ uint32_t tmem_cols(int BN, int passes) {
+  const uint32_t need = (uint32_t)BN * (passes == 3 ? 2u : 1u);
+  uint32_t c = 32u;
+  while (c < need) c <<= 1;
+  return c;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
@@ -245,8 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     // 3-pass mode keeps two accumulators: D1 = hi*hi, D2 = the two cross terms.  The tensor core truncates when
     // it adds into a running fp32 sum (measured: error grows linearly with the number of accumulations), so the
     // small terms must not ride on the big sum; D1 + D2 is formed once, in the epilogue, with a rounded fp32 add.
-    uint32_t ncols = (uint32_t)p.BN * (p.passes == 3 ? 2u : 1u);
-    if (ncols < 32u) ncols = 32u;
+    const uint32_t ncols = tmem_cols(p.BN, p.passes);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                  "r"(ncols)
                  : "memory");
@@ -440,6 +450,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       const int col = ncol0 + c0;
       if (col >= p.N) continue;
       float* optr = p.out + roff + col;
+      if (p.scatter) {
+        // (tap, channel) of the first column; all lanes walk the same columns, so this is warp-uniform
+        int tap = col / p.sc_Cn, co = col - tap * p.sc_Cn;
+        int rr = tap / p.sc_kw, ss = tap - rr * p.sc_kw;
+        const int hb = gp * p.sc_st - p.sc_padh, wb = dq * p.sc_st - p.sc_padw;
+        float* obase_n = p.out + (int64_t)gn * p.sc_H * p.sc_W * p.sc_Cn;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col + j < p.N) {
+            const int h = hb + rr, w = wb + ss;
+            if ((unsigned)h < (unsigned)p.sc_H && (unsigned)w < (unsigned)p.sc_W)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase_n + ((int64_t)h * p.sc_W + w) * p.sc_Cn + co),
+                           "f"(__uint_as_float(v[j]))
+                           : "memory");
+          }
+          if (++co == p.sc_Cn) { co = 0; if (++ss == p.sc_kw) { ss = 0; ++rr; } }
+        }
+        continue;
+      }
       if (p.atomic_out) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -487,8 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    uint32_t ncols = (uint32_t)p.BN * (p.passes == 3 ? 2u : 1u);
-    if (ncols < 32u) ncols = 32u;
+    const uint32_t ncols = tmem_cols(p.BN, p.passes);
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
@@ -818,6 +846,71 @@ int tc_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2
   return CTX_OK;
 }
 
+// ---- transposed conv with few output channels: ONE pixel x (tap, channel) GEMM + scatter-add epilogue ---------------
+// y[n, p*st + r - pad_h, q*st + s - pad_w, co] += sum_c cat[n,p,q,c] * w[r,s,co,c]: the filter [kh,kw,Cn,Ck] IS a
+// K-major [kh*kw*Cn, Ck] matrix, so the whole layer is a single GEMM with N = kh*kw*Cn columns whose epilogue
+// scatters each column to its output pixel (col2im) with fp32 reductions.  The input is read once (the per-phase
+// formulation re-reads it once per tap, which costs 25x the traffic when Cn = 3 cannot amortise it).
+// y must already hold the bias (or zeros / the value to accumulate into).
+int tc_conv2d_transpose_scatter_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g) {
+  int bp, nb, tpi;
+  if (C1 % 32 != 0 || C2 % 32 != 0) return 0;
+  if (g.kh * g.kw * Cn > 256) return 0;
+  if (!tile_grid(g.P, g.Q, 128, &bp, &nb, &tpi)) return 0;
+  if (C2 > 0 && nb > 1 && x2_batch % nb != 0) return 0;
+  return 1;
+}
+
+int tc_conv2d_transpose_scatter(const float* x1, int C1, const float* x2, int C2, int x2_batch, const float* w,
+                                float* y, int Cn, const ctx_conv_geom& g, int passes, cudaStream_t stream) {
+  CTX_REQUIRE(aligned16(x1) && aligned16(w) && (x2 == nullptr || aligned16(x2)),
+              "conv2d_transpose(tc scatter): pointers must be 16-byte aligned");
+  TcParams p;
+  fill_common(p, passes, make_epi(nullptr));
+  int tpi;
+  if (!tile_grid(g.P, g.Q, 128, &p.BP, &p.NB, &tpi)) return CTX_ERR_UNSUPPORTED;
+  p.tiles_per_img = tpi;
+  p.a_mode = A_PIX; p.b_mode = B_K;
+  const int Ck = C1 + C2, N = g.kh * g.kw * Cn;
+  p.BN = (int)cdiv(N, 16) * 16;
+  p.NG = g.N; p.PG = g.P; p.QG = g.Q;
+  p.M = g.N * g.P * g.Q; p.N = N;
+  p.a_wrap = x2_batch > 0 ? x2_batch : 1;
+  const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
+  {
+    int64_t dims[4] = {C1, g.Q, g.P, g.N}, str[4] = {1, C1, (int64_t)g.Q * C1, (int64_t)g.P * g.Q * C1};
+    int box[4] = {32, g.Q, p.BP, p.NB};
+    int rc = make_map(&p.mapA[0], x1, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  if (C2 > 0) {
+    int64_t dims[4] = {C2, g.Q, g.P, x2_batch}, str[4] = {1, C2, (int64_t)g.Q * C2, (int64_t)g.P * g.Q * C2};
+    int box[4] = {32, g.Q, p.BP, p.NB};
+    int rc = make_map(&p.mapA[1], x2, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    int64_t dims[2] = {Ck, N}, str[2] = {1, Ck};       // rows past N are zero-filled by the TMA unit
+    int box[2] = {32, p.BN};
+    int rc = make_map(&p.mapB[0], w, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  p.nseg = C2 > 0 ? 2 : 1;
+  for (int src = 0; src < p.nseg; ++src) {
+    Seg& sg = p.seg[src];
+    sg.mapA = (uint8_t)src; sg.wrap = (uint8_t)src; sg.dh = 0; sg.dw = 0;
+    sg.nblk = (uint16_t)((src ? C2 : C1) / 32); sg.bk0 = src ? C1 : 0; sg.br0 = 0;
+  }
+  p.total_kblocks = Ck / 32;
+  p.kblocks_per_split = p.total_kblocks;
+  p.out = y;
+  p.sN = 0; p.sP = 0; p.sQ = 0; p.obase = 0;
+  p.atomic_out = 0;
+  p.scatter = 1; p.sc_kw = g.kw; p.sc_Cn = Cn; p.sc_st = g.stride; p.sc_padh = g.pad_h; p.sc_padw = g.pad_w;
+  p.sc_H = g.H; p.sc_W = g.W;
+  return launch_tc(p, m_tiles, 1, stream, "tc_conv2d_transpose_scatter");
+}
+
 // ---- conv filter gradient ------------------------------------------------------------------------------------------
 int tc_conv2d_wgrad_eligible(int Ca, int Cb1, int Cb2, int s2_batch, const ctx_conv_geom& g) {
   int bp, nb, tpi;
@@ -829,14 +922,25 @@ int tc_conv2d_wgrad_eligible(int Ca, int Cb1, int Cb2, int s2_batch, const ctx_c
   return 1;
 }
 
+// Split-K factor: one CTA per SM is resident (the operand ring takes the whole shared memory), so the launch runs in
+// waves of sm_count CTAs.  Choose the split that minimises  waves x (k-blocks per CTA + fixed cost per CTA), the
+// fixed cost (prologue, TMEM allocation, atomic epilogue) being worth about `ovh` k-blocks.
 static int pick_splits(int tiles, int kblocks, int min_per_split) {
   const int sms = sm_count();
-  int want = (int)cdiv(2 * (int64_t)sms, tiles);
   int maxs = kblocks / min_per_split;
   if (maxs < 1) maxs = 1;
-  if (want > maxs) want = maxs;
-  if (want < 1) want = 1;
-  return want;
+  if (maxs > 4 * sms) maxs = 4 * sms;
+  const int64_t ovh = 10;
+  int best = 1;
+  int64_t best_cost = -1;
+  for (int s = 1; s <= maxs; ++s) {
+    const int64_t per = cdiv(kblocks, s);
+    const int64_t real = cdiv(kblocks, per);                 // splits that actually get work
+    const int64_t waves = cdiv((int64_t)tiles * real, sms);
+    const int64_t cost = waves * (per + ovh);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 int tc_conv2d_wgrad(const float* big, int Ca, const float* s1, int Cb1, const float* s2, int Cb2, int s2_batch,
@@ -891,10 +995,10 @@ int tc_gemm_eligible(int tA, int tB, int M, int N, int K, const float* A, int ld
                      const float* C, int ldc) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return 0;
-  if (lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0 || N % 4 != 0 || K % 4 != 0) return 0;
+  // TMA needs 16-byte strides; M and K are free (out-of-range rows / columns are zero-filled by the TMA unit)
+  if (lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0 || N % 4 != 0) return 0;
   if (N < 32) return 0;
   if (tA && tB) return 0;                          // MN-major A with K-major B is not wired up (unused by the graph)
-  if (tA && (M % 32 != 0)) return 0;
   if (!tB && (N % 32 != 0)) return 0;
   return 1;
 }

@@ -98,9 +98,9 @@ class _ContextModel:
         n = cat.shape[0]
         t0 = torch.empty((n, F), device=cat.device)
         tz = torch.empty((n, F), device=cat.device)
-        net._gemm(False, False, n, F, 2 * F, cat.data_ptr(), 2 * F, net.P["translate/trans_h0/Matrix"].data_ptr(), F,
+        net._gemm(False, False, n, F, 2 * F, cat.data_ptr(), 2 * F, net.Wf["translate/trans_h0/Matrix"].data_ptr(), F,
                   t0.data_ptr(), F, bias=net.P["translate/trans_h0/bias"], act=True)
-        net._gemm(False, False, n, F, F, t0.data_ptr(), F, net.P["translate/trans_z/Matrix"].data_ptr(), F,
+        net._gemm(False, False, n, F, F, t0.data_ptr(), F, net.Wf["translate/trans_z/Matrix"].data_ptr(), F,
                   tz.data_ptr(), F, bias=net.P["translate/trans_z/bias"], act=False)
         return tz
 

@@ -39,19 +39,23 @@ def _numel(shape) -> int:
 class ContextNet:
     """One network instance bound to a device, a per-rank batch size and a precision mode.
 
-    precision = "tf32x3" (default): tcgen05 kernels with the 3-pass TF32 split (hi*hi + hi*lo + lo*hi, fp32
+    precision = "mixed" (default): forward in the 3-pass TF32 split (below), backward (data and filter gradients)
+                        in single-pass TF32 with gradients rounded to nearest by the producing epilogue.  The forward
+                        pass decides every lrelu mask, so it keeps fp32-grade accuracy; the backward GEMMs are smooth
+                        in their operands, where TF32's unbiased 2^-12 rounding averages out.
+    precision = "tf32x3": tcgen05 kernels with the 3-pass TF32 split (hi*hi + hi*lo + lo*hi, fp32
                         accumulate; ~2^-21 per product, i.e. fp32-faithful) wherever the shape qualifies, the exact
-                        fp32 SIMT kernels elsewhere.  This is the parity mode.
+                        fp32 SIMT kernels elsewhere.  The strictest tensor-core mode.
     precision = "fp32": every GEMM-shaped op uses the exact-fp32 SIMT kernels.
     precision = "tf32": single-pass TF32 (operands rounded to nearest by the producing epilogue) wherever the
                         shape qualifies.  Fast mode: forward outputs stay within ~1e-3, but lrelu masks flip for
                         ~3e-4 of the units, so gradients only agree in aggregate (relative L2 ~1e-2).
     """
 
-    def __init__(self, spec: NetSpec, batch: int, device="cuda", precision: str = "tf32x3", seed: int = 0,
+    def __init__(self, spec: NetSpec, batch: int, device="cuda", precision: str = "mixed", seed: int = 0,
                  global_batch: Optional[int] = None, ablation_type: str = "None", params_from: "ContextNet" = None):
-        if precision not in ("fp32", "tf32x3", "tf32"):
-            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32'")
+        if precision not in ("fp32", "tf32x3", "tf32", "mixed"):
+            raise ValueError("precision must be 'mixed', 'tf32x3', 'tf32' or 'fp32'")
         _lib.load()                                   # fail loudly if the extension is missing
         self.spec = spec
         self.B = int(batch)
@@ -59,8 +63,11 @@ class ContextNet:
         if self.device.type != "cuda":
             raise _lib.CtxError("ContextNet needs a CUDA device: the B200 path has no CPU fallback")
         self.precision = precision
-        self.impl = {"fp32": IMPL_SIMT, "tf32x3": IMPL_AUTO, "tf32": IMPL_FAST}[precision]
-        self.round = precision == "tf32"
+        self.impl = {"fp32": IMPL_SIMT, "tf32x3": IMPL_AUTO, "tf32": IMPL_FAST, "mixed": IMPL_AUTO}[precision]
+        self.impl_b = IMPL_FAST if precision == "mixed" else self.impl       # backward GEMMs
+        self.round = precision == "tf32"                                      # round forward activations to TF32
+        self.round_b = precision in ("tf32", "mixed")                         # round backward gradients to TF32
+        self.use_tc = precision != "fp32"
         self.global_batch = int(global_batch) if global_batch else self.B
         self.ablation_type = ablation_type
         self._w_recon = {"None": (1.0, 1.0), "L2": (1.0, 1.0), "L2L3": (1.0, 0.0), "L1": (0.0, 1.0)}[ablation_type]
@@ -88,8 +95,22 @@ class ContextNet:
         self.flat_v = None
         self.P = {n: self._view(self.flat_p, n) for n in self.shapes}
         self.G: Dict[str, torch.Tensor] = {}
+        # Single-pass tensor-core GEMMs read a shadow copy of the parameters rounded to the nearest TF32 (refreshed by
+        # the Adam kernel): the hardware truncates fp32 operands, which would shrink every product by ~2^-11.
+        self.flat_pr = None
+        fwd_single, bwd_single = precision == "tf32", precision in ("tf32", "mixed")
+        if fwd_single or bwd_single:
+            if params_from is not None and params_from.flat_pr is not None:
+                self.flat_pr = params_from.flat_pr
+            else:
+                self.flat_pr = torch.zeros(off, device=self.device, dtype=torch.float32)
+        PR = {n: self._view(self.flat_pr, n) for n in self.shapes} if self.flat_pr is not None else self.P
+        self.Wf = PR if fwd_single else self.P          # weights read by forward GEMMs
+        self.Wb = PR if bwd_single else self.P          # weights read by backward (data-gradient) GEMMs
         if params_from is None:
             self.init_params(seed)
+        else:
+            self.sync_shadow()
         self.ctx_scope = "conv_context" if spec.separate_ctx_encoder else "conv"
         self.sizes = [(spec.height, spec.width)] + spec.enc_sizes()
         self.chans = spec.enc_channels()
@@ -139,6 +160,12 @@ class ContextNet:
                         t = torch.where(bad, torch.randn(shp, generator=g) * 0.02, t)
                     t = t.clamp(-0.04, 0.04)
             self.P[name].copy_(t.to(self.device))
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        """Refresh the TF32-rounded shadow parameters after the fp32 masters were written from outside."""
+        if self.flat_pr is not None:
+            ops.round_tf32(self.flat_p, out=self.flat_pr)
 
     def state_dict(self) -> Dict[str, np.ndarray]:
         """TF-checkpoint-keyed parameters (SURVEY.md §8b 'Checkpoint keys')."""
@@ -154,6 +181,7 @@ class ContextNet:
             if tuple(v.shape) != tuple(self.shapes[n]):
                 raise ValueError("parameter %s has shape %s, expected %s" % (key, tuple(v.shape), self.shapes[n]))
             self.P[n].copy_(v.to(device=self.device, dtype=torch.float32))
+        self.sync_shadow()
 
     # ---- inputs ---------------------------------------------------------------------------------------------------
     def _input_buffers(self):
@@ -184,26 +212,54 @@ class ContextNet:
         """4 x (conv5x5/3x3 SAME + bias + lrelu) — arm_shaping.py:1283-1286."""
         h = x
         for j in range(4):
-            ops.conv2d(h, self.P["%s/h%d_conv/w" % (scope, j)], self.P["%s/h%d_conv/biases" % (scope, j)],
-                       stride=self.spec.strides[j], act=True, out=outs[j], round_tf32=self.round, impl=self.impl)
+            w, b = self.Wf["%s/h%d_conv/w" % (scope, j)], self.P["%s/h%d_conv/biases" % (scope, j)]
+            k, Cin, Co = self.spec.kernels[j], h.shape[3], w.shape[3]
+            if self._few(Cin, k) and Co % 4 == 0:
+                K = k * k * Cin
+                pt = self._patches("patch_%s_h%d_%d" % (scope, j, h.shape[0]), h, k, self.spec.strides[j])
+                ops.gemm(pt[:, :K], w.view(K, Co), out=outs[j].view(-1, Co), bias=b, act=True, round_tf32=self.round,
+                         impl=self.impl)
+            else:
+                ops.conv2d(h, w, b, stride=self.spec.strides[j], act=True, out=outs[j], round_tf32=self.round,
+                           impl=self.impl)
             h = outs[j]
 
     def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, bias=None, act=False, act_ref=None,
-              accumulate=False, round_=None):
+              accumulate=False, round_=None, bwd=False):
+        if round_ is None:
+            round_ = self.round_b if bwd else self.round
         epi = _lib.Epilogue(None if bias is None else bias.data_ptr(), act_ref, ops.LRELU_SLOPE, int(act),
-                            int(accumulate), int(self.round if round_ is None else round_))
-        ops.gemm_raw(tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, epi, self.impl)
+                            int(accumulate), int(round_))
+        ops.gemm_raw(tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, epi, self.impl_b if bwd else self.impl)
+
+    # ---- few-channel layers (the 3-channel image side): patch matrix + dense tensor-core GEMM ----------------------
+    def _few(self, C: int, k: int) -> bool:
+        """True when a conv over a C-channel tensor cannot take the TMA tap path (C % 32) but its whole filter
+        footprint fits a short GEMM K: then  im2col (ctx_im2col) + ctx_gemm  replaces the SIMT implicit GEMM."""
+        return self.use_tc and C % 32 != 0 and C * k * k <= 256 and ops.tc_available()
+
+    @staticmethod
+    def _patch_ld(C: int, k: int) -> int:
+        return -(-(C * k * k) // 4) * 4
+
+    def _patches(self, name: str, x: torch.Tensor, k: int, stride: int, round_tf32: bool = False) -> torch.Tensor:
+        n, H, W_, C = x.shape
+        ld = self._patch_ld(C, k)
+        rows = n * (-(-H // stride)) * (-(-W_ // stride))
+        buf = self._buf(name, (rows, ld))
+        ops.im2col(x, k, stride, ld, out=buf, round_tf32=round_tf32)
+        return buf
 
     def _fwd_encoder(self, scope: str, x: torch.Tensor, hs: List[torch.Tensor], h4: torch.Tensor):
         n = x.shape[0]
         self.encode_convs(scope, x, hs)
         self._gemm(False, False, n, self.F, self.flat, hs[3].data_ptr(), self.flat,
-                   self.P[scope + "/h4_lin/Matrix"].data_ptr(), self.F, h4.data_ptr(), self.F,
+                   self.Wf[scope + "/h4_lin/Matrix"].data_ptr(), self.F, h4.data_ptr(), self.F,
                    bias=self.P[scope + "/h4_lin/bias"], act=True)
 
     def _fwd_hz(self, scope: str, h4_rows: torch.Tensor, out_ptr: int, ldo: int, act: bool):
         self._gemm(False, False, h4_rows.shape[0], self.F, self.F, h4_rows.data_ptr(), self.F,
-                   self.P[scope + "/hz_lin/Matrix"].data_ptr(), self.F, out_ptr, ldo,
+                   self.Wf[scope + "/hz_lin/Matrix"].data_ptr(), self.F, out_ptr, ldo,
                    bias=self.P[scope + "/hz_lin/bias"], act=act)
 
     def _enc_buffers(self, n_rows: int, tag: str):
@@ -246,9 +302,9 @@ class ContextNet:
             self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
             th0 = self._buf("th0", (B, F))
             self._gemm(False, False, B, F, 2 * F, cat.data_ptr(), 2 * F,
-                       self.P["translate/trans_h0/Matrix"].data_ptr(), F, th0.data_ptr(), F,
+                       self.Wf["translate/trans_h0/Matrix"].data_ptr(), F, th0.data_ptr(), F,
                        bias=self.P["translate/trans_h0/bias"], act=True)
-            self._gemm(False, False, B, F, F, th0.data_ptr(), F, self.P["translate/trans_z/Matrix"].data_ptr(), F,
+            self._gemm(False, False, B, F, F, th0.data_ptr(), F, self.Wf["translate/trans_z/Matrix"].data_ptr(), F,
                        z2.data_ptr(), F, bias=self.P["translate/trans_z/bias"], act=False)      # trans_z -> z2[:B]
             nd = B
             if level == FWD_ALL:
@@ -271,11 +327,11 @@ class ContextNet:
         """arm_shaping.py:1314-1329 for all stacked passes at once; skips = ctx (h0,h1,h2,h3), batch B."""
         n = z.shape[0]
         self._gemm(False, False, n, self.flat, self.F, z.data_ptr(), self.F,
-                   self.P["deconv/d_h0_lin/Matrix"].data_ptr(), self.flat, d[0].data_ptr(), self.flat,
+                   self.Wf["deconv/d_h0_lin/Matrix"].data_ptr(), self.flat, d[0].data_ptr(), self.flat,
                    bias=self.P["deconv/d_h0_lin/bias"], act=True)
         for i, L in enumerate(self.dec):
             last = i == 3
-            ops.conv2d_transpose(d[i], self.P["deconv/%s/w" % L["name"]], L["out_hw"],
+            ops.conv2d_transpose(d[i], self.Wf["deconv/%s/w" % L["name"]], L["out_hw"],
                                  bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2=skips[3 - i],
                                  act=not last, out=d[i + 1], round_tf32=self.round and not last, impl=self.impl)
 
@@ -305,7 +361,7 @@ class ContextNet:
             raise _lib.CtxError("backward() needs forward(FWD_ALL) first")
         self._ensure_grads()
         sp, B, F, flat = self.spec, self.B, self.F, self.flat
-        P, G, bufs = self.P, self.G, self._bufs
+        P, G, bufs, Wb = self.P, self.G, self._bufs, self.Wb
         f4 = 4
         xe, xc = self._input_buffers()
         n_e = xe.shape[0]
@@ -328,28 +384,43 @@ class ContextNet:
 
         # ---- decoder: d_h4 .. d_h1 -------------------------------------------------------------------------------
         g_out = bufs["g_d4"]                              # d loss / d d4 (written by the loss kernel)
+        ib, rb = self.impl_b, self.round_b
         for i in (3, 2, 1, 0):
             L = self.dec[i]
             wname = "deconv/%s/w" % L["name"]
             state, skip = d[i], c_hs[3 - i]
-            # filter gradient: big = g_out [2B, out_hw, Cout], small = [state ‖ skip]
-            ops.conv2d_wgrad(g_out, state, L["k"], L["stride"], small2=skip, dw=G[wname], impl=self.impl)
-            ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
-            # data gradient of the concatenated input = SAME conv of g_out with the [kh,kw,Cout,Cin] filter as HWIO
-            dcat = self._buf("dcat%d" % i, (2 * B,) + tuple(L["in_hw"]) + (L["c_state"] + L["c_skip"],))
-            ops.conv2d(g_out, P[wname], None, stride=L["stride"], act=False, out=dcat, impl=self.impl)
+            Cs, Ck, Co, k = L["c_state"], L["c_state"] + L["c_skip"], L["c_out"], L["k"]
+            dcat = self._buf("dcat%d" % i, (2 * B,) + tuple(L["in_hw"]) + (Ck,))
+            if self._few(Co, k):
+                # few output channels (the image): patch matrix of g_out, then three dense GEMMs
+                K = k * k * Co
+                pt = self._patches("patch_g_d%d" % (i + 1), g_out, k, L["stride"], round_tf32=rb)[:, :K]
+                rows = pt.shape[0] // 2                    # rows of one decoder pass (the skip is shared by both)
+                dw2 = G[wname].view(K, Ck)
+                ops.gemm(pt, state.view(-1, Cs), out=dw2[:, :Cs], transA=True, accumulate=True, impl=ib)
+                for g_ in range(2):
+                    ops.gemm(pt[g_ * rows:(g_ + 1) * rows], skip.view(-1, Ck - Cs), out=dw2[:, Cs:], transA=True,
+                             accumulate=True, impl=ib)
+                ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+                ops.gemm(pt, Wb[wname].view(K, Ck), out=dcat.view(-1, Ck), impl=ib)
+            else:
+                # filter gradient: big = g_out [2B, out_hw, Cout], small = [state ‖ skip]
+                ops.conv2d_wgrad(g_out, state, k, L["stride"], small2=skip, dw=G[wname], impl=ib)
+                ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+                # data gradient of the concatenated input = SAME conv of g_out with the [kh,kw,Cout,Cin] filter as HWIO
+                ops.conv2d(g_out, Wb[wname], None, stride=L["stride"], act=False, out=dcat, impl=ib)
             g_state = self._buf("g_d%d" % i, tuple(state.shape))
-            ops.split_skip_grad(dcat, 2, B, L["c_state"], L["c_skip"], g_state, gc_hs[3 - i],
-                                state_ref=state, skip_ref=skip, accumulate_skip=False)
+            ops.split_skip_grad(dcat, 2, B, Cs, Ck - Cs, g_state, gc_hs[3 - i],
+                                state_ref=state, skip_ref=skip, accumulate_skip=False, round_tf32=rb)
             g_out = g_state
         # ---- d_h0_lin ------------------------------------------------------------------------------------------------
         g_d0 = g_out                                       # [2B, flat], lrelu' applied
-        Wd0 = P["deconv/d_h0_lin/Matrix"]
+        Wd0 = Wb["deconv/d_h0_lin/Matrix"]
         self._gemm(True, False, F, flat, 2 * B, z2.data_ptr(), F, g_d0.data_ptr(), flat,
-                   G["deconv/d_h0_lin/Matrix"].data_ptr(), flat, accumulate=True, round_=False)
+                   G["deconv/d_h0_lin/Matrix"].data_ptr(), flat, accumulate=True, round_=False, bwd=True)
         ops.bias_grad(g_d0.view(2 * B, flat), G["deconv/d_h0_lin/bias"])
         g_z2 = self._buf("g_z2", (2 * B, F))
-        self._gemm(False, True, 2 * B, F, flat, g_d0.data_ptr(), flat, Wd0.data_ptr(), flat, g_z2.data_ptr(), F)
+        self._gemm(False, True, 2 * B, F, flat, g_d0.data_ptr(), flat, Wd0.data_ptr(), flat, g_z2.data_ptr(), F, bwd=True)
         if on_stage:
             on_stage("deconv")
         # ---- feature-alignment loss gradient (mean over the GLOBAL batch so DP ranks sum correctly) ---------------
@@ -361,34 +432,34 @@ class ContextNet:
         ops.lrelu_bwd(g_tz, z2[B:], out=g_tz)              # tgt_z = lrelu(hz_lin(.))
         # ---- translator -------------------------------------------------------------------------------------------------
         self._gemm(True, False, F, F, B, th0.data_ptr(), F, g_transz.data_ptr(), F,
-                   G["translate/trans_z/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+                   G["translate/trans_z/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
         ops.bias_grad(g_transz, G["translate/trans_z/bias"])
         g_th0 = self._buf("g_th0", (B, F))
-        self._gemm(False, True, B, F, F, g_transz.data_ptr(), F, P["translate/trans_z/Matrix"].data_ptr(), F,
-                   g_th0.data_ptr(), F, act_ref=th0.data_ptr())
+        self._gemm(False, True, B, F, F, g_transz.data_ptr(), F, Wb["translate/trans_z/Matrix"].data_ptr(), F,
+                   g_th0.data_ptr(), F, act_ref=th0.data_ptr(), bwd=True)
         self._gemm(True, False, 2 * F, F, B, cat.data_ptr(), 2 * F, g_th0.data_ptr(), F,
-                   G["translate/trans_h0/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+                   G["translate/trans_h0/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
         ops.bias_grad(g_th0, G["translate/trans_h0/bias"])
         g_cat = self._buf("g_cat", (B, 2 * F))
-        Wt0 = P["translate/trans_h0/Matrix"]               # [2F, F]
+        Wt0 = Wb["translate/trans_h0/Matrix"]               # [2F, F]
         # src half: masked by lrelu'(src_z); ctx half: masked only if the ctx hz_lin has an lrelu
         self._gemm(False, True, B, F, F, g_th0.data_ptr(), F, Wt0.data_ptr(), F, g_cat.data_ptr(), 2 * F,
-                   act_ref=cat.data_ptr())
+                   act_ref=cat.data_ptr(), bwd=True)
         self._gemm(False, True, B, F, F, g_th0.data_ptr(), F, Wt0.data_ptr() + F * F * f4, F,
                    g_cat.data_ptr() + F * f4, 2 * F,
-                   act_ref=(cat.data_ptr() + F * f4) if sp.ctx_hz_lrelu else None)
+                   act_ref=(cat.data_ptr() + F * f4) if sp.ctx_hz_lrelu else None, bwd=True)
         if on_stage:
             on_stage("translate")
         # ---- hz_lin of the three roles -> gradient w.r.t. h4 (lrelu' fused) -------------------------------------------
         def hz_backward(scope, g_ptr, ldg, h4_rows, gh4_rows):
             n = h4_rows.shape[0]
             self._gemm(True, False, F, F, n, h4_rows.data_ptr(), F, g_ptr, ldg,
-                       G[scope + "/hz_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+                       G[scope + "/hz_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
             check = _lib.check
             check(_lib.load().ctx_bias_grad(g_ptr, n, F, ldg, G[scope + "/hz_lin/bias"].data_ptr(), ops._stream()),
                   "ctx_bias_grad")
-            self._gemm(False, True, n, F, F, g_ptr, ldg, P[scope + "/hz_lin/Matrix"].data_ptr(), F,
-                       gh4_rows.data_ptr(), F, act_ref=h4_rows.data_ptr())
+            self._gemm(False, True, n, F, F, g_ptr, ldg, Wb[scope + "/hz_lin/Matrix"].data_ptr(), F,
+                       gh4_rows.data_ptr(), F, act_ref=h4_rows.data_ptr(), bwd=True)
 
         hz_backward("conv", g_cat.data_ptr(), 2 * F, e_h4[:B], ge_h4[:B])                     # src
         hz_backward("conv", g_tz.data_ptr(), F, e_h4[B:2 * B], ge_h4[B:2 * B])               # tgt
@@ -399,22 +470,29 @@ class ContextNet:
             """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate."""
             n = x.shape[0]
             self._gemm(True, False, flat, F, n, hs[3].data_ptr(), flat, g_h4.data_ptr(), F,
-                       G[scope + "/h4_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False)
+                       G[scope + "/h4_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
             ops.bias_grad(g_h4, G[scope + "/h4_lin/bias"])
             for (r0, nr, acc) in groups:
                 self._gemm(False, True, nr, flat, F, g_h4[r0:r0 + nr].data_ptr(), F,
-                           P[scope + "/h4_lin/Matrix"].data_ptr(), F, g_hs[3][r0:r0 + nr].data_ptr(), flat,
-                           act_ref=hs[3][r0:r0 + nr].data_ptr(), accumulate=acc)
+                           Wb[scope + "/h4_lin/Matrix"].data_ptr(), F, g_hs[3][r0:r0 + nr].data_ptr(), flat,
+                           act_ref=hs[3][r0:r0 + nr].data_ptr(), accumulate=acc, bwd=True)
             for j in (3, 2, 1, 0):
                 wname = "%s/h%d_conv/w" % (scope, j)
                 src = hs[j - 1] if j > 0 else x
-                ops.conv2d_wgrad(src, g_hs[j], sp.kernels[j], sp.strides[j], dw=G[wname], impl=self.impl)
+                kj, Cin = sp.kernels[j], src.shape[3]
+                if self._few(Cin, kj) and g_hs[j].shape[3] % 4 == 0:
+                    K = kj * kj * Cin
+                    pt = self._patches("patch_%s_h%d_%d" % (scope, j, n), src, kj, sp.strides[j])   # (forward's buffer)
+                    ops.gemm(pt[:, :K], g_hs[j].view(-1, g_hs[j].shape[3]), out=G[wname].view(K, -1), transA=True,
+                             accumulate=True, impl=self.impl_b)
+                else:
+                    ops.conv2d_wgrad(src, g_hs[j], kj, sp.strides[j], dw=G[wname], impl=self.impl_b)
                 ops.bias_grad(g_hs[j], G["%s/h%d_conv/biases" % (scope, j)])
                 if j > 0:
                     for (r0, nr, acc) in groups:
-                        ops.conv2d_transpose(g_hs[j][r0:r0 + nr], P[wname], self.sizes[j], stride=sp.strides[j],
+                        ops.conv2d_transpose(g_hs[j][r0:r0 + nr], Wb[wname], self.sizes[j], stride=sp.strides[j],
                                              out=g_hs[j - 1][r0:r0 + nr], act_ref=hs[j - 1][r0:r0 + nr],
-                                             accumulate=acc, round_tf32=self.round, impl=self.impl)
+                                             accumulate=acc, round_tf32=self.round_b, impl=self.impl_b)
 
         if sp.separate_ctx_encoder:
             encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False)])
@@ -435,7 +513,7 @@ class ContextNet:
         self.step_count += 1
         t = self.step_count
         lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
-        ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr_t, b1, b2, eps)
+        ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr_t, b1, b2, eps, p_tf32=self.flat_pr)
 
     def attach_allreduce(self, group=None):
         """Data parallelism: after this, every optimiser step sum-all-reduces the flat gradient (bucketed, launched

@@ -236,11 +236,11 @@ def mse_scaled_fwd_bwd(a, b, scale, inv_count, loss=None, da=None, db=None, grad
 
 
 def split_skip_grad(dcat, G, B, C1, C2, dstate, dskip, state_ref=None, skip_ref=None, accumulate_skip=False,
-                    slope=LRELU_SLOPE):
+                    slope=LRELU_SLOPE, round_tf32=False):
     pix = dcat.numel() // (G * B * (C1 + C2))
     check(_lib.load().ctx_split_skip_grad(_req(dcat, "dcat"), G, B, pix, C1, C2, _opt(state_ref, "state_ref"),
                                           _opt(skip_ref, "skip_ref"), slope, _req(dstate, "dstate"),
-                                          _req(dskip, "dskip"), int(accumulate_skip), _stream()),
+                                          _req(dskip, "dskip"), int(accumulate_skip), int(round_tf32), _stream()),
           "ctx_split_skip_grad")
 
 
@@ -253,9 +253,20 @@ def add_bcast(a, b, out=None):
     return out
 
 
-def adam_step(p, g, m, v, lr_t, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+def im2col(x, k: int, stride: int, ld: int, out=None, round_tf32=False):
+    """Patch matrix [N*P*Q, ld] of a SAME conv over a few-channel NHWC tensor (columns (r,s,c), zero padded)."""
+    N, H, W_, Cc = x.shape
+    g = conv_geom(N, (H, W_), k, stride)
+    if out is None:
+        out = torch.empty((N * g.P * g.Q, ld), device=x.device, dtype=torch.float32)
+    check(_lib.load().ctx_im2col(_req(x, "x"), Cc, _req(out, "out"), ld, C.byref(g), int(round_tf32), _stream()),
+          "ctx_im2col")
+    return out
+
+
+def adam_step(p, g, m, v, lr_t, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, p_tf32=None):
     check(_lib.load().ctx_adam_step(_req(p, "p"), _req(g, "g"), _req(m, "m"), _req(v, "v"), p.numel(), lr_t, b1, b2,
-                                    eps, grad_scale, _stream()), "ctx_adam_step")
+                                    eps, grad_scale, _opt(p_tf32, "p_tf32"), _stream()), "ctx_adam_step")
 
 
 def round_tf32(x, out=None):

@@ -148,20 +148,32 @@ int ctx_mse_scaled_fwd_bwd(const float* a, int32_t lda, const float* b, int32_t 
 /* Split the data-gradient of a decoder level, dcat [G*B, pix, C1+C2], into
  *   dstate[G*B, pix, C1] = dcat[..., :C1] * lrelu'(state_ref)           (state_ref may be NULL: no mask)
  *   dskip [B,   pix, C2] (+)= (sum_g dcat[g*B+b, pix, C1:]) * lrelu'(skip_ref)
- * — the gradient of tf.concat([h, skip], 3) (arm_shaping.py:1323-1329) with the skip shared by G passes. */
+ * — the gradient of tf.concat([h, skip], 3) (arm_shaping.py:1323-1329) with the skip shared by G passes.
+ * round_tf32: round both outputs to the nearest TF32 (they are the next tensor-core operands). */
 int ctx_split_skip_grad(const float* dcat, int32_t G, int64_t B, int64_t pix, int32_t C1, int32_t C2,
                         const float* state_ref, const float* skip_ref, float slope,
-                        float* dstate, float* dskip, int32_t accumulate_skip, void* stream);
+                        float* dstate, float* dskip, int32_t accumulate_skip, int32_t round_tf32, void* stream);
 
 /* out[rows, C] = a[rows, C] + b[rows % b_rows, C]   (residual output of ContextAEInception2). */
 int ctx_add_bcast(const float* a, const float* b, float* out, int64_t rows, int64_t b_rows, int64_t C,
                   void* stream);
 
+/* Patch matrix of a SAME conv over a FEW-channel NHWC tensor (the 3-channel image side of the first encoder conv and
+ * the last decoder layer, arm_shaping.py:1283,1329), so those layers run as dense tensor-core GEMMs (K = kh*kw*C):
+ *   out[(n,p,q), (r*kw+s)*C + c] = x[n, p*st+r-pad_h, q*st+s-pad_w, c];  0 outside the image and in columns
+ *   kh*kw*C .. ld-1.   out is [N*P*Q, ld], ld >= kh*kw*C (ld % 4 == 0 for the tensor-core GEMM).
+ * round_tf32: round the gathered values to the nearest TF32 (operand of a single-pass tensor-core GEMM).
+ * (TMA cannot gather a 12-byte pixel; every layer with >= 32 channels stays im2col-free.) */
+int ctx_im2col(const float* x, int32_t C, float* out, int32_t ld, const ctx_conv_geom* g, int32_t round_tf32,
+               void* stream);
+
 /* TF-style Adam on flat buffers (scripts/train_script.py:128; epsilon outside the bias correction):
  *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr_t * m / (sqrt(v) + eps)
- * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  grad_scale multiplies g first (1.0 normally). */
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  grad_scale multiplies g first (1.0 normally).
+ * p_tf32 (optional, may be NULL): receives round_to_nearest_tf32(p) — the shadow copy the single-pass tensor-core
+ * GEMMs read, so that the hardware's operand truncation cannot bias them. */
 int ctx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
-                  float eps, float grad_scale, void* stream);
+                  float eps, float grad_scale, float* p_tf32, void* stream);
 
 /* y = round_to_nearest_tf32(x) (keeps fp32 storage) — operand preparation for the tcgen05 path. */
 int ctx_round_tf32(const float* x, float* y, int64_t n, void* stream);

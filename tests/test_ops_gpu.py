@@ -75,6 +75,61 @@ def test_conv2d_transpose_dual_source(N, P, Q, H, W, C1, C2, NB, Cn, k, st, impl
     assert rel_err(y.cpu(), ref) < tol
 
 
+# few output channels (the image side): one GEMM over (tap, channel) columns + scatter-add epilogue on the tcgen05 path
+@pytest.mark.parametrize("N,P,Q,H,W,C1,C2,NB,Cn,k,st,expect_tc", [
+    (2, 32, 32, 64, 64, 64, 64, 2, 3, 5, 2, True), (4, 16, 16, 32, 32, 32, 0, 0, 3, 5, 2, True),
+    (2, 8, 8, 8, 8, 64, 64, 2, 8, 3, 1, True), (3, 4, 4, 8, 8, 32, 32, 3, 5, 5, 2, False),
+    (2, 24, 24, 48, 48, 64, 64, 2, 3, 5, 2, False)])
+@pytest.mark.parametrize("impl,tol", [(IMPL_AUTO, FP32_TOL), (IMPL_FAST, TF32_TOL)])
+def test_conv2d_transpose_few_channels(N, P, Q, H, W, C1, C2, NB, Cn, k, st, expect_tc, impl, tol):
+    x1 = rnd((N, P, Q, C1), 40)
+    x2 = rnd((NB, P, Q, C2), 41) if C2 else None
+    w = rnd((k, k, Cn, C1 + C2), 42, (k * k * (C1 + C2) / st ** 2) ** -0.5)
+    b = rnd((Cn,), 43, 0.1)
+    cat = x1 if x2 is None else torch.cat([x1, x2.repeat((N // NB, 1, 1, 1))], 3)
+    ref = O.conv2d_transpose(cat.double(), w.double(), b.double(), (H, W), st)
+    y = ops.conv2d_transpose(x1.cuda(), w.cuda(), (H, W), bias=b.cuda(), stride=st,
+                             x2=None if x2 is None else x2.cuda(), act=False, impl=impl)
+    used = int(_lib.load().ctx_last_impl())
+    assert rel_err(y.cpu(), ref) < tol
+    if expect_tc and ops.tc_available():
+        assert used != IMPL_SIMT, "the few-channel transposed conv should take the tcgen05 scatter path"
+    prev = rnd((N, H, W, Cn), 44)
+    out = prev.clone().cuda()
+    ops.conv2d_transpose(x1.cuda(), w.cuda(), (H, W), bias=b.cuda(), stride=st,
+                         x2=None if x2 is None else x2.cuda(), act=False, out=out, accumulate=True, impl=impl)
+    assert rel_err(out.cpu(), ref + prev.double()) < tol
+
+
+@pytest.mark.parametrize("N,H,W,C,k,st,ld", [(2, 64, 64, 3, 5, 2, 76), (3, 7, 9, 5, 3, 2, 48), (2, 36, 64, 3, 5, 1, 80),
+                                             (1, 6, 6, 8, 3, 1, 72)])
+def test_im2col_bit_exact_and_gemm_equals_conv(N, H, W, C, k, st, ld):
+    x = rnd((N, H, W, C), 45)
+    pt = ops.im2col(x.cuda(), k, st, ld).cpu()
+    Pn, Qn = -(-H // st), -(-W // st)
+    lo_h, lo_w = O._same(H, k, st)[1], O._same(W, k, st)[1]
+    ref = torch.zeros((N, Pn, Qn, ld))
+    xp = torch.zeros((N, H + 2 * k, W + 2 * k, C))
+    xp[:, k:k + H, k:k + W] = x
+    for r in range(k):
+        for s_ in range(k):
+            h0, w0 = k + r - lo_h, k + s_ - lo_w
+            ref[..., (r * k + s_) * C:(r * k + s_ + 1) * C] = xp[:, h0:h0 + Pn * st:st, w0:w0 + Qn * st:st][:, :Pn, :Qn]
+    assert torch.equal(pt, ref.view(-1, ld))                   # a gather: bit-exact
+    # the few-channel conv as a dense GEMM over the patch matrix (K = k*k*C need not be a multiple of 4 or 32)
+    Co, K = 64, k * k * C
+    w, b = rnd((k, k, C, Co), 46, K ** -0.5), rnd((Co,), 47, 0.1)
+    refc = O.lrelu(O.conv2d(x.double(), w.double(), b.double(), st))
+    for impl, tol in _impls():
+        y = ops.gemm(pt.cuda()[:, :K], w.cuda().view(K, Co), bias=b.cuda(), act=True, impl=impl)
+        assert rel_err(y.cpu().view(refc.shape), refc) < tol
+        # ... and its filter gradient: patches^T @ dy (M = K rows, not a multiple of 32)
+        dy = rnd((N * Pn * Qn, Co), 48)
+        dw = torch.zeros((K, Co), device="cuda")
+        ops.gemm(pt.cuda()[:, :K], dy.cuda(), out=dw, transA=True, accumulate=True, impl=impl)
+        assert rel_err(dw.cpu(), pt[:, :K].double().t() @ dy.double()) < tol
+
+
 @pytest.mark.parametrize("impl,tol", _impls())
 def test_conv2d_transpose_backward_epilogue(impl, tol):
     """dgrad with fused lrelu' mask and accumulation (what the encoder backward uses)."""
@@ -210,6 +265,23 @@ def test_split_skip_grad():
     assert rel_err(ds.cpu(), dcat[..., :C1] * torch.where(sref >= 0, 1.0, 0.2)) < 1e-6
     ksum = dcat[..., C1:].view(G, B, pix, C2).sum(0)
     assert rel_err(dk.cpu(), prev + ksum * torch.where(kref >= 0, 1.0, 0.2)) < 1e-6
+
+
+def test_split_skip_grad_vectorised_and_rounded():
+    G, B, pix, C1, C2 = 2, 4, 64, 64, 32
+    dcat = rnd((G * B, pix, C1 + C2), 52)
+    sref, kref = rnd((G * B, pix, C1), 53), rnd((B, pix, C2), 54)
+    for rnd_flag in (False, True):
+        ds = torch.empty((G * B, pix, C1)).cuda()
+        dk = torch.empty((B, pix, C2)).cuda()
+        ops.split_skip_grad(dcat.cuda(), G, B, C1, C2, ds, dk, state_ref=sref.cuda(), skip_ref=kref.cuda(),
+                            round_tf32=rnd_flag)
+        tol = 6e-4 if rnd_flag else 1e-6
+        assert rel_err(ds.cpu(), dcat[..., :C1] * torch.where(sref >= 0, 1.0, 0.2)) < tol
+        ksum = dcat[..., C1:].view(G, B, pix, C2).sum(0)
+        assert rel_err(dk.cpu(), ksum * torch.where(kref >= 0, 1.0, 0.2)) < tol
+        if rnd_flag:                                             # low 13 mantissa bits are zero after rounding
+            assert int((ds.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
 def test_adam_step_matches_tf_formula():

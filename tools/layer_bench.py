@@ -1,0 +1,134 @@
+"""Per-layer timing of the GEMM-shaped ops of the bench workload (ContextSkipNew 64x64x3, B triples), each op in
+isolation: CUDA events around `reps` back-to-back launches after warm-up.  Prints TFLOP/s (algorithmic flops).
+
+    python tools/layer_bench.py [--batch 256] [--impl x3,x1] [--only fprop,transpose,wgrad,gemm] [--reps 10]
+    python tools/layer_bench.py --one fprop:h2 --impl x3 --reps 3      # a short ncu target
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from imitation_from_observation_b200 import ops                                   # noqa: E402
+from imitation_from_observation_b200._lib import IMPL_AUTO, IMPL_FAST, IMPL_SIMT  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--impl", default="x3,x1")
+ap.add_argument("--only", default="")
+ap.add_argument("--one", default="")
+ap.add_argument("--reps", type=int, default=10)
+a = ap.parse_args()
+B = a.batch
+dev = "cuda"
+IMPLS = {"x3": IMPL_AUTO, "x1": IMPL_FAST, "simt": IMPL_SIMT}
+
+
+def rnd(*shape):
+    return torch.randn(shape, device=dev) * 0.1
+
+
+cases = []   # (kind, name, flops, fn(impl))
+
+
+def add_fprop(name, N, H, C, Co, k=5, st=2):
+    x, w, b = rnd(N, H, H, C), rnd(k, k, C, Co), rnd(Co)
+    P = -(-H // st)
+    y = torch.empty((N, P, P, Co), device=dev)
+    cases.append(("fprop", name, 2.0 * N * P * P * Co * k * k * C,
+                  lambda impl: ops.conv2d(x, w, b, stride=st, act=True, out=y, impl=impl)))
+
+
+def add_trans(name, N, P, C1, C2, NB, Cn, k=5, st=2):
+    x1 = rnd(N, P, P, C1)
+    x2 = rnd(NB, P, P, C2) if C2 else None
+    w, b = rnd(k, k, Cn, C1 + C2), rnd(Cn)
+    y = torch.empty((N, P * st, P * st, Cn), device=dev)
+    cases.append(("transpose", name, 2.0 * N * P * P * Cn * k * k * (C1 + C2),
+                  lambda impl: ops.conv2d_transpose(x1, w, (P * st, P * st), bias=b, stride=st, x2=x2, act=True, out=y,
+                                                    impl=impl)))
+
+
+def add_wgrad(name, N, H, Ca, Cb1, Cb2, NB, k=5, st=2):
+    P = -(-H // st)
+    big, s1 = rnd(N, H, H, Ca), rnd(N, P, P, Cb1)
+    s2 = rnd(NB, P, P, Cb2) if Cb2 else None
+    dw = torch.zeros((k, k, Ca, Cb1 + Cb2), device=dev)
+    cases.append(("wgrad", name, 2.0 * N * P * P * (Cb1 + Cb2) * k * k * Ca,
+                  lambda impl: ops.conv2d_wgrad(big, s1, k, st, small2=s2, dw=dw, impl=impl)))
+
+
+def add_gemm(name, M, N, K, tA=False, tB=False, bias=True, accumulate=False):
+    A = rnd(*((K, M) if tA else (M, K)))
+    Bm = rnd(*((N, K) if tB else (K, N)))
+    bv = rnd(N) if bias else None
+    Cm = torch.zeros((M, N), device=dev)
+    cases.append(("gemm", name, 2.0 * M * N * K,
+                  lambda impl: ops.gemm(A, Bm, out=Cm, transA=tA, transB=tB, bias=bv, act=bias, accumulate=accumulate,
+                                        impl=impl)))
+
+
+E = 2 * B   # images through scope "conv" (src, tgt); ctx encoder has B
+D = 2 * B   # decoder passes
+# forward
+add_fprop("h0 (3->64 @64)", E, 64, 3, 64)
+add_fprop("h1", E, 32, 64, 128)
+add_fprop("h2", E, 16, 128, 256)
+add_fprop("h3", E, 8, 256, 512)
+add_gemm("h4_lin", E, 1024, 8192)
+add_gemm("hz_lin", B, 1024, 1024)
+add_gemm("d_h0_lin", D, 8192, 1024)
+add_trans("d_h1", D, 4, 512, 512, B, 256)
+add_trans("d_h2", D, 8, 256, 256, B, 128)
+add_trans("d_h3", D, 16, 128, 128, B, 64)
+add_trans("d_h4 (128->3 @64)", D, 32, 64, 64, B, 3)
+# backward: decoder
+add_wgrad("d_h4.wgrad (3 x 128)", D, 64, 3, 64, 64, B)
+add_fprop("d_h4.dgrad (3->128)", D, 64, 3, 128)
+add_wgrad("d_h3.wgrad", D, 32, 64, 128, 128, B)
+add_fprop("d_h3.dgrad", D, 32, 64, 256)
+add_wgrad("d_h2.wgrad", D, 16, 128, 256, 256, B)
+add_fprop("d_h2.dgrad", D, 16, 128, 512)
+add_wgrad("d_h1.wgrad", D, 8, 256, 512, 512, B)
+add_fprop("d_h1.dgrad", D, 8, 256, 1024)
+add_gemm("d_h0_lin.wgrad", 1024, 8192, D, tA=True, bias=False, accumulate=True)
+add_gemm("d_h0_lin.dgrad", D, 1024, 8192, tB=True, bias=False)
+# backward: encoder
+add_gemm("h4_lin.wgrad", 8192, 1024, E, tA=True, bias=False, accumulate=True)
+add_gemm("h4_lin.dgrad", E, 8192, 1024, tB=True, bias=False)
+add_wgrad("h3.wgrad", E, 8, 256, 512, 0, 0)
+add_trans("h3.dgrad", E, 4, 512, 0, 0, 256)
+add_wgrad("h2.wgrad", E, 16, 128, 256, 0, 0)
+add_trans("h2.dgrad", E, 8, 256, 0, 0, 128)
+add_wgrad("h1.wgrad", E, 32, 64, 128, 0, 0)
+add_trans("h1.dgrad", E, 16, 128, 0, 0, 64)
+add_wgrad("h0.wgrad (3 x 64)", E, 64, 3, 64, 0, 0)
+
+only = set(x for x in a.only.split(",") if x)
+tot = {}
+for kind, name, flops, fn in cases:
+    if only and kind not in only:
+        continue
+    if a.one and a.one != "%s:%s" % (kind, name.split(" ")[0]):
+        continue
+    line = "%-10s %-22s %8.2f GF " % (kind, name, flops / 1e9)
+    for tag in a.impl.split(","):
+        impl = IMPLS[tag]
+        for _ in range(2):
+            fn(impl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.reps):
+            fn(impl)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.reps
+        used = {1: "simt", 2: "tc1", 3: "tc3"}.get(int(ops._lib.load().ctx_last_impl()), "?")
+        tot[tag] = tot.get(tag, 0.0) + ms
+        line += "| %s(%s) %8.1f us %7.1f TF/s " % (tag, used, ms * 1e3, flops / ms / 1e9)
+    print(line, flush=True)
+print("total ms: " + ", ".join("%s %.2f" % kv for kv in tot.items()))

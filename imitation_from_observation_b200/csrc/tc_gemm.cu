@@ -27,6 +27,7 @@
 #include <unordered_map>
 #include <string>
 #include <string.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace ctx {
@@ -78,6 +79,10 @@ struct TcParams {
   int32_t N;                       // valid cols of D
   // B_MN second source (wgrad over [small1 ‖ small2])
   int32_t Cb1;                     // columns < Cb1 come from mapB[0], the rest from mapB[1] (pixel rows wrapped)
+  // MN-major operands: 32-column atoms fetched per TMA instruction.  One instruction costs the TMA unit a few hundred
+  // cycles whatever its size, so the atoms of a tile are fetched together through a rank+1 tensor map whose
+  // outermost dimension walks the atoms (b_atoms0 / b_atoms1 for the two B sources; 0 = one instruction per atom).
+  int32_t a_atoms, b_atoms0, b_atoms1;
   // output
   float* out;
   int64_t sN, sP, sQ, obase;       // element strides of D rows over (n, p, q)
@@ -137,6 +142,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -289,6 +307,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
               tma_load_4d(sa, &p.mapA[s.mapA], full_bar(stage), cb * 32, s.dw, p0 + s.dh, nimg);
               if (p.b_mode == B_K) {
                 tma_load_2d(sb, &p.mapB[0], full_bar(stage), s.bk0 + cb * 32, s.br0 + ncol0);
+              } else if (p.b_atoms0 > 0) {
+                tma_load_3d(sb, &p.mapB[0], full_bar(stage), 0, s.bk0 + cb * 32, ncol0 >> 5);
               } else {
                 for (int a = 0; a < p.BN / 32; ++a)
                   tma_load_2d(sb + a * 4096, &p.mapB[0], full_bar(stage), ncol0 + a * 32, s.bk0 + cb * 32);
@@ -309,21 +329,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             int natomA = 0;
             for (int j = 0; j < 4; ++j) natomA += (m0 + 32 * j < p.M) ? 1 : 0;
             mbar_arrive_expect_tx(full_bar(stage), (uint32_t)natomA * 4096u + b_tile_bytes);
-            for (int j = 0; j < 4; ++j) {
+            const int astep = p.a_atoms > 1 ? p.a_atoms : 1;
+            for (int j = 0; j < 4; j += astep) {
               const int m = m0 + 32 * j;
               if (m >= p.M) break;
               const int tap = m / p.Ca, a0 = m - tap * p.Ca;
               const Seg s = p.seg[tap];
-              tma_load_4d(sa + j * 4096, &p.mapA[s.mapA], full_bar(stage), a0, s.dw, kp0 + s.dh, kn0);
+              if (p.a_atoms > 1)
+                tma_load_5d(sa + j * 4096, &p.mapA[s.mapA], full_bar(stage), 0, s.dw, kp0 + s.dh, kn0, a0 >> 5);
+              else
+                tma_load_4d(sa + j * 4096, &p.mapA[s.mapA], full_bar(stage), a0, s.dw, kp0 + s.dh, kn0);
             }
             const int prow = (kn0 * p.kPG + kp0) * p.kQG;               // first pixel row of this K block
-            for (int a = 0; a < p.BN / 32; ++a) {
-              const int n = ncol0 + a * 32;
-              if (n < p.Cb1 || p.N <= p.Cb1) {       // (columns past N are zero-filled by the TMA unit)
-                tma_load_2d(sb + a * 4096, &p.mapB[0], full_bar(stage), n, prow);
+            const int prow2 = ((kn0 % p.a_wrap) * p.kPG + kp0) * p.kQG;
+            if (p.b_atoms0 > 0) {
+              if (ncol0 < p.Cb1 || p.N <= p.Cb1) {
+                tma_load_3d(sb, &p.mapB[0], full_bar(stage), 0, prow, ncol0 >> 5);
+                if (p.b_atoms1 > 0 && ncol0 + 32 * p.b_atoms0 < ncol0 + p.BN && p.N > p.Cb1)
+                  tma_load_3d(sb + p.b_atoms0 * 4096, &p.mapB[1], full_bar(stage), 0, prow2, 0);
               } else {
-                const int prow2 = ((kn0 % p.a_wrap) * p.kPG + kp0) * p.kQG;
-                tma_load_2d(sb + a * 4096, &p.mapB[1], full_bar(stage), n - p.Cb1, prow2);
+                tma_load_3d(sb, &p.mapB[1], full_bar(stage), 0, prow2, (ncol0 - p.Cb1) >> 5);
+              }
+            } else {
+              for (int a = 0; a < p.BN / 32; ++a) {
+                const int n = ncol0 + a * 32;
+                if (n < p.Cb1 || p.N <= p.Cb1) {       // (columns past N are zero-filled by the TMA unit)
+                  tma_load_2d(sb + a * 4096, &p.mapB[0], full_bar(stage), n, prow);
+                } else {
+                  tma_load_2d(sb + a * 4096, &p.mapB[1], full_bar(stage), n - p.Cb1, prow2);
+                }
               }
             }
             if (++stage == R) { stage = 0; phase ^= 1; }
@@ -544,15 +578,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// fp32 tensor map, rank <= 4, zero fill; 128-byte swizzle of 16-byte chunks (K-major operand tiles) or of
+// fp32 tensor map, rank <= 5, zero fill; 128-byte swizzle of 16-byte chunks (K-major operand tiles) or of
 // 32-byte chunks (mn_major: the only layout tcgen05 accepts for MN-major 32-bit operands).  dims/box innermost first; strides in ELEMENTS for
 // dims 1..rank-1.
 static int make_map(CUtensorMap* out, const float* base, int rank, const int64_t* dims, const int64_t* strides,
                     const int* box, bool mn_major = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return CTX_ERR_CUDA; }
-  cuuint64_t gd[4], gs[3];
-  cuuint32_t bx[4], es[4];
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
     gd[i] = (cuuint64_t)dims[i];
     bx[i] = (cuuint32_t)box[i];
@@ -593,8 +627,28 @@ static bool tile_grid(int P, int Q, int rows, int* BP, int* NB, int* tiles_per_i
 
 // N tile: 128 for the 3-pass mode (with a 5-deep raw ring it is the best-balanced 1-CTA shape: tensor 768, splitter
 // ~512, TMA ~42 B/cycle per k-block), 256 for single-pass; halved while the grid would not fill the SMs.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+// experiment knobs (environment, read once): CTX_TC_BN3 = N tile of the 3-pass mode, CTX_TC_OCC = CTAs per SM the
+// shared-memory ring is sized for
+static int knob_bn3() { static int v = env_int("CTX_TC_BN3", 128); return v; }
+static int knob_occ() { static int v = env_int("CTX_TC_OCC", 0); return v; }
+
+// CTAs per SM the operand ring is sized for.  Two co-resident CTAs overlap each other's prologue / epilogue /
+// pipeline-fill bubbles and double the TMA instructions in flight: measured +30..70 % for single-pass tiles
+// (profiles/r1_layer_bench_*.txt).  The 3-pass mode is bound by shared-memory bandwidth at BN = 128 and needs its
+// two-slot lo ring, so it keeps one CTA per SM except for narrow (BN <= 64) or very short (<= 8 k-blocks) tiles.
+static int tc_occupancy(int passes, int BN, int kblocks) {
+  const int k = knob_occ();
+  if (k == 1 || k == 2) return k;
+  if (passes != 3) return 2;
+  return (BN <= 64 || kblocks <= 8) ? 2 : 1;
+}
+
 static int pick_bn(int N, int64_t m_tiles, int passes) {
-  int bn = passes == 3 ? 128 : 256;
+  int bn = passes == 3 ? knob_bn3() : 256;
   const int sms = sm_count();
   while (bn > 64 && (N <= bn / 2 || m_tiles * cdiv(N, bn) < sms)) bn /= 2;
   return bn;
@@ -615,8 +669,10 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
     CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     max_dyn = dyn;
   }
-  const int slots = (int)(((uint32_t)max_dyn - 1024u) / raw);          // 1024: alignment slack
-  p.lo_slots = p.passes == 3 ? 2 : 0;
+  const int occ = tc_occupancy(p.passes, p.BN, p.nphase > 1 ? p.ph_kblocks[0] : p.kblocks_per_split);
+  const uint32_t budget = occ == 1 ? (uint32_t)max_dyn : (uint32_t)(max_dyn - 2048) / 2u;
+  const int slots = (int)((budget - 1024u) / raw);          // 1024: alignment slack
+  p.lo_slots = p.passes == 3 ? (slots >= 4 ? 2 : 1) : 0;
   p.raw_slots = slots - p.lo_slots;
   if (p.raw_slots > 8) p.raw_slots = 8;
   if (p.raw_slots < 2) { set_error("%s: tile does not fit shared memory", name); return CTX_ERR_ARG; }
@@ -654,23 +710,36 @@ int tc_conv2d_fprop_eligible(int C, int Co, const ctx_conv_geom& g) {
 // Tensor maps of a (possibly stride-2) NHWC tensor read at conv-tap offsets.  For stride 2, map[hp*2+wp] is the
 // parity view x[n, 2*h2+hp, 2*w2+wp, c]; a tap r (relative to the output pixel: r' = r - pad) reads parity
 // hp = r' & 1 at row offset (r' - hp) / 2.
+// atoms > 1 (MN-major only, C % 32 == 0): rank-5 maps whose outermost dimension walks the 32-channel atoms, so one
+// TMA instruction fetches `atoms` consecutive atoms (coordinates {0, w, h, n, channel / 32}).
 static int make_tap_maps(CUtensorMap* maps, const float* x, int C, int N, int H, int W, int stride, int box_q,
-                         int box_p, int box_n, bool mn_major) {
+                         int box_p, int box_n, bool mn_major, int atoms = 1) {
+  const int rank = atoms > 1 ? 5 : 4;
+  const int c0 = atoms > 1 ? 32 : C;
   if (stride == 1) {
-    int64_t dims[4] = {C, W, H, N}, str[4] = {1, C, (int64_t)W * C, (int64_t)H * W * C};
-    int box[4] = {32, box_q, box_p, box_n};
-    return make_map(&maps[0], x, 4, dims, str, box, mn_major);
+    int64_t dims[5] = {c0, W, H, N, C / 32}, str[5] = {1, C, (int64_t)W * C, (int64_t)H * W * C, 32};
+    int box[5] = {32, box_q, box_p, box_n, atoms};
+    return make_map(&maps[0], x, rank, dims, str, box, mn_major);
   }
   for (int hp = 0; hp < 2; ++hp)
     for (int wp = 0; wp < 2; ++wp) {
       const int Hh = (H - hp + 1) / 2, Wh = (W - wp + 1) / 2;
       if (Hh <= 0 || Wh <= 0) { memset(&maps[hp * 2 + wp], 0, sizeof(CUtensorMap)); continue; }
-      int64_t dims[4] = {C, Wh, Hh, N}, str[4] = {1, 2 * (int64_t)C, 2 * (int64_t)W * C, (int64_t)H * W * C};
-      int box[4] = {32, box_q, box_p, box_n};
-      int rc = make_map(&maps[hp * 2 + wp], x + ((int64_t)hp * W + wp) * C, 4, dims, str, box, mn_major);
+      int64_t dims[5] = {c0, Wh, Hh, N, C / 32};
+      int64_t str[5] = {1, 2 * (int64_t)C, 2 * (int64_t)W * C, (int64_t)H * W * C, 32};
+      int box[5] = {32, box_q, box_p, box_n, atoms};
+      int rc = make_map(&maps[hp * 2 + wp], x + ((int64_t)hp * W + wp) * C, rank, dims, str, box, mn_major);
       if (rc) return rc;
     }
   return CTX_OK;
+}
+
+// MN-major B operand [K rows, N columns] (row stride ld): all BN/32 atoms of a tile in ONE instruction through a
+// rank-3 map {32, K, N/32} (coordinates {0, k, column / 32}); needs N % 32 == 0.
+static int make_bmn_map(CUtensorMap* map, const float* B, int64_t K, int N, int64_t ld, int atoms) {
+  int64_t dims[3] = {32, K, N / 32}, str[3] = {1, ld, 32};
+  int box[3] = {32, 32, atoms};
+  return make_map(map, B, 3, dims, str, box, true);
 }
 
 static void tap_seg(Seg& s, int r, int sx, const ctx_conv_geom& g) {
@@ -697,12 +766,9 @@ int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, con
   p.M = g.N * g.P * g.Q; p.N = Co;
   int rc = make_tap_maps(p.mapA, x, C, g.N, g.H, g.W, g.stride, g.Q, p.BP, p.NB, false);
   if (rc) return rc;
-  {
-    int64_t dims[2] = {Co, (int64_t)g.kh * g.kw * C}, str[2] = {1, Co};
-    int box[2] = {32, 32};
-    rc = make_map(&p.mapB[0], w, 2, dims, str, box, true);
-    if (rc) return rc;
-  }
+  p.b_atoms0 = p.BN / 32;                              // (Co % 32 == 0 is an eligibility condition)
+  rc = make_bmn_map(&p.mapB[0], w, (int64_t)g.kh * g.kw * C, Co, Co, p.b_atoms0);
+  if (rc) return rc;
   p.nseg = g.kh * g.kw;
   for (int r = 0; r < g.kh; ++r)
     for (int s = 0; s < g.kw; ++s) {
@@ -922,11 +988,10 @@ int tc_conv2d_wgrad_eligible(int Ca, int Cb1, int Cb2, int s2_batch, const ctx_c
   return 1;
 }
 
-// Split-K factor: one CTA per SM is resident (the operand ring takes the whole shared memory), so the launch runs in
-// waves of sm_count CTAs.  Choose the split that minimises  waves x (k-blocks per CTA + fixed cost per CTA), the
+// Split-K factor: one or two CTAs per SM are resident (tc_occupancy), so the launch runs in waves of that many CTAs.  Choose the split that minimises  waves x (k-blocks per CTA + fixed cost per CTA), the
 // fixed cost (prologue, TMEM allocation, atomic epilogue) being worth about `ovh` k-blocks.
-static int pick_splits(int tiles, int kblocks, int min_per_split) {
-  const int sms = sm_count();
+static int pick_splits(int tiles, int kblocks, int min_per_split, int passes, int BN) {
+  const int sms = sm_count() * tc_occupancy(passes, BN, kblocks);
   int maxs = kblocks / min_per_split;
   if (maxs < 1) maxs = 1;
   if (maxs > 4 * sms) maxs = 4 * sms;
@@ -958,19 +1023,34 @@ int tc_conv2d_wgrad(const float* big, int Ca, const float* s1, int Cb1, const fl
   p.kPG = g.P; p.kQG = g.Q;
   p.Ca = Ca; p.M = g.kh * g.kw * Ca; p.N = N;
   p.Cb1 = Cb1; p.a_wrap = s2_batch > 0 ? s2_batch : 1;
-  int rc = make_tap_maps(p.mapA, big, Ca, g.N, g.H, g.W, g.stride, g.Q, p.kBP, p.kNB, true);
+  // atoms of an M tile that share a filter tap are consecutive 32-channel blocks: fetch them together
+  p.a_atoms = (Ca % 128 == 0) ? 4 : (Ca % 64 == 0) ? 2 : 1;
+  int rc = make_tap_maps(p.mapA, big, Ca, g.N, g.H, g.W, g.stride, g.Q, p.kBP, p.kNB, true, p.a_atoms);
   if (rc) return rc;
-  {
-    int64_t dims[2] = {Cb1, (int64_t)g.N * g.P * g.Q}, str[2] = {1, Cb1};
-    int box[2] = {32, 32};
-    rc = make_map(&p.mapB[0], s1, 2, dims, str, box, true);
+  // B tile atoms: all from one source (tile inside small1 or inside small2), or the single tile [small1 ‖ small2]
+  if (Cb2 == 0 || (Cb1 % p.BN == 0 && Cb2 % p.BN == 0)) { p.b_atoms0 = p.BN / 32; p.b_atoms1 = Cb2 > 0 ? p.BN / 32 : 0; }
+  else if (Cb1 + Cb2 <= p.BN) { p.b_atoms0 = Cb1 / 32; p.b_atoms1 = (p.BN - Cb1) / 32; }
+  else { p.b_atoms0 = p.b_atoms1 = 0; }
+  if (p.b_atoms0 > 0) {
+    rc = make_bmn_map(&p.mapB[0], s1, (int64_t)g.N * g.P * g.Q, Cb1, Cb1, p.b_atoms0);
     if (rc) return rc;
-  }
-  if (Cb2 > 0) {
-    int64_t dims[2] = {Cb2, (int64_t)s2_batch * g.P * g.Q}, str[2] = {1, Cb2};
-    int box[2] = {32, 32};
-    rc = make_map(&p.mapB[1], s2, 2, dims, str, box, true);
-    if (rc) return rc;
+    if (Cb2 > 0) {
+      rc = make_bmn_map(&p.mapB[1], s2, (int64_t)s2_batch * g.P * g.Q, Cb2, Cb2, p.b_atoms1);
+      if (rc) return rc;
+    }
+  } else {
+    {
+      int64_t dims[2] = {Cb1, (int64_t)g.N * g.P * g.Q}, str[2] = {1, Cb1};
+      int box[2] = {32, 32};
+      rc = make_map(&p.mapB[0], s1, 2, dims, str, box, true);
+      if (rc) return rc;
+    }
+    if (Cb2 > 0) {
+      int64_t dims[2] = {Cb2, (int64_t)s2_batch * g.P * g.Q}, str[2] = {1, Cb2};
+      int box[2] = {32, 32};
+      rc = make_map(&p.mapB[1], s2, 2, dims, str, box, true);
+      if (rc) return rc;
+    }
   }
   p.nseg = g.kh * g.kw;
   for (int r = 0; r < g.kh; ++r)
@@ -979,7 +1059,7 @@ int tc_conv2d_wgrad(const float* big, int Ca, const float* s1, int Cb1, const fl
   // epilogue row grid: rows are dw rows
   const int m_tiles = (int)cdiv(p.M, 128);
   const int n_tiles = (int)cdiv(N, p.BN);
-  const int splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8);
+  const int splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8, passes, p.BN);
   p.kblocks_per_split = (int)cdiv(p.total_kblocks, splits);
   const int real_splits = (int)cdiv(p.total_kblocks, p.kblocks_per_split);
   p.out = dw;
@@ -1039,10 +1119,9 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
     p.total_kblocks = (int)cdiv(K, 32);
   }
   if (!tB) {
-    p.b_mode = B_MN;                                 // B [K,N] row-major
-    int64_t dims[2] = {N, K}, str[2] = {1, ldb};
-    int box[2] = {32, 32};
-    rc = make_map(&p.mapB[0], B, 2, dims, str, box, true);
+    p.b_mode = B_MN;                                 // B [K,N] row-major (N % 32 == 0 is an eligibility condition)
+    p.b_atoms0 = p.BN / 32;
+    rc = make_bmn_map(&p.mapB[0], B, K, N, ldb, p.b_atoms0);
   } else {
     p.b_mode = B_K;                                  // B stored [N,K]
     int64_t dims[2] = {K, N}, str[2] = {1, ldb};
@@ -1052,7 +1131,7 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
   if (rc) return rc;
   const int n_tiles = (int)cdiv(N, p.BN);
   int splits = 1;
-  if (plain_accumulate) splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8);
+  if (plain_accumulate) splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8, passes, p.BN);
   p.kblocks_per_split = (int)cdiv(p.total_kblocks, splits);
   splits = (int)cdiv(p.total_kblocks, p.kblocks_per_split);
   p.atomic_out = (plain_accumulate && splits > 1) ? 1 : 0;

@@ -242,10 +242,15 @@ class ContextNet:
     def _patch_ld(C: int, k: int) -> int:
         return -(-(C * k * k) // 4) * 4
 
-    def _patches(self, name: str, x: torch.Tensor, k: int, stride: int, round_tf32: bool = False) -> torch.Tensor:
+    def _patches(self, name: str, x: torch.Tensor, k: int, stride: int, round_tf32: bool = False,
+                 reuse: bool = False) -> torch.Tensor:
+        """Patch matrix of x in a named buffer; reuse=True returns the buffer forward() filled for the same x."""
         n, H, W_, C = x.shape
         ld = self._patch_ld(C, k)
         rows = n * (-(-H // stride)) * (-(-W_ // stride))
+        have = self._bufs.get(name)
+        if reuse and have is not None and tuple(have.shape) == (rows, ld):
+            return have
         buf = self._buf(name, (rows, ld))
         ops.im2col(x, k, stride, ld, out=buf, round_tf32=round_tf32)
         return buf
@@ -482,7 +487,7 @@ class ContextNet:
                 kj, Cin = sp.kernels[j], src.shape[3]
                 if self._few(Cin, kj) and g_hs[j].shape[3] % 4 == 0:
                     K = kj * kj * Cin
-                    pt = self._patches("patch_%s_h%d_%d" % (scope, j, n), src, kj, sp.strides[j])   # (forward's buffer)
+                    pt = self._patches("patch_%s_h%d_%d" % (scope, j, n), src, kj, sp.strides[j], reuse=True)
                     ops.gemm(pt[:, :K], g_hs[j].view(-1, g_hs[j].shape[3]), out=G[wname].view(K, -1), transA=True,
                              accumulate=True, impl=self.impl_b)
                 else:

@@ -42,13 +42,21 @@ def add_fprop(name, N, H, C, Co, k=5, st=2):
                   lambda impl: ops.conv2d(x, w, b, stride=st, act=True, out=y, impl=impl)))
 
 
-def add_trans(name, N, P, C1, C2, NB, Cn, k=5, st=2):
+def add_im2col(name, N, H, C, k=5, st=2):
+    x = rnd(N, H, H, C)
+    ld = -(-(C * k * k) // 4) * 4
+    P = -(-H // st)
+    out = torch.empty((N * P * P, ld), device=dev)
+    cases.append(("im2col", name, float(N * P * P * ld), lambda impl: ops.im2col(x, k, st, ld, out=out)))
+
+
+def add_trans(name, N, P, C1, C2, NB, Cn, k=5, st=2, act=True):
     x1 = rnd(N, P, P, C1)
     x2 = rnd(NB, P, P, C2) if C2 else None
     w, b = rnd(k, k, Cn, C1 + C2), rnd(Cn)
     y = torch.empty((N, P * st, P * st, Cn), device=dev)
     cases.append(("transpose", name, 2.0 * N * P * P * Cn * k * k * (C1 + C2),
-                  lambda impl: ops.conv2d_transpose(x1, w, (P * st, P * st), bias=b, stride=st, x2=x2, act=True, out=y,
+                  lambda impl: ops.conv2d_transpose(x1, w, (P * st, P * st), bias=b, stride=st, x2=x2, act=act, out=y,
                                                     impl=impl)))
 
 
@@ -61,8 +69,11 @@ def add_wgrad(name, N, H, Ca, Cb1, Cb2, NB, k=5, st=2):
                   lambda impl: ops.conv2d_wgrad(big, s1, k, st, small2=s2, dw=dw, impl=impl)))
 
 
-def add_gemm(name, M, N, K, tA=False, tB=False, bias=True, accumulate=False):
-    A = rnd(*((K, M) if tA else (M, K)))
+def add_gemm(name, M, N, K, tA=False, tB=False, bias=True, accumulate=False, pad=0):
+    if pad:            # patch-matrix operand: K (or M) columns of a wider row
+        A = rnd(*((K, M + pad) if tA else (M, K + pad)))[:, :(M if tA else K)]
+    else:
+        A = rnd(*((K, M) if tA else (M, K)))
     Bm = rnd(*((N, K) if tB else (K, N)))
     bv = rnd(N) if bias else None
     Cm = torch.zeros((M, N), device=dev)
@@ -74,7 +85,8 @@ def add_gemm(name, M, N, K, tA=False, tB=False, bias=True, accumulate=False):
 E = 2 * B   # images through scope "conv" (src, tgt); ctx encoder has B
 D = 2 * B   # decoder passes
 # forward
-add_fprop("h0 (3->64 @64)", E, 64, 3, 64)
+add_im2col("h0.im2col", E, 64, 3)
+add_gemm("h0.gemm (K=75)", E * 1024, 64, 75, pad=1)
 add_fprop("h1", E, 32, 64, 128)
 add_fprop("h2", E, 16, 128, 256)
 add_fprop("h3", E, 8, 256, 512)
@@ -84,10 +96,10 @@ add_gemm("d_h0_lin", D, 8192, 1024)
 add_trans("d_h1", D, 4, 512, 512, B, 256)
 add_trans("d_h2", D, 8, 256, 256, B, 128)
 add_trans("d_h3", D, 16, 128, 128, B, 64)
-add_trans("d_h4 (128->3 @64)", D, 32, 64, 64, B, 3)
+add_trans("d_h4 (128->3 @64)", D, 32, 64, 64, B, 3, act=False)
 # backward: decoder
-add_wgrad("d_h4.wgrad (3 x 128)", D, 64, 3, 64, 64, B)
-add_fprop("d_h4.dgrad (3->128)", D, 64, 3, 128)
+add_gemm("d_h4.wgrad (M=75)", 75, 64, D * 1024, tA=True, bias=False, accumulate=True, pad=1)
+add_gemm("d_h4.dgrad (K=75)", D * 1024, 128, 75, bias=False, pad=1)
 add_wgrad("d_h3.wgrad", D, 32, 64, 128, 128, B)
 add_fprop("d_h3.dgrad", D, 32, 64, 256)
 add_wgrad("d_h2.wgrad", D, 16, 128, 256, 256, B)
@@ -105,7 +117,7 @@ add_wgrad("h2.wgrad", E, 16, 128, 256, 0, 0)
 add_trans("h2.dgrad", E, 8, 256, 0, 0, 128)
 add_wgrad("h1.wgrad", E, 32, 64, 128, 0, 0)
 add_trans("h1.dgrad", E, 16, 128, 0, 0, 64)
-add_wgrad("h0.wgrad (3 x 64)", E, 64, 3, 64, 0, 0)
+add_gemm("h0.wgrad (M=75)", 75, 64, E * 1024, tA=True, bias=False, accumulate=True, pad=1)
 
 only = set(x for x in a.only.split(",") if x)
 tot = {}

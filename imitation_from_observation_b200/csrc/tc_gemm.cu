@@ -60,6 +60,8 @@ struct TcParams {
   int32_t passes;                  // 1 | 3
   int32_t BN;                      // 64 | 128 | 256
   int32_t raw_slots, lo_slots;     // ring depths: fp32 tiles landed by TMA | their lo parts (3-pass only)
+  int32_t a_tmem;                  // 3-pass, K-major A: the splitters put A (hi, lo) into TENSOR MEMORY, the MMAs read
+                                   // A from there — shared memory then only serves B (see the kernel header)
   int32_t total_kblocks;           // whole K loop (all splits)
   int32_t kblocks_per_split;
   // stride phases of a transposed conv merged into one launch (blockIdx.z = phase; no split-K then)
@@ -170,6 +172,72 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (rows = lanes, K along 32-bit columns), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns: thread t of the warp writes row (lane_base + t), columns col .. col+31
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Warp-convergent forms: every lane executes the statement, `lead` (non-zero in exactly one lane) predicates the
+// tcgen05 instruction inside the asm.  The surrounding loop then stays convergent, so the compiler keeps descriptors
+// and addresses in uniform registers instead of shuffling them through a per-lane waterfall for every MMA.
+__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(lead)
+      : "memory");
+}
+// descriptor words: lo = address[17:4] | LBO << 16 ; hi = SBO | version 1 << 14 | layout type << 29
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -211,11 +279,29 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 constexpr uint32_t kATileBytes = 128 * 128;          // 128 rows (or 4 atoms x 32 rows) x 128 B
 
 // TMEM columns to allocate: one accumulator (two in 3-pass mode) of BN columns, rounded up to a power of two >= 32
-__host__ __device__ __forceinline__ uint32_t tmem_cols(int BN, int passes) {
-  const uint32_t need = (uint32_t)BN * (passes == 3 ? 2u : 1u);
+// (+ 2 stages x (A_hi, A_lo) x 32 columns when the A operand lives in tensor memory)
+__host__ __device__ __forceinline__ uint32_t tmem_cols(int BN, int passes, int a_tmem) {
+  const uint32_t need = (uint32_t)BN * (passes == 3 ? 2u : 1u) + (a_tmem ? 128u : 0u);
   uint32_t c = 32u;
   while (c < need) c <<= 1;
   return c;
+}
+
+// lo part of NC 16-byte chunks spaced 128 chunks apart: all loads first, then mask / subtract / store
+template <int NC>
+__device__ __forceinline__ void split_chunks(const float4* __restrict__ s4, float4* __restrict__ d4) {
+  float4 v[NC];
+#pragma unroll
+  for (int u = 0; u < NC; ++u) v[u] = s4[u * 128];
+#pragma unroll
+  for (int u = 0; u < NC; ++u) {
+    float4 l;
+    l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u);
+    l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u);
+    l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u);
+    l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u);
+    d4[u * 128] = l;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_constant__ TcParams p) {
@@ -230,6 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   // the lo ring only bridges splitter -> tensor core.
   const int R = p.raw_slots, L = p.lo_slots;
   const uint32_t lo_base = smem_base + (uint32_t)R * raw_bytes;
+  // a lo slot holds (A_lo | B_lo), or only B_lo when A lives in tensor memory
+  const uint32_t lo_bytes = p.a_tmem ? b_tile_bytes : raw_bytes;
+  const uint32_t lo_b_off = p.a_tmem ? 0u : kATileBytes;
 
   __shared__ __align__(8) uint64_t bars[8 + 4 + 8 + 4 + 1];        // full[R], ready[L], raw_empty[R], lo_empty[L], acc
   __shared__ uint32_t tmem_slot;
@@ -274,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     // 3-pass mode keeps two accumulators: D1 = hi*hi, D2 = the two cross terms.  The tensor core truncates when
     // it adds into a running fp32 sum (measured: error grows linearly with the number of accumulations), so the
     // small terms must not ride on the big sum; D1 + D2 is formed once, in the epilogue, with a rounded fp32 add.
-    const uint32_t ncols = tmem_cols(p.BN, p.passes);
+    const uint32_t ncols = tmem_cols(p.BN, p.passes, p.a_tmem);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                  "r"(ncols)
                  : "memory");
@@ -365,84 +454,110 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         }
       }
     } else if (warp == 1) {
-      // =============================== MMA issuer (one lane) ===================================================
-      if (lane == 0) {
+      // =============================== MMA issuer (whole warp, one lane issues) ==================================
+      {
+        const uint32_t lead = lane == 0 ? 1u : 0u;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.a_mode == A_MN ? 1u : 0u) << 15) |
                                ((p.b_mode == B_MN ? 1u : 0u) << 16) | ((uint32_t)(p.BN >> 3) << 17) |
                                ((128u >> 4) << 24);
         const bool amn = p.a_mode == A_MN, bmn = p.b_mode == B_MN;
-        const uint32_t a_lbo = amn ? 4096u : 16u, a_sbo = amn ? 512u : 1024u, a_step = amn ? 1024u : 32u;
-        const uint32_t b_lbo = bmn ? 4096u : 16u, b_sbo = bmn ? 512u : 1024u, b_step = bmn ? 1024u : 32u;
-        const uint32_t a_lt = amn ? 1u : 2u, b_lt = bmn ? 1u : 2u;
+        const uint32_t a_lbo = amn ? 4096u : 16u, a_step = amn ? 64u : 2u;     // steps in 16-byte units
+        const uint32_t b_lbo = bmn ? 4096u : 16u, b_step = bmn ? 64u : 2u;
+        const uint32_t a_hi = desc_hi(amn ? 512u : 1024u, amn ? 1u : 2u);
+        const uint32_t b_hi = desc_hi(bmn ? 512u : 1024u, bmn ? 1u : 2u);
+        const uint32_t d1 = tmem_base, d2 = tmem_base + (uint32_t)p.BN;
+        const bool x3 = p.passes == 3, atm = p.a_tmem != 0;
         int stage = 0, lst = 0;
         uint32_t phase = 0, lphase = 0;
         for (int i = 0; i < nkb; ++i) {
-          if (p.passes == 3) mbar_wait(ready_bar(lst), lphase, p.err_flag, 3);
+          if (x3) mbar_wait(ready_bar(lst), lphase, p.err_flag, 3);
           else mbar_wait(full_bar(stage), phase, p.err_flag, 3);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * raw_bytes;
-          const uint32_t sb = sa + kATileBytes;
-          const uint32_t la = lo_base + lst * raw_bytes;
-          const uint32_t lb = la + kATileBytes;
+          const uint32_t la = lo_base + lst * lo_bytes;
+          const uint32_t a0 = desc_lo(sa, a_lbo), b0 = desc_lo(sa + kATileBytes, b_lbo);
+          const uint32_t al0 = desc_lo(la, a_lbo), bl0 = desc_lo(la + lo_b_off, b_lbo);
+          const uint32_t ta_hi = tmem_base + 2u * (uint32_t)p.BN + 64u * (uint32_t)lst, ta_lo = ta_hi + 32u;
+          const uint32_t first = i ? 1u : 0u;
+          if (atm) {
+            // A (hi, lo) of this k-block sit in tensor memory columns [2*BN + 64*lst, +64): 8 columns per K = 8 step
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_desc(sa + ks * a_step, a_lbo, a_sbo, a_lt);
-            const uint64_t bd = make_desc(sb + ks * b_step, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_base, ad, bd, idesc, (i | ks) ? 1u : 0u);
-            if (p.passes == 3) {
-              const uint64_t ad_lo = make_desc(la + ks * a_step, a_lbo, a_sbo, a_lt);
-              const uint64_t bd_lo = make_desc(lb + ks * b_step, b_lbo, b_sbo, b_lt);
-              umma_tf32(tmem_base + (uint32_t)p.BN, ad, bd_lo, idesc, (i | ks) ? 1u : 0u);
-              umma_tf32(tmem_base + (uint32_t)p.BN, ad_lo, bd, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = ks ? 1u : first;
+              umma_tf32_ts_p(d1, ta_hi + 8u * ks, b0 + ks * b_step, b_hi, idesc, acc, lead);
+              umma_tf32_ts_p(d2, ta_hi + 8u * ks, bl0 + ks * b_step, b_hi, idesc, acc, lead);
+              umma_tf32_ts_p(d2, ta_lo + 8u * ks, b0 + ks * b_step, b_hi, idesc, 1u, lead);
             }
+          } else if (x3) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = ks ? 1u : first;
+              umma_tf32_p(d1, a0 + ks * a_step, a_hi, b0 + ks * b_step, b_hi, idesc, acc, lead);
+              umma_tf32_p(d2, a0 + ks * a_step, a_hi, bl0 + ks * b_step, b_hi, idesc, acc, lead);
+              umma_tf32_p(d2, al0 + ks * a_step, a_hi, b0 + ks * b_step, b_hi, idesc, 1u, lead);
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32_p(d1, a0 + ks * a_step, a_hi, b0 + ks * b_step, b_hi, idesc, ks ? 1u : first, lead);
           }
-          umma_commit(empty_bar(stage));          // frees the raw slot once these MMAs have read it
+          umma_commit_p(empty_bar(stage), lead);          // frees the raw slot once these MMAs have read it
           if (++stage == R) { stage = 0; phase ^= 1; }
-          if (p.passes == 3) {
-            umma_commit(lo_empty_bar(lst));       // ... and the lo slot
+          if (x3) {
+            umma_commit_p(lo_empty_bar(lst), lead);       // ... and the lo slot
             if (++lst == L) { lst = 0; lphase ^= 1; }
           }
         }
-        umma_commit(acc_bar);                      // accumulator complete
+        umma_commit_p(acc_bar, lead);                      // accumulator complete
       }
     } else if (p.passes == 3) {
       // =============================== splitters: fp32 tile -> (hi, lo) =======================================
       const int t = threadIdx.x - 64;              // 0..127
-      const int nchunk = (int)(raw_bytes >> 4);
+      const int arow = (warp & 3) * 32 + lane;     // tensor-memory lane quarter this warp may access = tile row
+      // generic pointer to the 1024-byte aligned operand ring (plain loads / stores: the compiler schedules them
+      // freely between the barrier waits, which are compiler memory barriers)
+      uint8_t* const ring = smem_raw + (smem_base - smem_u32(smem_raw));
+      const int a_chunks = p.a_tmem ? 0 : (int)(kATileBytes >> 4) / 128;          // 16-byte chunks per thread
+      const int b_chunks = (int)(b_tile_bytes >> 4) / 128;                        // = BN / 16
       int stage = 0, lst = 0;
       uint32_t phase = 0, lphase = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(full_bar(stage), phase, p.err_flag, 4);
         mbar_wait(lo_empty_bar(lst), lphase ^ 1, p.err_flag, 6);
-        const uint32_t base = smem_base + stage * raw_bytes;
-        const uint32_t lbase = lo_base + lst * raw_bytes;
-        // batches of 8 chunks per thread: all loads first (8 LDS.128 in flight), then mask / subtract / store —
-        // inline asm statements are never reordered by the compiler, so the batching has to be explicit
-        for (int c0 = t; c0 < nchunk; c0 += 8 * 128) {
-          float4 v[8];
+        const uint8_t* src = ring + (size_t)stage * raw_bytes;
+        uint8_t* dst = ring + (size_t)R * raw_bytes + (size_t)lst * lo_bytes;
+        if (p.a_tmem) {
+          // A: this thread owns tile row `arow` (128 B = 32 K-elements, 16-byte chunks XOR-swizzled by row & 7);
+          // hi (= the raw word, the tensor core ignores the low 13 bits) and lo go to tensor memory
+          tc_fence_after();
+          uint32_t x[32];
+          const uint4* row = reinterpret_cast<const uint4*>(src + (size_t)arow * 128);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int c = c0 + u * 128;
-            if (c < nchunk)
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                           : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(base + ((uint32_t)c << 4)));
+          for (int c = 0; c < 8; ++c) {
+            const uint4 q4 = row[c ^ (arow & 7)];
+            x[4 * c] = q4.x; x[4 * c + 1] = q4.y; x[4 * c + 2] = q4.z; x[4 * c + 3] = q4.w;
           }
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * (uint32_t)p.BN + 64u * (uint32_t)lst;
+          tmem_st32(ta, x);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int c = c0 + u * 128;
-            if (c < nchunk) {
-              const uint32_t off = (uint32_t)c << 4;
-              // the tensor core reads an fp32 word as TF32 by ignoring its low 13 bits (verified on B200:
-              // tools/tc_check.py "trunc"), so the raw tile already IS the hi part; lo = x - trunc(x) is exact
-              float4 l;
-              l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u);
-              l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u);
-              l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u);
-              l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lbase + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-            }
-          }
+          for (int e = 0; e < 32; ++e)
+            x[e] = __float_as_uint(__uint_as_float(x[e]) - __uint_as_float(x[e] & 0xFFFFE000u));
+          tmem_st32(ta + 32u, x);
+          src += kATileBytes;                              // the shared-memory pass below only covers B
         }
+        // the tensor core reads an fp32 word as TF32 by ignoring its low 13 bits (verified on B200:
+        // tools/tc_check.py "trunc"), so the raw tile already IS the hi part; lo = x - trunc(x) is exact.
+        // Elementwise, hence layout-agnostic: thread t takes chunks t, t+128, ... in branch-free batches.
+        {
+          const float4* s4 = reinterpret_cast<const float4*>(src) + t;
+          float4* d4 = reinterpret_cast<float4*>(dst) + t;
+          int left = a_chunks + b_chunks;
+          for (; left >= 8; left -= 8, s4 += 8 * 128, d4 += 8 * 128) split_chunks<8>(s4, d4);
+          if (left >= 4) { split_chunks<4>(s4, d4); s4 += 4 * 128; d4 += 4 * 128; left -= 4; }
+          if (left >= 2) { split_chunks<2>(s4, d4); s4 += 2 * 128; d4 += 2 * 128; left -= 2; }
+          if (left >= 1) split_chunks<1>(s4, d4);
+        }
+        if (p.a_tmem) { tmem_st_wait(); tc_fence_before(); }
         fence_async_smem();                        // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(ready_bar(lst));
         if (++stage == R) { stage = 0; phase ^= 1; }
@@ -550,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    const uint32_t ncols = tmem_cols(p.BN, p.passes);
+    const uint32_t ncols = tmem_cols(p.BN, p.passes, p.a_tmem);
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
@@ -634,6 +749,7 @@ static int env_int(const char* name, int dflt) {
 // experiment knobs (environment, read once): CTX_TC_BN3 = N tile of the 3-pass mode, CTX_TC_OCC = CTAs per SM the
 // shared-memory ring is sized for
 static int knob_bn3() { static int v = env_int("CTX_TC_BN3", 128); return v; }
+static int knob_atmem() { static int v = env_int("CTX_TC_ATMEM", 1); return v; }
 static int knob_occ() { static int v = env_int("CTX_TC_OCC", 0); return v; }
 
 // CTAs per SM the operand ring is sized for.  Two co-resident CTAs overlap each other's prologue / epilogue /
@@ -671,12 +787,17 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
   }
   const int occ = tc_occupancy(p.passes, p.BN, p.nphase > 1 ? p.ph_kblocks[0] : p.kblocks_per_split);
   const uint32_t budget = occ == 1 ? (uint32_t)max_dyn : (uint32_t)(max_dyn - 2048) / 2u;
-  const int slots = (int)((budget - 1024u) / raw);          // 1024: alignment slack
-  p.lo_slots = p.passes == 3 ? (slots >= 4 ? 2 : 1) : 0;
-  p.raw_slots = slots - p.lo_slots;
+  // 3-pass with a K-major A operand: A (hi, lo) goes through tensor memory when the columns are there
+  // (2 accumulators + 2 stages x 64 columns; 512 columns per SM shared by the resident CTAs)
+  p.a_tmem = (knob_atmem() && p.passes == 3 && p.a_mode == A_PIX && !p.scatter &&
+              2 * p.BN + 128 <= (occ == 2 ? 256 : 512)) ? 1 : 0;
+  const uint32_t lo_b = p.passes == 3 ? (p.a_tmem ? (uint32_t)p.BN * 128u : raw) : 0u;
+  p.lo_slots = p.passes == 3 ? ((budget - 1024u) >= 2 * raw + 2 * lo_b ? 2 : 1) : 0;
+  const int slots = (int)((budget - 1024u - (uint32_t)p.lo_slots * lo_b) / raw);
+  p.raw_slots = slots;
   if (p.raw_slots > 8) p.raw_slots = 8;
   if (p.raw_slots < 2) { set_error("%s: tile does not fit shared memory", name); return CTX_ERR_ARG; }
-  const size_t smem = (size_t)(p.raw_slots + p.lo_slots) * raw + 1024;
+  const size_t smem = (size_t)p.raw_slots * raw + (size_t)p.lo_slots * lo_b + 1024;
   p.err_flag = nullptr;
   const int n_tiles = (int)cdiv(p.N, p.BN);
   if (n_tiles > 65535 || splits > 65535) { set_error("%s: grid too large", name); return CTX_ERR_ARG; }

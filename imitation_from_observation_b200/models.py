@@ -36,7 +36,7 @@ class Fetch:
 class _ContextModel:
     """Common machinery; subclasses only pick the :class:`spec.NetSpec`."""
 
-    precision = "tf32x3"      # class-level default; override per instance or via build(..., precision=)
+    precision = "mixed"       # class-level default; override per instance or via build(..., precision=)
 
     def _make_spec(self, height: int, width: int, c_dim: int) -> _spec.NetSpec:
         raise NotImplementedError

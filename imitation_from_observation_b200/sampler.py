@@ -33,7 +33,7 @@ class RewardFeaturizer:
 
     def __init__(self, mode: str = "ours", name: str = "push", imsize=(48, 48), nvp: int = 1, scale: float = 1.0,
                  modelname: Optional[str] = None, modeldata: Optional[str] = None, ablation_type: str = "None",
-                 precision: str = "tf32x3", model: Optional[_ContextModel] = None, device="cuda", **unused_kwargs):
+                 precision: str = "mixed", model: Optional[_ContextModel] = None, device="cuda", **unused_kwargs):
         if not mode.startswith("ours") or mode == "oursinception":
             raise _lib.CtxError("RewardFeaturizer covers mode='ours' (base.py:192-257); inception modes need the "
                                 "InceptionV3 front-end, which is outside this hot path's first scope")

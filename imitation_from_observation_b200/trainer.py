@@ -23,7 +23,7 @@ from .models import MODEL_REGISTRY
 
 class ModelTrainer:
     def __init__(self, idims, nvideos, ntrain, batch_size, model, nitr, save_every, nlen, nskip, rescale=True,
-                 inception=False, strides=None, kernels=None, filters=None, data=None, seed=0, precision="tf32x3",
+                 inception=False, strides=None, kernels=None, filters=None, data=None, seed=0, precision="mixed",
                  log: Optional[Callable[[str], None]] = print, basedir="model/"):
         self.idims = tuple(idims)
         self.nvideos, self.ntrain, self.batch_size = nvideos, ntrain, batch_size

@@ -40,7 +40,8 @@ enum { B_K = 0, B_MN = 1 };       // B operand: K-major 2-D rows | MN-major 2-D 
 
 constexpr int kMaxSeg = 64;
 constexpr int kMaxMapsA = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 splitters + epilogue
+constexpr int kWorkers = 256;     // splitter / epilogue threads (two warps per tensor-memory lane quarter)
 
 struct Seg {                       // one K segment = one filter tap of one source tensor
   int16_t dh, dw;                  // pixel offset of the A box
@@ -133,6 +134,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t
     }
   }
 }
+// Warp-uniform wait (all 32 lanes call it): the loop condition is a vote, so control flow stays convergent and
+// the compiler can keep the caller's loop state in uniform registers.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int32_t* err_flag, int id) {
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (++spins > 40000000u) {
+      if (err_flag) atomicExch(err_flag, 0x1000 + id);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -192,6 +204,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -287,12 +307,12 @@ __host__ __device__ __forceinline__ uint32_t tmem_cols(int BN, int passes, int a
   return c;
 }
 
-// lo part of NC 16-byte chunks spaced 128 chunks apart: all loads first, then mask / subtract / store
+// lo part of NC 16-byte chunks spaced kWorkers chunks apart: all loads first, then mask / subtract / store
 template <int NC>
 __device__ __forceinline__ void split_chunks(const float4* __restrict__ s4, float4* __restrict__ d4) {
   float4 v[NC];
 #pragma unroll
-  for (int u = 0; u < NC; ++u) v[u] = s4[u * 128];
+  for (int u = 0; u < NC; ++u) v[u] = s4[u * kWorkers];
 #pragma unroll
   for (int u = 0; u < NC; ++u) {
     float4 l;
@@ -300,11 +320,11 @@ __device__ __forceinline__ void split_chunks(const float4* __restrict__ s4, floa
     l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u);
     l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u);
     l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u);
-    d4[u * 128] = l;
+    d4[u * kWorkers] = l;
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -353,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < L; ++s) {
-      mbar_init(ready_bar(s), 128);
+      mbar_init(ready_bar(s), kWorkers);
       mbar_init(lo_empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
@@ -467,20 +487,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         const uint32_t b_hi = desc_hi(bmn ? 512u : 1024u, bmn ? 1u : 2u);
         const uint32_t d1 = tmem_base, d2 = tmem_base + (uint32_t)p.BN;
         const bool x3 = p.passes == 3, atm = p.a_tmem != 0;
+        // descriptor low words of ring slot 0; they advance by one slot per k-block (loop-carried, warp-uniform)
+        const uint32_t raw16 = raw_bytes >> 4, lo16 = lo_bytes >> 4;
+        const uint32_t a_base = desc_lo(smem_base, a_lbo), b_base = desc_lo(smem_base + kATileBytes, b_lbo);
+        const uint32_t al_base = desc_lo(lo_base, a_lbo), bl_base = desc_lo(lo_base + lo_b_off, b_lbo);
+        const uint32_t ta_base = tmem_base + 2u * (uint32_t)p.BN;
+        uint32_t a0 = a_base, b0 = b_base, al0 = al_base, bl0 = bl_base, ta_hi = ta_base;
         int stage = 0, lst = 0;
         uint32_t phase = 0, lphase = 0;
         for (int i = 0; i < nkb; ++i) {
-          if (x3) mbar_wait(ready_bar(lst), lphase, p.err_flag, 3);
-          else mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+          if (x3) mbar_wait_warp(ready_bar(lst), lphase, p.err_flag, 3);
+          else mbar_wait_warp(full_bar(stage), phase, p.err_flag, 3);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * raw_bytes;
-          const uint32_t la = lo_base + lst * lo_bytes;
-          const uint32_t a0 = desc_lo(sa, a_lbo), b0 = desc_lo(sa + kATileBytes, b_lbo);
-          const uint32_t al0 = desc_lo(la, a_lbo), bl0 = desc_lo(la + lo_b_off, b_lbo);
-          const uint32_t ta_hi = tmem_base + 2u * (uint32_t)p.BN + 64u * (uint32_t)lst, ta_lo = ta_hi + 32u;
           const uint32_t first = i ? 1u : 0u;
           if (atm) {
             // A (hi, lo) of this k-block sit in tensor memory columns [2*BN + 64*lst, +64): 8 columns per K = 8 step
+            const uint32_t ta_lo = ta_hi + 32u;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t acc = ks ? 1u : first;
@@ -502,23 +524,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
               umma_tf32_p(d1, a0 + ks * a_step, a_hi, b0 + ks * b_step, b_hi, idesc, ks ? 1u : first, lead);
           }
           umma_commit_p(empty_bar(stage), lead);          // frees the raw slot once these MMAs have read it
-          if (++stage == R) { stage = 0; phase ^= 1; }
+          a0 += raw16; b0 += raw16;
+          if (++stage == R) { stage = 0; phase ^= 1; a0 = a_base; b0 = b_base; }
           if (x3) {
             umma_commit_p(lo_empty_bar(lst), lead);       // ... and the lo slot
-            if (++lst == L) { lst = 0; lphase ^= 1; }
+            al0 += lo16; bl0 += lo16; ta_hi += 64u;
+            if (++lst == L) { lst = 0; lphase ^= 1; al0 = al_base; bl0 = bl_base; ta_hi = ta_base; }
           }
         }
         umma_commit_p(acc_bar, lead);                      // accumulator complete
       }
     } else if (p.passes == 3) {
       // =============================== splitters: fp32 tile -> (hi, lo) =======================================
-      const int t = threadIdx.x - 64;              // 0..127
+      const int t = threadIdx.x - 64;              // 0..255
       const int arow = (warp & 3) * 32 + lane;     // tensor-memory lane quarter this warp may access = tile row
+      const int ahalf = (warp - 2) >> 2;           // the two warps of a quarter take K columns 0..15 / 16..31
       // generic pointer to the 1024-byte aligned operand ring (plain loads / stores: the compiler schedules them
       // freely between the barrier waits, which are compiler memory barriers)
       uint8_t* const ring = smem_raw + (smem_base - smem_u32(smem_raw));
-      const int a_chunks = p.a_tmem ? 0 : (int)(kATileBytes >> 4) / 128;          // 16-byte chunks per thread
-      const int b_chunks = (int)(b_tile_bytes >> 4) / 128;                        // = BN / 16
+      const int a_chunks = p.a_tmem ? 0 : (int)(kATileBytes >> 4) / kWorkers;     // 16-byte chunks per thread
+      const int b_chunks = (int)(b_tile_bytes >> 4) / kWorkers;                   // = BN / 32 (exact: BN % 32 == 0
+      const int tail = (int)(b_tile_bytes >> 4) - b_chunks * kWorkers;            //   except BN = 80 -> tail chunks)
       int stage = 0, lst = 0;
       uint32_t phase = 0, lphase = 0;
       for (int i = 0; i < nkb; ++i) {
@@ -527,35 +553,37 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         const uint8_t* src = ring + (size_t)stage * raw_bytes;
         uint8_t* dst = ring + (size_t)R * raw_bytes + (size_t)lst * lo_bytes;
         if (p.a_tmem) {
-          // A: this thread owns tile row `arow` (128 B = 32 K-elements, 16-byte chunks XOR-swizzled by row & 7);
-          // hi (= the raw word, the tensor core ignores the low 13 bits) and lo go to tensor memory
+          // A: this thread owns half of tile row `arow` (64 B = 16 K-elements; 16-byte chunks XOR-swizzled by
+          // row & 7); hi (= the raw word, the tensor core ignores the low 13 bits) and lo go to tensor memory
           tc_fence_after();
-          uint32_t x[32];
+          uint32_t x[16];
           const uint4* row = reinterpret_cast<const uint4*>(src + (size_t)arow * 128);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 q4 = row[c ^ (arow & 7)];
+          for (int c = 0; c < 4; ++c) {
+            const uint4 q4 = row[(4 * ahalf + c) ^ (arow & 7)];
             x[4 * c] = q4.x; x[4 * c + 1] = q4.y; x[4 * c + 2] = q4.z; x[4 * c + 3] = q4.w;
           }
-          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * (uint32_t)p.BN + 64u * (uint32_t)lst;
-          tmem_st32(ta, x);
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * (uint32_t)p.BN +
+                              64u * (uint32_t)lst + 16u * (uint32_t)ahalf;
+          tmem_st16(ta, x);
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
+          for (int e = 0; e < 16; ++e)
             x[e] = __float_as_uint(__uint_as_float(x[e]) - __uint_as_float(x[e] & 0xFFFFE000u));
-          tmem_st32(ta + 32u, x);
+          tmem_st16(ta + 32u, x);
           src += kATileBytes;                              // the shared-memory pass below only covers B
         }
         // the tensor core reads an fp32 word as TF32 by ignoring its low 13 bits (verified on B200:
         // tools/tc_check.py "trunc"), so the raw tile already IS the hi part; lo = x - trunc(x) is exact.
-        // Elementwise, hence layout-agnostic: thread t takes chunks t, t+128, ... in branch-free batches.
+        // Elementwise, hence layout-agnostic: thread t takes chunks t, t+256, ... in branch-free batches.
         {
           const float4* s4 = reinterpret_cast<const float4*>(src) + t;
           float4* d4 = reinterpret_cast<float4*>(dst) + t;
           int left = a_chunks + b_chunks;
-          for (; left >= 8; left -= 8, s4 += 8 * 128, d4 += 8 * 128) split_chunks<8>(s4, d4);
-          if (left >= 4) { split_chunks<4>(s4, d4); s4 += 4 * 128; d4 += 4 * 128; left -= 4; }
-          if (left >= 2) { split_chunks<2>(s4, d4); s4 += 2 * 128; d4 += 2 * 128; left -= 2; }
-          if (left >= 1) split_chunks<1>(s4, d4);
+          for (; left >= 8; left -= 8, s4 += 8 * kWorkers, d4 += 8 * kWorkers) split_chunks<8>(s4, d4);
+          if (left >= 4) { split_chunks<4>(s4, d4); s4 += 4 * kWorkers; d4 += 4 * kWorkers; left -= 4; }
+          if (left >= 2) { split_chunks<2>(s4, d4); s4 += 2 * kWorkers; d4 += 2 * kWorkers; left -= 2; }
+          if (left >= 1) { split_chunks<1>(s4, d4); s4 += kWorkers; d4 += kWorkers; }
+          if (t < tail) split_chunks<1>(s4, d4);
         }
         if (p.a_tmem) { tmem_st_wait(); tc_fence_before(); }
         fence_async_smem();                        // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -566,10 +594,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     }
   }
 
-  // ================================= epilogue: warps 2..5 ======================================================
+  // ================================= epilogue: warps 2..9 ======================================================
+  // warp w reads TMEM lane quarter w % 4 (hardware rule); the two warps of a quarter split the 32-column chunks
   if (warp >= 2) {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                   // tile row
+    const int nch = (p.BN + 31) >> 5, ch_half = (nch + 1) >> 1;
+    const int c_begin = ((warp - 2) >> 2) ? ch_half * 32 : 0, c_end = ((warp - 2) >> 2) ? p.BN : min(p.BN, ch_half * 32);
     if (nkb > 0) {
       mbar_wait(acc_bar, 0, p.err_flag, 5);
       tc_fence_after();
@@ -581,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     const int gn = n0 + dn, gp = p0 + dp;
     const bool row_ok = gn < p.NG && gp < p.PG && (nkb > 0 || !p.atomic_out);
     const int64_t roff = obase + (int64_t)gn * p.sN + (int64_t)gp * p.sP + (int64_t)dq * p.sQ;
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       uint32_t v[32];
       if (nkb > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);

@@ -1235,8 +1235,46 @@ int tc_gemm_eligible(int tA, int tB, int M, int N, int K, const float* A, int ld
   return 1;
 }
 
+// Deferred epilogue of a split-K GEMM: C holds the raw sums, apply bias / lrelu / lrelu' mask / TF32 rounding in place.
+__global__ void gemm_epilogue_kernel(float* C, int M, int N, int ldc, Epi epi) {
+  const int64_t total = (int64_t)M * (N >> 2);
+  const int nq = N >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / nq;
+    const int n = (int)(i - m * nq) << 2;
+    const int64_t off = m * ldc + n;
+    float4 v = *reinterpret_cast<float4*>(C + off);
+    v.x = epi.apply(v.x, n, off, C); v.y = epi.apply(v.y, n + 1, off + 1, C);
+    v.z = epi.apply(v.z, n + 2, off + 2, C); v.w = epi.apply(v.w, n + 3, off + 3, C);
+    *reinterpret_cast<float4*>(C + off) = v;
+  }
+}
+
 int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const Epi& epi, int passes, cudaStream_t stream) {
+  // Skinny GEMMs (the `linear` layers: M = batch <= a few hundred rows, K up to 8192) leave most SMs idle and run a
+  // long serial K loop.  When the fused epilogue is not a plain accumulation, split K anyway: zero C, accumulate
+  // the raw partial sums with the split-K path, then apply the epilogue in a second, tiny pass over C.
+  if (!epi.accumulate) {
+    const int bn = pick_bn(N, 1 << 20, passes);
+    const int64_t tiles = cdiv(M, 128) * cdiv(N, bn);
+    const int kblocks = (int)cdiv(K, 32);
+    if (tiles * 2 <= sm_count() * tc_occupancy(passes, bn, kblocks) && kblocks >= 64 && !(epi.act_ref && ldc != N)) {
+      CTX_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream));
+      Epi acc = make_epi(nullptr);
+      acc.accumulate = 1;
+      int rc = tc_gemm(tA, tB, M, N, K, A, lda, B, ldb, C, ldc, acc, passes, stream);
+      if (rc) return rc;
+      if (epi.bias || epi.act || epi.act_ref || epi.round) {
+        const int64_t work = (int64_t)M * (N >> 2);
+        int blocks = (int)cdiv(work, 256);
+        if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+        gemm_epilogue_kernel<<<blocks, 256, 0, stream>>>(C, M, N, ldc, epi);
+        CTX_LAUNCH_CHECK("gemm_epilogue");
+      }
+      return CTX_OK;
+    }
+  }
   TcParams p;
   fill_common(p, passes, epi);
   const bool plain_accumulate = epi.accumulate && !epi.bias && !epi.act && !epi.act_ref && !epi.round;

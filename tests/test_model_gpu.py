@@ -103,6 +103,20 @@ def test_reference_faithful_48x48_and_real_36x64(precision):
             assert rel_l2(net.G[k].cpu(), G[k]) < max(GTOL[precision], 5e-3), (spec.name, k)
 
 
+def test_striker_128x128_four_layer_vs_oracle():
+    """BASELINE.json configs[3] names 128x128 frames; the reference's builder at that size is the same 4-layer graph
+    (flat = 8*8*512 = 32768).  Small batch, default precision, forward + gradients vs the oracle."""
+    spec, B = S.context_skip_new(128, 128), 4
+    P = O.init_params(spec, seed=5)
+    image = torch.rand((3, B, 128, 128, 3), generator=torch.Generator().manual_seed(6)) * 2 - 1
+    ref, G = O.loss_and_grads(spec, {k: v.double() for k, v in P.items()}, image.double())
+    net = run_net(spec, B, P, image, "mixed")
+    for k in ("translated_z", "out", "out2", "loss"):
+        assert rel_err(net.fetch(k).cpu(), ref[k]) < TOL["mixed"], k
+    for k in spec.param_shapes():
+        assert rel_l2(net.G[k].cpu(), G[k]) < GBAR["mixed"][0], k
+
+
 def test_forward_levels_prune_like_tf():
     """input_z needs only the source encoder; translated_z/out need no target encoder (base.py:216,234)."""
     spec, B = gen_golden.CASES["skipnew_16x16"]

@@ -61,6 +61,8 @@ struct TcParams {
   int32_t passes;                  // 1 | 3
   int32_t BN;                      // 64 | 128 | 256
   int32_t raw_slots, lo_slots;     // ring depths: fp32 tiles landed by TMA | their lo parts (3-pass only)
+  int32_t pair;                    // cta_group::2: two CTAs (a cluster of 2 along the M tiles) run ONE 256 x BN MMA; each
+                                   // CTA stages its own 128 rows of A and HALF of the B tile (see the kernel)
   int32_t a_tmem;                  // 3-pass, K-major A: the splitters put A (hi, lo) into TENSOR MEMORY, the MMAs read
                                    // A from there — shared memory then only serves B (see the kernel header)
   int32_t total_kblocks;           // whole K loop (all splits)
@@ -139,7 +141,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int32_t* err_flag, int id) {
   uint32_t spins = 0;
   while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-    if (++spins > 40000000u) {
+    if (++spins > 2000000u) {
       if (err_flag) atomicExch(err_flag, 0x1000 + id);
       __trap();
     }
@@ -250,6 +252,70 @@ __device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t lead) {
       ::"r"(bar), "r"(lead)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.  Relaxed: the arrival only
+// carries "my tiles are split" — the tiles themselves stay in this CTA's tensor / shared memory, are read by this
+// SM's own MMA datapath, and were already ordered by the splitters' proxy fence + local barrier; a cluster-scope
+// release here puts a full memory barrier per k-block on the follower's critical path (measured: the pair ran 20 % slower).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_warp_cluster(uint32_t bar, uint32_t parity, int32_t* err_flag, int id) {
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) {
+    if (++spins > 2000000u) {
+      if (err_flag) atomicExch(err_flag, 0x1000 + id);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void umma2_tf32_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of pair MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit_p(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+
 // descriptor words: lo = address[17:4] | LBO << 16 ; hi = SBO | version 1 << 14 | layout type << 29
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
@@ -299,9 +365,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 constexpr uint32_t kATileBytes = 128 * 128;          // 128 rows (or 4 atoms x 32 rows) x 128 B
 
 // TMEM columns to allocate: one accumulator (two in 3-pass mode) of BN columns, rounded up to a power of two >= 32
-// (+ 2 stages x (A_hi, A_lo) x 32 columns when the A operand lives in tensor memory)
+// (+ a_tmem stages x (A_hi, A_lo) x 32 columns when the A operand lives in tensor memory; a_tmem = lo ring depth)
 __host__ __device__ __forceinline__ uint32_t tmem_cols(int BN, int passes, int a_tmem) {
-  const uint32_t need = (uint32_t)BN * (passes == 3 ? 2u : 1u) + (a_tmem ? 128u : 0u);
+  const uint32_t need = (uint32_t)BN * (passes == 3 ? 2u : 1u) + (a_tmem ? 64u * (uint32_t)a_tmem : 0u);
   uint32_t c = 32u;
   while (c < need) c <<= 1;
   return c;
@@ -324,13 +390,20 @@ __device__ __forceinline__ void split_chunks(const float4* __restrict__ s4, floa
   }
 }
 
+// kPair = true is the cta_group::2 build: a kernel that contains pair instructions can only be launched as a cluster
+// of even size, so the CTA-pair variant is a separate instantiation.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t b_tile_bytes = (uint32_t)p.BN * 128u;
+  // CTA pair: this CTA stages (and splits) only its half of the B tile
+  constexpr bool pair = kPair;
+  uint32_t cta_rank = 0u;
+  if constexpr (kPair) cta_rank = cluster_ctarank();
+  const uint32_t b_tile_bytes = (uint32_t)(pair ? p.BN / 2 : p.BN) * 128u;
   const uint32_t raw_bytes = kATileBytes + b_tile_bytes;            // fp32 tiles as landed by TMA
   // smem: [raw ring: R x (A | B)] [lo ring: L x (A_lo | B_lo)].  The raw ring is deep (it hides the TMA latency),
   // the lo ring only bridges splitter -> tensor core.
@@ -340,13 +413,15 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
   const uint32_t lo_bytes = p.a_tmem ? b_tile_bytes : raw_bytes;
   const uint32_t lo_b_off = p.a_tmem ? 0u : kATileBytes;
 
-  __shared__ __align__(8) uint64_t bars[8 + 4 + 8 + 4 + 1];        // full[R], ready[L], raw_empty[R], lo_empty[L], acc
+  // full[R], ready[L], raw_empty[R], lo_empty[L], acc, peer_ready[L] (pair leader: the other CTA's tiles are split)
+  __shared__ __align__(8) uint64_t bars[8 + 4 + 8 + 4 + 1 + 4];
   __shared__ uint32_t tmem_slot;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto ready_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[12 + s]); };
   auto lo_empty_bar = [&](int s) { return smem_u32(&bars[20 + s]); };
   const uint32_t acc_bar = smem_u32(&bars[24]);
+  auto peer_ready_bar = [&](int s) { return smem_u32(&bars[25 + s]); };
 
   // this CTA's K range: split-K over blockIdx.z, or (merged transposed-conv phases) the whole K of phase z
   int kb_begin, kb_end, seg0 = 0, nseg = p.nseg;
@@ -375,6 +450,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
     for (int s = 0; s < L; ++s) {
       mbar_init(ready_bar(s), kWorkers);
       mbar_init(lo_empty_bar(s), 1);
+      mbar_init(peer_ready_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -384,13 +460,21 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
     // it adds into a running fp32 sum (measured: error grows linearly with the number of accumulations), so the
     // small terms must not ride on the big sum; D1 + D2 is formed once, in the epilogue, with a rounded fp32 add.
     const uint32_t ncols = tmem_cols(p.BN, p.passes, p.a_tmem);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                   "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                   "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();         // both CTAs' barriers exist before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -414,10 +498,11 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
               mbar_arrive_expect_tx(full_bar(stage), raw_bytes);
               const int nimg = s.wrap ? (n0 % p.a_wrap) : n0;
               tma_load_4d(sa, &p.mapA[s.mapA], full_bar(stage), cb * 32, s.dw, p0 + s.dh, nimg);
+              const int nb0 = ncol0 + (int)cta_rank * (p.BN / 2);      // pair: this CTA's half of the B tile
               if (p.b_mode == B_K) {
-                tma_load_2d(sb, &p.mapB[0], full_bar(stage), s.bk0 + cb * 32, s.br0 + ncol0);
+                tma_load_2d(sb, &p.mapB[0], full_bar(stage), s.bk0 + cb * 32, s.br0 + nb0);
               } else if (p.b_atoms0 > 0) {
-                tma_load_3d(sb, &p.mapB[0], full_bar(stage), 0, s.bk0 + cb * 32, ncol0 >> 5);
+                tma_load_3d(sb, &p.mapB[0], full_bar(stage), 0, s.bk0 + cb * 32, nb0 >> 5);
               } else {
                 for (int a = 0; a < p.BN / 32; ++a)
                   tma_load_2d(sb + a * 4096, &p.mapB[0], full_bar(stage), ncol0 + a * 32, s.bk0 + cb * 32);
@@ -475,11 +560,21 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
       }
     } else if (warp == 1) {
       // =============================== MMA issuer (whole warp, one lane issues) ==================================
-      {
+      if (kPair && cta_rank != 0) {
+        // pair follower: the leader CTA issues the 256-row MMAs; this warp only forwards "my tiles are split"
+        int lst = 0;
+        uint32_t lphase = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait_warp(ready_bar(lst), lphase, p.err_flag, 7);
+          if constexpr (kPair) { if (lane == 0) mbar_arrive_remote(peer_ready_bar(lst), 0u); }
+          __syncwarp();
+          if (++lst == L) { lst = 0; lphase ^= 1; }
+        }
+      } else {
         const uint32_t lead = lane == 0 ? 1u : 0u;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.a_mode == A_MN ? 1u : 0u) << 15) |
                                ((p.b_mode == B_MN ? 1u : 0u) << 16) | ((uint32_t)(p.BN >> 3) << 17) |
-                               ((128u >> 4) << 24);
+                               (((pair ? 256u : 128u) >> 4) << 24);
         const bool amn = p.a_mode == A_MN, bmn = p.b_mode == B_MN;
         const uint32_t a_lbo = amn ? 4096u : 16u, a_step = amn ? 64u : 2u;     // steps in 16-byte units
         const uint32_t b_lbo = bmn ? 4096u : 16u, b_step = bmn ? 64u : 2u;
@@ -498,9 +593,21 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
         for (int i = 0; i < nkb; ++i) {
           if (x3) mbar_wait_warp(ready_bar(lst), lphase, p.err_flag, 3);
           else mbar_wait_warp(full_bar(stage), phase, p.err_flag, 3);
+          if constexpr (kPair) mbar_wait_warp(peer_ready_bar(lst), lphase, p.err_flag, 8);
           tc_fence_after();
           const uint32_t first = i ? 1u : 0u;
-          if (atm) {
+          if constexpr (kPair) {
+            // one 256 x BN MMA per step for the CTA pair: A from each CTA's tensor memory, B halves from each
+            // CTA's shared memory (same offsets in both CTAs)
+            const uint32_t ta_lo = ta_hi + 32u;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = ks ? 1u : first;
+              umma2_tf32_ts_p(d1, ta_hi + 8u * ks, b0 + ks * b_step, b_hi, idesc, acc);
+              umma2_tf32_ts_p(d2, ta_hi + 8u * ks, bl0 + ks * b_step, b_hi, idesc, acc);
+              umma2_tf32_ts_p(d2, ta_lo + 8u * ks, b0 + ks * b_step, b_hi, idesc, 1u);
+            }
+          } else if (atm) {
             // A (hi, lo) of this k-block sit in tensor memory columns [2*BN + 64*lst, +64): 8 columns per K = 8 step
             const uint32_t ta_lo = ta_hi + 32u;
 #pragma unroll
@@ -523,16 +630,19 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
             for (int ks = 0; ks < 4; ++ks)
               umma_tf32_p(d1, a0 + ks * a_step, a_hi, b0 + ks * b_step, b_hi, idesc, ks ? 1u : first, lead);
           }
-          umma_commit_p(empty_bar(stage), lead);          // frees the raw slot once these MMAs have read it
+          if constexpr (kPair) umma2_commit_p(empty_bar(stage));     // (both CTAs' slots)
+          else umma_commit_p(empty_bar(stage), lead);     // frees the raw slot once these MMAs have read it
           a0 += raw16; b0 += raw16;
           if (++stage == R) { stage = 0; phase ^= 1; a0 = a_base; b0 = b_base; }
           if (x3) {
-            umma_commit_p(lo_empty_bar(lst), lead);       // ... and the lo slot
+            if constexpr (kPair) umma2_commit_p(lo_empty_bar(lst));
+            else umma_commit_p(lo_empty_bar(lst), lead);  // ... and the lo slot
             al0 += lo16; bl0 += lo16; ta_hi += 64u;
             if (++lst == L) { lst = 0; lphase ^= 1; al0 = al_base; bl0 = bl_base; ta_hi = ta_base; }
           }
         }
-        umma_commit_p(acc_bar, lead);                      // accumulator complete
+        if constexpr (kPair) umma2_commit_p(acc_bar);
+        else umma_commit_p(acc_bar, lead);                 // accumulator complete
       }
     } else if (p.passes == 3) {
       // =============================== splitters: fp32 tile -> (hi, lo) =======================================
@@ -695,9 +805,11 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();         // the peer may still be reading this CTA's tensor / shared memory
   if (warp == 1) {
     const uint32_t ncols = tmem_cols(p.BN, p.passes, p.a_tmem);
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    if constexpr (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
 
@@ -780,6 +892,8 @@ static int env_int(const char* name, int dflt) {
 // experiment knobs (environment, read once): CTX_TC_BN3 = N tile of the 3-pass mode, CTX_TC_OCC = CTAs per SM the
 // shared-memory ring is sized for
 static int knob_bn3() { static int v = env_int("CTX_TC_BN3", 128); return v; }
+static int knob_lo_depth() { static int v = env_int("CTX_TC_LO_DEPTH", 4); return v < 1 ? 1 : (v > 4 ? 4 : v); }
+static int knob_pair() { static int v = env_int("CTX_TC_PAIR", 1); return v; }
 static int knob_atmem() { static int v = env_int("CTX_TC_ATMEM", 1); return v; }
 static int knob_occ() { static int v = env_int("CTX_TC_OCC", 0); return v; }
 
@@ -801,29 +915,52 @@ static int pick_bn(int N, int64_t m_tiles, int passes) {
   return bn;
 }
 
+// CTA pairs (cta_group::2) for the 3-pass K-major tiles: the pair runs one 256 x 128 MMA per step, each CTA staging and
+// splitting only half of the B tile — the 1-CTA 3-pass tile is bound by shared-memory bandwidth, and B is the
+// operand both CTAs would otherwise each stage, split and feed in full.  Decided before the B tensor map is built
+// (its box is half as tall).
+static bool want_pair(int passes, int a_mode, int BN, int N, int m_tiles, int kblocks) {
+  return knob_pair() && knob_atmem() && passes == 3 && a_mode == A_PIX && BN == 128 && N % 128 == 0 && m_tiles >= 2 &&
+         tc_occupancy(passes, BN, kblocks) == 1;
+}
+
 static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, const char* name) {
   const int sms = sm_count();
   if (sms <= 0) return cuda_fail(cudaErrorNoDevice, name);
-  const uint32_t raw = kATileBytes + (uint32_t)p.BN * 128u;
+  const uint32_t bn_cta = (uint32_t)(p.pair ? p.BN / 2 : p.BN);          // B rows staged by one CTA
+  const uint32_t raw = kATileBytes + bn_cta * 128u;
   static int max_dyn = 0;
   if (max_dyn == 0) {
-    cudaFuncAttributes fa;
-    CTX_CUDA(cudaFuncGetAttributes(&fa, tc_igemm_kernel));
+    cudaFuncAttributes fa, fa2;
+    CTX_CUDA(cudaFuncGetAttributes(&fa, tc_igemm_kernel<false>));
+    CTX_CUDA(cudaFuncGetAttributes(&fa2, tc_igemm_kernel<true>));
     int dev = 0, optin = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int dyn = optin - (int)fa.sharedSizeBytes;
-    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    const int stat = (int)(fa.sharedSizeBytes > fa2.sharedSizeBytes ? fa.sharedSizeBytes : fa2.sharedSizeBytes);
+    const int dyn = optin - stat;
+    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     max_dyn = dyn;
   }
   const int occ = tc_occupancy(p.passes, p.BN, p.nphase > 1 ? p.ph_kblocks[0] : p.kblocks_per_split);
   const uint32_t budget = occ == 1 ? (uint32_t)max_dyn : (uint32_t)(max_dyn - 2048) / 2u;
   // 3-pass with a K-major A operand: A (hi, lo) goes through tensor memory when the columns are there
   // (2 accumulators + 2 stages x 64 columns; 512 columns per SM shared by the resident CTAs)
-  p.a_tmem = (knob_atmem() && p.passes == 3 && p.a_mode == A_PIX && !p.scatter &&
-              2 * p.BN + 128 <= (occ == 2 ? 256 : 512)) ? 1 : 0;
-  const uint32_t lo_b = p.passes == 3 ? (p.a_tmem ? (uint32_t)p.BN * 128u : raw) : 0u;
-  p.lo_slots = p.passes == 3 ? ((budget - 1024u) >= 2 * raw + 2 * lo_b ? 2 : 1) : 0;
+  const int tmem_budget = occ == 2 ? 256 : 512;
+  const bool atm = knob_atmem() && p.passes == 3 && p.a_mode == A_PIX && !p.scatter && 2 * p.BN + 128 <= tmem_budget;
+  if (p.pair && (!atm || occ != 1)) { set_error("%s: internal: CTA pair without tensor-memory A", name); return CTX_ERR_ARG; }
+  const uint32_t lo_b = p.passes == 3 ? (atm ? bn_cta * 128u : raw) : 0u;
+  if (atm) {
+    // lo ring depth = tensor-memory A stages: as many as the columns allow (<= 4); a CTA pair needs the depth to
+    // hide the follower -> leader "tiles are split" hop
+    int depth = (tmem_budget - 2 * p.BN) / 64;
+    if (depth > knob_lo_depth()) depth = knob_lo_depth();
+    p.lo_slots = depth;
+  } else {
+    p.lo_slots = p.passes == 3 ? ((budget - 1024u) >= 2 * raw + 2 * lo_b ? 2 : 1) : 0;
+  }
+  p.a_tmem = atm ? p.lo_slots : 0;
   const int slots = (int)((budget - 1024u - (uint32_t)p.lo_slots * lo_b) / raw);
   p.raw_slots = slots;
   if (p.raw_slots > 8) p.raw_slots = 8;
@@ -832,8 +969,35 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
   p.err_flag = nullptr;
   const int n_tiles = (int)cdiv(p.N, p.BN);
   if (n_tiles > 65535 || splits > 65535) { set_error("%s: grid too large", name); return CTX_ERR_ARG; }
+  if (p.pair) {
+    // cluster of 2 CTAs along the M tiles (an odd last tile gets an all-out-of-range partner: TMA zero-fills it and
+    // the epilogue masks its rows)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)((m_tiles + 1) & ~1), (unsigned)n_tiles, (unsigned)splits);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_igemm_kernel<true>, p);
+    if (e != cudaSuccess) {
+      int nclusters = -1;
+      cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nclusters, tc_igemm_kernel<true>, &cfg);
+      cudaGetLastError();
+      set_error("CUDA error in %s (CTA pair launch): %s; grid %u x %u x %u, smem %zu, max active clusters %d (query: %s)",
+                name, cudaGetErrorName(e), cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z, smem, nclusters,
+                cudaGetErrorName(e2));
+      return CTX_ERR_CUDA;
+    }
+    count_launch();
+    return CTX_OK;
+  }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
-  tc_igemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  tc_igemm_kernel<false><<<grid, kThreads, smem, stream>>>(p);
   CTX_LAUNCH_CHECK(name);
   return CTX_OK;
 }
@@ -918,7 +1082,8 @@ int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, con
   p.M = g.N * g.P * g.Q; p.N = Co;
   int rc = make_tap_maps(p.mapA, x, C, g.N, g.H, g.W, g.stride, g.Q, p.BP, p.NB, false);
   if (rc) return rc;
-  p.b_atoms0 = p.BN / 32;                              // (Co % 32 == 0 is an eligibility condition)
+  p.pair = want_pair(passes, A_PIX, p.BN, Co, m_tiles, g.kh * g.kw * (C / 32)) ? 1 : 0;
+  p.b_atoms0 = (p.pair ? p.BN / 2 : p.BN) / 32;        // (Co % 32 == 0 is an eligibility condition)
   rc = make_bmn_map(&p.mapB[0], w, (int64_t)g.kh * g.kw * C, Co, Co, p.b_atoms0);
   if (rc) return rc;
   p.nseg = g.kh * g.kw;
@@ -1020,6 +1185,7 @@ int tc_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2
     p.a_mode = A_PIX; p.b_mode = B_K;
     const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * q0.tpi;
     p.BN = pick_bn(Cn, (int64_t)m_tiles * count, passes);
+    p.pair = want_pair(passes, A_PIX, p.BN, Cn, m_tiles, q0.taps * (Ck / 32)) ? 1 : 0;
     p.NG = g.N; p.PG = q0.Hp; p.QG = q0.Wp;
     p.M = g.N * q0.Hp * q0.Wp; p.N = Cn;
     p.a_wrap = x2_batch > 0 ? x2_batch : 1;
@@ -1037,7 +1203,7 @@ int tc_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2
     }
     {
       int64_t dims[2] = {Ck, (int64_t)g.kh * g.kw * Cn}, str[2] = {1, Ck};
-      int box[2] = {32, p.BN};
+      int box[2] = {32, p.pair ? p.BN / 2 : p.BN};
       int rc = make_map(&p.mapB[0], w, 2, dims, str, box);
       if (rc) return rc;
     }

@@ -392,7 +392,7 @@ __device__ __forceinline__ void split_chunks(const float4* __restrict__ s4, floa
 
 // kPair = true is the cta_group::2 build: a kernel that contains pair instructions can only be launched as a cluster
 // of even size, so the CTA-pair variant is a separate instantiation.
-template <bool kPair>
+template <bool kPair, bool kX3>
 __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
     // 3-pass mode keeps two accumulators: D1 = hi*hi, D2 = the two cross terms.  The tensor core truncates when
     // it adds into a running fp32 sum (measured: error grows linearly with the number of accumulations), so the
     // small terms must not ride on the big sum; D1 + D2 is formed once, in the epilogue, with a rounded fp32 add.
-    const uint32_t ncols = tmem_cols(p.BN, p.passes, p.a_tmem);
+    const uint32_t ncols = tmem_cols(p.BN, kX3 ? 3 : 1, p.a_tmem);
     if constexpr (kPair) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                    "r"(ncols)
@@ -581,7 +581,8 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
         const uint32_t a_hi = desc_hi(amn ? 512u : 1024u, amn ? 1u : 2u);
         const uint32_t b_hi = desc_hi(bmn ? 512u : 1024u, bmn ? 1u : 2u);
         const uint32_t d1 = tmem_base, d2 = tmem_base + (uint32_t)p.BN;
-        const bool x3 = p.passes == 3, atm = p.a_tmem != 0;
+        constexpr bool x3 = kX3;
+        const bool atm = kX3 && p.a_tmem != 0;
         // descriptor low words of ring slot 0; they advance by one slot per k-block (loop-carried, warp-uniform)
         const uint32_t raw16 = raw_bytes >> 4, lo16 = lo_bytes >> 4;
         const uint32_t a_base = desc_lo(smem_base, a_lbo), b_base = desc_lo(smem_base + kATileBytes, b_lbo);
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
         if constexpr (kPair) umma2_commit_p(acc_bar);
         else umma_commit_p(acc_bar, lead);                 // accumulator complete
       }
-    } else if (p.passes == 3) {
+    } else if constexpr (kX3) {
       // =============================== splitters: fp32 tile -> (hi, lo) =======================================
       const int t = threadIdx.x - 64;              // 0..255
       const int arow = (warp & 3) * 32 + lane;     // tensor-memory lane quarter this warp may access = tile row
@@ -726,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
       uint32_t v[32];
       if (nkb > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (p.passes == 3) {
+        if (kX3) {
           uint32_t v2[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), v2);
 #pragma unroll
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
   __syncthreads();
   if constexpr (kPair) cluster_sync_all();         // the peer may still be reading this CTA's tensor / shared memory
   if (warp == 1) {
-    const uint32_t ncols = tmem_cols(p.BN, p.passes, p.a_tmem);
+    const uint32_t ncols = tmem_cols(p.BN, kX3 ? 3 : 1, p.a_tmem);
     if constexpr (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
@@ -931,16 +932,19 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
   const uint32_t raw = kATileBytes + bn_cta * 128u;
   static int max_dyn = 0;
   if (max_dyn == 0) {
-    cudaFuncAttributes fa, fa2;
-    CTX_CUDA(cudaFuncGetAttributes(&fa, tc_igemm_kernel<false>));
-    CTX_CUDA(cudaFuncGetAttributes(&fa2, tc_igemm_kernel<true>));
+    cudaFuncAttributes fa[3];
+    CTX_CUDA(cudaFuncGetAttributes(&fa[0], tc_igemm_kernel<false, false>));
+    CTX_CUDA(cudaFuncGetAttributes(&fa[1], tc_igemm_kernel<false, true>));
+    CTX_CUDA(cudaFuncGetAttributes(&fa[2], tc_igemm_kernel<true, true>));
     int dev = 0, optin = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int stat = (int)(fa.sharedSizeBytes > fa2.sharedSizeBytes ? fa.sharedSizeBytes : fa2.sharedSizeBytes);
-    const int dyn = optin - stat;
-    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    size_t stat = 0;
+    for (int i = 0; i < 3; ++i) stat = fa[i].sharedSizeBytes > stat ? fa[i].sharedSizeBytes : stat;
+    const int dyn = optin - (int)stat;
+    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     max_dyn = dyn;
   }
   const int occ = tc_occupancy(p.passes, p.BN, p.nphase > 1 ? p.ph_kblocks[0] : p.kblocks_per_split);
@@ -983,10 +987,10 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_igemm_kernel<true>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_igemm_kernel<true, true>, p);
     if (e != cudaSuccess) {
       int nclusters = -1;
-      cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nclusters, tc_igemm_kernel<true>, &cfg);
+      cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nclusters, tc_igemm_kernel<true, true>, &cfg);
       cudaGetLastError();
       set_error("CUDA error in %s (CTA pair launch): %s; grid %u x %u x %u, smem %zu, max active clusters %d (query: %s)",
                 name, cudaGetErrorName(e), cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z, smem, nclusters,
@@ -997,7 +1001,8 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
     return CTX_OK;
   }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
-  tc_igemm_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+  if (p.passes == 3) tc_igemm_kernel<false, true><<<grid, kThreads, smem, stream>>>(p);
+  else tc_igemm_kernel<false, false><<<grid, kThreads, smem, stream>>>(p);
   CTX_LAUNCH_CHECK(name);
   return CTX_OK;
 }

@@ -56,6 +56,8 @@ SIGNATURES = {
                                       c_float, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "ctx_add_bcast": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "ctx_im2col": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, POINTER(ConvGeom), c_int32, c_void_p]),
+    "ctx_pool2d": (c_int32, [c_void_p, c_void_p, c_int32, POINTER(ConvGeom), c_int32, c_void_p]),
+    "ctx_copy_channels": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int64, c_void_p]),
     "ctx_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_void_p, c_void_p]),
     "ctx_round_tf32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -268,6 +268,50 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ o
   }
 }
 
+// ---- pooling (slim max_pool2d / avg_pool2d, nets/inception_v3.py:119-413) -----------------------------------------
+// mode 0: max over the in-range window elements; mode 1: average over the IN-RANGE elements (TF's SAME average pooling
+// divides by the number of valid positions, not by kh*kw).  One thread per output element, channel fastest.
+__global__ void pool2d_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int C, int H, int W,
+                              int P, int Q, int kh, int kw, int st, int padh, int padw, int mode) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int q = (int)(t % Q); t /= Q;
+    const int pp = (int)(t % P);
+    const int64_t n = t / P;
+    const int h0 = pp * st - padh, w0 = q * st - padw;
+    float acc = mode == 0 ? -3.402823466e38f : 0.f;
+    int cnt = 0;
+    for (int r = 0; r < kh; ++r) {
+      const int h = h0 + r;
+      if ((unsigned)h >= (unsigned)H) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int w = w0 + s;
+        if ((unsigned)w >= (unsigned)W) continue;
+        const float v = __ldg(x + ((n * H + h) * W + w) * C + c);
+        acc = mode == 0 ? fmaxf(acc, v) : acc + v;
+        ++cnt;
+      }
+    }
+    y[i] = mode == 0 ? acc : (cnt > 0 ? acc / (float)cnt : 0.f);
+  }
+}
+
+// dst[r, c_off + c] = src[r, c]: channel concatenation of NHWC tensors (tf.concat(axis=3), inception_v3.py:177 ...)
+__global__ void copy_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int Cs,
+                                     int Cd, int coff) {
+  const int64_t total = rows * Cs;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int64_t r = i / Cs;
+    const int c = (int)(i - r * Cs);
+    dst[r * Cd + coff + c] = src[i];
+  }
+}
+
 // ---- fused TF-Adam ----------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps,
@@ -532,6 +576,28 @@ extern "C" int ctx_im2col(const float* x, int32_t C, float* out, int32_t ld, con
       FastDiv(ld),
       FastDiv(C), FastDiv(g->kw), FastDiv(g->Q), FastDiv(g->P));
   CTX_LAUNCH_CHECK("im2col");
+  return CTX_OK;
+}
+
+extern "C" int ctx_pool2d(const float* x, float* y, int32_t C, const ctx_conv_geom* g, int32_t mode, void* stream) {
+  CTX_REQUIRE(x && y && g && C > 0 && (mode == 0 || mode == 1), "pool2d: bad arguments");
+  CTX_REQUIRE(g->kh > 0 && g->kw > 0 && g->stride > 0 && g->P > 0 && g->Q > 0 && g->H > 0 && g->W > 0 &&
+                  g->pad_h >= 0 && g->pad_w >= 0, "pool2d: bad geometry");
+  const int64_t total = (int64_t)g->N * g->P * g->Q * C;
+  if (total == 0) return CTX_OK;
+  pool2d_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, g->H, g->W, g->P, g->Q, g->kh,
+                                                                            g->kw, g->stride, g->pad_h, g->pad_w, mode);
+  CTX_LAUNCH_CHECK("pool2d");
+  return CTX_OK;
+}
+
+extern "C" int ctx_copy_channels(const float* src, int32_t Cs, float* dst, int32_t Cd, int32_t c_off, int64_t rows,
+                                 void* stream) {
+  CTX_REQUIRE(src && dst && Cs > 0 && Cd > 0 && c_off >= 0 && c_off + Cs <= Cd && rows >= 0,
+              "copy_channels: bad arguments (Cs=%d Cd=%d c_off=%d)", Cs, Cd, c_off);
+  if (rows == 0) return CTX_OK;
+  copy_channels_kernel<<<grid_for(rows * Cs, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, Cs, Cd, c_off);
+  CTX_LAUNCH_CHECK("copy_channels");
   return CTX_OK;
 }
 

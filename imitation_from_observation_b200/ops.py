@@ -150,6 +150,60 @@ def conv2d_wgrad(big, small1, k: int, stride: int, small2=None, dw=None, impl=IM
     return dw
 
 
+def _geom_general(n, H, W_, kh, kw, stride, padding):
+    """TF geometry for a rectangular window: padding 'SAME' (asymmetric, low half first) or 'VALID'."""
+    if padding == "SAME":
+        P, Q = same_out(H, stride), same_out(W_, stride)
+        ph, pw = same_pad(H, kh, stride)[0], same_pad(W_, kw, stride)[0]
+    elif padding == "VALID":
+        P, Q = (H - kh) // stride + 1, (W_ - kw) // stride + 1
+        ph = pw = 0
+    else:
+        raise _lib.CtxError("padding must be 'SAME' or 'VALID'")
+    if P <= 0 or Q <= 0:
+        raise _lib.CtxError("window %dx%d does not fit a %dx%d input" % (kh, kw, H, W_))
+    return ConvGeom(n, H, W_, P, Q, kh, kw, stride, ph, pw)
+
+
+def conv2d_general(x, w, bias=None, stride: int = 1, padding: str = "SAME", act: bool = False, slope: float = 0.0,
+                   out=None, impl=IMPL_AUTO):
+    """slim.conv2d as InceptionV3 uses it (nets/inception_v3.py:104-413): rectangular kernels (1x7, 7x1, 1x3, 3x1),
+    SAME or VALID, folded-BN bias, activation max(v, slope*v) (slope 0 = ReLU).  x [N,H,W,C], w [kh,kw,C,Co]."""
+    N, H, W_, Cin = x.shape
+    kh, kw, Cw, Co = w.shape
+    if Cw != Cin:
+        raise _lib.CtxError("conv2d_general: filter %s does not match input %s" % (tuple(w.shape), tuple(x.shape)))
+    g = _geom_general(N, H, W_, kh, kw, stride, padding)
+    if out is None:
+        out = torch.empty((N, g.P, g.Q, Co), device=x.device, dtype=torch.float32)
+    epi = make_epilogue(bias, act, None, False, False, slope)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * kh * kw * Cin)
+    check(_lib.load().ctx_conv2d_fprop(_req(x, "x"), Cin, _req(w, "w"), _req(out, "out"), Co, C.byref(g),
+                                       C.byref(epi), impl, _stream()), "ctx_conv2d_fprop")
+    pr.done()
+    return out
+
+
+def pool2d(x, k: int, stride: int, padding: str, mode: str, out=None):
+    """slim.max_pool2d / avg_pool2d on NHWC (avg: TF's count-valid divisor)."""
+    N, H, W_, Cc = x.shape
+    g = _geom_general(N, H, W_, k, k, stride, padding)
+    if out is None:
+        out = torch.empty((N, g.P, g.Q, Cc), device=x.device, dtype=torch.float32)
+    check(_lib.load().ctx_pool2d(_req(x, "x"), _req(out, "out"), Cc, C.byref(g), {"max": 0, "avg": 1}[mode], _stream()),
+          "ctx_pool2d")
+    return out
+
+
+def copy_channels(src, dst, c_off: int):
+    """dst[..., c_off:c_off+Cs] = src  (tf.concat(axis=3) into a pre-allocated NHWC tensor)."""
+    Cs, Cd = src.shape[-1], dst.shape[-1]
+    rows = src.numel() // Cs
+    check(_lib.load().ctx_copy_channels(_req(src, "src"), Cs, _req(dst, "dst"), Cd, c_off, rows, _stream()),
+          "ctx_copy_channels")
+    return dst
+
+
 # ---- dense -------------------------------------------------------------------------------------------------------
 def gemm_raw(tA: bool, tB: bool, M: int, N: int, K: int, A_ptr: int, lda: int, B_ptr: int, ldb: int, C_ptr: int,
              ldc: int, epi: Optional[Epilogue] = None, impl=IMPL_AUTO):
@@ -168,7 +222,7 @@ def _mat(t: torch.Tensor, name: str):
 
 
 def gemm(A, B, out=None, transA=False, transB=False, bias=None, act=False, act_ref=None, accumulate=False,
-         round_tf32=False, impl=IMPL_AUTO):
+         round_tf32=False, impl=IMPL_AUTO, slope: float = LRELU_SLOPE):
     """C = opA(A) @ opB(B) with the fused epilogue (tf.matmul + bias, arm_shaping.py:48-59, and its gradients).
     A, B, out may be row-slices / column-slices of larger row-major matrices."""
     pa, ar, ac, lda = _mat(A, "A")
@@ -184,7 +238,7 @@ def gemm(A, B, out=None, transA=False, transB=False, bias=None, act=False, act_r
         raise _lib.CtxError("gemm: out has shape %s, expected %s" % ((cr, cc), (M, N)))
     if act_ref is not None and (not act_ref.is_contiguous() or ldc != N):
         raise _lib.CtxError("gemm: act_ref requires a dense output")
-    epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
+    epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32, slope)
     gemm_raw(transA, transB, M, N, K, pa, lda, pb, ldb, pc, ldc, epi, impl)
     return out
 
@@ -253,10 +307,10 @@ def add_bcast(a, b, out=None):
     return out
 
 
-def im2col(x, k: int, stride: int, ld: int, out=None, round_tf32=False):
-    """Patch matrix [N*P*Q, ld] of a SAME conv over a few-channel NHWC tensor (columns (r,s,c), zero padded)."""
+def im2col(x, k: int, stride: int, ld: int, out=None, round_tf32=False, padding: str = "SAME"):
+    """Patch matrix [N*P*Q, ld] of a SAME / VALID conv over a few-channel NHWC tensor (columns (r,s,c), zero padded)."""
     N, H, W_, Cc = x.shape
-    g = conv_geom(N, (H, W_), k, stride)
+    g = _geom_general(N, H, W_, k, k, stride, padding)
     if out is None:
         out = torch.empty((N * g.P * g.Q, ld), device=x.device, dtype=torch.float32)
     check(_lib.load().ctx_im2col(_req(x, "x"), Cc, _req(out, "out"), ld, C.byref(g), int(round_tf32), _stream()),

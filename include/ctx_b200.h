@@ -167,6 +167,15 @@ int ctx_add_bcast(const float* a, const float* b, float* out, int64_t rows, int6
 int ctx_im2col(const float* x, int32_t C, float* out, int32_t ld, const ctx_conv_geom* g, int32_t round_tf32,
                void* stream);
 
+/* slim.max_pool2d (mode 0) / slim.avg_pool2d (mode 1) over an NHWC tensor — nets/inception_v3.py:119,134,158 ...
+ * g gives the window (kh, kw, stride), the low padding (pad_h, pad_w; 0 for VALID) and the output grid (P, Q).
+ * Average pooling divides by the number of IN-RANGE window elements (TensorFlow's SAME semantics). */
+int ctx_pool2d(const float* x, float* y, int32_t C, const ctx_conv_geom* g, int32_t mode, void* stream);
+
+/* dst[r, c_off + c] = src[r, c] for r < rows: tf.concat(axis=3) of NHWC tensors into a wider one
+ * (nets/inception_v3.py:177 and every Mixed_* block). */
+int ctx_copy_channels(const float* src, int32_t Cs, float* dst, int32_t Cd, int32_t c_off, int64_t rows, void* stream);
+
 /* TF-style Adam on flat buffers (scripts/train_script.py:128; epsilon outside the bias correction):
  *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr_t * m / (sqrt(v) + eps)
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  grad_scale multiplies g first (1.0 normally).

@@ -1,0 +1,96 @@
+"""GPU parity of the InceptionV3 feature extractor (nets/inception_v3.py) and the Inception reward against the CPU
+oracle, through the C-ABI.  Random (variance-scaling) weights: the reference ships no checkpoint."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from imitation_from_observation_b200 import _lib, inception as I, ops
+from oracle import inception_v3 as OI
+from test_oracle import _inception_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k,stride,padding,mode", [(3, 2, "VALID", "max"), (3, 1, "SAME", "avg"), (8, 1, "VALID", "avg"),
+                                                   (3, 2, "SAME", "max")])
+def test_pool2d(k, stride, padding, mode):
+    hw = 8 if k == 8 else 17
+    x = torch.randn((2, hw, hw, 12), generator=torch.Generator().manual_seed(3))
+    xc = x.permute(0, 3, 1, 2)
+    Fn = torch.nn.functional
+    if padding == "VALID":
+        ref = Fn.max_pool2d(xc, k, stride) if mode == "max" else Fn.avg_pool2d(xc, k, stride)
+    elif mode == "avg":
+        ref = OI._avg_pool_same(xc, k)                               # divides by the number of in-range elements
+    else:                                                            # SAME max pooling: padding never wins
+        out = -(-hw // stride)
+        tot = max((out - 1) * stride + k - hw, 0)
+        ref = Fn.max_pool2d(Fn.pad(xc, (tot // 2, tot - tot // 2, tot // 2, tot - tot // 2), value=float("-inf")), k, stride)
+    y = ops.pool2d(x.cuda(), k, stride, padding, mode)
+    assert tuple(y.shape) == tuple(ref.permute(0, 2, 3, 1).shape)
+    assert rel_err(y.cpu(), ref.permute(0, 2, 3, 1)) < 1e-6
+
+
+def test_copy_channels_is_concat():
+    a, b = torch.randn(3, 4, 5, 8), torch.randn(3, 4, 5, 5)
+    out = torch.zeros(3, 4, 5, 13).cuda()
+    ops.copy_channels(a.cuda(), out, 0)
+    ops.copy_channels(b.cuda(), out, 8)
+    assert torch.equal(out.cpu(), torch.cat([a, b], 3))
+
+
+@pytest.mark.parametrize("kh,kw,stride,padding", [(1, 7, 1, "SAME"), (7, 1, 1, "SAME"), (1, 3, 1, "SAME"), (3, 3, 2, "VALID"),
+                                                  (3, 3, 1, "VALID"), (1, 1, 1, "SAME"), (5, 5, 1, "SAME")])
+@pytest.mark.parametrize("hw,c,co", [(17, 128, 192), (8, 64, 96), (9, 48, 64)])
+def test_conv2d_general_rectangular_and_valid(kh, kw, stride, padding, hw, c, co):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, hw, hw, c), generator=g)
+    w = torch.randn((kh, kw, c, co), generator=g) * (kh * kw * c) ** -0.5
+    b = torch.randn((co,), generator=g) * 0.1
+    xc = x.double().permute(0, 3, 1, 2)
+    if padding == "SAME":
+        xc = OI._pad_same(xc, kh, kw, stride)
+    ref = torch.relu(torch.nn.functional.conv2d(xc, w.double().permute(3, 2, 0, 1), b.double(), stride=stride))
+    for impl, tol in ((_lib.IMPL_SIMT, 2e-5), (_lib.IMPL_AUTO, 2e-5)):
+        y = ops.conv2d_general(x.cuda(), w.cuda(), b.cuda(), stride=stride, padding=padding, act=True, slope=0.0, impl=impl)
+        assert rel_err(y.cpu(), ref.permute(0, 2, 3, 1)) < tol, impl
+
+
+def test_inception_v3_endpoints_match_oracle():
+    """B = 2, 299x299 uint8 frames (as base.py:72-76 feeds them): Mixed_5d / Mixed_6e / Mixed_7c / PreLogits vs the
+    fp64 oracle, 1e-3 relative (north_star tolerance); 94 folded conv launches."""
+    P = _inception_params(seed=11)
+    frames = torch.randint(0, 256, (2, 299, 299, 3), generator=torch.Generator().manual_seed(12), dtype=torch.uint8)
+    x = ((frames.float() * (1.0 / 255.0)) - 0.5) * 2.0
+    ref = OI.forward({k: v.double() for k, v in P.items()}, x.double())
+    net = I.InceptionV3(precision="mixed")
+    net.load_state_dict(P)
+    got = net.forward(frames.cuda(), endpoints=("Mixed_5d", "Mixed_6e", "Mixed_7c", "PreLogits"))
+    torch.cuda.synchronize()
+    for k in ("Mixed_5d", "Mixed_6e", "Mixed_7c", "PreLogits"):
+        assert tuple(got[k].shape) == tuple(ref[k].shape), k
+        assert rel_err(got[k].cpu(), ref[k]) < 1e-3, k
+    # early exit: asking for an early end point does not run the rest
+    n0 = ops.launch_count()
+    net.forward(frames.cuda(), endpoints=("Mixed_5b",))
+    n1 = ops.launch_count()
+    net.forward(frames.cuda(), endpoints=("Mixed_7c",))
+    assert n1 - n0 < ops.launch_count() - n1
+
+
+def test_inception_reward_kernel_matches_reference_loop():
+    T, paths = 25, 6
+    g = torch.Generator().manual_seed(13)
+    feat = torch.rand((paths * T, 4, 4, 32), generator=g)
+    means, std = torch.rand((T, 4, 4, 32), generator=g), torch.rand((T, 4, 4, 32), generator=g)
+    std[:, :, :, ::5] = 0
+    rewards = torch.zeros((paths, 2 * T), dtype=torch.float64)
+    ref = rewards.clone()
+    for p in range(paths):
+        c = OI.reward_inception(feat[p * T:(p + 1) * T].reshape(T, -1), means.reshape(T, -1), std.reshape(T, -1))
+        for j in range(T):
+            ref[p, 2 * j + 1] -= float(c[j]) * j * j
+    r = rewards.cuda()
+    ops.reward_inception(feat.cuda(), means.cuda(), std.cuda(), paths, T, rewards=r)
+    assert rel_err(r.cpu(), ref) < 1e-5

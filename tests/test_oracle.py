@@ -177,3 +177,57 @@ def test_trainer_batch_assembly_matches_reference_indexing():
     a = synthetic.trainer_batch(bank, 7, 5, 4, np.random.RandomState(3))
     b = O.trainer_batch(bank, 7, 5, np.random.RandomState(3), 4)
     assert np.array_equal(a, b) and a.shape == (3, 7, 8, 8, 3)
+
+
+# ---- InceptionV3 (nets/inception_v3.py): what the reference's own tests pin --------------------------------------------
+def _inception_params(seed=0, dtype=torch.float32):
+    from imitation_from_observation_b200 import inception as I          # static table only
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    for name, shp in I.param_shapes().items():
+        if name.endswith("/weights"):
+            P[name] = (torch.randn(shp, generator=g) * (2.0 / (shp[0] * shp[1] * shp[2])) ** 0.5).to(dtype)
+        elif name.endswith("moving_variance"):
+            P[name] = (torch.rand(shp, generator=g) * 0.5 + 0.75).to(dtype)
+        else:
+            P[name] = (torch.randn(shp, generator=g) * 0.1).to(dtype)
+    return P
+
+
+def test_inception_v3_shape_and_parameter_pins():
+    """nets/inception_v3_test.py:80-110 (every end-point shape at 299x299), :112-120 (21 802 784 parameters of the
+    base network), :141-144 (PreLogits [B,1,1,2048]) — against BOTH the product's table and the oracle's forward."""
+    from imitation_from_observation_b200 import inception as I
+    from oracle import inception_v3 as OI
+    table = I.conv_table()
+    assert len(table) == 94
+    assert sum(kh * kw * ci * co + 3 * co for _, kh, kw, ci, co in table) == 21802784
+    pins = {"Conv2d_1a_3x3": (149, 149, 32), "Conv2d_2a_3x3": (147, 147, 32), "Conv2d_2b_3x3": (147, 147, 64),
+            "MaxPool_3a_3x3": (73, 73, 64), "Conv2d_3b_1x1": (73, 73, 80), "Conv2d_4a_3x3": (71, 71, 192),
+            "MaxPool_5a_3x3": (35, 35, 192), "Mixed_5b": (35, 35, 256), "Mixed_5c": (35, 35, 288),
+            "Mixed_5d": (35, 35, 288), "Mixed_6a": (17, 17, 768), "Mixed_6b": (17, 17, 768), "Mixed_6c": (17, 17, 768),
+            "Mixed_6d": (17, 17, 768), "Mixed_6e": (17, 17, 768), "Mixed_7a": (8, 8, 1280), "Mixed_7b": (8, 8, 2048),
+            "Mixed_7c": (8, 8, 2048), "PreLogits": (1, 1, 2048)}
+    P = _inception_params()
+    x = torch.rand((1, 299, 299, 3), generator=torch.Generator().manual_seed(1)) * 2 - 1
+    ep = OI.forward(P, x)
+    assert ep.pop("_convs_used") == 94                              # the oracle touched every conv of the table
+    assert set(ep) == set(pins) == set(I.ENDPOINTS)
+    for k, shp in pins.items():
+        assert tuple(ep[k].shape) == (1,) + shp, k
+    assert float(ep["Mixed_7c"].abs().max()) > 0 and torch.isfinite(ep["PreLogits"]).all()
+
+
+def test_inception_reward_formula():
+    from oracle import inception_v3 as OI
+    T, n = 5, 12
+    feat, means = torch.rand(T, n), torch.rand(T, n)
+    std = torch.rand(T, n)
+    std[:, ::3] = 0
+    got = OI.reward_inception(feat, means, std)
+    ref = []
+    for j in range(T):                                               # base.py:184-189 written out
+        d = (means[j] - feat[j]).clone()
+        d[std[j] == 0] = 0
+        ref.append(float(np.mean((d.numpy() ** 2) / (std[j].numpy() + 1e-5))))
+    assert np.allclose(got.numpy(), ref, rtol=1e-6)

@@ -299,6 +299,39 @@ __global__ void pool2d_kernel(const float* __restrict__ x, float* __restrict__ y
   }
 }
 
+// 128-bit version (C % 4 == 0): one thread per 4 channels of an output pixel; 32-bit index arithmetic
+__global__ void pool2d_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y, int total, int Cq, int H, int W,
+                                  int kh, int kw, int st, int padh, int padw, int mode, FastDiv divC, FastDiv divQ,
+                                  FastDiv divP) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t, c, q, n, pp;
+    divC.divmod(i, t, c);
+    divQ.divmod(t, t, q);
+    divP.divmod(t, n, pp);
+    const int h0 = pp * st - padh, w0 = q * st - padw;
+    float4 acc = mode == 0 ? make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    for (int r = 0; r < kh; ++r) {
+      const int h = h0 + r;
+      if ((unsigned)h >= (unsigned)H) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int w = w0 + s;
+        if ((unsigned)w >= (unsigned)W) continue;
+        const float4 v = __ldg(x + ((int64_t)(n * H + h) * W + w) * Cq + c);
+        if (mode == 0) { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
+        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        ++cnt;
+      }
+    }
+    if (mode == 1) {
+      acc.x = cnt > 0 ? acc.x / (float)cnt : 0.f; acc.y = cnt > 0 ? acc.y / (float)cnt : 0.f;
+      acc.z = cnt > 0 ? acc.z / (float)cnt : 0.f; acc.w = cnt > 0 ? acc.w / (float)cnt : 0.f;
+    }
+    y[i] = acc;
+  }
+}
+
 // dst[r, c_off + c] = src[r, c]: channel concatenation of NHWC tensors (tf.concat(axis=3), inception_v3.py:177 ...)
 __global__ void copy_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int Cs,
                                      int Cd, int coff) {
@@ -309,6 +342,15 @@ __global__ void copy_channels_kernel(const float* __restrict__ src, float* __res
     const int64_t r = i / Cs;
     const int c = (int)(i - r * Cs);
     dst[r * Cd + coff + c] = src[i];
+  }
+}
+
+__global__ void copy_channels_vec_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int total, int Csq,
+                                         int Cdq, int coffq, FastDiv divCs) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int r, c;
+    divCs.divmod(i, r, c);
+    dst[(int64_t)r * Cdq + coffq + c] = __ldg(src + i);
   }
 }
 
@@ -585,8 +627,14 @@ extern "C" int ctx_pool2d(const float* x, float* y, int32_t C, const ctx_conv_ge
                   g->pad_h >= 0 && g->pad_w >= 0, "pool2d: bad geometry");
   const int64_t total = (int64_t)g->N * g->P * g->Q * C;
   if (total == 0) return CTX_OK;
-  pool2d_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, g->H, g->W, g->P, g->Q, g->kh,
-                                                                            g->kw, g->stride, g->pad_h, g->pad_w, mode);
+  if (C % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && total / 4 < (1ll << 31)) {
+    const int tq = (int)(total / 4);
+    pool2d_vec_kernel<<<grid_for(tq, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), tq, C / 4, g->H, g->W, g->kh, g->kw, g->stride,
+        g->pad_h, g->pad_w, mode, FastDiv(C / 4), FastDiv(g->Q), FastDiv(g->P));
+  } else
+    pool2d_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, g->H, g->W, g->P, g->Q, g->kh,
+                                                                              g->kw, g->stride, g->pad_h, g->pad_w, mode);
   CTX_LAUNCH_CHECK("pool2d");
   return CTX_OK;
 }
@@ -596,7 +644,13 @@ extern "C" int ctx_copy_channels(const float* src, int32_t Cs, float* dst, int32
   CTX_REQUIRE(src && dst && Cs > 0 && Cd > 0 && c_off >= 0 && c_off + Cs <= Cd && rows >= 0,
               "copy_channels: bad arguments (Cs=%d Cd=%d c_off=%d)", Cs, Cd, c_off);
   if (rows == 0) return CTX_OK;
-  copy_channels_kernel<<<grid_for(rows * Cs, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, Cs, Cd, c_off);
+  if (Cs % 4 == 0 && Cd % 4 == 0 && c_off % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 &&
+      rows * (Cs / 4) < (1ll << 31)) {
+    const int tq = (int)(rows * (Cs / 4));
+    copy_channels_vec_kernel<<<grid_for(tq, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), tq, Cs / 4, Cd / 4, c_off / 4, FastDiv(Cs / 4));
+  } else
+    copy_channels_kernel<<<grid_for(rows * Cs, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, Cs, Cd, c_off);
   CTX_LAUNCH_CHECK("copy_channels");
   return CTX_OK;
 }

@@ -74,7 +74,11 @@ struct TcParams {
   // row grid of the A/D tile: rows r -> (dn, dp, dq)
   int32_t NG, PG, QG;              // grid extents (images, rows, cols); A_MN: NG = M, PG = QG = 1
   int32_t BP, NB;                  // tile = NB images x BP rows x QG cols  (== 128 rows), or 32 for A_MN k-blocks
-  int32_t tiles_per_img;           // PG / BP when NB == 1, else 1
+  int32_t tiles_per_img;           // row tiles per image (PG / BP, rounded up) when NB == 1, else 1
+  // partial tiles (conv fprop on grids that do not tile into 128 pixels): the A box is BQ x BP x NB <= 128 pixels
+  // (a_rows), q_tiles column tiles per image row band; MMA rows past a_rows are dead and masked by the epilogue.
+  // 0 = exact tiling (BQ = QG, one column tile, 128 rows).
+  int32_t BQ, q_tiles, a_rows;
   int32_t a_wrap;                  // batch of the wrapped source
   // A_MN: K blocks are 32-pixel boxes of this pixel grid (images x kPG x kQG), kNB images x kBP rows each
   int32_t kPG, kQG, kBP, kNB, k_tiles_per_img;
@@ -437,8 +441,14 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
   const int nkb = kb_end - kb_begin;
   // tile origin on the row grid
   const int tile_m = blockIdx.x;
-  int n0, p0;
-  if (p.NB > 1 || p.tiles_per_img == 1) { n0 = tile_m * p.NB; p0 = 0; }
+  int n0, p0, q0 = 0;
+  const int BQ = p.BQ > 0 ? p.BQ : p.QG, a_rows = p.a_rows > 0 ? p.a_rows : 128;
+  if (p.q_tiles > 1) {
+    const int per = p.tiles_per_img * p.q_tiles;
+    n0 = tile_m / per;
+    const int rem_t = tile_m - n0 * per, pt = rem_t / p.q_tiles;
+    p0 = pt * p.BP; q0 = (rem_t - pt * p.q_tiles) * BQ;
+  } else if (p.NB > 1 || p.tiles_per_img == 1) { n0 = tile_m * p.NB; p0 = 0; }
   else { n0 = tile_m / p.tiles_per_img; p0 = (tile_m - n0 * p.tiles_per_img) * p.BP; }
   const int ncol0 = blockIdx.y * p.BN;
 
@@ -495,9 +505,9 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
               mbar_wait(empty_bar(stage), phase ^ 1, p.err_flag, 1);
               const uint32_t sa = smem_base + stage * raw_bytes;
               const uint32_t sb = sa + kATileBytes;
-              mbar_arrive_expect_tx(full_bar(stage), raw_bytes);
+              mbar_arrive_expect_tx(full_bar(stage), (uint32_t)a_rows * 128u + b_tile_bytes);
               const int nimg = s.wrap ? (n0 % p.a_wrap) : n0;
-              tma_load_4d(sa, &p.mapA[s.mapA], full_bar(stage), cb * 32, s.dw, p0 + s.dh, nimg);
+              tma_load_4d(sa, &p.mapA[s.mapA], full_bar(stage), cb * 32, q0 + s.dw, p0 + s.dh, nimg);
               const int nb0 = ncol0 + (int)cta_rank * (p.BN / 2);      // pair: this CTA's half of the B tile
               if (p.b_mode == B_K) {
                 tma_load_2d(sb, &p.mapB[0], full_bar(stage), s.bk0 + cb * 32, s.br0 + nb0);
@@ -717,12 +727,12 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
       tc_fence_after();
     }
     // row -> (n, p, q) -> output offset
-    const int per_img = p.BP * p.QG;
+    const int per_img = p.BP * BQ;
     const int dn = r / per_img, rem = r - dn * per_img;
-    const int dp = rem / p.QG, dq = rem - dp * p.QG;
-    const int gn = n0 + dn, gp = p0 + dp;
-    const bool row_ok = gn < p.NG && gp < p.PG && (nkb > 0 || !p.atomic_out);
-    const int64_t roff = obase + (int64_t)gn * p.sN + (int64_t)gp * p.sP + (int64_t)dq * p.sQ;
+    const int dp = rem / BQ, dq = rem - dp * BQ;
+    const int gn = n0 + dn, gp = p0 + dp, gq = q0 + dq;
+    const bool row_ok = r < a_rows && gn < p.NG && gp < p.PG && gq < p.QG && (nkb > 0 || !p.atomic_out);
+    const int64_t roff = obase + (int64_t)gn * p.sN + (int64_t)gp * p.sP + (int64_t)gq * p.sQ;
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       uint32_t v[32];
       if (nkb > 0) {
@@ -745,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
         // (tap, channel) of the first column; all lanes walk the same columns, so this is warp-uniform
         int tap = col / p.sc_Cn, co = col - tap * p.sc_Cn;
         int rr = tap / p.sc_kw, ss = tap - rr * p.sc_kw;
-        const int hb = gp * p.sc_st - p.sc_padh, wb = dq * p.sc_st - p.sc_padw;
+        const int hb = gp * p.sc_st - p.sc_padh, wb = gq * p.sc_st - p.sc_padw;
         float* obase_n = p.out + (int64_t)gn * p.sc_H * p.sc_W * p.sc_Cn;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -884,6 +894,21 @@ static bool tile_grid(int P, int Q, int rows, int* BP, int* NB, int* tiles_per_i
   return true;
 }
 
+// Partial tiling of a P x Q pixel grid for conv fprop when it does not tile exactly into 128 pixels (InceptionV3's
+// 17x17, 35x35, 71..149-wide maps): the A box is BQ x BP x NB <= 128 pixels.
+static void plan_partial(int P, int Q, int* BQ, int* BP, int* NB, int* tiles_p, int* tiles_q) {
+  if (Q > 128) {
+    *tiles_q = (Q + 127) / 128; *BQ = (Q + *tiles_q - 1) / *tiles_q; *BP = 1; *NB = 1; *tiles_p = P;
+    return;
+  }
+  *BQ = Q; *tiles_q = 1;
+  int bp = 128 / Q;
+  if (bp >= P) { *BP = P; *NB = 128 / (P * Q); if (*NB < 1) *NB = 1; *tiles_p = 1; return; }
+  *tiles_p = (P + bp - 1) / bp;
+  *BP = (P + *tiles_p - 1) / *tiles_p;              // even out the row bands
+  *NB = 1;
+}
+
 // N tile: 128 for the 3-pass mode (with a 5-deep raw ring it is the best-balanced 1-CTA shape: tensor 768, splitter
 // ~512, TMA ~42 B/cycle per k-block), 256 for single-pass; halved while the grid would not fill the SMs.
 static int env_int(const char* name, int dflt) {
@@ -1020,12 +1045,12 @@ static bool aligned16(const void* ptr) { return ((uintptr_t)ptr & 15) == 0; }
 
 // ---- conv fprop ------------------------------------------------------------------------------------------------
 int tc_conv2d_fprop_eligible(int C, int Co, const ctx_conv_geom& g) {
-  int bp, nb, tpi;
-  if (C % 32 != 0 || Co % 32 != 0) return 0;
+  // channels: 16-byte TMA strides (C, Co % 4); a ragged last 32-channel block is zero-filled by the TMA unit (A: channel
+  // coordinates past C; B: the matching rows are multiplied by those zeros, rows past kh*kw*C are zero-filled too)
+  if (C % 4 != 0 || Co % 4 != 0 || C < 32 || Co < 32) return 0;
   if (g.stride != 1 && g.stride != 2) return 0;
   if (g.kh * g.kw > kMaxSeg) return 0;
-  if (!tile_grid(g.P, g.Q, 128, &bp, &nb, &tpi)) return 0;
-  return 1;
+  return 1;                                          // any P x Q grid: exact 128-pixel tiles or partial tiles
 }
 
 // Tensor maps of a (possibly stride-2) NHWC tensor read at conv-tap offsets.  For stride 2, map[hp*2+wp] is the
@@ -1076,29 +1101,45 @@ int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, con
                     const Epi& epi, int passes, cudaStream_t stream) {
   TcParams p;
   fill_common(p, passes, epi);
-  int tpi;
-  if (!tile_grid(g.P, g.Q, 128, &p.BP, &p.NB, &tpi)) return CTX_ERR_UNSUPPORTED;
+  int tpi, box_q = g.Q, m_tiles;
   CTX_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), "conv2d_fprop(tc): pointers must be 16-byte aligned");
-  p.tiles_per_img = tpi;
+  if (tile_grid(g.P, g.Q, 128, &p.BP, &p.NB, &tpi)) {
+    p.tiles_per_img = tpi;
+    m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
+  } else {
+    int tq;
+    plan_partial(g.P, g.Q, &p.BQ, &p.BP, &p.NB, &tpi, &tq);
+    p.tiles_per_img = tpi; p.q_tiles = tq; p.a_rows = p.BQ * p.BP * p.NB;
+    box_q = p.BQ;
+    m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi * tq;
+    if (tq == 1 && p.NB == 1 && tpi > 1) p.q_tiles = 0;   // plain row bands: same decode as exact tiling
+  }
   p.a_mode = A_PIX; p.b_mode = B_MN;
-  const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
   p.BN = pick_bn(Co, m_tiles, passes);
   p.NG = g.N; p.PG = g.P; p.QG = g.Q;
   p.M = g.N * g.P * g.Q; p.N = Co;
-  int rc = make_tap_maps(p.mapA, x, C, g.N, g.H, g.W, g.stride, g.Q, p.BP, p.NB, false);
+  int rc = make_tap_maps(p.mapA, x, C, g.N, g.H, g.W, g.stride, box_q, p.BP, p.NB, false);
   if (rc) return rc;
-  p.pair = want_pair(passes, A_PIX, p.BN, Co, m_tiles, g.kh * g.kw * (C / 32)) ? 1 : 0;
-  p.b_atoms0 = (p.pair ? p.BN / 2 : p.BN) / 32;        // (Co % 32 == 0 is an eligibility condition)
-  rc = make_bmn_map(&p.mapB[0], w, (int64_t)g.kh * g.kw * C, Co, Co, p.b_atoms0);
+  const int cblk = (int)cdiv(C, 32);
+  p.pair = (Co % 32 == 0 && want_pair(passes, A_PIX, p.BN, Co, m_tiles, g.kh * g.kw * cblk)) ? 1 : 0;
+  if (Co % 32 == 0) {
+    p.b_atoms0 = (p.pair ? p.BN / 2 : p.BN) / 32;      // all atoms of the tile in one instruction
+    rc = make_bmn_map(&p.mapB[0], w, (int64_t)g.kh * g.kw * C, Co, Co, p.b_atoms0);
+  } else {
+    p.b_atoms0 = 0;                                    // ragged last atom: one (zero-filled) box per atom
+    int64_t dims[2] = {Co, (int64_t)g.kh * g.kw * C}, str[2] = {1, Co};
+    int box[2] = {32, 32};
+    rc = make_map(&p.mapB[0], w, 2, dims, str, box, true);
+  }
   if (rc) return rc;
   p.nseg = g.kh * g.kw;
   for (int r = 0; r < g.kh; ++r)
     for (int s = 0; s < g.kw; ++s) {
       Seg& sg = p.seg[r * g.kw + s];
       tap_seg(sg, r, s, g);
-      sg.wrap = 0; sg.nblk = (uint16_t)(C / 32); sg.bk0 = (r * g.kw + s) * C; sg.br0 = 0;
+      sg.wrap = 0; sg.nblk = (uint16_t)cblk; sg.bk0 = (r * g.kw + s) * C; sg.br0 = 0;
     }
-  p.total_kblocks = p.nseg * (C / 32);
+  p.total_kblocks = p.nseg * cblk;
   p.kblocks_per_split = p.total_kblocks;
   p.out = y;
   p.sN = (int64_t)g.P * g.Q * Co; p.sP = (int64_t)g.Q * Co; p.sQ = Co; p.obase = 0;

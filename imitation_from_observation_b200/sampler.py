@@ -33,10 +33,15 @@ class RewardFeaturizer:
 
     def __init__(self, mode: str = "ours", name: str = "push", imsize=(48, 48), nvp: int = 1, scale: float = 1.0,
                  modelname: Optional[str] = None, modeldata: Optional[str] = None, ablation_type: str = "None",
-                 precision: str = "mixed", model: Optional[_ContextModel] = None, device="cuda", **unused_kwargs):
-        if not mode.startswith("ours") or mode == "oursinception":
-            raise _lib.CtxError("RewardFeaturizer covers mode='ours' (base.py:192-257); inception modes need the "
-                                "InceptionV3 front-end, which is outside this hot path's first scope")
+                 precision: str = "mixed", model: Optional[_ContextModel] = None, device="cuda", layer: str = "Mixed_7c",
+                 meanfile: Optional[str] = None, inception=None, chunk_paths: int = 8, **unused_kwargs):
+        if mode == "oursinception":
+            raise _lib.CtxError("mode='oursinception' (ContextAEInception2 behind a frozen InceptionV3, base.py:121-132) "
+                                "is not wired up yet; 'ours*' and 'inception*' are")
+        if not (mode.startswith("ours") or mode.startswith("inception")):
+            raise _lib.CtxError("RewardFeaturizer covers mode 'ours*' (base.py:192-257) and 'inception*' (:69-111,179-189)")
+        self.layer, self.meanfile, self.inception, self.chunk_paths = layer, meanfile, inception, int(chunk_paths)
+        self.std: Optional[torch.Tensor] = None
         if ablation_type not in ("None", "nofeat", "noimage"):
             raise _lib.CtxError("ablation_type %r is broken in the reference (base.py:250-252 uses an undefined "
                                 "image_recon) and is not provided" % ablation_type)
@@ -50,6 +55,18 @@ class RewardFeaturizer:
 
     # -- base.py:113-154 ---------------------------------------------------------------------------------------------
     def initialize(self):
+        if self.mode.startswith("inception"):
+            # base.py:69-111: InceptionV3(is_training=False); expert statistics from `meanfile` (layer, layer+'std')
+            from .inception import InceptionV3
+            if self.inception is None:
+                self.inception = InceptionV3(device=self.device, precision=self.precision)
+                if self.modelname:
+                    self.inception.load_state_dict(dict(np.load(self.modelname)))
+            if self.meanfile:
+                data = np.load(self.meanfile)
+                self.set_inception_statistics(data[self.layer], data[self.layer + "std"])
+            self.initialized = True
+            return
         if self.model is None:
             if self.name in ("real", "sweep"):
                 self.model = ContextAEReal()                                   # base.py:134-135
@@ -97,11 +114,51 @@ class RewardFeaturizer:
             self.means.append((sum_z / N).float().contiguous())
             self.imgs.append((sum_img / N).float().contiguous())
 
+    # -- base.py:94-110: expert statistics of the Inception baseline ------------------------------------------------
+    def set_inception_statistics(self, means: np.ndarray, std: np.ndarray):
+        """means / std [T, h, w, c] of the chosen end point over expert rollouts (np.mean / np.std, base.py:103-104)."""
+        self.means = [torch.as_tensor(np.ascontiguousarray(means), dtype=torch.float32).to(self.device)]
+        self.std = torch.as_tensor(np.ascontiguousarray(std), dtype=torch.float32).to(self.device)
+
+    def inception_features(self, frames_u8: torch.Tensor) -> torch.Tensor:
+        """End point `layer` for uint8 frames [n, H, W, 3] on the device (base.py:183)."""
+        return self.inception.forward(frames_u8, (self.layer,))[self.layer]
+
+    def _process_paths_inception(self, paths: List[dict]) -> np.ndarray:
+        """base.py:179-189, batched: `chunk_paths` trajectories (x 25 frames) per InceptionV3 pass, one reward kernel."""
+        if not self.means or self.std is None:
+            raise _lib.CtxError("Inception statistics missing: pass meanfile= or call set_inception_statistics()")
+        P, H, W = len(paths), self.imsize[0], self.imsize[1]
+        costs = np.zeros((P, self.T), np.float32)
+        for c0 in range(0, P, self.chunk_paths):
+            chunk = paths[c0:c0 + self.chunk_paths]
+            n = len(chunk)
+            L = max(len(p["rewards"]) for p in chunk)
+            frames = torch.empty((n, self.T, H, W, 3), dtype=torch.uint8).pin_memory()
+            rewards = torch.zeros((n, L), dtype=torch.float64).pin_memory()
+            for i, path in enumerate(chunk):
+                imgs = [im[0] for im in path["env_infos"]["imgs"] if im is not None]          # base.py:182
+                if len(imgs) != self.T:
+                    raise _lib.CtxError("path %d has %d frames, expected %d" % (c0 + i, len(imgs), self.T))
+                frames.numpy()[i] = np.asarray(imgs)
+                rewards.numpy()[i, :len(path["rewards"])] = path["rewards"]
+            feat = self.inception_features(frames.to(self.device, non_blocking=True).view(n * self.T, H, W, 3))
+            d_rewards = rewards.to(self.device, non_blocking=True)
+            d_cost = torch.zeros((n, self.T), device=self.device, dtype=torch.float32)
+            ops.reward_inception(feat, self.means[0], self.std, n, self.T, rewards=d_rewards, cost=d_cost)
+            out = d_rewards.cpu().numpy()
+            costs[c0:c0 + n] = d_cost.cpu().numpy()
+            for i, path in enumerate(chunk):
+                path["rewards"][:] = out[i, :len(path["rewards"])]
+        return costs
+
     # -- base.py:232-257: the hot loop ---------------------------------------------------------------------------------
     def process_paths(self, paths: List[dict]) -> np.ndarray:
         """Subtract the feature/pixel distance from every path's rewards, in place; returns the costs [paths,T]."""
         if not self.initialized:
             self.initialize()
+        if self.mode.startswith("inception"):
+            return self._process_paths_inception(paths)
         if not self.means:
             raise _lib.CtxError("expert statistics missing: call compute_expert_means() first (base.py:195-223)")
         P = len(paths)

@@ -94,3 +94,36 @@ def test_inception_reward_kernel_matches_reference_loop():
     r = rewards.cuda()
     ops.reward_inception(feat.cuda(), means.cuda(), std.cuda(), paths, T, rewards=r)
     assert rel_err(r.cpu(), ref) < 1e-5
+
+
+def test_reward_featurizer_inception_mode_matches_reference_loop():
+    """rllab/sampler/base.py:179-189 end to end: uint8 frames -> InceptionV3 end point -> variance-normalised distance
+    -> rewards[2j+1] -= m_j * j^2, batched over paths, against the per-path reference loop on the oracle's features."""
+    from imitation_from_observation_b200.sampler import RewardFeaturizer
+    T, paths_n, hw = 25, 3, 75                                      # 75x75 frames keep the CPU oracle quick
+    P = _inception_params(seed=21)
+    net = I.InceptionV3(precision="mixed")
+    net.load_state_dict(P)
+    rng = np.random.RandomState(0)
+    paths = [dict(rewards=np.zeros(2 * T), env_infos=dict(imgs=[None if k % 2 else [rng.randint(0, 256, (hw, hw, 3)).astype(np.uint8)]
+                                                                for k in range(2 * T)])) for _ in range(paths_n)]
+    def feats(frames_u8):
+        x = ((torch.from_numpy(frames_u8).float() * (1.0 / 255.0)) - 0.5) * 2.0
+        return OI.forward(P, x)["Mixed_5d"]
+    all_frames = [np.asarray([im[0] for im in p["env_infos"]["imgs"] if im is not None]) for p in paths]
+    f0 = feats(all_frames[0])
+    means = (f0 * 0.9).numpy()
+    std = (f0.abs() * 0.5).numpy()
+    std[..., ::7] = 0
+    ref = [p["rewards"].copy() for p in paths]
+    for i in range(paths_n):
+        c = OI.reward_inception(feats(all_frames[i]).reshape(T, -1), torch.from_numpy(means).reshape(T, -1),
+                                torch.from_numpy(std).reshape(T, -1))
+        for j in range(T):
+            ref[i][2 * j + 1] -= float(c[j]) * j * j
+    fz = RewardFeaturizer(mode="inception", name="push", imsize=(hw, hw), layer="Mixed_5d", inception=net, chunk_paths=2)
+    fz.initialize()
+    fz.set_inception_statistics(means, std)
+    fz.process_paths(paths)
+    for i in range(paths_n):
+        assert rel_err(paths[i]["rewards"], ref[i]) < 1e-3

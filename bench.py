@@ -316,6 +316,129 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# secondary workload (BASELINE configs[4]): InceptionV3 inference, 299x299x3 uint8, B=128 per GPU, end point Mixed_7c
+# ----------------------------------------------------------------------------------------------------------------
+INC_METRIC = "images/sec InceptionV3 inference (Mixed_7c), 299x299x3 uint8, B=128 per GPU"
+INC_FLOP_PER_IMG = 2 * 5.711e9
+
+
+def inception_cpu_time(n_img, threads):
+    import torch
+    from imitation_from_observation_b200 import inception as I
+    from oracle import inception_v3 as OI
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    P = {}
+    for name, shp in I.param_shapes().items():
+        P[name] = (torch.rand(shp, generator=g) * 0.5 + 0.75) if name.endswith("moving_variance") else \
+            torch.randn(shp, generator=g) * (0.05 if name.endswith("weights") else 0.1)
+    x = torch.rand((n_img, 299, 299, 3), generator=g) * 2 - 1
+    with torch.no_grad():
+        OI.forward(P, x[:1])
+        t0 = time.perf_counter()
+        OI.forward(P, x)
+        return time.perf_counter() - t0
+
+
+def run_inception(args):
+    import torch
+    import torch.distributed as dist
+    from imitation_from_observation_b200 import inception as I, ops, parallel
+    rank, world, local = parallel.init_distributed()
+    threads = os.cpu_count() or 1
+    B = args.batch if args.batch != 256 else 128
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = 8
+        t = inception_cpu_time(n, threads)
+        v = n / t
+        print(json.dumps(dict(metric=INC_METRIC, value=v, unit="images/s", n_gpus=args.gpus, steps=1, warmup=1,
+                              ms_per_step=1e3 * t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                              data="synthetic", impl="reference",
+                              config=dict(workload="InceptionV3 forward on %d images per step on the host cores" % n),
+                              cpu_baseline=dict(value=v, unit="images/s", cores=threads, kind="port",
+                                                sample="%d-image forward, PyTorch-CPU fp32 restatement" % n),
+                              e2e=dict(value=v, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    net = I.InceptionV3(device=dev, precision=args.precision, seed=0)
+    host = [torch.randint(0, 256, (B, 299, 299, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    devb = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        net.forward(devb[i % 2], ("Mixed_7c",))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        net.forward(devb[i % 2], ("Mixed_7c",))
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = ops.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / args.steps
+    e0.record()
+    for i in range(args.steps):
+        f = net.forward(host[i % 2].to(dev, non_blocking=True), ("PreLogits",))["PreLogits"]
+        pre = f.cpu()                                    # [B,1,1,2048] features back to the host (base.py:183)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    roofline = None
+    cpu = None
+    if rank == 0:
+        peaks = load_peaks()
+        ops.PROFILE = []
+        net.forward(devb[0], ("Mixed_7c",))
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        fl = sum(p[2] for p in prof if p[1] in (2, 3))
+        tt = sum(p[3].elapsed_time(p[4]) for p in prof if p[1] in (2, 3)) * 1e-3
+        if tt > 0:
+            ach = fl / tt / 1e12
+            peak = peaks["bf16_tflops_sustained"] / 2.0
+            roofline = dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                            kernel="tc_igemm_kernel", peak_basis="TF32 dense = %s bf16 sustained / 2" % peaks["source"],
+                            share_of_step=tt * 1e3 / ms_step)
+        if world == 1 and not args.no_cpu_baseline:
+            n = 8
+            t = inception_cpu_time(n, threads)
+            cpu = dict(value=n / t, unit="images/s", cores=threads, kind="port",
+                       sample="%d-image forward, PyTorch-CPU fp32 restatement (oracle/inception_v3.py)" % n)
+        print(json.dumps(dict(metric=INC_METRIC, value=B * world / (ms_step * 1e-3), unit="images/s", n_gpus=world,
+                              steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
+                              scaling="weak", vs_baseline=None, dtype="f32 (tensor-core operands tf32, %s)" % args.precision,
+                              data="synthetic (random uint8 frames, variance-scaling weights: no checkpoint ships)",
+                              config=dict(workload="InceptionV3 299x299x3 uint8, %d images/GPU, end point Mixed_7c "
+                                                   "(BASELINE configs[4])" % B, images_per_gpu=B, precision=args.precision,
+                                          l2="two 34 MB input batches rotate; activations ~2 GB exceed L2"),
+                              clocks=clocks,
+                              e2e=dict(value=B * world / (float(ms2.item()) / args.steps * 1e-3), unit="images/s",
+                                       h2d_bytes_per_step=int(host[0].numel()), d2h_bytes_per_step=int(pre.numel() * 4),
+                                       api="InceptionV3.forward(pinned uint8 frames) -> PreLogits on the host"),
+                              gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
+                              gflop_per_step=B * INC_FLOP_PER_IMG / 1e9)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,8 +449,12 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="triples per GPU")
     ap.add_argument("--ref-batch", type=int, default=256, help="max triples per step of the CPU reference (reduced to fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "inception"],
+                    help="train = the headline metric (default); inception = BASELINE configs[4], a secondary line")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "inception":
+        run_inception(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

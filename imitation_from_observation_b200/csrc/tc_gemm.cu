@@ -1069,12 +1069,17 @@ static int make_tap_maps(CUtensorMap* maps, const float* x, int C, int N, int H,
   }
   for (int hp = 0; hp < 2; ++hp)
     for (int wp = 0; wp < 2; ++wp) {
-      const int Hh = (H - hp + 1) / 2, Wh = (W - wp + 1) / 2;
-      if (Hh <= 0 || Wh <= 0) { memset(&maps[hp * 2 + wp], 0, sizeof(CUtensorMap)); continue; }
+      int Hh = (H - hp + 1) / 2, Wh = (W - wp + 1) / 2;
+      const float* base = x + ((int64_t)hp * W + wp) * C;
+      if (Hh <= 0 || Wh <= 0) {
+        // empty parity view (a 1-pixel-high / wide input): keep a VALID descriptor over one pixel of x; tap_seg()
+        // pushes every access through it out of range, so the TMA unit zero-fills (the taps contribute nothing)
+        Hh = Hh <= 0 ? 1 : Hh; Wh = Wh <= 0 ? 1 : Wh; base = x;
+      }
       int64_t dims[5] = {c0, Wh, Hh, N, C / 32};
       int64_t str[5] = {1, 2 * (int64_t)C, 2 * (int64_t)W * C, (int64_t)H * W * C, 32};
       int box[5] = {32, box_q, box_p, box_n, atoms};
-      int rc = make_map(&maps[hp * 2 + wp], x + ((int64_t)hp * W + wp) * C, rank, dims, str, box, mn_major);
+      int rc = make_map(&maps[hp * 2 + wp], base, rank, dims, str, box, mn_major);
       if (rc) return rc;
     }
   return CTX_OK;
@@ -1095,6 +1100,7 @@ static void tap_seg(Seg& s, int r, int sx, const ctx_conv_geom& g) {
   s.mapA = (uint8_t)(hp * 2 + wp);
   s.dh = (int16_t)((rr - hp) / 2);
   s.dw = (int16_t)((ss - wp) / 2);
+  if ((g.H - hp + 1) / 2 <= 0 || (g.W - wp + 1) / 2 <= 0) s.dh = 16000;   // empty parity view: always out of range
 }
 
 int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, const ctx_conv_geom& g,

@@ -35,9 +35,6 @@ class RewardFeaturizer:
                  modelname: Optional[str] = None, modeldata: Optional[str] = None, ablation_type: str = "None",
                  precision: str = "mixed", model: Optional[_ContextModel] = None, device="cuda", layer: str = "Mixed_7c",
                  meanfile: Optional[str] = None, inception=None, chunk_paths: int = 8, **unused_kwargs):
-        if mode == "oursinception":
-            raise _lib.CtxError("mode='oursinception' (ContextAEInception2 behind a frozen InceptionV3, base.py:121-132) "
-                                "is not wired up yet; 'ours*' and 'inception*' are")
         if not (mode.startswith("ours") or mode.startswith("inception")):
             raise _lib.CtxError("RewardFeaturizer covers mode 'ours*' (base.py:192-257) and 'inception*' (:69-111,179-189)")
         self.layer, self.meanfile, self.inception, self.chunk_paths = layer, meanfile, inception, int(chunk_paths)
@@ -67,6 +64,24 @@ class RewardFeaturizer:
                 self.set_inception_statistics(data[self.layer], data[self.layer + "std"])
             self.initialized = True
             return
+        if self.mode == "oursinception" and self.model is None:
+            # base.py:121-132: frozen InceptionV3 -> Mixed_7c feature maps [3,25,8,8,2048] -> ContextAEInception2
+            from .inception import InceptionV3
+            from .models import ContextAEInception2
+            if self.inception is None:
+                self.inception = InceptionV3(device=self.device, precision=self.precision)
+            self.model = ContextAEInception2(strides=[1, 2, 1, 2], kernels=[3, 3, 3, 3], filters=[1024, 1024, 512, 512])
+            fh = self._inception_map_size(self.imsize[0])
+            fw = self._inception_map_size(self.imsize[1])
+            self.model.build(torch.empty((3, self.T, fh, fw, 2048), dtype=torch.float32, device="meta"),
+                             device=self.device, precision=self.precision)
+            if self.modelname:
+                sd = dict(np.load(self.modelname if self.modelname.endswith(".npz") else self.modelname + ".npz"))
+                prefix = "contextmodel/" if any(k.startswith("contextmodel/") for k in sd) else ""
+                self.model.net.load_state_dict({k: v for k, v in sd.items() if not k.startswith("InceptionV3/")},
+                                               prefix=prefix)
+                if any(k.startswith("InceptionV3/") for k in sd):
+                    self.inception.load_state_dict({k: v for k, v in sd.items() if k.startswith("InceptionV3/")})
         if self.model is None:
             if self.name in ("real", "sweep"):
                 self.model = ContextAEReal()                                   # base.py:134-135
@@ -83,6 +98,33 @@ class RewardFeaturizer:
                 self.model.net.load_state_dict(sd, prefix=prefix)
         self.initialized = True
 
+    @staticmethod
+    def _inception_map_size(n: int) -> int:
+        """Spatial size of Mixed_7c for an n-pixel side (VALID/stride chain of nets/inception_v3.py:100-378)."""
+        n = (n - 3) // 2 + 1          # Conv2d_1a_3x3 s2 VALID
+        n = n - 2                     # Conv2d_2a_3x3 VALID   (2b is SAME)
+        n = (n - 3) // 2 + 1          # MaxPool_3a
+        n = n - 2                     # Conv2d_4a_3x3 VALID   (3b is 1x1)
+        n = (n - 3) // 2 + 1          # MaxPool_5a
+        n = (n - 3) // 2 + 1          # Mixed_6a
+        return (n - 3) // 2 + 1       # Mixed_7a
+
+    def _model_input(self, frames_u8: torch.Tensor) -> torch.Tensor:
+        """What the context model sees for uint8 frames [n,H,W,3]: the normalised frames (base.py:116-119), or — mode
+        'oursinception' — their Mixed_7c feature maps (base.py:122-131; `image_trans` is then the feature tensor)."""
+        if self.mode == "oursinception":
+            n, chunk = frames_u8.shape[0], 128                       # bound the InceptionV3 activation footprint
+            if n <= chunk:
+                return self.inception.forward(frames_u8, ("Mixed_7c",))["Mixed_7c"].clone()
+            out = None
+            for c0 in range(0, n, chunk):
+                f = self.inception.forward(frames_u8[c0:c0 + chunk], ("Mixed_7c",))["Mixed_7c"]
+                if out is None:
+                    out = torch.empty((n,) + tuple(f.shape[1:]), device=f.device, dtype=torch.float32)
+                out[c0:c0 + f.shape[0]].copy_(f)
+            return out
+        return ops.u8_normalize(frames_u8.contiguous())
+
     # -- base.py:195-223: expert statistics, once per process ----------------------------------------------------------
     def compute_expert_means(self, validdata: np.ndarray, contexts: Sequence[np.ndarray], chunk_videos: int = 64):
         """validdata [nlen, N, H, W, 3] float in [-1,1] (the trainer's vdata .npy); contexts[vp] = first frame of the
@@ -90,7 +132,10 @@ class RewardFeaturizer:
         if not self.initialized:
             self.initialize()
         skip = 2 if self.name in ("real", "sweep") else 1                      # base.py:208-210
-        demo = ((validdata[::skip] + 1) * 127.5).astype(np.uint8)             # base.py:214, [T, N, H, W, 3]
+        if self.mode == "oursinception":
+            demo = np.asarray(validdata[::skip, :50]).astype(np.uint8)        # base.py:204-205,211-212: 50 videos, as stored
+        else:
+            demo = ((validdata[::skip] + 1) * 127.5).astype(np.uint8)         # base.py:214, [T, N, H, W, 3]
         if demo.shape[0] != self.T:
             raise _lib.CtxError("demos have %d frames after skip, expected %d" % (demo.shape[0], self.T))
         N = demo.shape[1]
@@ -98,19 +143,21 @@ class RewardFeaturizer:
         self.means, self.imgs = [], []
         for vp in range(self.nvp):
             ctx = torch.as_tensor(np.ascontiguousarray(contexts[vp])).to(self.device)[None]   # [1,H,W,3] u8
+            ctx = self._model_input(ctx)                                                        # frames or feature maps
             z_ctx, skips = m.enc2(ctx)
+            per_frame = tuple(ctx.shape[1:])
             sum_z = torch.zeros((self.T, m.net.F), device=self.device, dtype=torch.float64)
-            sum_img = torch.zeros((self.T,) + self.imsize + (3,), device=self.device, dtype=torch.float64)
+            sum_img = torch.zeros((self.T,) + per_frame, device=self.device, dtype=torch.float64)
             for v0 in range(0, N, chunk_videos):
                 vids = demo[:, v0:v0 + chunk_videos]                             # [T, n, H, W, 3]
                 n = vids.shape[1]
                 frames = torch.as_tensor(np.ascontiguousarray(vids.transpose(1, 0, 2, 3, 4))).to(self.device)
-                frames = frames.reshape((n * self.T,) + self.imsize + (3,))
+                frames = self._model_input(frames.reshape((n * self.T,) + self.imsize + (3,)))
                 z_src = m.enc1(frames)
                 tz = m.translate(z_src, z_ctx.expand(n * self.T, -1))
                 out = m.dec(tz, skips, ctx_frames=ctx)
                 sum_z += tz.view(n, self.T, -1).sum(0, dtype=torch.float64)
-                sum_img += out.view((n, self.T) + self.imsize + (3,)).sum(0, dtype=torch.float64)
+                sum_img += out.view((n, self.T) + per_frame).sum(0, dtype=torch.float64)
             self.means.append((sum_z / N).float().contiguous())
             self.imgs.append((sum_img / N).float().contiguous())
 
@@ -188,7 +235,7 @@ class RewardFeaturizer:
         total = torch.zeros((P, self.T), device=self.device, dtype=torch.float32)
         for vp in range(self.nvp):
             u8 = d_frames[vp].reshape((P * self.T, H, W, 3))
-            x = ops.u8_normalize(u8)                                                     # image_trans[0]
+            x = self._model_input(u8)                                                    # image_trans[0]
             z = self.model.enc1(x)                                                       # input_z, base.py:234
             ops.reward_ours(z, x, self.means[vp], self.imgs[vp], P, self.T, self.scale, rewards=d_rewards,
                             cost=d_cost, feat_weight=fw, img_weight=iw)

@@ -127,3 +127,42 @@ def test_reward_featurizer_inception_mode_matches_reference_loop():
     fz.process_paths(paths)
     for i in range(paths_n):
         assert rel_err(paths[i]["rewards"], ref[i]) < 1e-3
+
+
+def test_reward_featurizer_oursinception_mode():
+    """base.py:121-132 + 232-257: uint8 frames -> frozen InceptionV3 Mixed_7c -> ContextAEInception2 source encoder ->
+    feature + feature-map distance.  75x75 frames (Mixed_7c is 1x1x2048 there) against the two oracles chained."""
+    from imitation_from_observation_b200 import spec as S
+    from imitation_from_observation_b200.sampler import RewardFeaturizer
+    from oracle import tf_semantics as O
+    T, paths_n, hw, scale = 25, 2, 75, 0.5
+    PI = _inception_params(seed=31)
+    inc = I.InceptionV3(precision="mixed")
+    inc.load_state_dict(PI)
+    fz = RewardFeaturizer(mode="oursinception", name="strike", imsize=(hw, hw), nvp=1, scale=scale, inception=inc)
+    fz.initialize()
+    spec = fz.model.spec
+    assert (spec.height, spec.width, spec.c_dim) == (1, 1, 2048) and spec.filters == (1024, 1024, 512, 512)
+    PM = O.init_params(spec, seed=32)
+    fz.model.net.load_state_dict(PM)
+    rng = np.random.RandomState(1)
+    paths = [dict(rewards=np.zeros(2 * T), env_infos=dict(imgs=[None if k % 2 else [rng.randint(0, 256, (hw, hw, 3)).astype(np.uint8)]
+                                                                for k in range(2 * T)])) for _ in range(paths_n)]
+    g = torch.Generator().manual_seed(33)
+    means = torch.randn((T, spec.featsize), generator=g) * 0.01
+    imgs = torch.rand((T, 1, 1, 2048), generator=g)
+    fz.means, fz.imgs = [means.cuda()], [imgs.cuda()]
+    ref = []
+    for p in paths:
+        fr = np.asarray([im[0] for im in p["env_infos"]["imgs"] if im is not None])
+        x = ((torch.from_numpy(fr).float() * (1.0 / 255.0)) - 0.5) * 2.0
+        feat = OI.forward(PI, x)["Mixed_7c"]                                       # [T,1,1,2048]
+        z = O.forward(spec, PM, torch.stack([feat, feat[:1].expand_as(feat), feat]))["input_z"]
+        cost = ((means - z) ** 2).sum(1) + scale * ((imgs - feat) ** 2).reshape(T, -1).sum(1)
+        r = np.zeros(2 * T)
+        for j in range(T):
+            r[2 * j + 1] -= float(cost[j]) * j * j
+        ref.append(r)
+    fz.process_paths(paths)
+    for i in range(paths_n):
+        assert rel_err(paths[i]["rewards"], ref[i]) < 1e-3

@@ -26,6 +26,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) to stdout unless
+# told otherwise — send it to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "frames/sec fwd+bwd+Adam, ContextSkipNew 64x64x3, B=256 triples per GPU"
 UNIT = "frames/s"

@@ -28,7 +28,21 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            # NCCL prints its version banner to stdout when the first communicator is created; callers such as
+            # bench.py own stdout (one JSON line), so create the communicator with fd 1 pointed at stderr
+            import sys
+            sys.stdout.flush()
+            saved = os.dup(1)
+            try:
+                os.dup2(2, 1)
+                dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+                warm = torch.zeros(1, device=torch.device("cuda", local))
+                dist.all_reduce(warm)
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, local

@@ -16,6 +16,7 @@ Design points:
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -73,6 +74,8 @@ class ContextNet:
         self._w_recon = {"None": (1.0, 1.0), "L2": (1.0, 1.0), "L2L3": (1.0, 0.0), "L1": (0.0, 1.0)}[ablation_type]
         self._w_sim = {"None": 1.0, "L2": 0.0, "L2L3": 0.0, "L1": 1.0}[ablation_type]
         self.step_count = 0
+        self.concurrent = os.environ.get("CTX_CONCURRENT", "1") != "0"
+        self._s2 = None
         self.allreduce = None          # parallel.BucketedAllReduce when data-parallel (attach_allreduce)
         self._bufs: Dict[str, torch.Tensor] = {}
 
@@ -118,6 +121,25 @@ class ContextNet:
         self.flat = spec.flat_dim()
         self.dec = spec.dec_layers()
         self._level = 0
+
+    # ---- second stream -----------------------------------------------------------------------------------------
+    # Independent launches run on a side stream so that one kernel's last, partly filled wave overlaps another
+    # kernel: the context encoder beside the source/target encoder in forward, every filter gradient (+ bias gradient)
+    # beside the data gradient of the same layer in backward.  Off while bench.py times single launches.
+    def _side(self):
+        """Context manager: run the enclosed launches on the side stream, after everything enqueued so far."""
+        import contextlib
+        if not self.concurrent or ops.PROFILE is not None:
+            return contextlib.nullcontext()
+        if self._s2 is None:
+            self._s2 = torch.cuda.Stream(device=self.device)
+        self._s2.wait_stream(torch.cuda.current_stream(self.device))
+        return torch.cuda.stream(self._s2)
+
+    def _join(self):
+        """The current stream waits for everything enqueued on the side stream."""
+        if self._s2 is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._s2)
 
     # ---- buffers ------------------------------------------------------------------------------------------------
     def _view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
@@ -292,6 +314,12 @@ class ContextNet:
             rows = None                                  # src rows and ctx rows, two launches
         else:
             rows = B
+        side_ctx = level >= FWD_TRANS and sp.separate_ctx_encoder
+        if side_ctx:
+            c_hs, c_h4 = self._enc_buffers(B, "c")
+            with self._side():                           # the context encoder has its own weights and input
+                self._fwd_encoder("conv_context", xc, c_hs, c_h4)
+                self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
         if rows is not None:
             self._fwd_encoder("conv", xe[:rows], [h[:rows] for h in e_hs], e_h4[:rows])
         else:
@@ -299,12 +327,11 @@ class ContextNet:
             self._fwd_encoder("conv", xe[2 * B:], [h[2 * B:] for h in e_hs], e_h4[2 * B:])
         self._fwd_hz("conv", e_h4[:B], cat.data_ptr(), 2 * F, act=True)                    # src z -> cat[:, :F]
         if level >= FWD_TRANS:
-            if sp.separate_ctx_encoder:
-                c_hs, c_h4 = self._enc_buffers(B, "c")
-                self._fwd_encoder("conv_context", xc, c_hs, c_h4)
+            if side_ctx:
+                self._join()
             else:
                 c_hs, c_h4 = [h[2 * B:] for h in e_hs], e_h4[2 * B:]
-            self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
+                self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
             th0 = self._buf("th0", (B, F))
             self._gemm(False, False, B, F, 2 * F, cat.data_ptr(), 2 * F,
                        self.Wf["translate/trans_h0/Matrix"].data_ptr(), F, th0.data_ptr(), F,
@@ -402,16 +429,18 @@ class ContextNet:
                 pt = self._patches("patch_g_d%d" % (i + 1), g_out, k, L["stride"], round_tf32=rb)[:, :K]
                 rows = pt.shape[0] // 2                    # rows of one decoder pass (the skip is shared by both)
                 dw2 = G[wname].view(K, Ck)
-                ops.gemm(pt, state.view(-1, Cs), out=dw2[:, :Cs], transA=True, accumulate=True, impl=ib)
-                for g_ in range(2):
-                    ops.gemm(pt[g_ * rows:(g_ + 1) * rows], skip.view(-1, Ck - Cs), out=dw2[:, Cs:], transA=True,
-                             accumulate=True, impl=ib)
-                ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+                with self._side():
+                    ops.gemm(pt, state.view(-1, Cs), out=dw2[:, :Cs], transA=True, accumulate=True, impl=ib)
+                    for g_ in range(2):
+                        ops.gemm(pt[g_ * rows:(g_ + 1) * rows], skip.view(-1, Ck - Cs), out=dw2[:, Cs:], transA=True,
+                                 accumulate=True, impl=ib)
+                    ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
                 ops.gemm(pt, Wb[wname].view(K, Ck), out=dcat.view(-1, Ck), impl=ib)
             else:
-                # filter gradient: big = g_out [2B, out_hw, Cout], small = [state ‖ skip]
-                ops.conv2d_wgrad(g_out, state, k, L["stride"], small2=skip, dw=G[wname], impl=ib)
-                ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+                # filter gradient: big = g_out [2B, out_hw, Cout], small = [state ‖ skip] (side stream)
+                with self._side():
+                    ops.conv2d_wgrad(g_out, state, k, L["stride"], small2=skip, dw=G[wname], impl=ib)
+                    ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
                 # data gradient of the concatenated input = SAME conv of g_out with the [kh,kw,Cout,Cin] filter as HWIO
                 ops.conv2d(g_out, Wb[wname], None, stride=L["stride"], act=False, out=dcat, impl=ib)
             g_state = self._buf("g_d%d" % i, tuple(state.shape))
@@ -421,12 +450,14 @@ class ContextNet:
         # ---- d_h0_lin ------------------------------------------------------------------------------------------------
         g_d0 = g_out                                       # [2B, flat], lrelu' applied
         Wd0 = Wb["deconv/d_h0_lin/Matrix"]
-        self._gemm(True, False, F, flat, 2 * B, z2.data_ptr(), F, g_d0.data_ptr(), flat,
-                   G["deconv/d_h0_lin/Matrix"].data_ptr(), flat, accumulate=True, round_=False, bwd=True)
-        ops.bias_grad(g_d0.view(2 * B, flat), G["deconv/d_h0_lin/bias"])
+        with self._side():
+            self._gemm(True, False, F, flat, 2 * B, z2.data_ptr(), F, g_d0.data_ptr(), flat,
+                       G["deconv/d_h0_lin/Matrix"].data_ptr(), flat, accumulate=True, round_=False, bwd=True)
+            ops.bias_grad(g_d0.view(2 * B, flat), G["deconv/d_h0_lin/bias"])
         g_z2 = self._buf("g_z2", (2 * B, F))
         self._gemm(False, True, 2 * B, F, flat, g_d0.data_ptr(), flat, Wd0.data_ptr(), flat, g_z2.data_ptr(), F, bwd=True)
         if on_stage:
+            self._join()                                   # every decoder gradient is enqueued and ordered
             on_stage("deconv")
         # ---- feature-alignment loss gradient (mean over the GLOBAL batch so DP ranks sum correctly) ---------------
         if self._w_sim != 0.0:
@@ -474,9 +505,10 @@ class ContextNet:
         def encoder_backward(scope, x, hs, h4, g_hs, g_h4, groups):
             """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate."""
             n = x.shape[0]
-            self._gemm(True, False, flat, F, n, hs[3].data_ptr(), flat, g_h4.data_ptr(), F,
-                       G[scope + "/h4_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
-            ops.bias_grad(g_h4, G[scope + "/h4_lin/bias"])
+            with self._side():
+                self._gemm(True, False, flat, F, n, hs[3].data_ptr(), flat, g_h4.data_ptr(), F,
+                           G[scope + "/h4_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
+                ops.bias_grad(g_h4, G[scope + "/h4_lin/bias"])
             for (r0, nr, acc) in groups:
                 self._gemm(False, True, nr, flat, F, g_h4[r0:r0 + nr].data_ptr(), F,
                            Wb[scope + "/h4_lin/Matrix"].data_ptr(), F, g_hs[3][r0:r0 + nr].data_ptr(), flat,
@@ -485,14 +517,15 @@ class ContextNet:
                 wname = "%s/h%d_conv/w" % (scope, j)
                 src = hs[j - 1] if j > 0 else x
                 kj, Cin = sp.kernels[j], src.shape[3]
-                if self._few(Cin, kj) and g_hs[j].shape[3] % 4 == 0:
-                    K = kj * kj * Cin
-                    pt = self._patches("patch_%s_h%d_%d" % (scope, j, n), src, kj, sp.strides[j], reuse=True)
-                    ops.gemm(pt[:, :K], g_hs[j].view(-1, g_hs[j].shape[3]), out=G[wname].view(K, -1), transA=True,
-                             accumulate=True, impl=self.impl_b)
-                else:
-                    ops.conv2d_wgrad(src, g_hs[j], kj, sp.strides[j], dw=G[wname], impl=self.impl_b)
-                ops.bias_grad(g_hs[j], G["%s/h%d_conv/biases" % (scope, j)])
+                with self._side():                         # filter + bias gradient beside the data gradient below
+                    if self._few(Cin, kj) and g_hs[j].shape[3] % 4 == 0:
+                        K = kj * kj * Cin
+                        pt = self._patches("patch_%s_h%d_%d" % (scope, j, n), src, kj, sp.strides[j], reuse=True)
+                        ops.gemm(pt[:, :K], g_hs[j].view(-1, g_hs[j].shape[3]), out=G[wname].view(K, -1), transA=True,
+                                 accumulate=True, impl=self.impl_b)
+                    else:
+                        ops.conv2d_wgrad(src, g_hs[j], kj, sp.strides[j], dw=G[wname], impl=self.impl_b)
+                    ops.bias_grad(g_hs[j], G["%s/h%d_conv/biases" % (scope, j)])
                 if j > 0:
                     for (r0, nr, acc) in groups:
                         ops.conv2d_transpose(g_hs[j][r0:r0 + nr], Wb[wname], self.sizes[j], stride=sp.strides[j],
@@ -502,14 +535,18 @@ class ContextNet:
         if sp.separate_ctx_encoder:
             encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False)])
             if on_stage:
+                self._join()
                 on_stage("conv")
             encoder_backward("conv_context", xc, c_hs, c_h4, gc_hs, gc_h4, [(0, B, True)])
             if on_stage:
+                self._join()
                 on_stage("conv_context")
         else:
             encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False), (2 * B, B, True)])
             if on_stage:
+                self._join()
                 on_stage("conv")
+        self._join()                                       # gradients complete on the caller's stream
 
     # ---- optimiser -------------------------------------------------------------------------------------------------------
     def adam_step(self, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):

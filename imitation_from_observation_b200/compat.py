@@ -58,7 +58,8 @@ class Placeholder:
     def _register_consumer(self, model):
         norm = (("convert_image_dtype",), ("subtract", 0.5), ("multiply", 2.0))
         if self.root.dtype == torch.uint8:
-            if self.chain != norm:
+            chain = self.chain[:-1] if self.chain and self.chain[-1][0] == "inception" else self.chain
+            if chain != norm:
                 raise _lib.CtxError("a uint8 placeholder must be normalised exactly as base.py:117-119 "
                                     "(convert_image_dtype, subtract 0.5, multiply 2.0); got %r" % (self.chain,))
         elif self.chain:
@@ -74,6 +75,17 @@ class image:                                                      # noqa: N801  
     @staticmethod
     def convert_image_dtype(x: Placeholder, dtype=float32) -> Placeholder:
         return x._derive(("convert_image_dtype",))
+
+
+def inception_mixed_7c(x: Placeholder, net) -> Placeholder:
+    """The frozen InceptionV3 front-end of train_script.py:100-115 / base.py:121-131: normalised frames [3,B,H,W,3]
+    -> `Mixed_7c` feature maps reshaped to [3,B,h,w,2048] (what `test.build(featreshape)` consumes).  `net` is an
+    `inception.InceptionV3`; it is evaluated by Session.run on every feed, never trained."""
+    from .sampler import RewardFeaturizer
+    three, B, H, W, _ = x.shape
+    fh, fw = RewardFeaturizer._inception_map_size(H), RewardFeaturizer._inception_map_size(W)
+    out = Placeholder(x.dtype, (three, B, fh, fw, 2048), x.name, x.chain + (("inception", net),), x.root)
+    return out
 
 
 def subtract(x: Placeholder, v: float) -> Placeholder:
@@ -218,7 +230,14 @@ class Session:
                 fed = [v for k, v in feed_dict.items() if isinstance(k, Placeholder) and k.root is root]
                 if not fed:
                     raise _lib.CtxError("no value fed for the model's image placeholder")
-                m.net.set_input(self._stage(m.placeholder, fed[0]))
+                staged = self._stage(m.placeholder, fed[0])
+                chain = m.placeholder.chain
+                if chain and chain[-1][0] == "inception":      # frozen front-end: frames -> Mixed_7c feature maps
+                    inc = chain[-1][1]
+                    three, Bf = staged.shape[0], staged.shape[1]
+                    feats = inc.forward(staged.reshape((three * Bf,) + tuple(staged.shape[2:])), ("Mixed_7c",))["Mixed_7c"]
+                    staged = feats.view((three, Bf) + tuple(feats.shape[1:]))
+                m.net.set_input(staged)
             mine = [f for f in flist if (f.loss.model if isinstance(f, _Minimize) else getattr(f, "model", None)) is m]
             mins = [f for f in mine if isinstance(f, _Minimize)]
             level = max([FWD_ALL] if mins else [f.level for f in mine])

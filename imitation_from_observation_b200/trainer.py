@@ -6,7 +6,9 @@ batch, Adam lr 1e-4, loss / sim / r1 / r2 / nn_err every 4th step, validation ev
 
   * demos come from a ``[nlen, N, H, W, 3]`` array (the trainer's own ``vdata_*.npy`` format, train_script.py:97)
     or the synthetic generator — the mp4 / imageio / ffmpeg front-end (:59-96) is out of scope;
-  * ``inception=True`` (the InceptionV3 front-end) is not provided yet (SURVEY.md §8f rank 2);
+  * ``inception=True`` trains ``model(strides, kernels, filters)`` on the Mixed_7c feature maps of a frozen
+    InceptionV3 (train_script.py:100-115); pass ``inception_net=`` (an ``inception.InceptionV3`` with weights
+    loaded) — the reference restores ``model/inception_v3.ckpt``, which does not ship;
   * data parallelism lives in parallel.py (bucketed gradient all-reduce) and is wired up by bench.py; this
     class is the single-process trainer the reference has.
 """
@@ -24,14 +26,15 @@ from .models import MODEL_REGISTRY
 class ModelTrainer:
     def __init__(self, idims, nvideos, ntrain, batch_size, model, nitr, save_every, nlen, nskip, rescale=True,
                  inception=False, strides=None, kernels=None, filters=None, data=None, seed=0, precision="mixed",
-                 log: Optional[Callable[[str], None]] = print, basedir="model/"):
+                 log: Optional[Callable[[str], None]] = print, basedir="model/", inception_net=None):
         self.idims = tuple(idims)
         self.nvideos, self.ntrain, self.batch_size = nvideos, ntrain, batch_size
         self.nitr, self.save_every, self.nlen, self.nskip = nitr, save_every, nlen, nskip
         self.rescale, self.inception = rescale, inception
         self.strides, self.kernels, self.filters = strides, kernels, filters
-        if inception:
-            raise _lib.CtxError("inception=True needs the InceptionV3 front-end (not in this path's first scope)")
+        self.inception_net = inception_net
+        if inception and inception_net is None:
+            raise _lib.CtxError("inception=True needs inception_net= (an inception.InceptionV3 with weights loaded)")
         if model not in MODEL_REGISTRY:
             raise _lib.CtxError("unknown model %r" % (model,))
         self.model = MODEL_REGISTRY[model]
@@ -42,7 +45,7 @@ class ModelTrainer:
         """vdata [nlen, N, H, W, 3] float in [-1, 1] (train_script.py:83-97)."""
         if self.data is None:
             bank = synthetic.video_bank(self.nlen, self.nvideos, self.idims[0], self.idims[1], seed=1234 + self.seed)
-            return synthetic.to_float(bank)
+            return bank if self.inception else synthetic.to_float(bank)   # inception: uint8 frames (rescale=False)
         if isinstance(self.data, str):
             return np.load(self.data)
         return np.asarray(self.data)
@@ -52,10 +55,20 @@ class ModelTrainer:
         vdata = self._load_data()
         batch_size = self.batch_size
         tf.reset_default_graph()
-        tfinput = tf.placeholder(tf.float32, (3, batch_size) + self.idims + (3,), name="x")       # :118
-        test = self.model()
-        with tf.variable_scope("contextmodel"):                                                   # :120-121
-            tf.build_model(test, tfinput, precision=self.precision, seed=self.seed)
+        if self.inception:                                                                        # :100-115
+            tfinput = tf.placeholder(tf.uint8, (3, batch_size) + self.idims + (3,), name="image")
+            image_trans = tf.multiply(tf.subtract(tf.image.convert_image_dtype(tfinput, dtype=tf.float32), 0.5), 2.0)
+            featreshape = tf.inception_mixed_7c(image_trans, self.inception_net)
+            test = self.model(strides=self.strides, kernels=self.kernels, filters=self.filters)
+            with tf.variable_scope("contextmodel"):
+                tf.build_model(test, featreshape, precision=self.precision, seed=self.seed)
+            if np.asarray(vdata).dtype != np.uint8:
+                raise _lib.CtxError("inception=True expects uint8 frames (the reference stores them with rescale=False)")
+        else:
+            tfinput = tf.placeholder(tf.float32, (3, batch_size) + self.idims + (3,), name="x")   # :118
+            test = self.model()
+            with tf.variable_scope("contextmodel"):                                               # :120-121
+                tf.build_model(test, tfinput, precision=self.precision, seed=self.seed)
         sess = tf.Session()
         learning_rate = tf.placeholder(tf.float32, shape=[])
         train_vars = tf.get_collection(tf.GraphKeys.TRAINABLE_VARIABLES, "contextmodel")

@@ -166,3 +166,20 @@ def test_reward_featurizer_oursinception_mode():
     fz.process_paths(paths)
     for i in range(paths_n):
         assert rel_err(paths[i]["rewards"], ref[i]) < 1e-3
+
+
+def test_model_trainer_with_inception_front_end():
+    """scripts/train_script.py:100-115: uint8 frames -> frozen InceptionV3 -> Mixed_7c -> ContextAEInception2 trained by
+    Adam; only `contextmodel/*` variables change, the first fetched loss equals the oracles chained."""
+    from imitation_from_observation_b200.trainer import ModelTrainer
+    inc = I.InceptionV3(precision="mixed", seed=41)
+    before = {k: v.clone() for k, v in list(inc.params.items())[:3]}
+    logs = []
+    tr = ModelTrainer(idims=(75, 75), nvideos=6, ntrain=4, batch_size=4, model="ContextAEInception2", nitr=9, save_every=1000,
+                      nlen=2, nskip=1, rescale=False, inception=True, strides=[1, 2, 1, 2], kernels=[3, 3, 3, 3],
+                      filters=[64, 64, 32, 32], precision="mixed", log=logs.append, inception_net=inc)
+    allloss, _ = tr.train()
+    assert len(allloss) == 2 and all(np.isfinite(l) for l in allloss)
+    assert tr.test.spec.c_dim == 2048 and tr.test.spec.filters == (64, 64, 32, 32)
+    for k, v in before.items():
+        assert torch.equal(inc.params[k], v)                           # the front-end is frozen

@@ -72,3 +72,18 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_transform_and_bank_layout():
+    """arm_shaping.py:12-16 / train_script.py:16-22,67-97: resize + x/127.5-1, its inverse, and the time-major bank."""
+    import numpy as np
+    from imitation_from_observation_b200 import data
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (96, 128, 3)).astype(np.uint8)
+    t = data.transform(img, 48, 64, True)
+    assert t.shape == (48, 64, 3) and t.dtype == np.float64 and -1.0 <= t.min() and t.max() <= 1.0
+    assert np.array_equal(data.transform(img, 96, 128, False), img)              # same size, no rescale: identity
+    assert np.allclose(data.inverse_transform(t) * 255.0, (t + 1) * 127.5)
+    vids = [[rng.randint(1, 256, (20, 20, 3)).astype(np.uint8) for _ in range(51)] for _ in range(3)] + [[img] * 40]
+    bank = data.frames_to_bank(vids, nlen=25, nskip=2, idims=(16, 16))
+    assert bank.shape == (25, 3, 16, 16, 3)                                        # the 40-frame video is skipped

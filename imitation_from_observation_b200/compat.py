@@ -186,14 +186,17 @@ def build_model(model: _ContextModel, image: Placeholder, **kw):
 class Session:
     def __init__(self, config=None):
         self._pinned: Dict[Any, torch.Tensor] = {}
+        self._pin_event: Dict[int, Any] = {}          # staging buffer -> event of the last H2D copy that read it
 
     def _stage(self, ph: Placeholder, value) -> torch.Tensor:
-        """Host value -> pinned staging buffer -> device (non_blocking), as one [3,B,H,W,C] tensor."""
+        """Host value -> pinned staging buffer (-> device for uint8 frames), as one [3,B,H,W,C] tensor.  A float batch
+        stays in pinned HOST memory: ContextNet.set_input copies it role by role, overlapped with the first kernels."""
         if torch.is_tensor(value) and value.is_cuda:
             return value
         want_t = torch.uint8 if ph.root.dtype == torch.uint8 else torch.float32
+        host_ok = want_t == torch.float32 and not ph.chain
         if torch.is_tensor(value) and value.dtype == want_t and value.is_contiguous() and value.is_pinned():
-            return value.to("cuda", non_blocking=True)                # caller already staged it in pinned memory
+            return value if host_ok else value.to("cuda", non_blocking=True)   # caller already staged it in pinned memory
         arr = np.asarray(value)
         want = np.uint8 if ph.root.dtype == torch.uint8 else np.float32
         key = (id(ph.root), arr.shape, want)
@@ -201,8 +204,11 @@ class Session:
         if pin is None:
             pin = torch.empty(arr.shape, dtype=torch.uint8 if want is np.uint8 else torch.float32).pin_memory()
             self._pinned[key] = pin
+        ev = self._pin_event.get(pin.data_ptr())
+        if ev is not None:
+            ev.synchronize()                                     # the previous step's async copy out of this buffer
         np.copyto(pin.numpy(), arr, casting="unsafe")            # f64 -> f32 cast happens here (train_script feed)
-        return pin.to("cuda", non_blocking=True)
+        return pin if host_ok else pin.to("cuda", non_blocking=True)
 
     def run(self, fetches, feed_dict: Optional[dict] = None):
         if fetches is None:                                   # sess.run(tf.global_variables_initializer())
@@ -238,6 +244,8 @@ class Session:
                     feats = inc.forward(staged.reshape((three * Bf,) + tuple(staged.shape[2:])), ("Mixed_7c",))["Mixed_7c"]
                     staged = feats.view((three, Bf) + tuple(feats.shape[1:]))
                 m.net.set_input(staged)
+                if not staged.is_cuda and m.net._in_events is not None:
+                    self._pin_event[staged.data_ptr()] = m.net._in_events[1]
             mine = [f for f in flist if (f.loss.model if isinstance(f, _Minimize) else getattr(f, "model", None)) is m]
             mins = [f for f in mine if isinstance(f, _Minimize)]
             level = max([FWD_ALL] if mins else [f.level for f in mine])

@@ -76,6 +76,8 @@ class ContextNet:
         self.step_count = 0
         self.concurrent = os.environ.get("CTX_CONCURRENT", "1") != "0"
         self._s2 = None
+        self._copy_stream = None
+        self._in_events = None
         self.allreduce = None          # parallel.BucketedAllReduce when data-parallel (attach_allreduce)
         self._bufs: Dict[str, torch.Tensor] = {}
 
@@ -223,11 +225,35 @@ class ContextNet:
                                 % ((B,) + self.sizes[0] + (self.chans[0],) + (tuple(image.shape),)))
         xe, xc = self._input_buffers()
         dst = (xe[:B], xc, xe[B:2 * B])
+        self._in_events = None
+        if not image.is_cuda:
+            # pinned host batch (Session.run): copy role by role on a copy stream, context frames first, so that the
+            # context encoder (side stream) starts while the source / target frames are still in flight
+            if image.dtype != torch.float32 or not image.is_pinned():
+                raise _lib.CtxError("a host input must be a pinned float32 tensor (uint8 frames are staged on the device)")
+            cur = torch.cuda.current_stream(self.device)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cs = self._copy_stream
+            cs.wait_stream(cur)                          # the previous step is done with the input buffers
+            with torch.cuda.stream(cs):
+                dst[1].copy_(image[1], non_blocking=True)
+                ev_ctx = cs.record_event()
+                dst[0].copy_(image[0], non_blocking=True)
+                dst[2].copy_(image[2], non_blocking=True)
+                ev_rest = cs.record_event()
+            self._in_events = (ev_ctx, ev_rest)
+            return
         for r in range(3):
             if image.dtype == torch.uint8:
                 ops.u8_normalize(image[r].contiguous(), out=dst[r])
             else:
                 dst[r].copy_(image[r])
+
+    def _wait_input(self, which: int):
+        """Make the current stream wait for the staged host input: 0 = context frames, 1 = everything."""
+        if self._in_events is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._in_events[which])
 
     # ---- forward pieces (also the functional enc1 / enc2 / translate / dec surface) ------------------------------
     def encode_convs(self, scope: str, x: torch.Tensor, outs: Sequence[torch.Tensor]):
@@ -318,8 +344,10 @@ class ContextNet:
         if side_ctx:
             c_hs, c_h4 = self._enc_buffers(B, "c")
             with self._side():                           # the context encoder has its own weights and input
+                self._wait_input(0)
                 self._fwd_encoder("conv_context", xc, c_hs, c_h4)
                 self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
+        self._wait_input(1)
         if rows is not None:
             self._fwd_encoder("conv", xe[:rows], [h[:rows] for h in e_hs], e_h4[:rows])
         else:

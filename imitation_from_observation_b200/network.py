@@ -76,6 +76,7 @@ class ContextNet:
         self.step_count = 0
         self.concurrent = os.environ.get("CTX_CONCURRENT", "1") != "0"
         self._s2 = None
+        self._s3 = None
         self._copy_stream = None
         self._in_events = None
         self.allreduce = None          # parallel.BucketedAllReduce when data-parallel (attach_allreduce)
@@ -599,9 +600,33 @@ class ContextNet:
         if self.allreduce is not None:
             self.backward(on_stage=self.allreduce.stage_done)
             self.allreduce.finish()
-        else:
+            self.adam_step(lr, b1, b2, eps)
+            return
+        if not self.concurrent or ops.PROFILE is not None:
             self.backward()
-        self.adam_step(lr, b1, b2, eps)
+            self.adam_step(lr, b1, b2, eps)
+            return
+        # Single process: a parameter scope is final (and its weights no longer read by this step) as soon as backward
+        # leaves it, so its slice of the HBM-bound Adam pass runs on a third stream under the remaining backward GEMMs.
+        from . import parallel
+        self._ensure_moments()
+        self.step_count += 1
+        t = self.step_count
+        lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        ranges = {sc: (a, b) for sc, a, b in parallel.scope_ranges(self.offsets, self.flat_size)}
+        if self._s3 is None:
+            self._s3 = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+
+        def adam_scope(scope):                             # called after backward's join: gradients of `scope` are final
+            a, b = ranges[scope]
+            self._s3.wait_stream(cur)
+            with torch.cuda.stream(self._s3):
+                ops.adam_step(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr_t, b1, b2, eps,
+                              p_tf32=None if self.flat_pr is None else self.flat_pr[a:b])
+
+        self.backward(on_stage=adam_scope)
+        cur.wait_stream(self._s3)
 
     def train_step(self, lr: float = 1e-4, allreduce=None):
         """forward + backward + (optional bucketed gradient all-reduce) + Adam: one `sess.run(optimizer, ...)`.

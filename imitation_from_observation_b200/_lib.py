@@ -39,6 +39,8 @@ SIGNATURES = {
     "ctx_last_impl": (c_int32, []),
     "ctx_conv2d_fprop": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, POINTER(ConvGeom),
                                    POINTER(Epilogue), c_int32, c_void_p]),
+    "ctx_conv2d_fprop_ld": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, POINTER(ConvGeom),
+                                      POINTER(Epilogue), c_int32, c_void_p]),
     "ctx_conv2d_transpose": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                        POINTER(ConvGeom), POINTER(Epilogue), c_int32, c_void_p]),
     "ctx_conv2d_wgrad": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p,

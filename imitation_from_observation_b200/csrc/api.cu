@@ -95,22 +95,32 @@ extern "C" int ctx_tc_available(void) {
   return (major == 10 && tc_compiled()) ? 1 : 0;
 }
 
-extern "C" int ctx_conv2d_fprop(const float* x, int32_t C, const float* w, float* y, int32_t Co,
-                                const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream) {
+extern "C" int ctx_conv2d_fprop_ld(const float* x, int32_t C, const float* w, float* y, int32_t y_ld, int32_t Co,
+                                   const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream) {
   int rc = check_geom(g, "conv2d_fprop");
   if (rc) return rc;
   CTX_REQUIRE(C > 0 && Co > 0, "conv2d_fprop: bad channel count");
+  CTX_REQUIRE(y_ld >= Co, "conv2d_fprop: destination pixel stride %d is smaller than Co = %d", y_ld, Co);
   if (g->N == 0) return CTX_OK;
   CTX_REQUIRE(x && w && y, "conv2d_fprop: null pointer");
   Epi e = make_epi(epi);
+  CTX_REQUIRE(y_ld == Co || (!e.act_ref && !e.accumulate), "conv2d_fprop: act_ref / accumulate need a dense output");
   const ImplChoice ic = impl_choice(impl);
   if (ic.tc) {
-    int ok = tc_conv2d_fprop_eligible(C, Co, *g);
-    if (ok && ctx_tc_available()) { g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC; return tc_conv2d_fprop(x, C, w, y, Co, *g, e, ic.passes, (cudaStream_t)stream); }
+    int ok = tc_conv2d_fprop_eligible(C, Co, *g) && y_ld % 4 == 0;
+    if (ok && ctx_tc_available()) {
+      g_last_impl = ic.passes == 3 ? CTX_IMPL_TC3 : CTX_IMPL_TC;
+      return tc_conv2d_fprop(x, C, w, y, y_ld, Co, *g, e, ic.passes, (cudaStream_t)stream);
+    }
     if (ic.force) { set_error("conv2d_fprop: shape not eligible for the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
   }
   g_last_impl = CTX_IMPL_SIMT;
-  return simt_conv2d_fprop(x, C, w, y, Co, *g, e, (cudaStream_t)stream);
+  return simt_conv2d_fprop(x, C, w, y, y_ld, Co, *g, e, (cudaStream_t)stream);
+}
+
+extern "C" int ctx_conv2d_fprop(const float* x, int32_t C, const float* w, float* y, int32_t Co,
+                                const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream) {
+  return ctx_conv2d_fprop_ld(x, C, w, y, Co, Co, g, epi, impl, stream);
 }
 
 extern "C" int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t x2_batch,

@@ -5,7 +5,7 @@
 namespace ctx {
 
 // simt_gemm.cu — exact-fp32 CUDA-core implicit GEMMs
-int simt_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, const ctx_conv_geom& g,
+int simt_conv2d_fprop(const float* x, int C, const float* w, float* y, int y_ld, int Co, const ctx_conv_geom& g,
                       const Epi& epi, cudaStream_t stream);
 int simt_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2_batch, const float* w,
                           float* y, int Cn, const ctx_conv_geom& g, const Epi& epi, cudaStream_t stream);
@@ -17,7 +17,7 @@ int simt_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, cons
 // tc_gemm.cu — tcgen05 / TMEM / TMA implicit GEMMs (TF32 operands, fp32 accumulate)
 bool tc_compiled();
 int tc_conv2d_fprop_eligible(int C, int Co, const ctx_conv_geom& g);
-int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, const ctx_conv_geom& g,
+int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int y_ld, int Co, const ctx_conv_geom& g,
                     const Epi& epi, int passes, cudaStream_t stream);
 int tc_conv2d_transpose_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g);
 int tc_conv2d_transpose(const float* x1, int C1, const float* x2, int C2, int x2_batch, const float* w,

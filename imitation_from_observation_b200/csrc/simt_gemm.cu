@@ -44,6 +44,7 @@ struct FpropProb {
   int M, N, K;                       // M = imgs*P*Q, N = Co, K = kh*kw*C
   const float* x; const float* w; float* y;
   int C, H, W, st, padh, padw, kw;
+  int ldy;                           // channels per pixel of the destination tensor (>= N: write into a wider tensor)
   FastDiv divPQ, divQ, divC, divKw;
   Epi epi;
   struct RowA { int64_t img; int h0, w0; bool ok; };
@@ -70,7 +71,7 @@ struct FpropProb {
   __device__ __forceinline__ float fetchB(const KInfo& k, const ColB& c) const {
     return (c.ok && k.ok) ? __ldg(w + (int64_t)k.k * N + c.n) : 0.f;
   }
-  __device__ __forceinline__ int64_t rowOut(int m) const { return (int64_t)m * N; }
+  __device__ __forceinline__ int64_t rowOut(int m) const { return (int64_t)m * ldy; }
   __device__ __forceinline__ float* out() const { return y; }
 };
 
@@ -337,13 +338,13 @@ static int launch_simt(const Prob& p, int max_splits, cudaStream_t stream, const
 
 static bool fits_i32(int64_t v) { return v >= 0 && v < (int64_t)2147483647; }
 
-int simt_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, const ctx_conv_geom& g,
+int simt_conv2d_fprop(const float* x, int C, const float* w, float* y, int y_ld, int Co, const ctx_conv_geom& g,
                       const Epi& epi, cudaStream_t stream) {
   FpropProb p;
   int64_t M = (int64_t)g.N * g.P * g.Q, K = (int64_t)g.kh * g.kw * C;
-  CTX_REQUIRE(fits_i32(M) && fits_i32(K) && fits_i32((int64_t)g.N * g.H * g.W * C) && fits_i32(M * Co),
+  CTX_REQUIRE(fits_i32(M) && fits_i32(K) && fits_i32((int64_t)g.N * g.H * g.W * C) && fits_i32(M * y_ld),
               "conv2d_fprop: tensor too large for 32-bit indexing");
-  p.M = (int)M; p.N = Co; p.K = (int)K;
+  p.M = (int)M; p.N = Co; p.K = (int)K; p.ldy = y_ld;
   p.x = x; p.w = w; p.y = y;
   p.C = C; p.H = g.H; p.W = g.W; p.st = g.stride; p.padh = g.pad_h; p.padw = g.pad_w; p.kw = g.kw;
   p.divPQ = FastDiv(g.P * g.Q); p.divQ = FastDiv(g.Q); p.divC = FastDiv(C); p.divKw = FastDiv(g.kw);

@@ -955,14 +955,17 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
   if (sms <= 0) return cuda_fail(cudaErrorNoDevice, name);
   const uint32_t bn_cta = (uint32_t)(p.pair ? p.BN / 2 : p.BN);          // B rows staged by one CTA
   const uint32_t raw = kATileBytes + bn_cta * 128u;
-  static int max_dyn = 0;
-  if (max_dyn == 0) {
+  // the opt-in shared-memory limit is a per-device function attribute: set it once for every device this process uses
+  static int max_dyn_dev[64] = {0};
+  int dev = 0;
+  CTX_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("%s: device ordinal %d out of range", name, dev); return CTX_ERR_ARG; }
+  if (max_dyn_dev[dev] == 0) {
     cudaFuncAttributes fa[3];
     CTX_CUDA(cudaFuncGetAttributes(&fa[0], tc_igemm_kernel<false, false>));
     CTX_CUDA(cudaFuncGetAttributes(&fa[1], tc_igemm_kernel<false, true>));
     CTX_CUDA(cudaFuncGetAttributes(&fa[2], tc_igemm_kernel<true, true>));
-    int dev = 0, optin = 0;
-    CTX_CUDA(cudaGetDevice(&dev));
+    int optin = 0;
     CTX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     size_t stat = 0;
     for (int i = 0; i < 3; ++i) stat = fa[i].sharedSizeBytes > stat ? fa[i].sharedSizeBytes : stat;
@@ -970,8 +973,9 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
     CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CTX_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    max_dyn = dyn;
+    max_dyn_dev[dev] = dyn;
   }
+  const int max_dyn = max_dyn_dev[dev];
   const int occ = tc_occupancy(p.passes, p.BN, p.nphase > 1 ? p.ph_kblocks[0] : p.kblocks_per_split);
   const uint32_t budget = occ == 1 ? (uint32_t)max_dyn : (uint32_t)(max_dyn - 2048) / 2u;
   // 3-pass with a K-major A operand: A (hi, lo) goes through tensor memory when the columns are there
@@ -1103,7 +1107,7 @@ static void tap_seg(Seg& s, int r, int sx, const ctx_conv_geom& g) {
   if ((g.H - hp + 1) / 2 <= 0 || (g.W - wp + 1) / 2 <= 0) s.dh = 16000;   // empty parity view: always out of range
 }
 
-int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, const ctx_conv_geom& g,
+int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int y_ld, int Co, const ctx_conv_geom& g,
                     const Epi& epi, int passes, cudaStream_t stream) {
   TcParams p;
   fill_common(p, passes, epi);
@@ -1148,7 +1152,7 @@ int tc_conv2d_fprop(const float* x, int C, const float* w, float* y, int Co, con
   p.total_kblocks = p.nseg * cblk;
   p.kblocks_per_split = p.total_kblocks;
   p.out = y;
-  p.sN = (int64_t)g.P * g.Q * Co; p.sP = (int64_t)g.Q * Co; p.sQ = Co; p.obase = 0;
+  p.sN = (int64_t)g.P * g.Q * y_ld; p.sP = (int64_t)g.Q * y_ld; p.sQ = y_ld; p.obase = 0;   // y_ld >= Co: wider destination
   p.atomic_out = 0;
   return launch_tc(p, m_tiles, 1, stream, "tc_conv2d_fprop");
 }

@@ -182,11 +182,14 @@ class InceptionV3:
             self._bufs[name] = t
         return t
 
-    def _conv(self, x, prefix, op):
+    def _conv(self, x, prefix, op, into=None, c_off=0):
         _, scope, co, kh, kw, stride, pad = op
         w, b = self.folded[prefix + scope]
         N, H, W_, C = x.shape
         g = ops._geom_general(N, H, W_, kh, kw, stride, pad)
+        if into is not None:                             # last conv of a branch: straight into the block's concat
+            return ops.conv2d_general(x, w, b, stride=stride, padding=pad, act=True, slope=0.0, impl=self.impl,
+                                      into=into, c_off=c_off)
         out = self._buf(prefix + scope, (N, g.P, g.Q, co))
         few = C % 32 != 0 and C * kh * kw <= 256 and co % 4 == 0 and kh == kw
         if few and self.impl != _lib.IMPL_SIMT and ops.tc_available():
@@ -198,20 +201,44 @@ class InceptionV3:
             return out
         return ops.conv2d_general(x, w, b, stride=stride, padding=pad, act=True, slope=0.0, out=out, impl=self.impl)
 
-    def _run(self, x, ops_list, prefix):
-        for op in ops_list:
+    def _run(self, x, ops_list, prefix, into=None, c_off=0):
+        """Run a chain of ops.  With `into`, the chain's result is written to channels [c_off, ...) of `into` (the
+        block's tf.concat result): convs write there directly, a trailing pool is copied."""
+        last = len(ops_list) - 1
+        for i, op in enumerate(ops_list):
+            dst = into if i == last else None
             if op[0] == "conv":
-                x = self._conv(x, prefix, op)
+                x = self._conv(x, prefix, op, dst, c_off)
             elif op[0] in ("maxpool", "avgpool"):
                 _, scope, k, stride, pad = op
                 N, H, W_, C = x.shape
                 g = ops._geom_general(N, H, W_, k, k, stride, pad)
                 x = ops.pool2d(x, k, stride, pad, "max" if op[0] == "maxpool" else "avg",
                                out=self._buf(prefix + scope, (N, g.P, g.Q, C)))
+                if dst is not None:
+                    ops.copy_channels(x, dst, c_off)
             elif op[0] == "fork":
-                heads = [self._conv(x, prefix, h) for h in op[1]]
-                x = self._concat(prefix + op[1][0][1] + ":fork", heads)
+                if dst is not None:
+                    off = c_off
+                    for h in op[1]:
+                        self._conv(x, prefix, h, dst, off)
+                        off += h[2]
+                    x = dst
+                else:
+                    heads = [self._conv(x, prefix, h) for h in op[1]]
+                    x = self._concat(prefix + op[1][0][1] + ":fork", heads)
         return x
+
+    @staticmethod
+    def _chain_out(ops_list, c_in):
+        """(channels, spatial stride factor is implicit) -> output channel count of a chain."""
+        c = c_in
+        for op in ops_list:
+            if op[0] == "conv":
+                c = op[2]
+            elif op[0] == "fork":
+                c = sum(h[2] for h in op[1])
+        return c
 
     def _concat(self, name, parts: Sequence[torch.Tensor]) -> torch.Tensor:
         N, H, W_ = parts[0].shape[:3]
@@ -244,8 +271,19 @@ class InceptionV3:
             if pos > last:
                 return got
         for name, branches in BLOCKS:
-            outs = [self._run(x, br, "InceptionV3/%s/" % name) for br in branches]
-            x = self._concat("InceptionV3/%s" % name, outs)
+            N, H, W_, C = x.shape
+            chans = [self._chain_out(br, C) for br in branches]
+            # output grid of the block = that of its first branch's geometry: every branch of a block ends on it
+            stride2 = any(op[0] in ("conv",) and op[5] == 2 for op in branches[0]) or \
+                any(op[0] == "maxpool" for br in branches for op in br)
+            P = (H - 3) // 2 + 1 if stride2 else H
+            Q = (W_ - 3) // 2 + 1 if stride2 else W_
+            blk = self._buf("InceptionV3/%s" % name, (N, P, Q, sum(chans)))
+            off = 0
+            for br, c in zip(branches, chans):
+                self._run(x, br, "InceptionV3/%s/" % name, into=blk, c_off=off)
+                off += c
+            x = blk
             if name in want:
                 got[name] = x
             pos += 1

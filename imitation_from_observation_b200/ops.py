@@ -166,7 +166,7 @@ def _geom_general(n, H, W_, kh, kw, stride, padding):
 
 
 def conv2d_general(x, w, bias=None, stride: int = 1, padding: str = "SAME", act: bool = False, slope: float = 0.0,
-                   out=None, impl=IMPL_AUTO):
+                   out=None, impl=IMPL_AUTO, into=None, c_off: int = 0):
     """slim.conv2d as InceptionV3 uses it (nets/inception_v3.py:104-413): rectangular kernels (1x7, 7x1, 1x3, 3x1),
     SAME or VALID, folded-BN bias, activation max(v, slope*v) (slope 0 = ReLU).  x [N,H,W,C], w [kh,kw,C,Co]."""
     N, H, W_, Cin = x.shape
@@ -174,10 +174,20 @@ def conv2d_general(x, w, bias=None, stride: int = 1, padding: str = "SAME", act:
     if Cw != Cin:
         raise _lib.CtxError("conv2d_general: filter %s does not match input %s" % (tuple(w.shape), tuple(x.shape)))
     g = _geom_general(N, H, W_, kh, kw, stride, padding)
-    if out is None:
-        out = torch.empty((N, g.P, g.Q, Co), device=x.device, dtype=torch.float32)
     epi = make_epilogue(bias, act, None, False, False, slope)
     pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * kh * kw * Cin)
+    if into is not None:
+        # write channels [c_off, c_off + Co) of the wider NHWC tensor `into` (the block's concat result)
+        if tuple(into.shape[:3]) != (N, g.P, g.Q) or c_off < 0 or c_off + Co > into.shape[3]:
+            raise _lib.CtxError("conv2d_general: destination %s does not take [%d,%d,%d,%d] at channel %d"
+                                % (tuple(into.shape), N, g.P, g.Q, Co, c_off))
+        check(_lib.load().ctx_conv2d_fprop_ld(_req(x, "x"), Cin, _req(w, "w"), _req(into, "into") + 4 * c_off,
+                                              into.shape[3], Co, C.byref(g), C.byref(epi), impl, _stream()),
+              "ctx_conv2d_fprop_ld")
+        pr.done()
+        return into
+    if out is None:
+        out = torch.empty((N, g.P, g.Q, Co), device=x.device, dtype=torch.float32)
     check(_lib.load().ctx_conv2d_fprop(_req(x, "x"), Cin, _req(w, "w"), _req(out, "out"), Co, C.byref(g),
                                        C.byref(epi), impl, _stream()), "ctx_conv2d_fprop")
     pr.done()

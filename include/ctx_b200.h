@@ -91,6 +91,12 @@ int ctx_last_impl(void);
 int ctx_conv2d_fprop(const float* x, int32_t C, const float* w, float* y, int32_t Co,
                      const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream);
 
+/* Same, writing into a WIDER NHWC tensor: y points at the first output channel inside it and y_ld >= Co is its channel
+ * count, so that a branch of an Inception block lands directly in the block's tf.concat(axis=3) result
+ * (nets/inception_v3.py:177 ...).  No act_ref / accumulate in this form. */
+int ctx_conv2d_fprop_ld(const float* x, int32_t C, const float* w, float* y, int32_t y_ld, int32_t Co,
+                        const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t impl, void* stream);
+
 /* y[N,H,W,Cn] = epi( sum_{p,q,r,s,k : p*st+r-pad_h == h, q*st+s-pad_w == w} x[n,p,q,k] * w[r,s,cn,k] )
  * with x the channel concatenation [x1 (C1 ch, batch N) ‖ x2 (C2 ch, batch x2_batch, image n % x2_batch)];
  * x2 may be NULL (C2 = 0).  w is [kh,kw,Cn,C1+C2].

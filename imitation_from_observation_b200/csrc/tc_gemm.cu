@@ -897,16 +897,23 @@ static bool tile_grid(int P, int Q, int rows, int* BP, int* NB, int* tiles_per_i
 // Partial tiling of a P x Q pixel grid for conv fprop when it does not tile exactly into 128 pixels (InceptionV3's
 // 17x17, 35x35, 71..149-wide maps): the A box is BQ x BP x NB <= 128 pixels.
 static void plan_partial(int P, int Q, int* BQ, int* BP, int* NB, int* tiles_p, int* tiles_q) {
-  if (Q > 128) {
-    *tiles_q = (Q + 127) / 128; *BQ = (Q + *tiles_q - 1) / *tiles_q; *BP = 1; *NB = 1; *tiles_p = P;
+  if (Q <= 128 && P * Q <= 128) {                       // whole images per tile
+    *BQ = Q; *BP = P; *NB = 128 / (P * Q); if (*NB < 1) *NB = 1; *tiles_p = 1; *tiles_q = 1;
     return;
   }
-  *BQ = Q; *tiles_q = 1;
-  int bp = 128 / Q;
-  if (bp >= P) { *BP = P; *NB = 128 / (P * Q); if (*NB < 1) *NB = 1; *tiles_p = 1; return; }
-  *tiles_p = (P + bp - 1) / bp;
-  *BP = (P + *tiles_p - 1) / *tiles_p;              // even out the row bands
-  *NB = 1;
+  // search the column split that wastes the fewest MMA rows: utilisation = P*Q / (tiles * 128)
+  int best_tq = 0, best_tiles = 0, best_bq = 0, best_bp = 0, best_tp = 0;
+  for (int tq = 1; tq <= 8; ++tq) {
+    const int bq = (Q + tq - 1) / tq;
+    if (bq > 128) continue;
+    int bp = 128 / bq;
+    if (bp > P) bp = P;
+    const int tp = (P + bp - 1) / bp;
+    bp = (P + tp - 1) / tp;                             // even out the row bands
+    const int tiles = tp * tq;
+    if (best_tq == 0 || tiles < best_tiles) { best_tq = tq; best_tiles = tiles; best_bq = bq; best_bp = bp; best_tp = tp; }
+  }
+  *BQ = best_bq; *BP = best_bp; *NB = 1; *tiles_p = best_tp; *tiles_q = best_tq;
 }
 
 // N tile: 128 for the 3-pass mode (with a 5-deep raw ring it is the best-balanced 1-CTA shape: tensor 768, splitter
@@ -931,10 +938,15 @@ static int tc_occupancy(int passes, int BN, int kblocks) {
   const int k = knob_occ();
   if (k == 1 || k == 2) return k;
   if (passes != 3) return 2;
+  if (BN > 128) return 1;                               // (2 x BN accumulator columns leave no room for a second CTA)
   return (BN <= 64 || kblocks <= 8) ? 2 : 1;
 }
 
 static int pick_bn(int N, int64_t m_tiles, int passes) {
+  // 128 < N <= 192 (InceptionV3's 192-channel layers): one exact 192-wide tile instead of 128 + a half-empty 128
+  // (fits the 3-pass TMEM budget: 2 x 192 accumulator columns + 2 stages of A)
+  if (N > 128 && N <= 192 && N % 32 == 0 && m_tiles >= sm_count()) return 192;
+  if (N <= 32) return 32;                               // (InceptionV3's 32-channel stem convs)
   int bn = passes == 3 ? knob_bn3() : 256;
   const int sms = sm_count();
   while (bn > 64 && (N <= bn / 2 || m_tiles * cdiv(N, bn) < sms)) bn /= 2;

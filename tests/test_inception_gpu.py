@@ -57,6 +57,33 @@ def test_conv2d_general_rectangular_and_valid(kh, kw, stride, padding, hw, c, co
         assert rel_err(y.cpu(), ref.permute(0, 2, 3, 1)) < tol, impl
 
 
+@pytest.mark.parametrize("hw,c,co,k,stride,padding", [
+    (147, 32, 64, 3, 1, "SAME"),      # wider than one 128-pixel tile: column tiles (q_tiles > 1)
+    (149, 32, 32, 3, 1, "VALID"),     # N = 32 tile
+    (73, 80, 192, 3, 1, "VALID"),     # ragged channel block (80 = 2.5 x 32), exact 192-wide tile, 71-wide output
+    (35, 288, 384, 3, 2, "VALID"),    # stride-2 parity views on an odd grid
+    (35, 48, 64, 5, 1, "SAME"),       # 35-wide grid: two column tiles of 18
+    (71, 192, 32, 1, 1, "SAME")])
+def test_conv2d_general_inception_stem_shapes(hw, c, co, k, stride, padding):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((2, hw, hw, c), generator=g)
+    w = torch.randn((k, k, c, co), generator=g) * (k * k * c) ** -0.5
+    b = torch.randn((co,), generator=g) * 0.1
+    xc = x.double().permute(0, 3, 1, 2)
+    if padding == "SAME":
+        xc = OI._pad_same(xc, k, k, stride)
+    ref = torch.relu(torch.nn.functional.conv2d(xc, w.double().permute(3, 2, 0, 1), b.double(), stride=stride))
+    for impl, tol in ((_lib.IMPL_AUTO, 2e-5), (_lib.IMPL_FAST, 3e-3)):
+        y = ops.conv2d_general(x.cuda(), w.cuda(), b.cuda(), stride=stride, padding=padding, act=True, slope=0.0, impl=impl)
+        assert int(_lib.load().ctx_last_impl()) != _lib.IMPL_SIMT
+        assert rel_err(y.cpu(), ref.permute(0, 2, 3, 1)) < tol, impl
+    # ... and into a wider destination (the block's concat buffer)
+    dst = torch.full((2, ref.shape[2], ref.shape[3], co + 24), 7.0).cuda()
+    ops.conv2d_general(x.cuda(), w.cuda(), b.cuda(), stride=stride, padding=padding, act=True, slope=0.0, into=dst, c_off=8)
+    assert rel_err(dst[..., 8:8 + co].cpu(), ref.permute(0, 2, 3, 1)) < 2e-5
+    assert float((dst[..., :8] - 7.0).abs().max()) == 0.0 and float((dst[..., 8 + co:] - 7.0).abs().max()) == 0.0
+
+
 def test_inception_v3_endpoints_match_oracle():
     """B = 2, 299x299 uint8 frames (as base.py:72-76 feeds them): Mixed_5d / Mixed_6e / Mixed_7c / PreLogits vs the
     fp64 oracle, 1e-3 relative (north_star tolerance); 94 folded conv launches."""

@@ -28,7 +28,14 @@ H = 299
 print("InceptionV3 %s B=%d: %.2f ms / batch, %.0f img/s, %.1f TFLOP/s (11.42 GFLOP/img)" %
       (a.precision, a.batch, ms, a.batch / ms * 1e3, a.batch * 11.42e9 / ms / 1e9))
 ops.PROFILE = []
+shapes = []
+_orig = ops.conv2d_general
+def _wrap(x, w, *a_, **k_):
+    shapes.append((tuple(x.shape), tuple(w.shape), k_.get("stride", 1), k_.get("padding", "SAME")))
+    return _orig(x, w, *a_, **k_)
+ops.conv2d_general = _wrap
 net.forward(frames, ("Mixed_7c",))
+ops.conv2d_general = _orig
 torch.cuda.synchronize()
 prof, ops.PROFILE = ops.PROFILE, None
 agg = {}
@@ -37,3 +44,12 @@ for kind, impl, flops, s, e in prof:
     d = agg.setdefault(k, [0, 0.0, 0.0]); d[0] += 1; d[1] += flops; d[2] += s.elapsed_time(e)
 for k, (n, f, t) in agg.items():
     print("  %-5s %3d conv/gemm launches  %7.2f ms  %6.1f TFLOP/s  (%.0f%% of conv flops)" % (k, n, t, f / t / 1e9, 100 * f / (a.batch * 11.42e9)))
+
+rows = []
+conv_prof = [p for p in prof if p[0] == "fprop"]
+for (xs, ws, st, pad), (kind, impl, flops, s_, e_) in zip(shapes, conv_prof):
+    rows.append((s_.elapsed_time(e_), flops, xs, ws, st, pad))
+rows.sort(reverse=True)
+print("slowest convs:")
+for t, f, xs, ws, st, pad in rows[:16]:
+    print("  %7.3f ms %6.1f TF/s  x%s w%s s%d %s" % (t, f / t / 1e9, xs[1:], ws, st, pad))

@@ -242,29 +242,33 @@ int bias_init(float* y, const float* bias, int64_t n, int C, int accumulate, cud
 // One thread per output element, column index fastest: stores are fully coalesced, loads hit L1/L2 (every input
 // element is read kh*kw/st^2 times from cache, once from HBM).
 __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int ld, int C, int H,
-                              int W, int kw, int K, int st, int padh, int padw, int rnd, FastDiv divLd,
-                              FastDiv divC, FastDiv divKw, FastDiv divQ, FastDiv divP) {
-  constexpr int R = 32;                                     // rows per block
+                              int W, int kw, int K, int st, int padh, int padw, int rnd, FastDiv divLd, FastDiv divC,
+                              FastDiv divKw, FastDiv divQ, FastDiv divP) {
+  // Thread t owns patch column k = t (its tap (r, s) and channel c are decoded once); the block walks R rows, whose
+  // pixel decode is the same for every thread.  Stores are coalesced along k; loads hit L1/L2.
+  constexpr int R = 64;                                     // rows per block
+  const int k = threadIdx.x;
+  if (k >= ld) return;
+  int tap, c, r, s;
+  divC.divmod(k < K ? k : 0, tap, c);
+  divKw.divmod(tap, r, s);
   const int row0 = blockIdx.x * R;
   const int nrow = min(R, rows - row0);
-  const int total = nrow * ld;
-  float* o = out + (int64_t)row0 * ld;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    int j, k;
-    divLd.divmod(e, j, k);
+  float* o = out + (int64_t)row0 * ld + k;
+  int t, q, n, pp;
+  divQ.divmod(row0, t, q);
+  divP.divmod(t, n, pp);
+  const int Q = (int)divQ.d, P = (int)divP.d;
+  for (int j = 0; j < nrow; ++j) {
     float v = 0.f;
     if (k < K) {
-      int tap, c, r, s, t, q, n, pp;
-      divC.divmod(k, tap, c);
-      divKw.divmod(tap, r, s);
-      divQ.divmod(row0 + j, t, q);
-      divP.divmod(t, n, pp);
       const int h = pp * st + r - padh, w = q * st + s - padw;
       if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
         v = __ldg(x + (((int64_t)n * H + h) * W + w) * C + c);
       if (rnd) v = round_tf32(v);
     }
-    o[e] = v;
+    o[(int64_t)j * ld] = v;
+    if (++q == Q) { q = 0; if (++pp == P) { pp = 0; ++n; } }
   }
 }
 
@@ -613,7 +617,8 @@ extern "C" int ctx_im2col(const float* x, int32_t C, float* out, int32_t ld, con
   const int64_t rows = (int64_t)g->N * g->P * g->Q;
   if (rows == 0) return CTX_OK;
   CTX_REQUIRE(rows < (1ll << 31) - 64 && ld <= 4096, "im2col: too many rows (%lld) or ld too large", (long long)rows);
-  im2col_kernel<<<(unsigned)cdiv(rows, 32), 256, 0, (cudaStream_t)stream>>>(
+  CTX_REQUIRE(ld <= 1024, "im2col: ld (%d) must be <= 1024", ld);
+  im2col_kernel<<<(unsigned)cdiv(rows, 64), ((ld + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(
       x, out, (int)rows, ld, C, g->H, g->W, g->kw, g->kh * g->kw * C, g->stride, g->pad_h, g->pad_w, round_tf32,
       FastDiv(ld),
       FastDiv(C), FastDiv(g->kw), FastDiv(g->Q), FastDiv(g->P));

@@ -10,18 +10,31 @@
 //   (base + (hp*W+wp)*C, strides doubled), so every tap is again a dense box.
 // * The channel concatenation of a decoder level ([state ‖ skip], arm_shaping.py:1323-1329) is two K segments
 //   with two tensor maps — it never exists in memory.
+// * Any P x Q pixel grid: exact 128-pixel tiles when the grid allows, else partial boxes BQ x BP x NB <= 128 pixels
+//   (column tiles for wide maps) whose unused MMA rows are masked by the epilogue; a ragged last 32-channel block is
+//   zero-filled by the TMA unit.  A transposed conv with few output channels (the 3-channel image) is ONE GEMM over
+//   (tap, channel) columns whose epilogue scatter-adds (col2im).
 // * Filter gradients use MN-major operands (pixels are the K dimension): the same pixel boxes, four 32-channel
-//   atoms per 128-row tile; split-K over pixel blocks, reduced with vector fp32 atomics.
-// * Precision (SURVEY.md §7 "hard parts"): passes == 1 is plain TF32 (operands must already be
-//   rounded to TF32 by the producer's epilogue).  passes == 3 is the fp32-faithful split
-//   a*b ~= hi(a)*hi(b) + hi(a)*lo(b) + lo(a)*hi(b): four "splitter" warps turn each landed fp32 tile into a
-//   (hi, lo) pair in shared memory (elementwise, so it is layout-agnostic), and the MMA warp issues three
-//   tcgen05.mma per K step.  Error per product ~2^-21, i.e. fp32-grade — needed because lrelu's derivative is
-//   discontinuous and single-pass TF32 flips ~3e-4 of the masks (measured).
+//   atoms per 128-row tile fetched with ONE rank-5 box (one TMA instruction costs the TMA unit a few hundred cycles
+//   whatever its size); split-K over pixel blocks sized per wave, reduced with vector fp32 atomics.
+// * Precision: single pass = plain TF32 (the hardware truncates fp32 operands: producers round to
+//   nearest, weights come from a rounded shadow copy).  3-pass = the fp32-faithful split
+//   a*b ~= hi(a)*hi(b) + hi(a)*lo(b) + lo(a)*hi(b): eight "splitter" warps turn each landed fp32 tile into (hi, lo);
+//   A's (hi, lo) go to TENSOR MEMORY (tcgen05.st, 4-deep ring) and are consumed by TS-form MMAs, B's lo goes to a
+//   small shared-memory ring; three tcgen05.mma per K step into two accumulators (the small cross terms must not
+//   ride on the big sum: the tensor core adds into its fp32 accumulator with truncation).  ~2^-21 per product.
 //
-// Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = splitters during the main loop, then the epilogue (TMEM -> registers -> fused bias / lrelu /
-// lrelu' / accumulate / TF32 rounding -> global, or vector atomics for split-K).
+// Three instantiations tc_igemm_kernel<pair, 3-pass>:
+//   <0,0> single pass, two CTAs per SM (they overlap each other's prologue / epilogue / pipeline-fill bubbles);
+//   <0,1> 3-pass, one CTA per SM (two for narrow or very short tiles);
+//   <1,1> 3-pass CTA PAIR (cta_group::2, cluster of 2 along M): one 256 x 128 MMA per step for two SMs; each CTA
+//         stages and splits its own 128 rows of A and HALF of the B tile; the follower forwards "my tiles are split"
+//         to the leader with a relaxed remote mbarrier arrive; commits are multicast to both CTAs.
+//
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + warp-convergent MMA issue
+// (elect.sync-predicated tcgen05.mma, vote-based barrier waits), warps 2..9 = splitters during the main loop, then the
+// epilogue (two warps per TMEM lane quarter: TMEM -> registers -> fused bias / lrelu / lrelu' / accumulate / TF32
+// rounding -> 128-bit stores, vector atomics for split-K, or scatter-add).
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>

@@ -140,21 +140,33 @@ def cpu_reference_step_time(spec, sample_B, steps, warmup, threads, budget_s=Non
     return float(np.mean(times)), sample_B
 
 
+def train_workload(args):
+    """(spec, model class name, label) of the training workload: the headline ContextSkipNew 64x64 (BASELINE
+    configs[1]) or, as a secondary line, configs[3]'s 6-layer 128x128 model."""
+    from imitation_from_observation_b200 import spec as S
+    if args.workload == "striker6":
+        return S.context_skip_deep(128, 128), "ContextSkipDeep", "ContextSkipDeep (6-layer) 128x128x3", "configs[3]"
+    return S.context_skip_new(64, 64), "ContextSkipNew", "ContextSkipNew 64x64x3", "configs[1]"
+
+
+def metric_name(args, label):
+    return METRIC if args.workload == "train" else "frames/sec fwd+bwd+Adam, %s, B=%d triples per GPU" % (label, args.batch)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from imitation_from_observation_b200 import spec as S
-    spec = S.context_skip_new(64, 64)
+    spec, _, label, _ = train_workload(args)
     threads = os.cpu_count() or 1
     t, sample_B = cpu_reference_step_time(spec, args.ref_batch, args.steps, args.warmup, threads, budget_s=150.0)
     value = 3.0 * sample_B / t
-    sample = "%d-triple slice of the B=256 batch per step (fwd+bwd+Adam), PyTorch-CPU fp32 restatement" % sample_B
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    sample = "%d-triple slice of the B=%d batch per step (fwd+bwd+Adam), PyTorch-CPU fp32 restatement" % (sample_B, args.batch)
+    line = dict(metric=metric_name(args, label), value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="ContextSkipNew 64x64x3 train step; reference arm runs %d triples per step on "
-                                     "the host cores" % sample_B, triples_per_step=sample_B),
+                config=dict(workload="%s train step; reference arm runs %d triples per step on "
+                                     "the host cores" % (label, sample_B), triples_per_step=sample_B),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -166,8 +178,8 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from imitation_from_observation_b200 import _lib, compat as tf, ops, parallel, spec as S
-    from imitation_from_observation_b200.models import ContextSkipNew
+    from imitation_from_observation_b200 import _lib, compat as tf, ops, parallel
+    from imitation_from_observation_b200.models import MODEL_REGISTRY
     from imitation_from_observation_b200.network import FWD_ALL
 
     rank, world, local = parallel.init_distributed()
@@ -177,13 +189,13 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     _lib.load()
     B = args.batch
-    spec = S.context_skip_new(64, 64)
+    spec, model_name, label, cfg_name = train_workload(args)
     peaks = load_peaks()
 
     # the reference-facing object graph (train_script.py:118-129)
     tf.reset_default_graph()
-    tfinput = tf.placeholder(tf.float32, (3, B, 64, 64, 3), name="x")
-    model = ContextSkipNew()
+    tfinput = tf.placeholder(tf.float32, (3, B, spec.height, spec.width, 3), name="x")
+    model = MODEL_REGISTRY[model_name]()
     with tf.variable_scope("contextmodel"):
         tf.build_model(model, tfinput, precision=args.precision, seed=0, global_batch=B * world, device=dev)
     net = model.net
@@ -294,7 +306,7 @@ def run_ours(args):
                           "restatement of the TF graph (oracle/tf_semantics.py)" % (sb, B))
 
     if rank == 0:
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        line = dict(metric=metric_name(args, label), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32 (%s)" % {"tf32x3": "tensor-core operands tf32, 3-pass split, fp32 accumulate",
                                         "mixed": "tensor-core operands tf32: 3-pass split forward, single pass backward; "
@@ -302,11 +314,11 @@ def run_ours(args):
                                         "tf32": "tensor-core operands tf32, single pass, fp32 accumulate",
                                         "fp32": "exact fp32 SIMT"}[args.precision],
                     data="synthetic",
-                    config=dict(workload="ContextSkipNew 64x64x3, %d triples/GPU (BASELINE configs[1]): fwd+bwd+TF-Adam" % B,
+                    config=dict(workload="%s, %d triples/GPU (BASELINE %s): fwd+bwd+TF-Adam" % (label, B, cfg_name),
                                 triples_per_gpu=B, global_triples=B * world, precision=args.precision,
                                 parallelism="dp%d" % world, params=spec.num_params(),
-                                l2="working set per step (params+grads+moments 0.76 GB, activations ~1.3 GB) exceeds L2; "
-                                   "%d distinct input batches rotate" % nb),
+                                l2="working set per step (params+grads+moments %.2f GB, activations > 1 GB) exceeds L2; "
+                                   "%d distinct input batches rotate" % (16e-9 * spec.num_params(), nb)),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                              api="compat.Session.run([optimizer, loss], feed_dict) with a pinned host batch",
@@ -452,8 +464,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="triples per GPU")
     ap.add_argument("--ref-batch", type=int, default=256, help="max triples per step of the CPU reference (reduced to fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "inception"],
-                    help="train = the headline metric (default); inception = BASELINE configs[4], a secondary line")
+    ap.add_argument("--workload", default="train", choices=["train", "striker6", "inception"],
+                    help="train = the headline metric (default); striker6 = BASELINE configs[3] (6-layer 128x128 model) "
+                         "and inception = configs[4], secondary lines")
     args = ap.parse_args()
     if args.workload == "inception":
         run_inception(args)

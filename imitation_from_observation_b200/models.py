@@ -75,7 +75,7 @@ class _ContextModel:
         net = self.net
         x = self._prep(frames)
         n = x.shape[0]
-        hs = [torch.empty((n,) + net.sizes[j + 1] + (net.chans[j + 1],), device=x.device) for j in range(4)]
+        hs = [torch.empty((n,) + net.sizes[j + 1] + (net.chans[j + 1],), device=x.device) for j in range(net.L)]
         h4 = torch.empty((n, net.F), device=x.device)
         z = torch.empty((n, net.F), device=x.device)
         net._fwd_encoder(scope, x, hs, h4)
@@ -108,11 +108,11 @@ class _ContextModel:
         """Scope "deconv" — arm_shaping.py:1314-1329.  `skips` = enc2 activations (batch may be smaller: n % batch)."""
         net = self.net
         n = z.shape[0]
-        d = [torch.empty((n,) + net.sizes[4] + (net.chans[4],), device=z.device)]
+        d = [torch.empty((n,) + net.sizes[net.L] + (net.chans[net.L],), device=z.device)]
         for L in net.dec:
             d.append(torch.empty((n,) + tuple(L["out_hw"]) + (L["c_out"],), device=z.device))
         net._fwd_decoder(z.contiguous(), skips, d)
-        out = d[4]
+        out = d[net.L]
         if self.spec.residual_out:
             if ctx_frames is None:
                 raise _lib.CtxError("dec(): this model adds the context input to the output; pass ctx_frames")
@@ -175,6 +175,23 @@ class ContextAEInception2(_ContextModel):
         return _spec.context_ae_inception2(H, W, C, self.strides, self.kernels, self.filters, self.featsize)
 
 
+class ContextSkipDeep(_ContextModel):
+    """BASELINE.json configs[3]: "Striker 128x128x3, deeper 6-layer enc/dec".  NOT a reference class — the reference's
+    builders are 4 layers deep; this is ContextSkipNew's graph with one conv / transposed conv per entry of `filters`
+    (spec.context_skip_deep).  Same kernels, same fetch surface, same checkpoint naming scheme
+    (`h<L>_lin`, `d_h1..d_h<L>`)."""
+
+    def __init__(self, filters=(64, 128, 256, 512, 512, 512), kernels=None, strides=None, featsize=1024):
+        self.filters = tuple(filters)
+        self.kernels = tuple(kernels) if kernels else None
+        self.strides = tuple(strides) if strides else None
+        self.featsize = featsize
+
+    def _make_spec(self, H, W, C):
+        return _spec.context_skip_deep(H, W, C, self.filters, self.kernels, self.strides, self.featsize)
+
+
 MODEL_REGISTRY = {"ContextSkipNew": ContextSkipNew, "ContextAEReal": ContextAEReal,
                   "ContextAEInception": ContextAEInception2,      # train_script.py:48-49 maps this name to ...2
-                  "ContextAEInception2": ContextAEInception2}
+                  "ContextAEInception2": ContextAEInception2,
+                  "ContextSkipDeep": ContextSkipDeep}             # not in the reference (BASELINE configs[3])

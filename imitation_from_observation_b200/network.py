@@ -123,6 +123,8 @@ class ContextNet:
         self.F = spec.featsize
         self.flat = spec.flat_dim()
         self.dec = spec.dec_layers()
+        self.L = spec.depth                              # encoder convs = decoder transposed convs (4 in the reference)
+        self.lin = spec.lin_name                         # "h4_lin" at the reference's depth
         self._level = 0
 
     # ---- second stream -----------------------------------------------------------------------------------------
@@ -258,9 +260,9 @@ class ContextNet:
 
     # ---- forward pieces (also the functional enc1 / enc2 / translate / dec surface) ------------------------------
     def encode_convs(self, scope: str, x: torch.Tensor, outs: Sequence[torch.Tensor]):
-        """4 x (conv5x5/3x3 SAME + bias + lrelu) — arm_shaping.py:1283-1286."""
+        """L x (conv SAME + bias + lrelu) — arm_shaping.py:1283-1286 (L = 4 there)."""
         h = x
-        for j in range(4):
+        for j in range(self.L):
             w, b = self.Wf["%s/h%d_conv/w" % (scope, j)], self.P["%s/h%d_conv/biases" % (scope, j)]
             k, Cin, Co = self.spec.kernels[j], h.shape[3], w.shape[3]
             if self._few(Cin, k) and Co % 4 == 0:
@@ -307,9 +309,9 @@ class ContextNet:
     def _fwd_encoder(self, scope: str, x: torch.Tensor, hs: List[torch.Tensor], h4: torch.Tensor):
         n = x.shape[0]
         self.encode_convs(scope, x, hs)
-        self._gemm(False, False, n, self.F, self.flat, hs[3].data_ptr(), self.flat,
-                   self.Wf[scope + "/h4_lin/Matrix"].data_ptr(), self.F, h4.data_ptr(), self.F,
-                   bias=self.P[scope + "/h4_lin/bias"], act=True)
+        self._gemm(False, False, n, self.F, self.flat, hs[-1].data_ptr(), self.flat,
+                   self.Wf["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), self.F, h4.data_ptr(), self.F,
+                   bias=self.P["%s/%s/bias" % (scope, self.lin)], act=True)
 
     def _fwd_hz(self, scope: str, h4_rows: torch.Tensor, out_ptr: int, ldo: int, act: bool):
         self._gemm(False, False, h4_rows.shape[0], self.F, self.F, h4_rows.data_ptr(), self.F,
@@ -317,7 +319,7 @@ class ContextNet:
                    bias=self.P[scope + "/hz_lin/bias"], act=act)
 
     def _enc_buffers(self, n_rows: int, tag: str):
-        hs = [self._buf("%s_h%d" % (tag, j), (n_rows,) + self.sizes[j + 1] + (self.chans[j + 1],)) for j in range(4)]
+        hs = [self._buf("%s_h%d" % (tag, j), (n_rows,) + self.sizes[j + 1] + (self.chans[j + 1],)) for j in range(self.L)]
         h4 = self._buf("%s_h4" % tag, (n_rows, self.F))
         return hs, h4
 
@@ -374,33 +376,33 @@ class ContextNet:
             d = self._dec_buffers()
             self._fwd_decoder(z2[:nd], [c[:B] for c in c_hs], [t[:nd] for t in d])
             if level == FWD_ALL:
-                self._fwd_losses(d[4], xe[B:2 * B], xc)
+                self._fwd_losses(d[self.L], xe[B:2 * B], xc)
         self._level = level
 
     def _dec_buffers(self):
         B = self.B
-        d = [self._buf("d0", (2 * B,) + self.sizes[4] + (self.chans[4],))]
+        d = [self._buf("d0", (2 * B,) + self.sizes[self.L] + (self.chans[self.L],))]
         for i, L in enumerate(self.dec):
             d.append(self._buf("d%d" % (i + 1), (2 * B,) + tuple(L["out_hw"]) + (L["c_out"],)))
         return d
 
     def _fwd_decoder(self, z: torch.Tensor, skips: Sequence[torch.Tensor], d: Sequence[torch.Tensor]):
-        """arm_shaping.py:1314-1329 for all stacked passes at once; skips = ctx (h0,h1,h2,h3), batch B."""
+        """arm_shaping.py:1314-1329 for all stacked passes at once; skips = ctx (h0..h_{L-1}), batch B."""
         n = z.shape[0]
         self._gemm(False, False, n, self.flat, self.F, z.data_ptr(), self.F,
                    self.Wf["deconv/d_h0_lin/Matrix"].data_ptr(), self.flat, d[0].data_ptr(), self.flat,
                    bias=self.P["deconv/d_h0_lin/bias"], act=True)
         for i, L in enumerate(self.dec):
-            last = i == 3
+            last = i == self.L - 1
             ops.conv2d_transpose(d[i], self.Wf["deconv/%s/w" % L["name"]], L["out_hw"],
-                                 bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2=skips[3 - i],
+                                 bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2=skips[self.L - 1 - i],
                                  act=not last, out=d[i + 1], round_tf32=self.round and not last, impl=self.impl)
 
     def _fwd_losses(self, d4: torch.Tensor, tgt: torch.Tensor, ctx: torch.Tensor):
         B, F = self.B, self.F
         losses = self._buf("losses", (4,))
         losses.zero_()
-        g_d4 = self._buf("g_d4", tuple(d4.shape))
+        g_d4 = self._buf("g_out", tuple(d4.shape))
         w = self._bufs.get("w_recon")
         if w is None:
             w = self._bufs["w_recon"] = torch.tensor(self._w_recon, device=self.device, dtype=torch.float32)
@@ -435,21 +437,22 @@ class ContextNet:
         cat, z2, th0 = bufs["cat"], bufs["z2"], bufs["th0"]
 
         # gradient buffers of the encoder activations (pre-activation gradients, i.e. lrelu' already applied)
-        ge_hs = [self._buf("g_e_h%d" % j, tuple(e_hs[j].shape)) for j in range(4)]
+        ge_hs = [self._buf("g_e_h%d" % j, tuple(e_hs[j].shape)) for j in range(self.L)]
         ge_h4 = self._buf("g_e_h4", tuple(e_h4.shape))
         if sp.separate_ctx_encoder:
-            gc_hs = [self._buf("g_c_h%d" % j, tuple(c_hs[j].shape)) for j in range(4)]
+            gc_hs = [self._buf("g_c_h%d" % j, tuple(c_hs[j].shape)) for j in range(self.L)]
             gc_h4 = self._buf("g_c_h4", tuple(c_h4.shape))
         else:
             gc_hs, gc_h4 = [g[2 * B:] for g in ge_hs], ge_h4[2 * B:]
 
-        # ---- decoder: d_h4 .. d_h1 -------------------------------------------------------------------------------
-        g_out = bufs["g_d4"]                              # d loss / d d4 (written by the loss kernel)
+        # ---- decoder: d_h<L> .. d_h1 ----------------------------------------------------------------------------
+        Ld = self.L
+        g_out = bufs["g_out"]                             # d loss / d d4 (written by the loss kernel)
         ib, rb = self.impl_b, self.round_b
-        for i in (3, 2, 1, 0):
+        for i in reversed(range(Ld)):
             L = self.dec[i]
             wname = "deconv/%s/w" % L["name"]
-            state, skip = d[i], c_hs[3 - i]
+            state, skip = d[i], c_hs[Ld - 1 - i]
             Cs, Ck, Co, k = L["c_state"], L["c_state"] + L["c_skip"], L["c_out"], L["k"]
             dcat = self._buf("dcat%d" % i, (2 * B,) + tuple(L["in_hw"]) + (Ck,))
             if self._few(Co, k):
@@ -473,7 +476,7 @@ class ContextNet:
                 # data gradient of the concatenated input = SAME conv of g_out with the [kh,kw,Cout,Cin] filter as HWIO
                 ops.conv2d(g_out, Wb[wname], None, stride=L["stride"], act=False, out=dcat, impl=ib)
             g_state = self._buf("g_d%d" % i, tuple(state.shape))
-            ops.split_skip_grad(dcat, 2, B, Cs, Ck - Cs, g_state, gc_hs[3 - i],
+            ops.split_skip_grad(dcat, 2, B, Cs, Ck - Cs, g_state, gc_hs[Ld - 1 - i],
                                 state_ref=state, skip_ref=skip, accumulate_skip=False, round_tf32=rb)
             g_out = g_state
         # ---- d_h0_lin ------------------------------------------------------------------------------------------------
@@ -530,19 +533,19 @@ class ContextNet:
         hz_backward("conv", g_tz.data_ptr(), F, e_h4[B:2 * B], ge_h4[B:2 * B])               # tgt
         hz_backward(self.ctx_scope, g_cat.data_ptr() + F * f4, 2 * F, c_h4, gc_h4)           # ctx
 
-        # ---- encoders: h4_lin then the four convs --------------------------------------------------------------------------
+        # ---- encoders: h<L>_lin then the convs -----------------------------------------------------------------------------
         def encoder_backward(scope, x, hs, h4, g_hs, g_h4, groups):
             """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate."""
             n = x.shape[0]
             with self._side():
-                self._gemm(True, False, flat, F, n, hs[3].data_ptr(), flat, g_h4.data_ptr(), F,
-                           G[scope + "/h4_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
-                ops.bias_grad(g_h4, G[scope + "/h4_lin/bias"])
+                self._gemm(True, False, flat, F, n, hs[-1].data_ptr(), flat, g_h4.data_ptr(), F,
+                           G["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), F, accumulate=True, round_=False, bwd=True)
+                ops.bias_grad(g_h4, G["%s/%s/bias" % (scope, self.lin)])
             for (r0, nr, acc) in groups:
                 self._gemm(False, True, nr, flat, F, g_h4[r0:r0 + nr].data_ptr(), F,
-                           Wb[scope + "/h4_lin/Matrix"].data_ptr(), F, g_hs[3][r0:r0 + nr].data_ptr(), flat,
-                           act_ref=hs[3][r0:r0 + nr].data_ptr(), accumulate=acc, bwd=True)
-            for j in (3, 2, 1, 0):
+                           Wb["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), F, g_hs[-1][r0:r0 + nr].data_ptr(), flat,
+                           act_ref=hs[-1][r0:r0 + nr].data_ptr(), accumulate=acc, bwd=True)
+            for j in reversed(range(Ld)):
                 wname = "%s/h%d_conv/w" % (scope, j)
                 src = hs[j - 1] if j > 0 else x
                 kj, Cin = sp.kernels[j], src.shape[3]
@@ -654,7 +657,7 @@ class ContextNet:
         if name == "target_z":
             return bufs["z2"][B:]
         if name in ("out", "out2"):
-            d4 = bufs["d4"]
+            d4 = bufs["d%d" % self.L]
             rows = d4[:B] if name == "out" else d4[B:]
             if self.spec.residual_out:
                 _, xc = self._input_buffers()

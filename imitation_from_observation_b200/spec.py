@@ -6,10 +6,13 @@ The reference builds three wired-up graph variants in gym/envs/mujoco/arm_shapin
 * ``ContextAEReal``        arm_shaping.py:1599-1684  (real / sweep)
 * ``ContextAEInception2``  arm_shaping.py:1786-1894  (feature-map model behind InceptionV3)
 
-All three are the same topology: 4 conv encoder layers + 2 dense layers, a 2-layer translator on
-``[src_z ‖ ctx_z]``, and a decoder (dense + 4 transposed convs) whose every level is channel-concatenated
+All three are the same topology: L = 4 conv encoder layers + 2 dense layers, a 2-layer translator on
+``[src_z ‖ ctx_z]``, and a decoder (dense + L transposed convs) whose every level is channel-concatenated
 with the *context* encoder's activation of the same resolution.  They differ only in the numbers held by
-:class:`NetSpec`.  Variable names / layouts follow the TF checkpoint keys (arm_shaping.py:25,29,52,54,67,79):
+:class:`NetSpec`.  The depth L is the length of ``filters``: the reference only wires up L = 4; BASELINE.json's
+configs[3] ("Striker 128x128, deeper 6-layer enc/dec") is the same graph with L = 6 (:func:`context_skip_deep`), with
+the dense layer after the last conv named ``h<L>_lin`` and the transposed convs ``d_h1 .. d_h<L>``, which for L = 4
+are exactly the reference's names.  Variable names / layouts follow the TF checkpoint keys (arm_shaping.py:25,29,52,54,67,79):
 
     {conv,conv_context,translate,deconv}/{h0_conv..h3_conv}/w        [kh,kw,Cin,Cout]   (HWIO)
     .../{d_h1..d_h4}/w                                              [kh,kw,Cout,Cin]
@@ -41,17 +44,31 @@ class NetSpec:
     height: int
     width: int
     c_dim: int
-    strides: Tuple[int, int, int, int]
-    kernels: Tuple[int, int, int, int]
-    filters: Tuple[int, int, int, int]
+    strides: Tuple[int, ...]
+    kernels: Tuple[int, ...]
+    filters: Tuple[int, ...]
     featsize: int
     separate_ctx_encoder: bool      # ContextSkipNew / Inception2: scope "conv_context" has its own weights
     ctx_hz_lrelu: bool              # ContextSkipNew: ctx hz_lin is linear (arm_shaping.py:1288); others lrelu
     residual_out: bool              # Inception2: out = dec(.) + ctx input (arm_shaping.py:1890-1891)
 
+    def __post_init__(self):
+        if not (len(self.strides) == len(self.kernels) == len(self.filters) >= 1):
+            raise ValueError("strides, kernels and filters must have the same, non-zero length")
+
     # ---- derived geometry -------------------------------------------------------------------------------
+    @property
+    def depth(self) -> int:
+        """Number of encoder convs = number of decoder transposed convs (4 in every reference model)."""
+        return len(self.filters)
+
+    @property
+    def lin_name(self) -> str:
+        """Dense layer after the last conv: `h4_lin` for the reference's depth."""
+        return "h%d_lin" % self.depth
+
     def enc_sizes(self) -> List[Tuple[int, int]]:
-        """Spatial size after each encoder conv (SAME): [(h0,w0),...,(h3,w3)]."""
+        """Spatial size after each encoder conv (SAME): [(h0,w0),...,(h_{L-1},w_{L-1})]."""
         h, w = self.height, self.width
         out = []
         for s in self.strides:
@@ -63,21 +80,21 @@ class NetSpec:
         return [self.c_dim] + list(self.filters)
 
     def flat_dim(self) -> int:
-        h3, w3 = self.enc_sizes()[3]
-        return h3 * w3 * self.filters[3]
+        h3, w3 = self.enc_sizes()[-1]
+        return h3 * w3 * self.filters[-1]
 
     def dec_layers(self) -> List[dict]:
-        """Decoder transposed-conv layers d_h1..d_h4, in execution order.
+        """Decoder transposed-conv layers d_h1..d_h<L>, in execution order.
 
-        Level i (1..4) consumes [state ‖ ctx skip h_{4-i}] at the resolution of encoder output 4-i and
-        produces the resolution of encoder output 3-i (the image for i=4), mirroring encoder layer 4-i's
+        Level i (1..L) consumes [state ‖ ctx skip h_{L-i}] at the resolution of encoder output L-i and
+        produces the resolution of encoder output L-1-i (the image for i=L), mirroring encoder layer L-i's
         kernel and stride (arm_shaping.py:1323-1329, 1662-1670, 1834-1848).
         """
         sizes = [(self.height, self.width)] + self.enc_sizes()   # sizes[j] = input of encoder layer j
         chans = self.enc_channels()                               # chans[j] = channels at sizes[j]
         layers = []
-        for i in range(1, 5):
-            e = 4 - i                                             # mirrored encoder layer
+        for i in range(1, self.depth + 1):
+            e = self.depth - i                                             # mirrored encoder layer
             layers.append(dict(
                 name="d_h%d" % i, k=self.kernels[e], stride=self.strides[e],
                 in_hw=sizes[e + 1], out_hw=sizes[e],
@@ -109,9 +126,9 @@ class NetSpec:
         for sc in scopes:
             shapes["%s/hz_lin/Matrix" % sc] = (F, F)
             shapes["%s/hz_lin/bias" % sc] = (F,)
-            shapes["%s/h4_lin/Matrix" % sc] = (self.flat_dim(), F)
-            shapes["%s/h4_lin/bias" % sc] = (F,)
-            for j in (3, 2, 1, 0):
+            shapes["%s/%s/Matrix" % (sc, self.lin_name)] = (self.flat_dim(), F)
+            shapes["%s/%s/bias" % (sc, self.lin_name)] = (F,)
+            for j in reversed(range(self.depth)):
                 k = self.kernels[j]
                 shapes["%s/h%d_conv/w" % (sc, j)] = (k, k, ch[j], ch[j + 1])
                 shapes["%s/h%d_conv/biases" % (sc, j)] = (ch[j + 1],)
@@ -132,7 +149,7 @@ class NetSpec:
         sizes = self.enc_sizes()
         ch = self.enc_channels()
         enc = 0
-        for j in range(4):
+        for j in range(self.depth):
             h, w = sizes[j]
             enc += h * w * ch[j + 1] * self.kernels[j] ** 2 * ch[j]
         enc += self.flat_dim() * self.featsize + self.featsize ** 2
@@ -166,3 +183,15 @@ def context_ae_inception2(height: int, width: int, c_dim: int, strides, kernels,
     """arm_shaping.py:1786-1894.  Generic (strides, kernels, filters) on a feature map, residual output."""
     return NetSpec("ContextAEInception2", height, width, c_dim, tuple(strides), tuple(kernels), tuple(filters),
                    featsize, separate_ctx_encoder=True, ctx_hz_lrelu=True, residual_out=True)
+
+
+def context_skip_deep(height: int = 128, width: int = 128, c_dim: int = 3,
+                      filters=(64, 128, 256, 512, 512, 512), kernels=None, strides=None,
+                      featsize: int = 1024) -> NetSpec:
+    """BASELINE.json configs[3] ("Striker 128x128x3, deeper 6-layer enc/dec").  Not in the reference: its builders
+    stop at 4 layers (arm_shaping.py:1282-1329).  Defined as ContextSkipNew's graph (separate context encoder with a
+    linear hz, skips at every level, no residual) with one conv / transposed conv per entry of `filters`; the default
+    is SURVEY.md §8d config 4: 5x5 stride-2 everywhere, 128 -> 2."""
+    L = len(filters)
+    return NetSpec("ContextSkipDeep", height, width, c_dim, tuple(strides or [2] * L), tuple(kernels or [5] * L),
+                   tuple(filters), featsize, separate_ctx_encoder=True, ctx_hz_lrelu=False, residual_out=False)

@@ -22,6 +22,8 @@ CASES = {
     "skipnew_16x16": (S.context_skip_new(16, 16, 3, df_dim=4, featsize=16), 3),
     "real_12x20": (S.context_ae_real(12, 20, 3, featsize=10, filters=(8, 4, 4, 4)), 2),
     "incep2_6x6": (S.context_ae_inception2(6, 6, 8, [1, 2, 1, 2], [3, 3, 3, 3], [8, 8, 4, 4], featsize=16), 2),
+    # BASELINE configs[3]'s 6-layer depth (not a reference model: SURVEY.md §8d config 4), 64 -> 1 in six stride-2 steps
+    "deep6_64x64": (S.context_skip_deep(64, 64, 3, filters=(4, 8, 8, 8, 16, 16), featsize=16), 2),
 }
 
 
@@ -63,7 +65,10 @@ def make_case(name):
 def main():
     here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     os.makedirs(here, exist_ok=True)
+    only = sys.argv[1:]
     for name in CASES:
+        if only and name not in only:
+            continue
         d = make_case(name)
         path = os.path.join(here, name + ".npz")
         np.savez_compressed(path, **d)

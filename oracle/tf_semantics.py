@@ -132,19 +132,22 @@ def init_params(spec, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Ten
 # the graph (arm_shaping.py:1272-1354 / 1611-1684 / 1792-1894)
 # ------------------------------------------------------------------------------------------------------------
 def encode(spec, P: Dict[str, torch.Tensor], scope: str, img: torch.Tensor, hz_lrelu: bool):
-    """One encoder pass.  Returns (h0,h1,h2,h3,h4,z)."""
+    """One encoder pass.  Returns (h0,..,h_{L-1}, h_L, z); L = len(spec.filters) = 4 in every reference model, where
+    this is the reference's (h0,h1,h2,h3,h4,z).  The dense layer after the last conv is named h<L>_lin."""
     hs = []
     h = img
-    for j in range(4):
+    nl = len(spec.filters)
+    lin = "%s/h%d_lin" % (scope, nl)
+    for j in range(nl):
         h = lrelu(conv2d(h, P["%s/h%d_conv/w" % (scope, j)], P["%s/h%d_conv/biases" % (scope, j)],
                          spec.strides[j]))
         hs.append(h)
-    flat = hs[3].reshape(hs[3].shape[0], -1)                       # (h,w,c) order
-    h4 = lrelu(linear(flat, P[scope + "/h4_lin/Matrix"], P[scope + "/h4_lin/bias"]))
+    flat = hs[-1].reshape(hs[-1].shape[0], -1)                     # (h,w,c) order
+    h4 = lrelu(linear(flat, P[lin + "/Matrix"], P[lin + "/bias"]))
     z = linear(h4, P[scope + "/hz_lin/Matrix"], P[scope + "/hz_lin/bias"])
     if hz_lrelu:
         z = lrelu(z)
-    return hs[0], hs[1], hs[2], hs[3], h4, z
+    return tuple(hs) + (h4, z)
 
 
 def translate(P, src_z: torch.Tensor, ctx_z: torch.Tensor) -> torch.Tensor:
@@ -154,16 +157,17 @@ def translate(P, src_z: torch.Tensor, ctx_z: torch.Tensor) -> torch.Tensor:
 
 
 def decode(spec, P, z: torch.Tensor, skips: Sequence[torch.Tensor]) -> torch.Tensor:
-    """arm_shaping.py:1314-1329.  ``skips`` = ctx encoder (h0,h1,h2,h3)."""
-    h3h, h3w = spec.enc_sizes()[3]
+    """arm_shaping.py:1314-1329.  ``skips`` = ctx encoder (h0,..,h_{L-1})."""
+    nl = len(spec.filters)
+    h3h, h3w = spec.enc_sizes()[-1]
     s = lrelu(linear(z, P["deconv/d_h0_lin/Matrix"], P["deconv/d_h0_lin/bias"]))
-    s = s.reshape(-1, h3h, h3w, spec.filters[3])
+    s = s.reshape(-1, h3h, h3w, spec.filters[-1])
     layers = spec.dec_layers()
     for i, L in enumerate(layers):
-        skip = skips[3 - i]
+        skip = skips[nl - 1 - i]
         s = conv2d_transpose(torch.cat([s, skip], 3), P["deconv/%s/w" % L["name"]],
                              P["deconv/%s/biases" % L["name"]], L["out_hw"], L["stride"])
-        if i < 3:
+        if i < nl - 1:
             s = lrelu(s)
     return s
 
@@ -175,18 +179,19 @@ def forward(spec, P: Dict[str, torch.Tensor], image: torch.Tensor) -> Dict[str, 
     c = encode(spec, P, ctx_scope, ctx, spec.ctx_hz_lrelu)
     s = encode(spec, P, "conv", src, True)
     t = encode(spec, P, "conv", tgt, True)
-    trans_z = translate(P, s[5], c[5])
-    out = decode(spec, P, trans_z, c[:4])
-    out2 = decode(spec, P, t[5], c[:4])
+    nl = len(spec.filters)
+    trans_z = translate(P, s[-1], c[-1])
+    out = decode(spec, P, trans_z, c[:nl])
+    out2 = decode(spec, P, t[-1], c[:nl])
     if spec.residual_out:
         out = out + ctx
         out2 = out2 + ctx
-    simloss = ((trans_z - t[5]) ** 2).mean() * 1e3                 # arm_shaping.py:1345
+    simloss = ((trans_z - t[-1]) ** 2).mean() * 1e3                # arm_shaping.py:1345
     recon1 = ((tgt - out) ** 2).sum() / 2                          # tf.nn.l2_loss, :1352
     recon2 = ((tgt - out2) ** 2).sum() / 2                         # :1353
-    return dict(input_z=s[5], translated_z=trans_z, target_z=t[5], ctx_z=c[5], out=out, out2=out2,
+    return dict(input_z=s[-1], translated_z=trans_z, target_z=t[-1], ctx_z=c[-1], out=out, out2=out2,
                 simloss=simloss, recon1=recon1, recon2=recon2, loss=recon1 + recon2 + simloss,
-                ctx_h=c[:4], src_h=s[:4])
+                ctx_h=c[:nl], src_h=s[:nl])
 
 
 def ablation_loss(r: Dict[str, torch.Tensor], ablation_type: str = "None") -> torch.Tensor:

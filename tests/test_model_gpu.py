@@ -117,6 +117,40 @@ def test_striker_128x128_four_layer_vs_oracle():
         assert rel_l2(net.G[k].cpu(), G[k]) < GBAR["mixed"][0], k
 
 
+def test_striker_128x128_six_layer_vs_oracle():
+    """BASELINE.json configs[3] as SURVEY.md §8d defines it: 128x128x3, six 5x5 stride-2 levels 64..512 channels,
+    128 -> 2, skips at every level (spec.context_skip_deep; not a reference model).  Full-size filters, small batch,
+    default precision, forward + every gradient vs the fp64 oracle; also through the model class and its registry."""
+    spec, B = S.context_skip_deep(128, 128), 4
+    assert spec.depth == 6 and spec.enc_sizes()[-1] == (2, 2) and spec.num_params() == 81199171
+    P = O.init_params(spec, seed=7)
+    image = torch.rand((3, B, 128, 128, 3), generator=torch.Generator().manual_seed(8)) * 2 - 1
+    ref, G = O.loss_and_grads(spec, {k: v.double() for k, v in P.items()}, image.double())
+    net = run_net(spec, B, P, image, "mixed")
+    # measured (tools/deep_check.py): z 7e-5, out 8e-6, simloss 1.3e-4 (a difference of two nearly equal z's) — six
+    # levels of tensor-core accumulation instead of four; bars: 2e-4, and north_star's 1e-3 for simloss
+    for k in ("input_z", "translated_z", "out", "out2", "recon1", "recon2", "simloss", "loss"):
+        assert rel_err(net.fetch(k).cpu(), ref[k]) < (1e-3 if k == "simloss" else 2e-4), k
+    for k in spec.param_shapes():
+        assert rel_l2(net.G[k].cpu(), G[k]) < GBAR["mixed"][0], k
+    # a few Adam steps keeps training (loss decreases on the same batch)
+    l0 = float(net.fetch("loss"))
+    for _ in range(3):
+        net.train_step(1e-4)
+    net.forward(FWD_ALL)
+    assert float(net.fetch("loss")) < l0
+    from imitation_from_observation_b200.models import MODEL_REGISTRY
+    m = MODEL_REGISTRY["ContextSkipDeep"]()
+    m.build(image, precision="mixed")
+    m.net.load_state_dict(P)
+    r = m.forward(image[0].cuda(), image[1].cuda(), image[2].cuda())
+    assert rel_err(r["out"].cpu(), ref["out"]) < TOL["mixed"]
+    z, hs = m.enc2(image[1].cuda())
+    assert len(hs) == 6 and tuple(hs[-1].shape) == (B, 2, 2, 512)
+    out = m.dec(m.translate(m.enc1(image[0].cuda()), z), hs)
+    assert rel_err(out.cpu(), ref["out"]) < TOL["mixed"]
+
+
 def test_forward_levels_prune_like_tf():
     """input_z needs only the source encoder; translated_z/out need no target encoder (base.py:216,234)."""
     spec, B = gen_golden.CASES["skipnew_16x16"]
@@ -244,7 +278,7 @@ def test_reward_featurizer_matches_reference_loop():
     for path in paths:
         cur = np.stack([im[0] for im in path["env_infos"]["imgs"] if im is not None])
         x = O.normalize_u8(torch.from_numpy(cur))
-        z = O.encode(model.spec, P, "conv", x, True)[5].numpy()
+        z = O.encode(model.spec, P, "conv", x, True)[-1].numpy()
         expected.append(O.reward_ours(z, x.numpy(), means, mimgs, 0.5, path["rewards"]))
     feat.process_paths(paths)
     for path, exp in zip(paths, expected):

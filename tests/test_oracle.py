@@ -79,7 +79,7 @@ def test_forward_structure_small():
     r = O.forward(s, P, img)
     # the ctx encoder's hz is linear (arm_shaping.py:1288), the src/tgt one goes through lrelu (:1297)
     c = O.encode(s, P, "conv_context", img[1], False)
-    assert torch.allclose(c[5], r["ctx_z"])
+    assert torch.allclose(c[-1], r["ctx_z"])
     assert float(r["loss"]) == pytest.approx(float(r["recon1"] + r["recon2"] + r["simloss"]))
     assert float(r["recon1"]) == pytest.approx(float(((img[2] - r["out"]) ** 2).sum() / 2), rel=1e-6)
     assert float(r["simloss"]) == pytest.approx(float(((r["translated_z"] - r["target_z"]) ** 2).mean() * 1e3), rel=1e-6)
@@ -105,6 +105,33 @@ def test_gradients_finite_difference():
             flat[i] = old
             fd = (lp - lm) / (2 * eps)
             assert fd == pytest.approx(float(G[name].reshape(-1)[i]), rel=2e-4, abs=1e-6), name
+
+
+def test_deep_spec_generalises_the_reference_depth():
+    """BASELINE configs[3] (6 layers): same graph, one level per entry of `filters`.  At depth 4
+    the generic spec IS ContextSkipNew — same names, shapes, order and flop count."""
+    a = S.context_skip_new(64, 64)
+    b = S.context_skip_deep(64, 64, 3, filters=(64, 128, 256, 512))
+    assert list(a.param_shapes().items()) == list(b.param_shapes().items())
+    assert a.fwd_macs_per_triple() == b.fwd_macs_per_triple() and a.dec_layers() == b.dec_layers()
+    d = S.context_skip_deep()
+    assert d.depth == 6 and d.lin_name == "h6_lin" and d.flat_dim() == 2048
+    assert d.enc_sizes() == [(64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (2, 2)]
+    sh = d.param_shapes()
+    assert sh["deconv/d_h6/w"] == (5, 5, 3, 128) and sh["deconv/d_h1/w"] == (5, 5, 512, 1024)
+    assert sh["conv/h6_lin/Matrix"] == (2048, 1024) and sh["conv_context/h5_conv/w"] == (5, 5, 512, 512)
+    assert d.num_params() == 81199171
+    with pytest.raises(ValueError):
+        S.context_skip_deep(filters=(4, 8), kernels=(5,))
+    # tiny instance through the oracle: shapes of every level, and the loss identity
+    t = S.context_skip_deep(64, 64, 3, filters=(4, 8, 8, 8, 16, 16), featsize=16)
+    P = gen_golden.golden_params(t, 2)
+    img = torch.rand((3, 2, 64, 64, 3), generator=torch.Generator().manual_seed(0)) * 2 - 1
+    r = O.forward(t, P, img)
+    assert [tuple(h.shape[1:]) for h in r["ctx_h"]] == [(32, 32, 4), (16, 16, 8), (8, 8, 8), (4, 4, 8), (2, 2, 16), (1, 1, 16)]
+    assert r["out"].shape == (2, 64, 64, 3)
+    assert torch.allclose(r["loss"], r["recon1"] + r["recon2"] + r["simloss"])
+
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))))

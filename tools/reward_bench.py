@@ -50,7 +50,7 @@ with torch.no_grad():
     for p in cp:
         cur = np.asarray([im[0] for im in p["env_infos"]["imgs"] if im is not None])
         x = O.normalize_u8(torch.from_numpy(cur))
-        z = O.encode(spec, P, "conv", x, True)[5].numpy()              # only the source encoder runs (TF prunes the rest)
+        z = O.encode(spec, P, "conv", x, True)[-1].numpy()              # only the source encoder runs (TF prunes the rest)
         cost = np.sum((means - z) ** 2, axis=1) + 1.0 * np.sum((imgs - x.numpy()) ** 2, axis=(1, 2, 3))
         for j in range(T):
             p["rewards"][2 * j + 1] -= cost[j] * j * j

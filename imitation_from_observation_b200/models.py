@@ -175,6 +175,19 @@ class ContextAEInception2(_ContextModel):
         return _spec.context_ae_inception2(H, W, C, self.strides, self.kernels, self.filters, self.featsize)
 
 
+class ContextAEInception(_ContextModel):
+    """arm_shaping.py:1687-1783 — the legacy 5x5 stride-2 feature-map model (note: train_script.py:48-49 maps the *name*
+    "ContextAEInception" to ContextAEInception2, and so does MODEL_REGISTRY; this class is the one arm_shaping defines)."""
+
+    def __init__(self, gf_dim=64, df_dim=64, gfc_dim=1024, dfc_dim=1024, c_dim=3, featsize=1024):
+        self.gf_dim, self.df_dim, self.c_dim, self.featsize = gf_dim, df_dim, c_dim, featsize
+        if gf_dim != df_dim:
+            raise _lib.CtxError("ContextAEInception: skip concatenation requires gf_dim == df_dim (as in the reference)")
+
+    def _make_spec(self, H, W, C):
+        return _spec.context_ae_inception(H, W, C, self.df_dim, self.featsize)
+
+
 class ContextSkipDeep(_ContextModel):
     """BASELINE.json configs[3]: "Striker 128x128x3, deeper 6-layer enc/dec".  NOT a reference class — the reference's
     builders are 4 layers deep; this is ContextSkipNew's graph with one conv / transposed conv per entry of `filters`

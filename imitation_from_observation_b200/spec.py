@@ -185,6 +185,16 @@ def context_ae_inception2(height: int, width: int, c_dim: int, strides, kernels,
                    featsize, separate_ctx_encoder=True, ctx_hz_lrelu=True, residual_out=True)
 
 
+def context_ae_inception(height: int = 35, width: int = 35, c_dim: int = 288, df_dim: int = 64,
+                         featsize: int = 1024) -> NetSpec:
+    """arm_shaping.py:1687-1783 (legacy; the strike-inception notebook runs it on Mixed_5d, 35x35x288).  ContextSkipNew's
+    graph — 5x5 stride-2, filters df..8df, linear context hz (:1711) — on a feature map, with the residual output of
+    :1778-1779 and every decoder size taken from the encoder's actual shapes (:1739-1743), so odd extents work."""
+    return NetSpec("ContextAEInception", height, width, c_dim, (2, 2, 2, 2), (5, 5, 5, 5),
+                   (df_dim, 2 * df_dim, 4 * df_dim, 8 * df_dim), featsize,
+                   separate_ctx_encoder=True, ctx_hz_lrelu=False, residual_out=True)
+
+
 def context_skip_deep(height: int = 128, width: int = 128, c_dim: int = 3,
                       filters=(64, 128, 256, 512, 512, 512), kernels=None, strides=None,
                       featsize: int = 1024) -> NetSpec:

@@ -117,6 +117,30 @@ def test_striker_128x128_four_layer_vs_oracle():
         assert rel_l2(net.G[k].cpu(), G[k]) < GBAR["mixed"][0], k
 
 
+def test_legacy_context_ae_inception_on_mixed_5d_shape():
+    """arm_shaping.py:1687-1783 on the strike-inception notebook's 35x35x288 feature map: odd extents at every level
+    (35 -> 18 -> 9 -> 5 -> 3), residual output, linear context hz."""
+    from imitation_from_observation_b200.models import ContextAEInception
+    spec, B = S.context_ae_inception(35, 35, 288), 4
+    assert spec.enc_sizes() == [(18, 18), (9, 9), (5, 5), (3, 3)] and spec.flat_dim() == 4608
+    P = O.init_params(spec, seed=9)
+    image = torch.rand((3, B, 35, 35, 288), generator=torch.Generator().manual_seed(10)) * 2 - 1
+    ref, G = O.loss_and_grads(spec, {k: v.double() for k, v in P.items()}, image.double())
+    m = ContextAEInception().build(image, precision="mixed")
+    assert m.spec == spec
+    m.net.load_state_dict(P)
+    net = m.net
+    net.set_input(image.cuda())
+    net.zero_grad()
+    net.forward(FWD_ALL)
+    net.backward()
+    for k in ("input_z", "translated_z", "out", "out2", "recon1", "recon2", "loss"):
+        assert rel_err(net.fetch(k).cpu(), ref[k]) < TOL["mixed"], k
+    assert rel_err(net.fetch("simloss").cpu(), ref["simloss"]) < 1e-3
+    for k in spec.param_shapes():
+        assert rel_l2(net.G[k].cpu(), G[k]) < GBAR["mixed"][0], k
+
+
 def test_striker_128x128_six_layer_vs_oracle():
     """BASELINE.json configs[3] as SURVEY.md §8d defines it: 128x128x3, six 5x5 stride-2 levels 64..512 channels,
     128 -> 2, skips at every level (spec.context_skip_deep; not a reference model).  Full-size filters, small batch,

@@ -34,6 +34,8 @@ FPROP_CASES = [
     (2, 48, 48, 3, 64, 5, 2), (2, 6, 6, 256, 512, 5, 2), (5, 3, 3, 64, 32, 5, 2),
     (2, 36, 64, 3, 32, 5, 1), (2, 18, 32, 16, 8, 5, 2), (2, 8, 8, 64, 32, 3, 1), (2, 8, 8, 32, 32, 3, 2),
     (1, 7, 9, 5, 7, 3, 2), (1, 1, 1, 4, 4, 5, 2), (2, 5, 5, 8, 130, 1, 1),
+    # odd extents with tensor-core channel counts (ContextAEInception on Mixed_5d: 35 -> 18 -> 9 -> 5 -> 3)
+    (2, 35, 35, 288, 64, 5, 2), (3, 9, 9, 128, 256, 5, 2), (2, 5, 5, 256, 512, 5, 2), (2, 17, 13, 64, 96, 3, 2),
 ]
 
 
@@ -58,6 +60,9 @@ TRANS_CASES = [
     (2, 18, 32, 18, 32, 16, 16, 2, 16, 5, 1), (2, 36, 64, 36, 64, 32, 32, 1, 3, 5, 1),
     (2, 4, 4, 8, 8, 32, 0, 0, 64, 3, 2), (2, 8, 8, 8, 8, 64, 64, 2, 32, 3, 1), (2, 2, 2, 3, 3, 8, 8, 2, 4, 3, 2),
     (3, 4, 5, 7, 9, 6, 0, 0, 5, 3, 2), (2, 4, 4, 8, 8, 4, 4, 2, 8, 1, 2),
+    # odd output extents on the tensor-core path (stride phases of unequal size)
+    (2, 3, 3, 5, 5, 512, 512, 2, 256, 5, 2), (4, 5, 5, 9, 9, 256, 256, 2, 128, 5, 2),
+    (2, 18, 18, 35, 35, 64, 64, 1, 288, 5, 2), (2, 9, 7, 17, 13, 96, 32, 2, 64, 3, 2),
 ]
 
 
@@ -147,6 +152,7 @@ WGRAD_CASES = [
     (4, 64, 64, 3, 64, 0, 0, 5, 2), (4, 16, 16, 128, 256, 0, 0, 5, 2), (8, 8, 8, 256, 512, 0, 0, 5, 2),
     (4, 8, 8, 256, 512, 512, 2, 5, 2), (4, 64, 64, 3, 64, 64, 2, 5, 2), (2, 36, 64, 3, 32, 32, 1, 5, 1),
     (2, 8, 8, 32, 16, 16, 2, 3, 2), (3, 7, 9, 5, 4, 0, 0, 3, 2), (2, 6, 6, 64, 32, 32, 2, 5, 2),
+    (2, 35, 35, 288, 64, 64, 2, 5, 2), (4, 9, 9, 128, 256, 256, 2, 5, 2), (2, 17, 13, 64, 96, 32, 2, 3, 2),
 ]
 
 

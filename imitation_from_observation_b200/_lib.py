@@ -48,6 +48,7 @@ SIGNATURES = {
     "ctx_gemm": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32,
                            c_void_p, c_int32, POINTER(Epilogue), c_int32, c_void_p]),
     "ctx_u8_normalize": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "ctx_gather_frames": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "ctx_lrelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_void_p]),
     "ctx_bias_grad": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "ctx_l2_loss_fwd_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p,

@@ -193,6 +193,9 @@ class Session:
         stays in pinned HOST memory: ContextNet.set_input copies it role by role, overlapped with the first kernels."""
         if torch.is_tensor(value) and value.is_cuda:
             return value
+        if isinstance(value, (list, tuple)) and len(value) == 3 and all(torch.is_tensor(v) and v.is_cuda for v in value):
+            # [src, ctx, tgt] device batches (data.DeviceBank): no staging, no host copy
+            return torch.stack(list(value)) if ph.chain else list(value)
         want_t = torch.uint8 if ph.root.dtype == torch.uint8 else torch.float32
         host_ok = want_t == torch.float32 and not ph.chain
         if torch.is_tensor(value) and value.dtype == want_t and value.is_contiguous() and value.is_pinned():
@@ -244,7 +247,7 @@ class Session:
                     feats = inc.forward(staged.reshape((three * Bf,) + tuple(staged.shape[2:])), ("Mixed_7c",))["Mixed_7c"]
                     staged = feats.view((three, Bf) + tuple(feats.shape[1:]))
                 m.net.set_input(staged)
-                if not staged.is_cuda and m.net._in_events is not None:
+                if torch.is_tensor(staged) and not staged.is_cuda and m.net._in_events is not None:
                     self._pin_event[staged.data_ptr()] = m.net._in_events[1]
             mine = [f for f in flist if (f.loss.model if isinstance(f, _Minimize) else getattr(f, "model", None)) is m]
             mins = [f for f in mine if isinstance(f, _Minimize)]

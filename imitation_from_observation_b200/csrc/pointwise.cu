@@ -61,6 +61,48 @@ __global__ void u8_normalize_kernel(const uint8_t* __restrict__ x, float* __rest
   }
 }
 
+// ---- demo-bank gather: out[b] = float(bank[frame_idx[b]]) ----------------------------------------------------------------
+// The trainer's batch assembly  traindata[arange(B) % nlen, choice]  (train_script.py:154-159) on a bank that lives in
+// HBM.  blockIdx.y = batch row, blockIdx.x strides over the frame.  A uint8 bank is mapped through a 256-entry table the
+// host fills with the reference's own arithmetic (arm_shaping.py:12-16: x / 127.5 - 1 in float64, cast to fp32 by the
+// feed), so the result is bit-identical to feeding the float bank.  A frame index outside the bank writes NaN (loud).
+template <bool kU8>
+__global__ void gather_frames_kernel(const void* __restrict__ bank, const float* __restrict__ lut, int64_t bank_frames,
+                                     int64_t frame_elems, const int64_t* __restrict__ frame_idx,
+                                     float* __restrict__ out) {
+  __shared__ float s_lut[256];
+  if (kU8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+  }
+  const int64_t f = frame_idx[blockIdx.y];
+  float* dst = out + (int64_t)blockIdx.y * frame_elems;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+  if (f < 0 || f >= bank_frames) {
+    for (int64_t j = t0; j < frame_elems; j += step) dst[j] = __int_as_float(0x7fc00000);
+    return;
+  }
+  if (kU8) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(bank) + f * frame_elems;
+    if ((((uintptr_t)src) & 3) == 0 && (((uintptr_t)dst) & 15) == 0 && frame_elems % 4 == 0) {
+      for (int64_t j = t0; j < frame_elems / 4; j += step) {
+        uchar4 u = reinterpret_cast<const uchar4*>(src)[j];
+        reinterpret_cast<float4*>(dst)[j] = make_float4(s_lut[u.x], s_lut[u.y], s_lut[u.z], s_lut[u.w]);
+      }
+    } else {
+      for (int64_t j = t0; j < frame_elems; j += step) dst[j] = s_lut[src[j]];
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(bank) + f * frame_elems;
+    if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)dst) & 15) == 0 && frame_elems % 4 == 0) {
+      for (int64_t j = t0; j < frame_elems / 4; j += step)
+        reinterpret_cast<float4*>(dst)[j] = reinterpret_cast<const float4*>(src)[j];
+    } else {
+      for (int64_t j = t0; j < frame_elems; j += step) dst[j] = src[j];
+    }
+  }
+}
+
 // ---- lrelu backward ------------------------------------------------------------------------------------------
 __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yref, float* out,
                                  int64_t n, float slope, int accumulate) {
@@ -527,6 +569,24 @@ extern "C" int ctx_u8_normalize(const uint8_t* x, float* y, int64_t n, void* str
   CTX_REQUIRE(x && y, "u8_normalize: null pointer");
   u8_normalize_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
   CTX_LAUNCH_CHECK("u8_normalize");
+  return CTX_OK;
+}
+
+extern "C" int ctx_gather_frames(const void* bank, int32_t bank_is_u8, const float* lut256, int64_t bank_frames,
+                                 int64_t frame_elems, const int64_t* frame_idx, int32_t n, float* out, void* stream) {
+  CTX_REQUIRE(n >= 0 && frame_elems >= 0 && bank_frames >= 0, "gather_frames: negative size");
+  if (n == 0 || frame_elems == 0) return CTX_OK;
+  CTX_REQUIRE(bank && frame_idx && out, "gather_frames: null pointer");
+  CTX_REQUIRE(!bank_is_u8 || lut256, "gather_frames: a uint8 bank needs the 256-entry value table");
+  CTX_REQUIRE(n <= 65535, "gather_frames: at most 65535 frames per call");
+  int64_t vec = (frame_elems + 3) / 4;
+  int gx = (int)std::min<int64_t>(cdiv(vec, 256), 64);
+  dim3 grid(gx, n);
+  if (bank_is_u8)
+    gather_frames_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(bank, lut256, bank_frames, frame_elems, frame_idx, out);
+  else
+    gather_frames_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(bank, lut256, bank_frames, frame_elems, frame_idx, out);
+  CTX_LAUNCH_CHECK("gather_frames");
   return CTX_OK;
 }
 

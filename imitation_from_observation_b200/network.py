@@ -223,12 +223,22 @@ class ContextNet:
         """image [3,B,H,W,C] (0 = src, 1 = ctx, 2 = tgt — arm_shaping.py:1278-1280), uint8 or fp32, on the device.
         uint8 is normalised on the fly (base.py:117-119)."""
         B = self.B
-        if tuple(image.shape) != (3, B) + self.sizes[0] + (self.chans[0],):
-            raise _lib.CtxError("input must be [3,%d,%d,%d,%d], got %s"
-                                % ((B,) + self.sizes[0] + (self.chans[0],) + (tuple(image.shape),)))
         xe, xc = self._input_buffers()
         dst = (xe[:B], xc, xe[B:2 * B])
         self._in_events = None
+        if isinstance(image, (list, tuple)):             # three device role batches (data.DeviceBank gathers)
+            want = (B,) + self.sizes[0] + (self.chans[0],)
+            if len(image) != 3 or any(tuple(r.shape) != want or not r.is_cuda for r in image):
+                raise _lib.CtxError("a role list must hold three CUDA tensors of shape %s" % (want,))
+            for r in range(3):
+                if image[r].dtype == torch.uint8:
+                    ops.u8_normalize(image[r].contiguous(), out=dst[r])
+                else:
+                    dst[r].copy_(image[r])
+            return
+        if tuple(image.shape) != (3, B) + self.sizes[0] + (self.chans[0],):
+            raise _lib.CtxError("input must be [3,%d,%d,%d,%d], got %s"
+                                % ((B,) + self.sizes[0] + (self.chans[0],) + (tuple(image.shape),)))
         if not image.is_cuda:
             # pinned host batch (Session.run): copy role by role on a copy stream, context frames first, so that the
             # context encoder (side stream) starts while the source / target frames are still in flight

@@ -263,6 +263,31 @@ def u8_normalize(x_u8, out=None):
     return out
 
 
+def gather_frames(bank, frame_idx, out=None, lut=None):
+    """out[b] = float(bank[frame_idx[b]]) — the trainer's batch assembly (train_script.py:154-159) on a device bank.
+    bank [frames, ...] fp32 or uint8 (uint8 needs `lut`, 256 floats on the device); frame_idx int64 on the device."""
+    if bank.dtype not in (torch.float32, torch.uint8):
+        raise _lib.CtxError("gather_frames: the bank must be float32 or uint8")
+    is_u8 = bank.dtype == torch.uint8
+    pb = _req(bank, "bank", bank.dtype)
+    pi = _req(frame_idx, "frame_idx", torch.int64)
+    n = frame_idx.numel()
+    frame_shape = tuple(bank.shape[1:])
+    elems = 1
+    for d in frame_shape:
+        elems *= int(d)
+    if out is None:
+        out = torch.empty((n,) + frame_shape, device=bank.device, dtype=torch.float32)
+    elif out.numel() != n * elems:
+        raise _lib.CtxError("gather_frames: out has %d elements, expected %d" % (out.numel(), n * elems))
+    pl = _req(lut, "lut") if is_u8 else None
+    if is_u8 and lut.numel() != 256:
+        raise _lib.CtxError("gather_frames: lut must hold 256 floats")
+    check(_lib.load().ctx_gather_frames(pb, int(is_u8), pl, bank.shape[0], elems, pi, n, _req(out, "out"), _stream()),
+          "ctx_gather_frames")
+    return out
+
+
 def lrelu_bwd(dy, y_ref, out=None, accumulate=False, slope=LRELU_SLOPE):
     if out is None:
         out = torch.empty_like(dy)

@@ -9,6 +9,9 @@ batch, Adam lr 1e-4, loss / sim / r1 / r2 / nn_err every 4th step, validation ev
   * ``inception=True`` trains ``model(strides, kernels, filters)`` on the Mixed_7c feature maps of a frozen
     InceptionV3 (train_script.py:100-115); pass ``inception_net=`` (an ``inception.InceptionV3`` with weights
     loaded) — the reference restores ``model/inception_v3.ckpt``, which does not ship;
+  * `device_bank=True` (default for pixel models) keeps vdata in HBM (`data.DeviceBank`): the loop's indexing
+    expressions are unchanged but return device batches assembled by `ctx_gather_frames` — no per-step host gather,
+    float64->float32 cast or H2D copy; the batches are bit-identical to the host path's;
   * data parallelism lives in parallel.py (bucketed gradient all-reduce) and is wired up by bench.py; this
     class is the single-process trainer the reference has.
 """
@@ -26,13 +29,15 @@ from .models import MODEL_REGISTRY
 class ModelTrainer:
     def __init__(self, idims, nvideos, ntrain, batch_size, model, nitr, save_every, nlen, nskip, rescale=True,
                  inception=False, strides=None, kernels=None, filters=None, data=None, seed=0, precision="mixed",
-                 log: Optional[Callable[[str], None]] = print, basedir="model/", inception_net=None):
+                 log: Optional[Callable[[str], None]] = print, basedir="model/", inception_net=None,
+                 device_bank=True):
         self.idims = tuple(idims)
         self.nvideos, self.ntrain, self.batch_size = nvideos, ntrain, batch_size
         self.nitr, self.save_every, self.nlen, self.nskip = nitr, save_every, nlen, nskip
         self.rescale, self.inception = rescale, inception
         self.strides, self.kernels, self.filters = strides, kernels, filters
         self.inception_net = inception_net
+        self.device_bank = bool(device_bank) and not inception
         if inception and inception_net is None:
             raise _lib.CtxError("inception=True needs inception_net= (an inception.InceptionV3 with weights loaded)")
         if model not in MODEL_REGISTRY:
@@ -70,6 +75,9 @@ class ModelTrainer:
             with tf.variable_scope("contextmodel"):                                               # :120-121
                 tf.build_model(test, tfinput, precision=self.precision, seed=self.seed)
         sess = tf.Session()
+        if self.device_bank:
+            from .data import DeviceBank
+            vdata = DeviceBank(vdata)
         learning_rate = tf.placeholder(tf.float32, shape=[])
         train_vars = tf.get_collection(tf.GraphKeys.TRAINABLE_VARIABLES, "contextmodel")
         optimizer = tf.train.AdamOptimizer(learning_rate).minimize(test.loss, var_list=train_vars)   # :128

@@ -128,6 +128,14 @@ int ctx_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
 /* y = (float(x) * (1/255) - 0.5) * 2 in fp32 — rllab/sampler/base.py:117-119, scripts/train_script.py:102-104. */
 int ctx_u8_normalize(const uint8_t* x, float* y, int64_t n, void* stream);
 
+/* out[b, :] = float(bank[frame_idx[b], :]) for b < n — the trainer's batch assembly traindata[arange(B) % nlen, choice]
+ * (scripts/train_script.py:154-159, 169-173) on a demo bank resident in HBM: `bank` is [bank_frames, frame_elems] fp32
+ * or uint8, frame_idx (device, int64) holds flat frame numbers t * N + video.  A uint8 bank is mapped through lut256
+ * (device, 256 floats), which the host fills with the reference's own pixel transform (arm_shaping.py:12-16) so that the
+ * result is bit-identical to gathering the float bank.  An index outside the bank yields NaN frames. */
+int ctx_gather_frames(const void* bank, int32_t bank_is_u8, const float* lut256, int64_t bank_frames,
+                      int64_t frame_elems, const int64_t* frame_idx, int32_t n, float* out, void* stream);
+
 /* out (+)= dy * (y_ref >= 0 ? 1 : slope) — derivative of arm_shaping.py:18-19 from the saved output. */
 int ctx_lrelu_bwd(const float* dy, const float* y_ref, float* out, int64_t n, float slope, int32_t accumulate,
                   void* stream);

@@ -87,3 +87,12 @@ def test_transform_and_bank_layout():
     vids = [[rng.randint(1, 256, (20, 20, 3)).astype(np.uint8) for _ in range(51)] for _ in range(3)] + [[img] * 40]
     bank = data.frames_to_bank(vids, nlen=25, nskip=2, idims=(16, 16))
     assert bank.shape == (25, 3, 16, 16, 3)                                        # the 40-frame video is skipped
+
+
+def test_pixel_table_is_the_reference_transform():
+    """DeviceBank's 256-entry table == float32(transform(v)) for every pixel value (arm_shaping.py:12-14)."""
+    import numpy as np
+    from imitation_from_observation_b200 import data, synthetic
+    v = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, 2)
+    assert np.array_equal(data.pixel_table()[v], data.transform(v, 16, 16, True).astype(np.float32))
+    assert np.array_equal(data.pixel_table()[v], synthetic.to_float(v).astype(np.float32))

@@ -267,6 +267,23 @@ def test_model_trainer_loop_runs_and_learns():
     assert all(isinstance(h["NNErr"], int) for h in tr.history)
 
 
+def test_model_trainer_device_bank_equals_host_feed():
+    """The HBM-resident bank (data.DeviceBank + ctx_gather_frames) feeds bit-identical batches: same losses and same
+    nn_err as the reference's host gather + float feed, on the same seed."""
+    hist = {}
+    for dev in (False, True):
+        tr = ModelTrainer(idims=(16, 16), nvideos=12, ntrain=8, batch_size=10, model="ContextSkipNew", nitr=14,
+                          save_every=1000, nlen=5, nskip=1, precision="fp32", log=None, device_bank=dev)
+        tr.model = lambda: ContextSkipNew(df_dim=8, gf_dim=8, featsize=32)
+        tr.train()
+        hist[dev] = tr.history
+    assert len(hist[True]) == len(hist[False]) == 3
+    for a, b in zip(hist[False], hist[True]):
+        assert a["NNErr"] == b["NNErr"]
+        for k in ("Loss", "Sim", "R1", "R2"):
+            assert abs(a[k] - b[k]) <= 1e-5 * abs(a[k]), (k, a[k], b[k])      # split-K atomics reorder fp32 sums
+
+
 def test_reward_featurizer_matches_reference_loop():
     """process_paths (batched) == the reference's per-path loop (base.py:232-257) evaluated with the oracle."""
     H = W = 16

@@ -361,3 +361,61 @@ def test_errors_are_reported_not_ub():
         ops.gemm(torch.zeros((4, 5)).cuda(), torch.zeros((6, 7)).cuda())
     empty = ops.conv2d(torch.zeros((0, 8, 8, 4)).cuda(), torch.zeros((5, 5, 4, 8)).cuda())
     assert tuple(empty.shape) == (0, 4, 4, 8)                      # empty batch is a no-op, not an error
+
+
+# ---- demo bank in HBM (train_script.py:150-173) ------------------------------------------------------------------------
+@pytest.mark.parametrize("frame_shape", [(16, 16, 3), (5, 7, 3), (3,)])
+def test_gather_frames_bit_exact(frame_shape):
+    rs = np.random.RandomState(0)
+    frames = 40
+    bank_f = rs.randn(frames, *frame_shape).astype(np.float32)
+    bank_u = rs.randint(0, 256, (frames,) + frame_shape).astype(np.uint8)
+    lut = rs.randn(256).astype(np.float32)
+    idx = rs.randint(0, frames, 33).astype(np.int64)
+    di = torch.from_numpy(idx).cuda()
+    assert np.array_equal(ops.gather_frames(torch.from_numpy(bank_f).cuda(), di).cpu().numpy(), bank_f[idx])
+    got = ops.gather_frames(torch.from_numpy(bank_u).cuda(), di, lut=torch.from_numpy(lut).cuda()).cpu().numpy()
+    assert np.array_equal(got, lut[bank_u[idx]])
+    # unaligned bank base (a view one element in) takes the scalar path
+    flat = torch.from_numpy(bank_f).cuda().reshape(-1)
+    elems = int(np.prod(frame_shape))
+    shifted = flat[1:1 + (frames - 1) * elems].view((frames - 1,) + frame_shape)
+    i2 = torch.from_numpy(idx % (frames - 1)).cuda()
+    ref = bank_f.reshape(-1)[1:1 + (frames - 1) * elems].reshape((frames - 1,) + frame_shape)[idx % (frames - 1)]
+    assert np.array_equal(ops.gather_frames(shifted.contiguous() if not shifted.is_contiguous() else shifted, i2).cpu().numpy(), ref)
+    # an index outside the bank is loud (NaN frame), the others are still right; empty gathers are fine
+    bad = idx.copy()
+    bad[3] = frames
+    out = ops.gather_frames(torch.from_numpy(bank_f).cuda(), torch.from_numpy(bad).cuda()).cpu().numpy()
+    assert np.isnan(out[3]).all() and np.array_equal(out[4], bank_f[idx[4]])
+    assert ops.gather_frames(torch.from_numpy(bank_f).cuda(), di[:0]).shape == (0,) + frame_shape
+    with pytest.raises(_lib.CtxError):
+        ops.gather_frames(torch.from_numpy(bank_u).cuda(), di)                    # uint8 bank without its table
+
+
+def test_device_bank_answers_the_trainer_expressions():
+    from imitation_from_observation_b200 import synthetic
+    from imitation_from_observation_b200.data import DeviceBank
+    nlen, N, B, ntrain = 5, 12, 10, 8
+    vdata = synthetic.to_float(synthetic.video_bank(nlen, N, 16, 16, seed=3))      # float64, as train_script.py:97 saves
+    bank = DeviceBank(vdata)
+    assert bank.quantised and bank.shape == vdata.shape and bank.store.dtype == torch.uint8
+    f32 = vdata.astype(np.float32)                                                # what feeding the float bank gives
+    rng = np.random.RandomState(1)
+    for host, dev in ((f32[:, :ntrain], bank[:, :ntrain]), (f32[:, ntrain:], bank[:, ntrain:])):
+        assert dev.shape == host.shape
+        choice = rng.choice(host.shape[1], B)
+        t_idx = np.arange(0, B) % nlen
+        assert np.array_equal(dev[t_idx, choice].cpu().numpy(), host[t_idx, choice])      # train_script.py:156-157
+        assert np.array_equal(dev[0, choice].cpu().numpy(), host[0, choice])              # :158 (context frames)
+        with pytest.raises(IndexError):
+            dev[t_idx, choice + host.shape[1]]
+    # a bank that is not made of transform()'s 256 values is kept in float32, still bit-identical
+    noisy = vdata + 1e-3 * rng.randn(*vdata.shape)
+    b2 = DeviceBank(noisy)
+    assert not b2.quantised and b2.store.dtype == torch.float32
+    choice = rng.choice(N, B)
+    assert np.array_equal(b2[np.arange(B) % nlen, choice].cpu().numpy(), noisy.astype(np.float32)[np.arange(B) % nlen, choice])
+    # raw uint8 pixels: gathered through the same table (rescale=True semantics)
+    raw = synthetic.video_bank(nlen, N, 16, 16, seed=3)
+    assert np.array_equal(DeviceBank(raw)[0, choice].cpu().numpy(), f32[0, choice])

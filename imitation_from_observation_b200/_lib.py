@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_i
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctx_b200.so")
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC3, IMPL_FAST = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC3, IMPL_FAST, IMPL_BF16X3 = 0, 1, 2, 3, 4, 5
 
 
 class CtxError(RuntimeError):
@@ -48,6 +48,14 @@ SIGNATURES = {
     "ctx_gemm": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32,
                            c_void_p, c_int32, POINTER(Epilogue), c_int32, c_void_p]),
     "ctx_u8_normalize": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "ctx_split_bf16": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "ctx_split_bf16_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "ctx_conv2d_fprop_bf16x3_eligible": (c_int32, [c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_fprop_bf16x3": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, POINTER(ConvGeom),
+                                          POINTER(Epilogue), c_void_p]),
+    "ctx_conv2d_transpose_bf16x3_eligible": (c_int32, [c_int32, c_int32, c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_transpose_bf16x3": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                              c_int32, POINTER(ConvGeom), POINTER(Epilogue), c_void_p]),
     "ctx_gather_frames": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "ctx_lrelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_void_p]),
     "ctx_bias_grad": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),

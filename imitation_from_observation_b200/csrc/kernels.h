@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared between the translation units of libctx_b200.so.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace ctx {
@@ -32,6 +33,15 @@ int tc_gemm_eligible(int tA, int tB, int M, int N, int K, const float* A, int ld
                      const float* C, int ldc);
 int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, const Epi& epi, int passes, cudaStream_t stream);
+
+// tc_bf16x3.cu — forward convolutions from pre-split bf16 (hi, lo) planes (kind::f16, three products, fp32 accumulate)
+int bf3_conv2d_fprop_eligible(int C, int Co, const ctx_conv_geom& g);
+int bf3_conv2d_fprop(const __nv_bfloat16* xp, int C, const __nv_bfloat16* wp, float* y, __nv_bfloat16* yp, int Co,
+                     const ctx_conv_geom& g, const Epi& epi, cudaStream_t stream);
+int bf3_conv2d_transpose_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g);
+int bf3_conv2d_transpose(const __nv_bfloat16* x1p, int C1, const __nv_bfloat16* x2p, int C2, int x2_batch,
+                         const __nv_bfloat16* wp, float* y, __nv_bfloat16* yp, int Cn, const ctx_conv_geom& g,
+                         const Epi& epi, cudaStream_t stream);
 
 // pointwise.cu
 int bias_init(float* y, const float* bias, int64_t n, int C, int accumulate, cudaStream_t stream);

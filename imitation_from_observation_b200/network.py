@@ -125,6 +125,23 @@ class ContextNet:
         self.dec = spec.dec_layers()
         self.L = spec.depth                              # encoder convs = decoder transposed convs (4 in the reference)
         self.lin = spec.lin_name                         # "h4_lin" at the reference's depth
+        # Forward convolutions on pre-split bf16 planes (csrc/tc_bf16x3.cu): the fp32-grade forward of "mixed" runs
+        # hi*hi + hi*lo + lo*hi on the bf16 tensor cores wherever channels % 64 == 0 and the pixel grid tiles exactly;
+        # the other layers (3-channel image side, dense layers) stay on the 3-pass TF32 kernel.  CTX_FWD_BF3=0 disables.
+        self._enc_bf3 = [False] * self.L
+        self._dec_bf3 = [False] * self.L
+        self._wp: Dict[str, torch.Tensor] = {}           # weight planes, refreshed after every parameter update
+        self._wp_stale = True
+        self._wp_shared = params_from is not None        # someone else updates the parameters: refresh every forward
+        if precision == "mixed" and os.environ.get("CTX_FWD_BF3", "1") != "0" and ops.tc_available():
+            for j in range(self.L):
+                self._enc_bf3[j] = ops.conv2d_bf16x3_eligible(2, self.sizes[j], self.chans[j], self.chans[j + 1],
+                                                              spec.kernels[j], spec.strides[j])
+            if spec.separate_ctx_encoder:                # (a shared encoder's skip rows are a slice: no plane view)
+                for i, Ld in enumerate(self.dec):
+                    self._dec_bf3[i] = ops.conv2d_transpose_bf16x3_eligible(
+                        2 * self.B, Ld["out_hw"], Ld["c_state"], Ld["c_skip"], self.B, Ld["c_out"], Ld["k"], Ld["stride"])
+        self.bf3 = any(self._enc_bf3) or any(self._dec_bf3)
         self._level = 0
 
     # ---- second stream -----------------------------------------------------------------------------------------
@@ -193,6 +210,7 @@ class ContextNet:
         """Refresh the TF32-rounded shadow parameters after the fp32 masters were written from outside."""
         if self.flat_pr is not None:
             ops.round_tf32(self.flat_p, out=self.flat_pr)
+        self._wp_stale = True
 
     def state_dict(self) -> Dict[str, np.ndarray]:
         """TF-checkpoint-keyed parameters (SURVEY.md §8b 'Checkpoint keys')."""
@@ -268,13 +286,57 @@ class ContextNet:
         if self._in_events is not None:
             torch.cuda.current_stream(self.device).wait_event(self._in_events[which])
 
+    # ---- bf16 (hi, lo) planes ----------------------------------------------------------------------------------------
+    def _planes(self, name: str, shape) -> torch.Tensor:
+        return self._buf(name, (2,) + tuple(shape), dtype=torch.bfloat16)
+
+    def _refresh_weight_planes(self, scope: Optional[str] = None):
+        """(hi, lo) planes of the filters the bf16x3 layers read, from the fp32 masters (one small launch per filter)."""
+        if not self.bf3:
+            return
+        sp = self.spec
+        scopes = ["conv"] + (["conv_context"] if sp.separate_ctx_encoder else [])
+        for sc in scopes:
+            if scope not in (None, sc):
+                continue
+            for j in range(self.L):
+                if self._enc_bf3[j]:
+                    name = "%s/h%d_conv/w" % (sc, j)
+                    k = sp.kernels[j]
+                    buf = self._planes("wp:" + name, (k * k * self.chans[j + 1], self.chans[j]))
+                    self._wp[name] = ops.split_bf16_conv_filter(self.P[name], out=buf)
+        if scope in (None, "deconv"):
+            for i, Ld in enumerate(self.dec):
+                if self._dec_bf3[i]:
+                    name = "deconv/%s/w" % Ld["name"]
+                    buf = self._planes("wp:" + name, (Ld["k"] * Ld["k"] * Ld["c_out"], Ld["c_state"] + Ld["c_skip"]))
+                    self._wp[name] = ops.split_bf16(self.P[name], out=buf)
+
     # ---- forward pieces (also the functional enc1 / enc2 / translate / dec surface) ------------------------------
-    def encode_convs(self, scope: str, x: torch.Tensor, outs: Sequence[torch.Tensor]):
-        """L x (conv SAME + bias + lrelu) — arm_shaping.py:1283-1286 (L = 4 there)."""
-        h = x
-        for j in range(self.L):
+    def encode_convs(self, scope: str, x: torch.Tensor, outs: Sequence[torch.Tensor], tag: Optional[str] = None,
+                     skip_planes: bool = False):
+        """L x (conv SAME + bias + lrelu) — arm_shaping.py:1283-1286 (L = 4 there).
+        tag: forward() passes a buffer tag, which enables the bf16-plane layers (the functional enc1 / enc2 surface runs
+        the fp32-input kernels).  Returns the planes of each level's output where they were produced (else None);
+        skip_planes: also produce them for the levels the decoder reads as skips."""
+        h, hp = x, None
+        L = self.L
+        produced: List[Optional[torch.Tensor]] = [None] * L
+        for j in range(L):
             w, b = self.Wf["%s/h%d_conv/w" % (scope, j)], self.P["%s/h%d_conv/biases" % (scope, j)]
             k, Cin, Co = self.spec.kernels[j], h.shape[3], w.shape[3]
+            use_bf = tag is not None and self._enc_bf3[j]
+            want_p = tag is not None and ((j + 1 < L and self._enc_bf3[j + 1]) or
+                                          (skip_planes and self._dec_bf3[L - 1 - j]))
+            op = self._planes("%s_h%d_p%d" % (tag, j, h.shape[0]), outs[j].shape) if want_p else None
+            if use_bf:
+                if hp is None:
+                    hp = ops.split_bf16(h, out=self._planes("%s_in%d_p%d" % (tag, j, h.shape[0]), h.shape))
+                ops.conv2d_bf16x3(hp, self._wp["%s/h%d_conv/w" % (scope, j)], k, bias=b, stride=self.spec.strides[j],
+                                  act=True, out=outs[j], out_planes=op)
+                h, hp = outs[j], op
+                produced[j] = op
+                continue
             if self._few(Cin, k) and Co % 4 == 0:
                 K = k * k * Cin
                 pt = self._patches("patch_%s_h%d_%d" % (scope, j, h.shape[0]), h, k, self.spec.strides[j])
@@ -284,6 +346,9 @@ class ContextNet:
                 ops.conv2d(h, w, b, stride=self.spec.strides[j], act=True, out=outs[j], round_tf32=self.round,
                            impl=self.impl)
             h = outs[j]
+            hp = ops.split_bf16(h, out=op) if want_p else None
+            produced[j] = hp
+        return produced
 
     def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, bias=None, act=False, act_ref=None,
               accumulate=False, round_=None, bwd=False):
@@ -316,12 +381,14 @@ class ContextNet:
         ops.im2col(x, k, stride, ld, out=buf, round_tf32=round_tf32)
         return buf
 
-    def _fwd_encoder(self, scope: str, x: torch.Tensor, hs: List[torch.Tensor], h4: torch.Tensor):
+    def _fwd_encoder(self, scope: str, x: torch.Tensor, hs: List[torch.Tensor], h4: torch.Tensor,
+                     tag: Optional[str] = None, skip_planes: bool = False):
         n = x.shape[0]
-        self.encode_convs(scope, x, hs)
+        produced = self.encode_convs(scope, x, hs, tag=tag, skip_planes=skip_planes)
         self._gemm(False, False, n, self.F, self.flat, hs[-1].data_ptr(), self.flat,
                    self.Wf["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), self.F, h4.data_ptr(), self.F,
                    bias=self.P["%s/%s/bias" % (scope, self.lin)], act=True)
+        return produced
 
     def _fwd_hz(self, scope: str, h4_rows: torch.Tensor, out_ptr: int, ldo: int, act: bool):
         self._gemm(False, False, h4_rows.shape[0], self.F, self.F, h4_rows.data_ptr(), self.F,
@@ -340,9 +407,13 @@ class ContextNet:
              FWD_ALL   — + target encoder, decoder on tgt_z, the three losses (training, train_script.py:163)
         """
         sp, B, F = self.spec, self.B, self.F
+        if self.bf3 and (self._wp_stale or self._wp_shared):
+            self._refresh_weight_planes()
+            self._wp_stale = False
         xe, xc = self._input_buffers()
         n_e = xe.shape[0]
         e_hs, e_h4 = self._enc_buffers(n_e, "e")
+        c_planes = None
         cat = self._buf("cat", (B, 2 * F))
         z2 = self._buf("z2", (2 * B, F))
         f4 = 4  # bytes per float
@@ -358,14 +429,14 @@ class ContextNet:
             c_hs, c_h4 = self._enc_buffers(B, "c")
             with self._side():                           # the context encoder has its own weights and input
                 self._wait_input(0)
-                self._fwd_encoder("conv_context", xc, c_hs, c_h4)
+                c_planes = self._fwd_encoder("conv_context", xc, c_hs, c_h4, tag="c", skip_planes=True)
                 self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
         self._wait_input(1)
         if rows is not None:
-            self._fwd_encoder("conv", xe[:rows], [h[:rows] for h in e_hs], e_h4[:rows])
+            self._fwd_encoder("conv", xe[:rows], [h[:rows] for h in e_hs], e_h4[:rows], tag="e")
         else:
-            self._fwd_encoder("conv", xe[:B], [h[:B] for h in e_hs], e_h4[:B])
-            self._fwd_encoder("conv", xe[2 * B:], [h[2 * B:] for h in e_hs], e_h4[2 * B:])
+            self._fwd_encoder("conv", xe[:B], [h[:B] for h in e_hs], e_h4[:B], tag="e")
+            self._fwd_encoder("conv", xe[2 * B:], [h[2 * B:] for h in e_hs], e_h4[2 * B:], tag="e2")
         self._fwd_hz("conv", e_h4[:B], cat.data_ptr(), 2 * F, act=True)                    # src z -> cat[:, :F]
         if level >= FWD_TRANS:
             if side_ctx:
@@ -384,7 +455,7 @@ class ContextNet:
                 self._fwd_hz("conv", e_h4[B:2 * B], z2.data_ptr() + B * F * f4, F, act=True)  # tgt z -> z2[B:]
                 nd = 2 * B
             d = self._dec_buffers()
-            self._fwd_decoder(z2[:nd], [c[:B] for c in c_hs], [t[:nd] for t in d])
+            self._fwd_decoder(z2[:nd], [c[:B] for c in c_hs], [t[:nd] for t in d], skip_planes=c_planes, tag="d")
             if level == FWD_ALL:
                 self._fwd_losses(d[self.L], xe[B:2 * B], xc)
         self._level = level
@@ -396,14 +467,34 @@ class ContextNet:
             d.append(self._buf("d%d" % (i + 1), (2 * B,) + tuple(L["out_hw"]) + (L["c_out"],)))
         return d
 
-    def _fwd_decoder(self, z: torch.Tensor, skips: Sequence[torch.Tensor], d: Sequence[torch.Tensor]):
-        """arm_shaping.py:1314-1329 for all stacked passes at once; skips = ctx (h0..h_{L-1}), batch B."""
+    def _fwd_decoder(self, z: torch.Tensor, skips: Sequence[torch.Tensor], d: Sequence[torch.Tensor],
+                     skip_planes: Optional[Sequence[Optional[torch.Tensor]]] = None, tag: Optional[str] = None):
+        """arm_shaping.py:1314-1329 for all stacked passes at once; skips = ctx (h0..h_{L-1}), batch B.
+        tag (forward() only) enables the bf16-plane levels; skip_planes[j] = planes of skips[j] where the context
+        encoder produced them."""
         n = z.shape[0]
+        dp = None                                          # planes of the running decoder state
         self._gemm(False, False, n, self.flat, self.F, z.data_ptr(), self.F,
                    self.Wf["deconv/d_h0_lin/Matrix"].data_ptr(), self.flat, d[0].data_ptr(), self.flat,
                    bias=self.P["deconv/d_h0_lin/bias"], act=True)
         for i, L in enumerate(self.dec):
             last = i == self.L - 1
+            if tag is not None and self._dec_bf3[i] and skips[self.L - 1 - i].shape[0] == self.B:
+                j = self.L - 1 - i
+                if dp is None:
+                    dp = ops.split_bf16(d[i], out=self._planes("%s%d_in_p%d" % (tag, i, n), d[i].shape))
+                sk = skip_planes[j] if skip_planes is not None else None
+                if sk is None:
+                    sk = ops.split_bf16(skips[j].contiguous(), out=self._planes("%s_skip%d_p" % (tag, j), skips[j].shape))
+                op = None
+                if not last and self._dec_bf3[i + 1]:
+                    op = self._planes("%s%d_p%d" % (tag, i + 1, n), d[i + 1].shape)
+                ops.conv2d_transpose_bf16x3(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
+                                            bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2p=sk,
+                                            act=not last, out=d[i + 1], out_planes=op)
+                dp = op
+                continue
+            dp = None
             ops.conv2d_transpose(d[i], self.Wf["deconv/%s/w" % L["name"]], L["out_hw"],
                                  bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2=skips[self.L - 1 - i],
                                  act=not last, out=d[i + 1], round_tf32=self.round and not last, impl=self.impl)
@@ -598,6 +689,7 @@ class ContextNet:
         t = self.step_count
         lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
         ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr_t, b1, b2, eps, p_tf32=self.flat_pr)
+        self._wp_stale = True
 
     def attach_allreduce(self, group=None):
         """Data parallelism: after this, every optimiser step sum-all-reduces the flat gradient (bucketed, launched
@@ -637,9 +729,11 @@ class ContextNet:
             with torch.cuda.stream(self._s3):
                 ops.adam_step(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr_t, b1, b2, eps,
                               p_tf32=None if self.flat_pr is None else self.flat_pr[a:b])
+                self._refresh_weight_planes(scope)         # next step's forward operands, under the remaining backward
 
         self.backward(on_stage=adam_scope)
         cur.wait_stream(self._s3)
+        self._wp_stale = False
 
     def train_step(self, lr: float = 1e-4, allreduce=None):
         """forward + backward + (optional bucketed gradient all-reduce) + Adam: one `sess.run(optimizer, ...)`.

@@ -131,6 +131,88 @@ def conv2d_transpose(x1, w, out_hw, bias=None, stride: int = 2, x2=None, act: bo
     return out
 
 
+# ---- forward convolutions from bf16 (hi, lo) planes ----------------------------------------------------------------
+# A planes tensor is torch.bfloat16 of shape (2,) + shape: [0] = hi = bf16(x), [1] = lo = bf16(x - hi).
+def split_bf16(x, out=None):
+    """fp32 tensor -> (hi, lo) bf16 planes (2, *x.shape)."""
+    p = _req(x, "x")
+    if out is None:
+        out = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.bfloat16)
+    elif out.numel() != 2 * x.numel():
+        raise _lib.CtxError("split_bf16: out has the wrong size")
+    check(_lib.load().ctx_split_bf16(p, x.numel(), _req(out, "out", torch.bfloat16), _stream()), "ctx_split_bf16")
+    return out
+
+
+def split_bf16_conv_filter(w, out=None):
+    """conv filter [kh,kw,Cin,Cout] -> planes (2, kh*kw*Cout, Cin): per-tap K-major rows for conv2d_bf16x3."""
+    kh, kw, Cin, Co = w.shape
+    if out is None:
+        out = torch.empty((2, kh * kw * Co, Cin), device=w.device, dtype=torch.bfloat16)
+    check(_lib.load().ctx_split_bf16_transpose(_req(w, "w"), kh * kw, Cin, Co, _req(out, "out", torch.bfloat16),
+                                               _stream()), "ctx_split_bf16_transpose")
+    return out
+
+
+def conv2d_bf16x3_eligible(n, in_hw, Cin, Co, k, stride) -> bool:
+    g = conv_geom(n, tuple(in_hw), k, stride)
+    return bool(_lib.load().ctx_conv2d_fprop_bf16x3_eligible(Cin, Co, C.byref(g)))
+
+
+def conv2d_bf16x3(xp, wp, k: int, bias=None, stride: int = 2, act: bool = False, out=None, out_planes=None):
+    """conv2d(SAME) + bias (+ lrelu) from planes: xp (2,N,H,W,C), wp (2,k*k*Co,C) -> out fp32 [N,P,Q,Co] (+ out_planes)."""
+    _, N, H, W_, Cin = xp.shape
+    Co = wp.shape[1] // (k * k)
+    if wp.shape[2] != Cin or wp.shape[1] != k * k * Co:
+        raise _lib.CtxError("conv2d_bf16x3: filter planes %s do not match input planes %s" % (tuple(wp.shape), tuple(xp.shape)))
+    g = conv_geom(N, (H, W_), k, stride)
+    if out is None:
+        out = torch.empty((N, g.P, g.Q, Co), device=xp.device, dtype=torch.float32)
+    if out_planes is not None and out_planes.numel() != 2 * out.numel():
+        raise _lib.CtxError("conv2d_bf16x3: out_planes has the wrong size")
+    epi = make_epilogue(bias, act)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * k * k * Cin)
+    check(_lib.load().ctx_conv2d_fprop_bf16x3(_req(xp, "xp", torch.bfloat16), Cin, _req(wp, "wp", torch.bfloat16),
+                                              _req(out, "out"),
+                                              None if out_planes is None else _req(out_planes, "out_planes", torch.bfloat16),
+                                              Co, C.byref(g), C.byref(epi), _stream()), "ctx_conv2d_fprop_bf16x3")
+    pr.done()
+    return out
+
+
+def conv2d_transpose_bf16x3_eligible(n, out_hw, C1, C2, x2_batch, Cn, k, stride) -> bool:
+    g = conv_geom(n, tuple(out_hw), k, stride)
+    return bool(_lib.load().ctx_conv2d_transpose_bf16x3_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
+
+
+def conv2d_transpose_bf16x3(x1p, wp, out_hw, k: int, bias=None, stride: int = 2, x2p=None, act: bool = False, out=None,
+                            out_planes=None):
+    """conv2d_transpose(SAME) + bias (+ lrelu) over concat([x1, x2], 3) from planes: x1p (2,N,P,Q,C1), x2p (2,N2,P,Q,C2),
+    wp (2, k*k*Cn, C1+C2) = split_bf16 of the filter [k,k,Cn,Ck] -> out fp32 [N,H,W,Cn] (+ out_planes)."""
+    _, N, P, Q, C1 = x1p.shape
+    C2 = 0 if x2p is None else x2p.shape[4]
+    Ck = wp.shape[-1]
+    Cn = wp.numel() // (2 * k * k * Ck)
+    if Ck != C1 + C2:
+        raise _lib.CtxError("conv2d_transpose_bf16x3: filter planes do not match the inputs")
+    g = conv_geom(N, tuple(out_hw), k, stride)
+    if (g.P, g.Q) != (P, Q):
+        raise _lib.CtxError("conv2d_transpose_bf16x3: output %s inconsistent with input grid %s" % (tuple(out_hw), (P, Q)))
+    if out is None:
+        out = torch.empty((N, g.H, g.W, Cn), device=x1p.device, dtype=torch.float32)
+    if out_planes is not None and out_planes.numel() != 2 * out.numel():
+        raise _lib.CtxError("conv2d_transpose_bf16x3: out_planes has the wrong size")
+    epi = make_epilogue(bias, act)
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * Ck)
+    check(_lib.load().ctx_conv2d_transpose_bf16x3(
+        _req(x1p, "x1p", torch.bfloat16), C1, None if x2p is None else _req(x2p, "x2p", torch.bfloat16), C2,
+        0 if x2p is None else x2p.shape[1], _req(wp, "wp", torch.bfloat16), _req(out, "out"),
+        None if out_planes is None else _req(out_planes, "out_planes", torch.bfloat16), Cn, C.byref(g), C.byref(epi),
+        _stream()), "ctx_conv2d_transpose_bf16x3")
+    pr.done()
+    return out
+
+
 def conv2d_wgrad(big, small1, k: int, stride: int, small2=None, dw=None, impl=IMPL_AUTO):
     """dw[k,k,Ca,Cb1+Cb2] += sum_pixels big[shifted] (x) [small1 ‖ small2].  big [N,H,W,Ca], small* [.,P,Q,Cb*]."""
     N, H, W_, Ca = big.shape

@@ -42,7 +42,8 @@ enum {
   CTX_IMPL_TC = 2,       /* force tcgen05, single-pass TF32 (operands must be TF32-rounded); error if the    */
                          /* shape is not eligible                                                            */
   CTX_IMPL_TC3 = 3,      /* force tcgen05, 3-pass split; error if the shape is not eligible                  */
-  CTX_IMPL_FAST = 4      /* single-pass TF32 when the shape qualifies, else SIMT                             */
+  CTX_IMPL_FAST = 4,     /* single-pass TF32 when the shape qualifies, else SIMT                             */
+  CTX_IMPL_BF16X3 = 5    /* reported by ctx_last_impl() after a ctx_*_bf16x3 call (not a selector)           */
 };
 
 /* Geometry of one SAME conv / transposed conv.  "big" is the conv input (= transposed-conv output) grid,
@@ -122,6 +123,38 @@ int ctx_conv2d_wgrad(const float* big, int32_t Ca, const float* small1, int32_t 
 int ctx_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
              const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
              const ctx_epilogue* epi, int32_t impl, void* stream);
+
+/* ---- forward convolutions from pre-split bf16 planes ------------------------------------------------------
+ * A "planes" tensor is [2][shape] bf16: plane 0 = hi = bf16_rn(x), plane 1 = lo = bf16_rn(x - hi), so hi + lo carries
+ * 16 significant bits of the fp32 value.  The kernels compute hi*hi + hi*lo + lo*hi on the bf16 tensor cores with fp32
+ * accumulation: fp32-grade results (max-norm error 5e-6..9e-6 per GEMM, measured) at half the tensor-core time of the
+ * 3-pass TF32 split, with no operand splitting inside the GEMM.  Same layer semantics as ctx_conv2d_fprop /
+ * ctx_conv2d_transpose (arm_shaping.py:21-32, 62-85, 1323-1329); epilogue: bias and lrelu only.  y is written in fp32
+ * and, when y_planes is not null, also as planes for the next layer.  Shapes: channels % 64 == 0, stride 1 or 2, output
+ * (phase) grids that tile exactly into 128 pixels — ask ctx_*_bf16x3_eligible; ineligible shapes return
+ * CTX_ERR_UNSUPPORTED (use the fp32-input entry points). */
+
+/* planes[0][i] = bf16_rn(x[i]); planes[1][i] = bf16_rn(x[i] - planes[0][i]) for i < n. */
+int ctx_split_bf16(const float* x, int64_t n, void* planes, void* stream);
+
+/* w [T][R][Cc] fp32 -> planes [2][T][Cc][R]: a conv filter [kh*kw][Cin][Cout] (arm_shaping.py:25) becomes the per-tap
+ * K-major matrix [kh*kw*Cout][Cin] ctx_conv2d_fprop_bf16x3 reads.  (A transposed-conv filter [kh,kw,Cout,Cin] is already
+ * K-major: use ctx_split_bf16.) */
+int ctx_split_bf16_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, void* planes, void* stream);
+
+int ctx_conv2d_fprop_bf16x3_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g);
+
+/* x_planes [2][N,H,W,C], w_planes [2][kh*kw*Co][C], y [N,P,Q,Co] fp32, y_planes [2][N,P,Q,Co] or NULL. */
+int ctx_conv2d_fprop_bf16x3(const void* x_planes, int32_t C, const void* w_planes, float* y, void* y_planes, int32_t Co,
+                            const ctx_conv_geom* g, const ctx_epilogue* epi, void* stream);
+
+int ctx_conv2d_transpose_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn, const ctx_conv_geom* g);
+
+/* x1_planes [2][N,P,Q,C1], x2_planes [2][x2_batch,P,Q,C2] or NULL (image n reads x2 image n % x2_batch: the fused
+ * skip concat), w_planes [2][kh*kw*Cn][C1+C2], y [N,H,W,Cn] fp32, y_planes [2][N,H,W,Cn] or NULL. */
+int ctx_conv2d_transpose_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2, int32_t x2_batch,
+                                const void* w_planes, float* y, void* y_planes, int32_t Cn, const ctx_conv_geom* g,
+                                const ctx_epilogue* epi, void* stream);
 
 /* ---- pointwise / reductions ------------------------------------------------------------------------------ */
 

@@ -30,6 +30,9 @@ FWD_SRC, FWD_TRANS, FWD_ALL = 1, 2, 3
 _ALIGN = 64          # floats; every parameter starts on a 256-byte boundary (TMA / 128-bit access friendly)
 
 
+_POISON = os.environ.get("CTX_POISON", "0") == "1"      # fill every fresh work buffer with NaN (set by tests/conftest.py)
+
+
 def _numel(shape) -> int:
     n = 1
     for d in shape:
@@ -173,6 +176,8 @@ class ContextNet:
         t = self._bufs.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+            if _POISON and t.is_floating_point():
+                t.fill_(float("nan"))                      # tests: a read-before-write shows up as NaN, not as luck
             self._bufs[name] = t
         return t
 
@@ -397,7 +402,7 @@ class ContextNet:
 
     def _enc_buffers(self, n_rows: int, tag: str):
         hs = [self._buf("%s_h%d" % (tag, j), (n_rows,) + self.sizes[j + 1] + (self.chans[j + 1],)) for j in range(self.L)]
-        h4 = self._buf("%s_h4" % tag, (n_rows, self.F))
+        h4 = self._buf("%s_lin" % tag, (n_rows, self.F))      # (not "_h4": that is conv level 4 of a deeper net)
         return hs, h4
 
     def forward(self, level: int = FWD_ALL):
@@ -539,10 +544,10 @@ class ContextNet:
 
         # gradient buffers of the encoder activations (pre-activation gradients, i.e. lrelu' already applied)
         ge_hs = [self._buf("g_e_h%d" % j, tuple(e_hs[j].shape)) for j in range(self.L)]
-        ge_h4 = self._buf("g_e_h4", tuple(e_h4.shape))
+        ge_h4 = self._buf("g_e_lin", tuple(e_h4.shape))
         if sp.separate_ctx_encoder:
             gc_hs = [self._buf("g_c_h%d" % j, tuple(c_hs[j].shape)) for j in range(self.L)]
-            gc_h4 = self._buf("g_c_h4", tuple(c_h4.shape))
+            gc_h4 = self._buf("g_c_lin", tuple(c_h4.shape))
         else:
             gc_hs, gc_h4 = [g[2 * B:] for g in ge_hs], ge_h4[2 * B:]
 

@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+# every fresh work buffer of ContextNet starts as NaN under test, so a kernel that reads a buffer nobody wrote fails
+# deterministically instead of passing on whatever the caching allocator handed back (network._POISON)
+os.environ.setdefault("CTX_POISON", "1")
 
 
 def pytest_configure(config):

@@ -24,7 +24,7 @@ ap.add_argument("--reps", type=int, default=10)
 a = ap.parse_args()
 B = a.batch
 dev = "cuda"
-IMPLS = {"x3": IMPL_AUTO, "x1": IMPL_FAST, "simt": IMPL_SIMT}
+IMPLS = {"x3": IMPL_AUTO, "x1": IMPL_FAST, "simt": IMPL_SIMT, "bf3": "bf3"}     # bf3 = bf16 (hi, lo) planes, forward layers
 
 
 def rnd(*shape):
@@ -38,8 +38,15 @@ def add_fprop(name, N, H, C, Co, k=5, st=2):
     x, w, b = rnd(N, H, H, C), rnd(k, k, C, Co), rnd(Co)
     P = -(-H // st)
     y = torch.empty((N, P, P, Co), device=dev)
-    cases.append(("fprop", name, 2.0 * N * P * P * Co * k * k * C,
-                  lambda impl: ops.conv2d(x, w, b, stride=st, act=True, out=y, impl=impl)))
+    bf = ops.conv2d_bf16x3_eligible(N, (H, H), C, Co, k, st)
+    xp, wp = (ops.split_bf16(x), ops.split_bf16_conv_filter(w)) if bf else (None, None)
+    yp = torch.empty((2, N, P, P, Co), device=dev, dtype=torch.bfloat16) if bf else None
+
+    def run(impl):
+        if impl == "bf3":
+            return ops.conv2d_bf16x3(xp, wp, k, bias=b, stride=st, act=True, out=y, out_planes=yp) if bf else None
+        return ops.conv2d(x, w, b, stride=st, act=True, out=y, impl=impl)
+    cases.append(("fprop", name, 2.0 * N * P * P * Co * k * k * C, run))
 
 
 def add_im2col(name, N, H, C, k=5, st=2):
@@ -55,9 +62,17 @@ def add_trans(name, N, P, C1, C2, NB, Cn, k=5, st=2, act=True):
     x2 = rnd(NB, P, P, C2) if C2 else None
     w, b = rnd(k, k, Cn, C1 + C2), rnd(Cn)
     y = torch.empty((N, P * st, P * st, Cn), device=dev)
-    cases.append(("transpose", name, 2.0 * N * P * P * Cn * k * k * (C1 + C2),
-                  lambda impl: ops.conv2d_transpose(x1, w, (P * st, P * st), bias=b, stride=st, x2=x2, act=act, out=y,
-                                                    impl=impl)))
+    bf = ops.conv2d_transpose_bf16x3_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
+    x1p, wp = (ops.split_bf16(x1), ops.split_bf16(w)) if bf else (None, None)
+    x2p = ops.split_bf16(x2) if bf and C2 else None
+    yp = torch.empty((2, N, P * st, P * st, Cn), device=dev, dtype=torch.bfloat16) if bf else None
+
+    def run(impl):
+        if impl == "bf3":
+            return ops.conv2d_transpose_bf16x3(x1p, wp, (P * st, P * st), k, bias=b, stride=st, x2p=x2p, act=act, out=y,
+                                               out_planes=yp) if bf else None
+        return ops.conv2d_transpose(x1, w, (P * st, P * st), bias=b, stride=st, x2=x2, act=act, out=y, impl=impl)
+    cases.append(("transpose", name, 2.0 * N * P * P * Cn * k * k * (C1 + C2), run))
 
 
 def add_wgrad(name, N, H, Ca, Cb1, Cb2, NB, k=5, st=2):
@@ -129,6 +144,9 @@ for kind, name, flops, fn in cases:
     line = "%-10s %-22s %8.2f GF " % (kind, name, flops / 1e9)
     for tag in a.impl.split(","):
         impl = IMPLS[tag]
+        if impl == "bf3" and (kind not in ("fprop", "transpose") or fn(impl) is None):
+            line += "| bf3      n/a                    "
+            continue
         for _ in range(2):
             fn(impl)
         torch.cuda.synchronize()
@@ -139,7 +157,7 @@ for kind, name, flops, fn in cases:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
-        used = {1: "simt", 2: "tc1", 3: "tc3"}.get(int(ops._lib.load().ctx_last_impl()), "?")
+        used = {1: "simt", 2: "tc1", 3: "tc3", 5: "bf3"}.get(int(ops._lib.load().ctx_last_impl()), "?")
         tot[tag] = tot.get(tag, 0.0) + ms
         line += "| %s(%s) %8.1f us %7.1f TF/s " % (tag, used, ms * 1e3, flops / ms / 1e9)
     print(line, flush=True)

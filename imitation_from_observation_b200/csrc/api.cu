@@ -201,6 +201,45 @@ extern "C" int ctx_conv2d_transpose_bf16x3(const void* x1_planes, int32_t C1, co
                               (cudaStream_t)stream);
 }
 
+extern "C" int ctx_conv2d_transpose_merged_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
+                                                           const ctx_conv_geom* g) {
+  if (!g || check_geom(g, "conv2d_transpose_merged_bf16x3")) return 0;
+  return (ctx_tc_available() && bf3_conv2d_transpose_merged_eligible(C1, C2, x2_batch, Cn, *g)) ? 1 : 0;
+}
+
+extern "C" int64_t ctx_conv2d_transpose_merged_rows(int32_t Cn, const ctx_conv_geom* g) {
+  if (!g || check_geom(g, "conv2d_transpose_merged_rows")) return 0;
+  return bf3_conv2d_transpose_merged_rows(Cn, *g);
+}
+
+extern "C" int ctx_conv2d_transpose_merged_pack(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g,
+                                                void* wm_planes, void* stream) {
+  int rc = check_geom(g, "conv2d_transpose_merged_pack");
+  if (rc) return rc;
+  CTX_REQUIRE(w && wm_planes && Ck > 0 && Cn > 0, "conv2d_transpose_merged_pack: bad arguments");
+  return bf3_conv2d_transpose_merged_pack(w, Ck, Cn, *g, (__nv_bfloat16*)wm_planes, (cudaStream_t)stream);
+}
+
+extern "C" int ctx_conv2d_transpose_merged_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
+                                                  int32_t x2_batch, const void* wm_planes, float* y, void* y_planes,
+                                                  int32_t Cn, const ctx_conv_geom* g, const ctx_epilogue* epi,
+                                                  void* stream) {
+  int rc = check_geom(g, "conv2d_transpose_merged_bf16x3");
+  if (rc) return rc;
+  if (g->N == 0) return CTX_OK;
+  CTX_REQUIRE(x1_planes && wm_planes && y, "conv2d_transpose_merged_bf16x3: null pointer");
+  CTX_REQUIRE((C2 == 0) == (x2_planes == nullptr), "conv2d_transpose_merged_bf16x3: x2 and C2 must both be set or both be empty");
+  if (!ctx_tc_available() || !bf3_conv2d_transpose_merged_eligible(C1, C2, x2_batch, Cn, *g)) {
+    set_error("conv2d_transpose_merged_bf16x3: shape not eligible (stride 2, 4 * Cn == 256, channels %% 64, even output, "
+              "input grid tiling into 128 pixels) or no sm_100 device");
+    return CTX_ERR_UNSUPPORTED;
+  }
+  g_last_impl = CTX_IMPL_BF16X3;
+  return bf3_conv2d_transpose_merged((const __nv_bfloat16*)x1_planes, C1, (const __nv_bfloat16*)x2_planes, C2, x2_batch,
+                                     (const __nv_bfloat16*)wm_planes, y, (__nv_bfloat16*)y_planes, Cn, *g, make_epi(epi),
+                                     (cudaStream_t)stream);
+}
+
 extern "C" int ctx_conv2d_wgrad(const float* big, int32_t Ca, const float* small1, int32_t Cb1, const float* small2,
                                 int32_t Cb2, int32_t small2_batch, float* dw, const ctx_conv_geom* g, int32_t impl,
                                 void* stream) {

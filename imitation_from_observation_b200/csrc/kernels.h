@@ -42,6 +42,13 @@ int bf3_conv2d_transpose_eligible(int C1, int C2, int x2_batch, int Cn, const ct
 int bf3_conv2d_transpose(const __nv_bfloat16* x1p, int C1, const __nv_bfloat16* x2p, int C2, int x2_batch,
                          const __nv_bfloat16* wp, float* y, __nv_bfloat16* yp, int Cn, const ctx_conv_geom& g,
                          const Epi& epi, cudaStream_t stream);
+int bf3_conv2d_transpose_merged_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g);
+int64_t bf3_conv2d_transpose_merged_rows(int Cn, const ctx_conv_geom& g);
+int bf3_conv2d_transpose_merged_pack(const float* w, int Ck, int Cn, const ctx_conv_geom& g, __nv_bfloat16* planes,
+                                     cudaStream_t stream);
+int bf3_conv2d_transpose_merged(const __nv_bfloat16* x1p, int C1, const __nv_bfloat16* x2p, int C2, int x2_batch,
+                                const __nv_bfloat16* wmp, float* y, __nv_bfloat16* yp, int Cn, const ctx_conv_geom& g,
+                                const Epi& epi, cudaStream_t stream);
 
 // pointwise.cu
 int bias_init(float* y, const float* bias, int64_t n, int C, int accumulate, cudaStream_t stream);

@@ -53,6 +53,9 @@ struct BfParams {
   const float* bias;
   float slope;
   int32_t act;
+  // phase-merged transposed conv: column j = phase * merge_cn + co, phase = ph * 2 + pw, goes to output pixel
+  // (2p + ph, 2q + pw) = out + roff + (ph * merge_W + pw) * merge_cn + co (0 = plain column addressing)
+  int32_t merge_cn, merge_W;
   int32_t* err_flag;
 };
 
@@ -285,15 +288,22 @@ __global__ void __launch_bounds__(kBfThreads, 1) bf3_kernel(const __grid_constan
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), v2);
       const int col = ncol0 + c0;
       if (!row_ok || col >= p.N) continue;
+      int co = col;                                      // output channel of the chunk's first column
+      int64_t ooff = roff + col;
+      if (p.merge_cn) {                                  // (warp-uniform: a 32-column chunk never straddles phases)
+        const int phase = col / p.merge_cn;
+        co = col - phase * p.merge_cn;
+        ooff = roff + ((int64_t)(phase >> 1) * p.merge_W + (phase & 1)) * p.merge_cn + co;
+      }
       float x[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float t = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-        if (p.bias) t += __ldg(p.bias + col + j);
+        if (p.bias) t += __ldg(p.bias + co + j);
         if (p.act) t = fmaxf(t, p.slope * t);
         x[j] = t;
       }
-      float* optr = p.out + roff + col;
+      float* optr = p.out + ooff;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(optr + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
       if (p.planes) {
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bf3_kernel(const __grid_constan
           lo[j] = pack_bf16x2(__float2bfloat16_rn(x[2 * j] - __bfloat162float(h0)),
                               __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(h1)));
         }
-        __nv_bfloat16* ph = p.planes + roff + col;
+        __nv_bfloat16* ph = p.planes + ooff;
         __nv_bfloat16* pl = ph + p.plane_stride;
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -622,6 +632,155 @@ int bf3_conv2d_transpose(const __nv_bfloat16* x1p, int C1, const __nv_bfloat16* 
   p.nphase = nph;
   p.sN = (int64_t)g.H * g.W * Cn; p.sP = (int64_t)st * g.W * Cn; p.sQ = (int64_t)st * Cn;
   return bf_launch(p, m_tiles, nph, stream, "bf3_conv2d_transpose");
+}
+
+// ---- transposed conv, stride 2, few output channels (4 * Cn == 256): the four stride phases merged along N ------------------
+// A 128 x 64 tile moves 48 KB of operands per k-block for 1/4 of the MACs of a 256-wide pair tile, and the per-phase
+// formulation re-reads every input pixel once per filter tap (25x for 5x5).  Here ONE GEMM covers all four phases:
+// rows = input pixels (p, q), columns = (phase, co), K = (distinct input offset (dh, dw), source, channel).  Phase
+// (ph, pw) at offset (dh, dw) uses exactly one tap (r, s) or none; the packed filter matrix Wm[offset][phase * Cn + co][c]
+// holds that tap's weights or zeros (ctx_conv2d_transpose_merged_pack).  The input is fetched once per distinct offset
+// (9 for 5x5 instead of 25), every tile is a 256-wide CTA pair, and the zero blocks cost MMA time only (36 k-block
+// columns issued for 25 needed).
+struct MergedPlan {
+  int nh, nw;                 // distinct row / column offsets
+  int dh[3], dw[3];
+  int tap_r[2][3], tap_s[2][3];   // [phase bit][offset index] -> filter row / column, or -1
+};
+
+static bool merged_plan(const ctx_conv_geom& g, MergedPlan* mp) {
+  if (g.stride != 2 || g.H != 2 * g.P || g.W != 2 * g.Q) return false;
+  // one axis at a time: phase bit b, taps r = r0 + 2a at input offset d = dh0 - a
+  auto axis = [&](int k, int pad, int* n, int* d, int (*tap)[3]) {
+    *n = 0;
+    for (int b = 0; b < 2; ++b) for (int j = 0; j < 3; ++j) tap[b][j] = -1;
+    for (int b = 0; b < 2; ++b) {
+      const int r0 = (b + pad) % 2, d0 = (b + pad - r0) / 2;
+      const int nr = r0 < k ? (k - r0 + 1) / 2 : 0;
+      if (nr == 0) return false;
+      for (int a = 0; a < nr; ++a) {
+        const int off = d0 - a;
+        int j = 0;
+        while (j < *n && d[j] != off) ++j;
+        if (j == *n) { if (*n == 3) return false; d[(*n)++] = off; }
+        tap[b][j] = r0 + 2 * a;
+      }
+    }
+    return true;
+  };
+  return axis(g.kh, g.pad_h, &mp->nh, mp->dh, mp->tap_r) && axis(g.kw, g.pad_w, &mp->nw, mp->dw, mp->tap_s);
+}
+
+int bf3_conv2d_transpose_merged_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g) {
+  MergedPlan mp;
+  int bp, nb, tpi;
+  if (4 * Cn != 256 || C1 % 64 != 0 || C2 % 64 != 0) return 0;
+  if (!merged_plan(g, &mp)) return 0;
+  if (!bf_tile_grid(g.P, g.Q, &bp, &nb, &tpi)) return 0;
+  if (C2 > 0 && nb > 1 && x2_batch % nb != 0) return 0;
+  return mp.nh * mp.nw * (C2 > 0 ? 2 : 1) <= kBfMaxSeg ? 1 : 0;
+}
+
+__global__ void merged_pack_kernel(const float* __restrict__ w, int kw, int Cn, int Ck, MergedPlan mp,
+                                   __nv_bfloat16* __restrict__ planes) {
+  // planes [2][noff * 4 * Cn][Ck]; one thread per (row, 4 channels)
+  const int64_t rows = (int64_t)mp.nh * mp.nw * 4 * Cn, total = rows * (Ck / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / (Ck / 4);
+    const int c4 = (int)(i - row * (Ck / 4)) * 4;
+    const int off = (int)(row / (4 * Cn)), rem = (int)(row - (int64_t)off * 4 * Cn);
+    const int phase = rem / Cn, co = rem - phase * Cn;
+    const int r = mp.tap_r[phase >> 1][off / mp.nw], s_ = mp.tap_s[phase & 1][off % mp.nw];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0 && s_ >= 0) v = *reinterpret_cast<const float4*>(w + (((int64_t)r * kw + s_) * Cn + co) * Ck + c4);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16* hi = planes + row * Ck + c4;
+    __nv_bfloat16* lo = hi + rows * Ck;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(x[e]);
+      hi[e] = h;
+      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h));
+    }
+  }
+}
+
+int64_t bf3_conv2d_transpose_merged_rows(int Cn, const ctx_conv_geom& g) {
+  MergedPlan mp;
+  if (!merged_plan(g, &mp)) return 0;
+  return (int64_t)mp.nh * mp.nw * 4 * Cn;
+}
+
+// w [kh,kw,Cn,Ck] fp32 -> packed planes [2][rows][Ck], rows = bf3_conv2d_transpose_merged_rows
+int bf3_conv2d_transpose_merged_pack(const float* w, int Ck, int Cn, const ctx_conv_geom& g, __nv_bfloat16* planes,
+                                     cudaStream_t stream) {
+  MergedPlan mp;
+  CTX_REQUIRE(merged_plan(g, &mp) && Ck % 4 == 0, "conv2d_transpose_merged_pack: geometry not eligible");
+  CTX_REQUIRE(bf_aligned16(w) && bf_aligned16(planes), "conv2d_transpose_merged_pack: pointers must be 16-byte aligned");
+  const int64_t total = (int64_t)mp.nh * mp.nw * 4 * Cn * (Ck / 4);
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  merged_pack_kernel<<<blocks, 256, 0, stream>>>(w, g.kw, Cn, Ck, mp, planes);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "merged_pack");
+  count_launch();
+  return CTX_OK;
+}
+
+int bf3_conv2d_transpose_merged(const __nv_bfloat16* x1p, int C1, const __nv_bfloat16* x2p, int C2, int x2_batch,
+                                const __nv_bfloat16* wmp, float* y, __nv_bfloat16* yp, int Cn, const ctx_conv_geom& g,
+                                const Epi& epi, cudaStream_t stream) {
+  CTX_REQUIRE(bf_aligned16(x1p) && bf_aligned16(x2p) && bf_aligned16(wmp) && bf_aligned16(y) && bf_aligned16(yp),
+              "conv2d_transpose_merged(bf16x3): pointers must be 16-byte aligned");
+  CTX_REQUIRE(!epi.act_ref && !epi.accumulate && !epi.round, "conv2d_transpose_merged(bf16x3): only bias / lrelu epilogues");
+  MergedPlan mp;
+  if (!merged_plan(g, &mp)) { set_error("conv2d_transpose_merged(bf16x3): geometry not eligible"); return CTX_ERR_UNSUPPORTED; }
+  const int Ck = C1 + C2;
+  BfParams p;
+  bf_fill_common(p, epi, y, yp, (int64_t)g.N * g.H * g.W * Cn);
+  int tpi;
+  if (!bf_tile_grid(g.P, g.Q, &p.BP, &p.NB, &tpi)) { set_error("conv2d_transpose_merged(bf16x3): grid does not tile"); return CTX_ERR_UNSUPPORTED; }
+  p.tiles_per_img = tpi;
+  const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
+  p.BN = 256;
+  p.NG = g.N; p.PG = g.P; p.QG = g.Q; p.N = 4 * Cn;
+  p.a_wrap = x2_batch > 0 ? x2_batch : 1;
+  p.merge_cn = Cn; p.merge_W = g.W;
+  {
+    const int64_t plane = (int64_t)g.N * g.P * g.Q * C1;
+    int64_t dims[5] = {C1, g.Q, g.P, g.N, 2}, str[5] = {1, C1, (int64_t)g.Q * C1, (int64_t)g.P * g.Q * C1, plane};
+    int box[5] = {64, g.Q, p.BP, p.NB, 2};
+    int rc = bf_make_map(&p.mapA[0], x1p, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  if (C2 > 0) {
+    const int64_t plane = (int64_t)x2_batch * g.P * g.Q * C2;
+    int64_t dims[5] = {C2, g.Q, g.P, x2_batch, 2}, str[5] = {1, C2, (int64_t)g.Q * C2, (int64_t)g.P * g.Q * C2, plane};
+    int box[5] = {64, g.Q, p.BP, p.NB, 2};
+    int rc = bf_make_map(&p.mapA[1], x2p, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const int64_t rows = (int64_t)mp.nh * mp.nw * 4 * Cn;
+    int64_t dims[3] = {Ck, rows, 2}, str[3] = {1, Ck, rows * Ck};
+    int box[3] = {64, 128, 2};
+    int rc = bf_make_map(&p.mapB, wmp, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  int nseg = 0, kblocks = 0;
+  for (int a = 0; a < mp.nh; ++a)
+    for (int b = 0; b < mp.nw; ++b)
+      for (int src = 0; src < (C2 > 0 ? 2 : 1); ++src) {
+        BfSeg& sg = p.seg[nseg++];
+        sg.mapA = (uint8_t)src; sg.wrap = (uint8_t)src;
+        sg.dh = (int16_t)mp.dh[a]; sg.dw = (int16_t)mp.dw[b];
+        sg.nblk = (uint16_t)((src ? C2 : C1) / 64);
+        sg.bk0 = src ? C1 : 0; sg.br0 = (a * mp.nw + b) * 4 * Cn;
+        kblocks += sg.nblk;
+      }
+  p.ph_seg0[0] = 0; p.ph_nseg[0] = nseg; p.ph_kblocks[0] = kblocks; p.ph_obase[0] = 0;
+  p.nphase = 1;
+  p.sN = (int64_t)g.H * g.W * Cn; p.sP = 2 * (int64_t)g.W * Cn; p.sQ = 2 * (int64_t)Cn;
+  return bf_launch(p, m_tiles, 1, stream, "bf3_conv2d_transpose_merged");
 }
 
 }  // namespace ctx

@@ -133,6 +133,7 @@ class ContextNet:
         # the other layers (3-channel image side, dense layers) stay on the 3-pass TF32 kernel.  CTX_FWD_BF3=0 disables.
         self._enc_bf3 = [False] * self.L
         self._dec_bf3 = [False] * self.L
+        self._dec_merged = [False] * self.L              # stride-2 levels with 64 output channels: phases merged along N
         self._wp: Dict[str, torch.Tensor] = {}           # weight planes, refreshed after every parameter update
         self._wp_stale = True
         self._wp_shared = params_from is not None        # someone else updates the parameters: refresh every forward
@@ -142,8 +143,10 @@ class ContextNet:
                                                               spec.kernels[j], spec.strides[j])
             if spec.separate_ctx_encoder:                # (a shared encoder's skip rows are a slice: no plane view)
                 for i, Ld in enumerate(self.dec):
-                    self._dec_bf3[i] = ops.conv2d_transpose_bf16x3_eligible(
-                        2 * self.B, Ld["out_hw"], Ld["c_state"], Ld["c_skip"], self.B, Ld["c_out"], Ld["k"], Ld["stride"])
+                    args = (2 * self.B, Ld["out_hw"], Ld["c_state"], Ld["c_skip"], self.B, Ld["c_out"], Ld["k"], Ld["stride"])
+                    self._dec_merged[i] = (os.environ.get("CTX_BF3_MERGE", "1") != "0" and
+                                           ops.conv2d_transpose_merged_eligible(*args))
+                    self._dec_bf3[i] = self._dec_merged[i] or ops.conv2d_transpose_bf16x3_eligible(*args)
         self.bf3 = any(self._enc_bf3) or any(self._dec_bf3)
         self._level = 0
 
@@ -314,6 +317,11 @@ class ContextNet:
             for i, Ld in enumerate(self.dec):
                 if self._dec_bf3[i]:
                     name = "deconv/%s/w" % Ld["name"]
+                    if self._dec_merged[i]:
+                        self._wp[name] = ops.conv2d_transpose_merged_pack(self.P[name], Ld["out_hw"], Ld["stride"],
+                                                                          out=self._bufs.get("wp:" + name))
+                        self._bufs["wp:" + name] = self._wp[name]
+                        continue
                     buf = self._planes("wp:" + name, (Ld["k"] * Ld["k"] * Ld["c_out"], Ld["c_state"] + Ld["c_skip"]))
                     self._wp[name] = ops.split_bf16(self.P[name], out=buf)
 
@@ -494,9 +502,15 @@ class ContextNet:
                 op = None
                 if not last and self._dec_bf3[i + 1]:
                     op = self._planes("%s%d_p%d" % (tag, i + 1, n), d[i + 1].shape)
-                ops.conv2d_transpose_bf16x3(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
-                                            bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2p=sk,
-                                            act=not last, out=d[i + 1], out_planes=op)
+                if self._dec_merged[i]:
+                    ops.conv2d_transpose_merged_bf16x3(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
+                                                       L["c_out"], bias=self.P["deconv/%s/biases" % L["name"]],
+                                                       stride=L["stride"], x2p=sk, act=not last, out=d[i + 1],
+                                                       out_planes=op)
+                else:
+                    ops.conv2d_transpose_bf16x3(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
+                                                bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2p=sk,
+                                                act=not last, out=d[i + 1], out_planes=op)
                 dp = op
                 continue
             dp = None

@@ -213,6 +213,53 @@ def conv2d_transpose_bf16x3(x1p, wp, out_hw, k: int, bias=None, stride: int = 2,
     return out
 
 
+def conv2d_transpose_merged_eligible(n, out_hw, C1, C2, x2_batch, Cn, k, stride) -> bool:
+    g = conv_geom(n, tuple(out_hw), k, stride)
+    return bool(_lib.load().ctx_conv2d_transpose_merged_bf16x3_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
+
+
+def conv2d_transpose_merged_pack(w, out_hw, stride: int = 2, out=None):
+    """Transposed-conv filter [k,k,Cn,Ck] -> packed planes (2, rows, Ck) for conv2d_transpose_merged_bf16x3."""
+    k, _, Cn, Ck = w.shape
+    g = conv_geom(1, tuple(out_hw), k, stride)
+    rows = int(_lib.load().ctx_conv2d_transpose_merged_rows(Cn, C.byref(g)))
+    if rows <= 0:
+        raise _lib.CtxError("conv2d_transpose_merged_pack: geometry not eligible")
+    if out is None:
+        out = torch.empty((2, rows, Ck), device=w.device, dtype=torch.bfloat16)
+    elif tuple(out.shape) != (2, rows, Ck):
+        raise _lib.CtxError("conv2d_transpose_merged_pack: out must be (2, %d, %d)" % (rows, Ck))
+    check(_lib.load().ctx_conv2d_transpose_merged_pack(_req(w, "w"), Ck, Cn, C.byref(g), _req(out, "out", torch.bfloat16),
+                                                       _stream()), "ctx_conv2d_transpose_merged_pack")
+    return out
+
+
+def conv2d_transpose_merged_bf16x3(x1p, wmp, out_hw, k: int, Cn: int, bias=None, stride: int = 2, x2p=None,
+                                   act: bool = False, out=None, out_planes=None):
+    """conv2d_transpose(SAME, stride 2) + bias (+ lrelu) with the four stride phases merged into one GEMM; wmp from
+    conv2d_transpose_merged_pack."""
+    _, N, P, Q, C1 = x1p.shape
+    C2 = 0 if x2p is None else x2p.shape[4]
+    if wmp.shape[-1] != C1 + C2:
+        raise _lib.CtxError("conv2d_transpose_merged_bf16x3: packed filter does not match the inputs")
+    g = conv_geom(N, tuple(out_hw), k, stride)
+    if (g.P, g.Q) != (P, Q):
+        raise _lib.CtxError("conv2d_transpose_merged_bf16x3: output %s inconsistent with input grid %s" % (tuple(out_hw), (P, Q)))
+    if out is None:
+        out = torch.empty((N, g.H, g.W, Cn), device=x1p.device, dtype=torch.float32)
+    if out_planes is not None and out_planes.numel() != 2 * out.numel():
+        raise _lib.CtxError("conv2d_transpose_merged_bf16x3: out_planes has the wrong size")
+    epi = make_epilogue(bias, act)
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * (C1 + C2))
+    check(_lib.load().ctx_conv2d_transpose_merged_bf16x3(
+        _req(x1p, "x1p", torch.bfloat16), C1, None if x2p is None else _req(x2p, "x2p", torch.bfloat16), C2,
+        0 if x2p is None else x2p.shape[1], _req(wmp, "wmp", torch.bfloat16), _req(out, "out"),
+        None if out_planes is None else _req(out_planes, "out_planes", torch.bfloat16), Cn, C.byref(g), C.byref(epi),
+        _stream()), "ctx_conv2d_transpose_merged_bf16x3")
+    pr.done()
+    return out
+
+
 def conv2d_wgrad(big, small1, k: int, stride: int, small2=None, dw=None, impl=IMPL_AUTO):
     """dw[k,k,Ca,Cb1+Cb2] += sum_pixels big[shifted] (x) [small1 ‖ small2].  big [N,H,W,Ca], small* [.,P,Q,Cb*]."""
     N, H, W_, Ca = big.shape

@@ -156,6 +156,21 @@ int ctx_conv2d_transpose_bf16x3(const void* x1_planes, int32_t C1, const void* x
                                 const void* w_planes, float* y, void* y_planes, int32_t Cn, const ctx_conv_geom* g,
                                 const ctx_epilogue* epi, void* stream);
 
+/* Stride-2 transposed conv with few output channels (4 * Cn == 256, e.g. d_h3: 256 -> 64 channels) as ONE GEMM over all
+ * four stride phases: rows = input pixels, columns = (phase, channel), K = (distinct input offset, source, channel) — the
+ * input is fetched once per distinct offset (9 for a 5x5 filter) instead of once per tap (25), in 256-wide CTA-pair tiles.
+ * The filter must first be packed (per parameter update) into wm_planes [2][ctx_conv2d_transpose_merged_rows(Cn, g)][Ck]:
+ * row (offset, phase, co) holds the weights of the one tap phase `phase` uses at that offset, or zeros.  Same semantics as
+ * ctx_conv2d_transpose_bf16x3. */
+int ctx_conv2d_transpose_merged_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
+                                                const ctx_conv_geom* g);
+int64_t ctx_conv2d_transpose_merged_rows(int32_t Cn, const ctx_conv_geom* g);
+int ctx_conv2d_transpose_merged_pack(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g, void* wm_planes,
+                                     void* stream);
+int ctx_conv2d_transpose_merged_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
+                                       int32_t x2_batch, const void* wm_planes, float* y, void* y_planes, int32_t Cn,
+                                       const ctx_conv_geom* g, const ctx_epilogue* epi, void* stream);
+
 /* ---- pointwise / reductions ------------------------------------------------------------------------------ */
 
 /* y = (float(x) * (1/255) - 0.5) * 2 in fp32 — rllab/sampler/base.py:117-119, scripts/train_script.py:102-104. */

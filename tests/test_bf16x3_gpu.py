@@ -92,3 +92,24 @@ def test_conv2d_transpose_bf16x3(N, P, Q, H, W, C1, C2, NB, Cn, k, st):
                                     x2p=None if x2 is None else ops.split_bf16(x2.cuda()), act=True, out_planes=yp)
     assert rel_err(y.cpu(), ref) < TOL
     assert torch.equal(yp.cpu().view(torch.int16), planes_ref(y.cpu()).view(torch.int16))
+
+
+# stride-2 transposed conv with 64 output channels: the four stride phases as ONE 256-column GEMM over packed filters
+@pytest.mark.parametrize("N,P,Q,C1,C2,NB,k", [(2, 16, 16, 128, 128, 1, 5), (4, 8, 8, 64, 64, 2, 3), (3, 16, 8, 64, 0, 0, 5),
+                                               (16, 4, 4, 128, 64, 8, 5), (2, 32, 32, 64, 64, 2, 5)])
+def test_conv2d_transpose_merged_bf16x3(N, P, Q, C1, C2, NB, k):
+    Cn, st, H, W = 64, 2, 2 * P, 2 * Q
+    x1 = rnd((N, P, Q, C1), 10)
+    x2 = rnd((NB, P, Q, C2), 11) if C2 else None
+    w = rnd((k, k, Cn, C1 + C2), 12, (k * k * (C1 + C2) / st ** 2) ** -0.5)
+    b = rnd((Cn,), 13, 0.1)
+    assert ops.conv2d_transpose_merged_eligible(N, (H, W), C1, C2, NB, Cn, k, st)
+    cat = x1 if x2 is None else torch.cat([x1, x2.repeat((N // NB, 1, 1, 1))], 3)
+    ref = O.lrelu(O.conv2d_transpose(cat.double(), w.double(), b.double(), (H, W), st))
+    wm = ops.conv2d_transpose_merged_pack(w.cuda(), (H, W), st)
+    yp = torch.zeros((2,) + tuple(ref.shape), device="cuda", dtype=torch.bfloat16)
+    y = ops.conv2d_transpose_merged_bf16x3(ops.split_bf16(x1.cuda()), wm, (H, W), k, Cn, bias=b.cuda(), stride=st,
+                                           x2p=None if x2 is None else ops.split_bf16(x2.cuda()), act=True, out_planes=yp)
+    assert rel_err(y.cpu(), ref) < TOL
+    assert torch.equal(yp.cpu().view(torch.int16), planes_ref(y.cpu()).view(torch.int16))
+    assert not ops.conv2d_transpose_merged_eligible(N, (H, W), C1, C2, NB, 128, k, st)      # 4 * Cn must be 256

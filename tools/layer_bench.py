@@ -63,11 +63,17 @@ def add_trans(name, N, P, C1, C2, NB, Cn, k=5, st=2, act=True):
     w, b = rnd(k, k, Cn, C1 + C2), rnd(Cn)
     y = torch.empty((N, P * st, P * st, Cn), device=dev)
     bf = ops.conv2d_transpose_bf16x3_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
+    merged = bf and os.environ.get("CTX_BF3_MERGE", "1") != "0" and \
+        ops.conv2d_transpose_merged_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
     x1p, wp = (ops.split_bf16(x1), ops.split_bf16(w)) if bf else (None, None)
+    wm = ops.conv2d_transpose_merged_pack(w, (P * st, P * st), st) if merged else None
     x2p = ops.split_bf16(x2) if bf and C2 else None
     yp = torch.empty((2, N, P * st, P * st, Cn), device=dev, dtype=torch.bfloat16) if bf else None
 
     def run(impl):
+        if impl == "bf3" and merged:
+            return ops.conv2d_transpose_merged_bf16x3(x1p, wm, (P * st, P * st), k, Cn, bias=b, stride=st, x2p=x2p, act=act,
+                                                      out=y, out_planes=yp)
         if impl == "bf3":
             return ops.conv2d_transpose_bf16x3(x1p, wp, (P * st, P * st), k, bias=b, stride=st, x2p=x2p, act=act, out=y,
                                                out_planes=yp) if bf else None

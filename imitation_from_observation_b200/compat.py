@@ -187,6 +187,7 @@ class Session:
     def __init__(self, config=None):
         self._pinned: Dict[Any, torch.Tensor] = {}
         self._pin_event: Dict[int, Any] = {}          # staging buffer -> event of the last H2D copy that read it
+        self._prefetch_of: Dict[int, Any] = {}        # model -> (fed object, staged tensor) of a pending prefetch
 
     def _stage(self, ph: Placeholder, value) -> torch.Tensor:
         """Host value -> pinned staging buffer (-> device for uint8 frames), as one [3,B,H,W,C] tensor.  A float batch
@@ -213,7 +214,21 @@ class Session:
         np.copyto(pin.numpy(), arr, casting="unsafe")            # f64 -> f32 cast happens here (train_script feed)
         return pin if host_ok else pin.to("cuda", non_blocking=True)
 
-    def run(self, fetches, feed_dict: Optional[dict] = None):
+    def prefetch(self, feed_dict: dict):
+        """Start the host->device copy of the NEXT step's batch while the current step computes (what tf.data's
+        prefetch_to_device does for a TF input pipeline).  The next run() fed with the same object only flips the
+        network's input slots.  Float image placeholders without a preprocessing chain only; other feeds are ignored."""
+        for k, v in feed_dict.items():
+            if not isinstance(k, Placeholder) or k.shape == () or k.chain or k.root.dtype == torch.uint8:
+                continue
+            for m in k.root.consumers:
+                staged = self._stage(k, v)
+                if torch.is_tensor(staged) and not staged.is_cuda:
+                    self._pin_event[staged.data_ptr()] = m.net.prefetch_input(staged)
+                    self._prefetch_of[id(m)] = (v, staged)
+
+    def run(self, fetches, feed_dict: Optional[dict] = None, prefetch: Optional[dict] = None):
+        """`prefetch`: the next call's feed_dict — its image batch is copied to the device under this step's kernels."""
         if fetches is None:                                   # sess.run(tf.global_variables_initializer())
             return None
         single = not isinstance(fetches, (list, tuple))
@@ -239,14 +254,16 @@ class Session:
                 fed = [v for k, v in feed_dict.items() if isinstance(k, Placeholder) and k.root is root]
                 if not fed:
                     raise _lib.CtxError("no value fed for the model's image placeholder")
-                staged = self._stage(m.placeholder, fed[0])
+                pre = self._prefetch_of.pop(id(m), None)
+                hit = pre is not None and pre[0] is fed[0]      # the batch a prefetch() already put in flight
+                staged = pre[1] if hit else self._stage(m.placeholder, fed[0])
                 chain = m.placeholder.chain
                 if chain and chain[-1][0] == "inception":      # frozen front-end: frames -> Mixed_7c feature maps
                     inc = chain[-1][1]
                     three, Bf = staged.shape[0], staged.shape[1]
                     feats = inc.forward(staged.reshape((three * Bf,) + tuple(staged.shape[2:])), ("Mixed_7c",))["Mixed_7c"]
                     staged = feats.view((three, Bf) + tuple(feats.shape[1:]))
-                m.net.set_input(staged)
+                m.net.set_input(staged, use_prefetched=hit)
                 if torch.is_tensor(staged) and not staged.is_cuda and m.net._in_events is not None:
                     self._pin_event[staged.data_ptr()] = m.net._in_events[1]
             mine = [f for f in flist if (f.loss.model if isinstance(f, _Minimize) else getattr(f, "model", None)) is m]
@@ -272,6 +289,8 @@ class Session:
                 m.net.forward(max(level, 1))
                 for f in mine:
                     results[id(f)] = m.net.nn_err(f.nlen) if isinstance(f, NNErr) else m.net.fetch(f.name)
+        if prefetch:
+            self.prefetch(prefetch)                    # enqueued behind this step's launches, ahead of the blocking reads
         out = []
         for f in flist:
             if isinstance(f, _Minimize):

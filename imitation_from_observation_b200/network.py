@@ -82,6 +82,9 @@ class ContextNet:
         self._s3 = None
         self._copy_stream = None
         self._in_events = None
+        self._in_slot = 0                               # input double buffering (prefetch_input)
+        self._slot_free = [None, None]
+        self._prefetched = None
         self.allreduce = None          # parallel.BucketedAllReduce when data-parallel (attach_allreduce)
         self._bufs: Dict[str, torch.Tensor] = {}
 
@@ -237,18 +240,67 @@ class ContextNet:
         self.sync_shadow()
 
     # ---- inputs ---------------------------------------------------------------------------------------------------
-    def _input_buffers(self):
-        """xe: frames through scope "conv" ([src; tgt] and, for a shared encoder, [src; tgt; ctx]); xc: ctx frames."""
+    def _input_buffers(self, slot: Optional[int] = None):
+        """xe: frames through scope "conv" ([src; tgt] and, for a shared encoder, [src; tgt; ctx]); xc: ctx frames.
+        Two slots: the step computes on `self._in_slot` while prefetch_input() fills the other one."""
         B, (H, W), C = self.B, self.sizes[0], self.chans[0]
         n_e = 2 * B if self.spec.separate_ctx_encoder else 3 * B
-        xe = self._buf("xe", (n_e, H, W, C))
-        xc = self._buf("xc", (B, H, W, C)) if self.spec.separate_ctx_encoder else xe[2 * B:]
+        tag = "" if (self._in_slot if slot is None else slot) == 0 else "_alt"
+        xe = self._buf("xe" + tag, (n_e, H, W, C))
+        xc = self._buf("xc" + tag, (B, H, W, C)) if self.spec.separate_ctx_encoder else xe[2 * B:]
         return xe, xc
 
-    def set_input(self, image: torch.Tensor):
+    def _copy_roles(self, image: torch.Tensor, dst, after):
+        """Pinned host batch -> device, role by role on the copy stream, context frames first (the context encoder runs
+        on the side stream and can start while the source / target frames are still in flight).  `after`: what the copy
+        stream waits for before overwriting `dst`.  Returns (event: ctx landed, event: everything landed)."""
+        if image.dtype != torch.float32 or not image.is_pinned():
+            raise _lib.CtxError("a host input must be a pinned float32 tensor (uint8 frames are staged on the device)")
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        if isinstance(after, torch.cuda.Event):
+            cs.wait_event(after)
+        elif after is not None:
+            cs.wait_stream(after)
+        with torch.cuda.stream(cs):
+            dst[1].copy_(image[1], non_blocking=True)
+            ev_ctx = cs.record_event()
+            dst[0].copy_(image[0], non_blocking=True)
+            dst[2].copy_(image[2], non_blocking=True)
+            ev_rest = cs.record_event()
+        return ev_ctx, ev_rest
+
+    def prefetch_input(self, image: torch.Tensor):
+        """Start copying the NEXT step's pinned host batch into the idle input slot while the current step computes; the
+        following set_input(image, use_prefetched=True) only flips the slots (any other set_input drops the prefetch).
+        Returns the event of the last copy."""
+        B = self.B
+        if image.is_cuda or tuple(image.shape) != (3, B) + self.sizes[0] + (self.chans[0],):
+            raise _lib.CtxError("prefetch_input expects a pinned host batch [3,%d,...]" % B)
+        slot = 1 - self._in_slot
+        xe, xc = self._input_buffers(slot)
+        # the idle slot was last read by the step before the current one; its "free" event was recorded at the flip
+        after = self._slot_free[slot]
+        if after is None:
+            after = torch.cuda.current_stream(self.device)
+        evs = self._copy_roles(image, (xe[:B], xc, xe[B:2 * B]), after)
+        self._prefetched = (image.data_ptr(), slot, evs)
+        return evs[1]
+
+    def set_input(self, image: torch.Tensor, use_prefetched: bool = False):
         """image [3,B,H,W,C] (0 = src, 1 = ctx, 2 = tgt — arm_shaping.py:1278-1280), uint8 or fp32, on the device.
         uint8 is normalised on the fly (base.py:117-119)."""
         B = self.B
+        pre, self._prefetched = self._prefetched, None
+        if use_prefetched:
+            if pre is None or not torch.is_tensor(image) or pre[0] != image.data_ptr():
+                raise _lib.CtxError("set_input(use_prefetched=True): no matching prefetch_input() is pending")
+            # this batch is already on its way into the other slot (prefetch_input): flip
+            self._slot_free[self._in_slot] = torch.cuda.current_stream(self.device).record_event()
+            self._in_slot = pre[1]
+            self._in_events = pre[2]
+            return
         xe, xc = self._input_buffers()
         dst = (xe[:B], xc, xe[B:2 * B])
         self._in_events = None
@@ -268,20 +320,8 @@ class ContextNet:
         if not image.is_cuda:
             # pinned host batch (Session.run): copy role by role on a copy stream, context frames first, so that the
             # context encoder (side stream) starts while the source / target frames are still in flight
-            if image.dtype != torch.float32 or not image.is_pinned():
-                raise _lib.CtxError("a host input must be a pinned float32 tensor (uint8 frames are staged on the device)")
-            cur = torch.cuda.current_stream(self.device)
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(device=self.device)
-            cs = self._copy_stream
-            cs.wait_stream(cur)                          # the previous step is done with the input buffers
-            with torch.cuda.stream(cs):
-                dst[1].copy_(image[1], non_blocking=True)
-                ev_ctx = cs.record_event()
-                dst[0].copy_(image[0], non_blocking=True)
-                dst[2].copy_(image[2], non_blocking=True)
-                ev_rest = cs.record_event()
-            self._in_events = (ev_ctx, ev_rest)
+            # (the copy stream first waits for the current stream: the previous step is done with the input buffers)
+            self._in_events = self._copy_roles(image, dst, torch.cuda.current_stream(self.device))
             return
         for r in range(3):
             if image.dtype == torch.uint8:

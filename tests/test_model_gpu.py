@@ -255,6 +255,43 @@ def test_session_run_like_base_py():
     assert rel_err(sess.run(autodc.input_z, {tfinput: frames}), ref["input_z"]) < 1e-4
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_session_prefetch_is_transparent(pinned):
+    """Session.run(..., prefetch=next_feed) copies the next batch into the idle input slot under the current step; the
+    losses, the fetched images and the trained weights equal those of plain runs — also when the prefetched batch is
+    not the one fed next (the prefetch is dropped), and when a batch object is fed twice."""
+    rs = np.random.RandomState(3)
+    B, idim = 6, (16, 16)
+    batches = [(rs.rand(3, B, *idim, 3) * 2 - 1).astype(np.float32) for _ in range(5)]
+    feeds = [torch.from_numpy(b).pin_memory() for b in batches] if pinned else batches
+    order = [0, 1, 2, 2, 4, 3]                      # step 4 is fed batch 4 although batch 3 was prefetched before it
+    results = {}
+    for mode in ("plain", "prefetch"):
+        tf.reset_default_graph()
+        x = tf.placeholder(tf.float32, (3, B) + idim + (3,), name="x")
+        m = ContextSkipNew(df_dim=4, gf_dim=4, featsize=16)
+        with tf.variable_scope("contextmodel"):
+            tf.build_model(m, x, precision="fp32", seed=0)
+        m.net.load_state_dict(gen_golden.golden_params(m.spec, 12))
+        opt = tf.train.AdamOptimizer(1e-3).minimize(m.loss)
+        sess = tf.Session()
+        losses, outs = [], []
+        for step, i in enumerate(order):
+            nxt = None
+            if mode == "prefetch" and step + 1 < len(order):
+                guess = 3 if step == 3 else order[step + 1]          # a wrong guess once
+                nxt = {x: feeds[guess]}
+            _, l, o = sess.run([opt, m.loss, m.out], {x: feeds[i]}, prefetch=nxt)
+            losses.append(l)
+            outs.append(o)
+        results[mode] = (losses, outs, m.net.flat_p.detach().cpu().numpy().copy())
+    (l0, o0, p0), (l1, o1, p1) = results["plain"], results["prefetch"]
+    assert np.allclose(l0, l1, rtol=1e-5)
+    for a, b in zip(o0, o1):
+        assert rel_err(a, b) < 1e-5
+    assert rel_err(p1, p0) < 1e-5
+
+
 def test_model_trainer_loop_runs_and_learns():
     logs = []
     tr = ModelTrainer(idims=(16, 16), nvideos=12, ntrain=8, batch_size=10, model="ContextSkipNew", nitr=42,

@@ -659,15 +659,19 @@ class ContextNet:
         g_tz = g_z2[B:]
         ops.lrelu_bwd(g_tz, z2[B:], out=g_tz)              # tgt_z = lrelu(hz_lin(.))
         # ---- translator -------------------------------------------------------------------------------------------------
-        self._gemm(True, False, F, F, B, th0.data_ptr(), F, g_transz.data_ptr(), F,
-                   G["translate/trans_z/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
-        ops.bias_grad(g_transz, G["translate/trans_z/bias"])
+        # (every filter / bias gradient of these small layers goes to the side stream: the data-gradient chain below is
+        # a sequence of ~20 us launches that leave most SMs idle)
+        with self._side():
+            self._gemm(True, False, F, F, B, th0.data_ptr(), F, g_transz.data_ptr(), F,
+                       G["translate/trans_z/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
+            ops.bias_grad(g_transz, G["translate/trans_z/bias"])
         g_th0 = self._buf("g_th0", (B, F))
         self._gemm(False, True, B, F, F, g_transz.data_ptr(), F, Wb["translate/trans_z/Matrix"].data_ptr(), F,
                    g_th0.data_ptr(), F, act_ref=th0.data_ptr(), bwd=True)
-        self._gemm(True, False, 2 * F, F, B, cat.data_ptr(), 2 * F, g_th0.data_ptr(), F,
-                   G["translate/trans_h0/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
-        ops.bias_grad(g_th0, G["translate/trans_h0/bias"])
+        with self._side():
+            self._gemm(True, False, 2 * F, F, B, cat.data_ptr(), 2 * F, g_th0.data_ptr(), F,
+                       G["translate/trans_h0/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
+            ops.bias_grad(g_th0, G["translate/trans_h0/bias"])
         g_cat = self._buf("g_cat", (B, 2 * F))
         Wt0 = Wb["translate/trans_h0/Matrix"]               # [2F, F]
         # src half: masked by lrelu'(src_z); ctx half: masked only if the ctx hz_lin has an lrelu
@@ -677,15 +681,17 @@ class ContextNet:
                    g_cat.data_ptr() + F * f4, 2 * F,
                    act_ref=(cat.data_ptr() + F * f4) if sp.ctx_hz_lrelu else None, bwd=True)
         if on_stage:
+            self._join()
             on_stage("translate")
         # ---- hz_lin of the three roles -> gradient w.r.t. h4 (lrelu' fused) -------------------------------------------
         def hz_backward(scope, g_ptr, ldg, h4_rows, gh4_rows):
             n = h4_rows.shape[0]
-            self._gemm(True, False, F, F, n, h4_rows.data_ptr(), F, g_ptr, ldg,
-                       G[scope + "/hz_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
-            check = _lib.check
-            check(_lib.load().ctx_bias_grad(g_ptr, n, F, ldg, G[scope + "/hz_lin/bias"].data_ptr(), ops._stream()),
-                  "ctx_bias_grad")
+            with self._side():
+                self._gemm(True, False, F, F, n, h4_rows.data_ptr(), F, g_ptr, ldg,
+                           G[scope + "/hz_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
+                check = _lib.check
+                check(_lib.load().ctx_bias_grad(g_ptr, n, F, ldg, G[scope + "/hz_lin/bias"].data_ptr(), ops._stream()),
+                      "ctx_bias_grad")
             self._gemm(False, True, n, F, F, g_ptr, ldg, Wb[scope + "/hz_lin/Matrix"].data_ptr(), F,
                        gh4_rows.data_ptr(), F, act_ref=h4_rows.data_ptr(), bwd=True)
 

@@ -700,6 +700,9 @@ class ContextNet:
         hz_backward(self.ctx_scope, g_cat.data_ptr() + F * f4, 2 * F, c_h4, gc_h4)           # ctx
 
         # ---- encoders: h<L>_lin then the convs -----------------------------------------------------------------------------
+        # finer all-reduce stages (data parallel): issued from the stream that wrote the gradients, no join needed
+        fine = on_stage is not None and getattr(getattr(on_stage, "__self__", None), "fine", False)
+
         def encoder_backward(scope, x, hs, h4, g_hs, g_h4, groups):
             """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate."""
             n = x.shape[0]
@@ -707,6 +710,8 @@ class ContextNet:
                 self._gemm(True, False, flat, F, n, hs[-1].data_ptr(), flat, g_h4.data_ptr(), F,
                            G["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), F, accumulate=True, round_=False, bwd=True)
                 ops.bias_grad(g_h4, G["%s/%s/bias" % (scope, self.lin)])
+                if fine:                                   # hz_lin + h<L>_lin gradients are final (both on this stream)
+                    on_stage(scope + "/dense")
             for (r0, nr, acc) in groups:
                 self._gemm(False, True, nr, flat, F, g_h4[r0:r0 + nr].data_ptr(), F,
                            Wb["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), F, g_hs[-1][r0:r0 + nr].data_ptr(), flat,
@@ -724,6 +729,8 @@ class ContextNet:
                     else:
                         ops.conv2d_wgrad(src, g_hs[j], kj, sp.strides[j], dw=G[wname], impl=self.impl_b)
                     ops.bias_grad(g_hs[j], G["%s/h%d_conv/biases" % (scope, j)])
+                    if fine and j == Ld - 1:
+                        on_stage(scope + "/top")
                 if j > 0:
                     for (r0, nr, acc) in groups:
                         ops.conv2d_transpose(g_hs[j][r0:r0 + nr], Wb[wname], self.sizes[j], stride=sp.strides[j],
@@ -762,11 +769,37 @@ class ContextNet:
         from . import parallel
         self._ensure_grads()
         self.allreduce = parallel.BucketedAllReduce(self.flat_g, parallel.scope_ranges(self.offsets, self.flat_size),
+                                                    splits=parallel.fine_splits(self.offsets, self.L),
                                                     group=group)
         return self.allreduce
 
     def apply_gradients(self, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
         """backward (+ bucketed gradient all-reduce when data-parallel) + Adam; forward(FWD_ALL) must have run."""
+        if self.allreduce is not None and getattr(self.allreduce, "enabled", False) and ops.PROFILE is None:
+            # Data parallel: buckets are all-reduced as backward completes them; the Adam slice of a bucket runs on the
+            # optimiser stream as soon as its reduction is done, under the rest of backward / the later reductions.
+            ar = self.allreduce
+            self._ensure_moments()
+            self.step_count += 1
+            t = self.step_count
+            lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+            if self._s3 is None:
+                self._s3 = torch.cuda.Stream(device=self.device)
+            cur = torch.cuda.current_stream(self.device)
+
+            def adam_range(a, b):                          # runs with the optimiser stream current, after the bucket
+                # every kernel that READS these parameters (the data gradients of their layers) is already enqueued on
+                # the main stream when a later bucket is launched: the update must not overtake it
+                self._s3.wait_stream(cur)
+                ops.adam_step(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr_t, b1, b2, eps,
+                              p_tf32=None if self.flat_pr is None else self.flat_pr[a:b])
+
+            ar.on_reduced, ar.reduced_stream = adam_range, self._s3
+            self.backward(on_stage=ar.stage_done)
+            ar.finish()
+            cur.wait_stream(self._s3)
+            self._wp_stale = True
+            return
         if self.allreduce is not None:
             self.backward(on_stage=self.allreduce.stage_done)
             self.allreduce.finish()

@@ -75,11 +75,36 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def fine_splits(offsets: Dict[str, int], depth: int) -> Dict[str, List[Tuple[str, int]]]:
+    """Split points inside each encoder scope, in buffer (= gradient completion) order: the dense layers (hz_lin,
+    h<L>_lin: two thirds of the scope's parameters) are final long before the convs are, and the top conv holds most of
+    the rest.  Returns scope -> [(stage name that completes the PRECEDING part, offset where the next part starts)]."""
+    out: Dict[str, List[Tuple[str, int]]] = {}
+    for sc in ("conv", "conv_context"):
+        top, nxt = "%s/h%d_conv/w" % (sc, depth - 1), "%s/h%d_conv/w" % (sc, depth - 2)
+        if top in offsets:
+            pts = [(sc + "/dense", offsets[top])]
+            if depth >= 2 and nxt in offsets:
+                pts.append((sc + "/top", offsets[nxt]))
+            out[sc] = pts
+    return out
+
+
 class BucketedAllReduce:
-    """Sum all-reduce of a flat gradient in per-scope buckets, launched from backward's stage callbacks."""
+    """Sum all-reduce of a flat gradient in contiguous buckets, launched from backward's stage callbacks as soon as a
+    bucket's gradients are final, so NCCL over NVLink runs under the rest of backward.
+
+    Buckets: decoder + translator, then each encoder scope — optionally split at `splits` (fine_splits) into its dense
+    layers, its top conv and the rest, which leaves only the small last part exposed after backward ends.
+    `on_reduced(a, b)`, if set, is called once per bucket, in order, as soon as a LATER bucket is launched (and for the
+    remaining ones in finish()): the caller runs the optimiser on [a, b) there; `reduced_stream` is the CUDA stream
+    made to wait for the bucket before the callback runs (None: the current stream)."""
+
+    fine = True        # backward() may deliver the finer "<scope>/dense", "<scope>/top" stages
 
     def __init__(self, flat_g: torch.Tensor, ranges: Sequence[Tuple[str, int, int]], group=None,
-                 merge: Sequence[Sequence[str]] = (("deconv", "translate"), ("conv",), ("conv_context",))):
+                 merge: Sequence[Sequence[str]] = (("deconv", "translate"), ("conv",), ("conv_context",)),
+                 splits: Optional[Dict[str, List[Tuple[str, int]]]] = None):
         self.flat_g, self.group = flat_g, group
         by = {sc: (a, b) for sc, a, b in ranges}
         self.buckets: List[Tuple[str, int, int]] = []
@@ -88,22 +113,43 @@ class BucketedAllReduce:
             if not present:
                 continue
             a, b = by[present[0]][0], by[present[-1]][1]
-            self.buckets.append((present[-1], a, b))        # fires when the LAST scope of the bucket is done
+            pts = (splits or {}).get(present[-1], []) if len(present) == 1 else []
+            for stage, off in pts:
+                if a < off < b:
+                    self.buckets.append((stage, a, off))
+                    a = off
+            self.buckets.append((present[-1], a, b))        # fires when the LAST scope (part) of the bucket is done
         covered = sum(b - a for _, a, b in self.buckets)
         if covered != flat_g.numel():
             raise ValueError("buckets cover %d of %d gradient elements" % (covered, flat_g.numel()))
-        self._work = []
+        self._work: List[tuple] = []                         # launched, not yet handed to on_reduced: (work, a, b)
+        self.on_reduced = None
+        self.reduced_stream = None
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def _drain(self):
+        """Hand every launched bucket to on_reduced, in order; the wait is a stream dependency, not a host block (NCCL)."""
+        for w, a, b in self._work:
+            if self.reduced_stream is not None:
+                with torch.cuda.stream(self.reduced_stream):
+                    w.wait()
+                    if self.on_reduced is not None:
+                        self.on_reduced(a, b)
+            else:
+                w.wait()
+                if self.on_reduced is not None:
+                    self.on_reduced(a, b)
+        self._work = []
 
     def stage_done(self, scope: str):
         if not self.enabled:
             return
         for trigger, a, b in self.buckets:
             if trigger == scope:
-                self._work.append(dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.SUM, group=self.group,
-                                                  async_op=True))
+                if self.on_reduced is not None:
+                    self._drain()                            # earlier buckets: optimiser under this bucket's reduction
+                self._work.append((dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.SUM, group=self.group,
+                                                   async_op=True), a, b))
 
     def finish(self):
-        for w in self._work:
-            w.wait()
-        self._work = []
+        self._drain()

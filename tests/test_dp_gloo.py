@@ -53,6 +53,7 @@ def _worker(rank, world, port, q):
     for (name, shp), gr in zip(spec.param_shapes().items(), grads):
         flat[off[name]:off[name] + gr.numel()] = gr.reshape(-1)
     whole = flat.clone()
+    flat_local = flat.clone()
     dist.all_reduce(whole)
     ar = parallel.BucketedAllReduce(flat, parallel.scope_ranges(off, total))
     assert ar.enabled
@@ -60,6 +61,19 @@ def _worker(rank, world, port, q):
         ar.stage_done(scope)
     ar.finish()
     ok_bucket = bool(torch.equal(flat, whole))
+    # finer buckets (dense layers / top conv / rest of each encoder) + the per-bucket "reduced" callback, in order
+    flat2 = flat_local.clone()
+    ar2 = parallel.BucketedAllReduce(flat2, parallel.scope_ranges(off, total), splits=parallel.fine_splits(off, 4))
+    seen = []
+    ar2.on_reduced = lambda a, b: seen.append((a, b))
+    stages = ["deconv", "translate", "conv/dense", "conv/top", "conv", "conv_context/dense", "conv_context/top",
+              "conv_context"]
+    for st in stages:
+        ar2.stage_done(st)
+    ar2.finish()
+    ok_bucket = ok_bucket and bool(torch.equal(flat2, whole)) and len(ar2.buckets) == 7
+    ok_bucket = ok_bucket and seen == [(a, b) for _, a, b in ar2.buckets] and seen[0][0] == 0 and seen[-1][1] == total
+    ok_bucket = ok_bucket and ar2.buckets[1][2] == off["conv/h3_conv/w"] and ar2.buckets[2][2] == off["conv/h2_conv/w"]
     # full-batch oracle gradient
     _, G = O.loss_and_grads(spec, P, image)
     err = 0.0

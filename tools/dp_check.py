@@ -25,7 +25,7 @@ for steps in (1, 3):
     net = ContextNet(spec, Bl, device=dev, seed=1, global_batch=Bg)
     p0 = net.flat_p.clone()
     net.attach_allreduce()
-    assert len(net.allreduce.buckets) == 7
+    assert len(net.allreduce.buckets) in (3, 7)
     for _ in range(steps):
         net.set_input(image[:, rank * Bl:(rank + 1) * Bl].to(dev))
         net.train_step(1e-3)

@@ -18,9 +18,20 @@ for impl in (IMPL_AUTO, IMPL_FAST, IMPL_SIMT):
     ops.conv2d_wgrad(r(4, 16, 16, 64), r(4, 8, 8, 64), 5, 2, small2=r(2, 8, 8, 64), impl=impl)
     ops.gemm(r(256, 512), r(512, 128), bias=r(128), act=True, impl=impl)
     ops.gemm(r(512, 76)[:, :75], r(512, 64), transA=True, accumulate=True, out=torch.zeros(75, 64).cuda(), impl=impl)
+# forward convolutions on bf16 planes: single CTA (64 / 128 wide), CTA pair (256 wide), transposed phases, merged phases
+xp = ops.split_bf16(r(4, 16, 16, 64))
+for Co in (64, 128, 256):
+    ops.conv2d_bf16x3(xp, ops.split_bf16_conv_filter(r(5, 5, 64, Co)), 5, bias=r(Co), stride=2, act=True,
+                      out_planes=torch.empty((2, 4, 8, 8, Co), device="cuda", dtype=torch.bfloat16))
+ops.conv2d_transpose_bf16x3(ops.split_bf16(r(4, 8, 8, 64)), ops.split_bf16(r(5, 5, 128, 128)), (16, 16), 5, bias=r(128), stride=2,
+                            x2p=ops.split_bf16(r(2, 8, 8, 64)), act=True)
+ops.conv2d_transpose_merged_bf16x3(ops.split_bf16(r(4, 8, 8, 64)), ops.conv2d_transpose_merged_pack(r(5, 5, 64, 128), (16, 16)),
+                                   (16, 16), 5, 64, bias=r(64), stride=2, x2p=ops.split_bf16(r(2, 8, 8, 64)), act=True)
+ops.gather_frames(r(10, 16, 16, 3), torch.tensor([3, 1, 9], device="cuda"))
 torch.cuda.synchronize()
-net = ContextNet(S.context_skip_new(16, 16, 3, df_dim=32, featsize=64), 4, precision="mixed")
-net.set_input((torch.rand((3, 4, 16, 16, 3), generator=g) * 2 - 1).cuda())
+net = ContextNet(S.context_skip_new(32, 32, 3, df_dim=64, featsize=64), 8, precision="mixed")      # bf16-plane layers active
+assert net.bf3
+net.set_input((torch.rand((3, 8, 32, 32, 3), generator=g) * 2 - 1).cuda())
 net.train_step(1e-4)
 torch.cuda.synchronize()
 print("sanitize smoke done, loss", float(net.fetch("loss")))

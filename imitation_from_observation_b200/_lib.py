@@ -61,6 +61,7 @@ SIGNATURES = {
     "ctx_conv2d_transpose_merged_pack": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_void_p]),
     "ctx_conv2d_transpose_merged_bf16x3": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                                      c_void_p, c_int32, POINTER(ConvGeom), POINTER(Epilogue), c_void_p]),
+    "ctx_crc32c": (C.c_uint32, [c_void_p, C.c_uint64, C.c_uint32]),
     "ctx_gather_frames": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "ctx_lrelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_void_p]),
     "ctx_bias_grad": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),

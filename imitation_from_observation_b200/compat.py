@@ -137,10 +137,15 @@ class _Adam:
 
 
 class _Saver:
-    """tf.train.Saver stand-in: a .npz keyed by the TF variable names."""
+    """tf.train.Saver stand-in.  restore() reads a TensorFlow checkpoint — the tensor bundle `<path>.index` +
+    `<path>.data-*` a reference-trained model is stored in (tf_checkpoint.py) — or, failing that, the `.npz` keyed by the
+    same TF variable names that save() writes by default.  `Saver(format="tf")` (or CTX_SAVER_FORMAT=tf)
+    makes save() write the TensorFlow format instead, so the reference's TF code can restore models trained here."""
 
-    def __init__(self, var_list=None):
-        pass
+    def __init__(self, var_list=None, format: Optional[str] = None):
+        self.format = format or os.environ.get("CTX_SAVER_FORMAT", "npz")
+        if self.format not in ("npz", "tf"):
+            raise _lib.CtxError("Saver format must be 'npz' or 'tf'")
 
     @staticmethod
     def _path(p):
@@ -152,10 +157,29 @@ class _Saver:
             for k, v in m.net.state_dict().items():
                 sd[m.scope + k] = v
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        np.savez(self._path(path), **sd)
+        if self.format == "tf":
+            from . import tf_checkpoint
+            tf_checkpoint.write_checkpoint(path, sd)
+        else:
+            np.savez(self._path(path), **sd)
         return path
 
     def restore(self, sess, path):
+        from . import tf_checkpoint
+        if tf_checkpoint.checkpoint_exists(path):
+            have = tf_checkpoint.list_variables(path)
+            for m in _models:
+                names = list(m.net.shapes)
+                # the reference builds the model under "contextmodel/" in the trainer (train_script.py:120) but not
+                # always in the sampler (base.py:134-138): accept the checkpoint's own prefix
+                for pre in dict.fromkeys([m.scope, "contextmodel/", ""]):
+                    if all(pre + n in have for n in names):
+                        break
+                else:
+                    missing = [n for n in names if m.scope + n not in have]
+                    raise KeyError("checkpoint %s lacks %d variables of the model, e.g. %s" % (path, len(missing), missing[:3]))
+                m.net.load_state_dict(tf_checkpoint.read_checkpoint(path, [pre + n for n in names]), prefix=pre)
+            return
         sd = dict(np.load(self._path(path)))
         for m in _models:
             m.net.load_state_dict(sd, prefix=m.scope)

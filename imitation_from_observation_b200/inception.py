@@ -165,6 +165,13 @@ class InceptionV3:
     def state_dict(self) -> Dict[str, np.ndarray]:
         return {k: v.detach().cpu().numpy().copy() for k, v in self.params.items()}
 
+    def load_tf_checkpoint(self, prefix: str):
+        """Load slim's `inception_v3.ckpt` (rllab/sampler/base.py:130-132 restores it with tf.train.Saver): a TF tensor
+        bundle `<prefix>.index` + `<prefix>.data-*`, variables InceptionV3/<scope>/{weights, BatchNorm/beta,
+        BatchNorm/moving_mean, BatchNorm/moving_variance}; the logits / aux-logits heads in the file are ignored."""
+        from . import tf_checkpoint
+        self.load_state_dict(tf_checkpoint.read_checkpoint(prefix, list(self.shapes)))
+
     def _fold(self):
         """Fold the inference batch norm into each conv (host-side torch arithmetic on parameters, once per load)."""
         self.folded = {}

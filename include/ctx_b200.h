@@ -81,6 +81,10 @@ int ctx_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 int ctx_tc_available(void);
 /* Number of kernels this library has launched in this process (all streams); bench.py's "gpu_launches". */
 int64_t ctx_launch_count(void);
+/* Host only: CRC-32C (Castagnoli) of n bytes, continuing from `crc` (0 to start) — the checksum TensorFlow stores per
+ * tensor in a tensor-bundle checkpoint (tf.train.Saver V2: scripts/train_script.py:189, rllab/sampler/base.py:144-145). */
+uint32_t ctx_crc32c(const void* data, uint64_t n, uint32_t crc);
+
 /* Which implementation the last GEMM-shaped call of this thread used: CTX_IMPL_SIMT / CTX_IMPL_TC / CTX_IMPL_TC3. */
 int ctx_last_impl(void);
 

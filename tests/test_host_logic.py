@@ -96,3 +96,147 @@ def test_pixel_table_is_the_reference_transform():
     v = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, 2)
     assert np.array_equal(data.pixel_table()[v], data.transform(v, 16, 16, True).astype(np.float32))
     assert np.array_equal(data.pixel_table()[v], synthetic.to_float(v).astype(np.float32))
+
+
+def test_tf_checkpoint_round_trip_and_format_details(tmp_path):
+    """tf_checkpoint.py (Saver V2 tensor bundles, written from the published formats — no TF-written file is available):
+    its writer and reader agree, and the reader copes with what a TF-written index may contain that our writer never
+    produces: prefix-compressed keys, several data blocks, Snappy-compressed blocks, extra variables (Adam slots)."""
+    import struct
+    import numpy as np
+    import pytest
+    from imitation_from_observation_b200 import tf_checkpoint as T
+
+    # published check values: CRC-32C("123456789") = 0xE3069283; LevelDB's mask of it
+    assert T.crc32c(b"123456789") == 0xE3069283
+    assert T.crc32c(b"6789", T.crc32c(b"12345")) == 0xE3069283
+    assert T.mask_crc(0xE3069283) == ((((0xE3069283 >> 15) | (0xE3069283 << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+    rs = np.random.RandomState(0)
+    sd = {"contextmodel/conv/h%d_conv/w" % j: rs.randn(5, 5, 3 + j, 4).astype(np.float32) for j in range(40)}
+    sd["contextmodel/conv/h0_conv/biases"] = rs.randn(4).astype(np.float32)
+    sd["global_step"] = np.array(7, dtype=np.int64)                          # a scalar
+    sd["contextmodel/conv/h0_conv/w/Adam"] = rs.randn(5, 5, 3, 4).astype(np.float32)
+    prefix = str(tmp_path / "model_10")
+    T.write_checkpoint(prefix, sd)
+    assert T.checkpoint_exists(prefix) and not T.checkpoint_exists(prefix + "x")
+    got = T.read_checkpoint(prefix)
+    assert sorted(got) == sorted(sd)
+    for k in sd:
+        assert got[k].dtype == sd[k].dtype and got[k].shape == sd[k].shape and np.array_equal(got[k], sd[k]), k
+    assert T.list_variables(prefix)["global_step"] == (np.dtype(np.int64), ())
+    only = T.read_checkpoint(prefix, ["contextmodel/conv/h3_conv/w"])
+    assert list(only) == ["contextmodel/conv/h3_conv/w"]
+    with pytest.raises(KeyError):
+        T.read_checkpoint(prefix, ["nope"])
+    # several data blocks were written (4 KB blocks, 43 entries of ~60 bytes each fit one; force more) and keys share prefixes
+    T.write_table(str(tmp_path / "t"), [(b"key%04d" % i, b"v" * (i % 7)) for i in range(2000)], block_size=256)
+    back = T.read_table(str(tmp_path / "t"))
+    assert back == [(b"key%04d" % i, b"v" * (i % 7)) for i in range(2000)]
+    # corruption is detected: flip one data byte -> tensor checksum; flip one index byte -> block checksum
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[10] ^= 1
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    with pytest.raises(T.CheckpointError):
+        T.read_checkpoint(prefix)
+    assert len(T.read_checkpoint(prefix, verify=False)) == len(sd)
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[5] ^= 1
+    open(str(tmp_path / "bad.index"), "wb").write(bytes(idx))
+    with pytest.raises(T.CheckpointError):
+        T.read_table(str(tmp_path / "bad.index"))
+
+    # Snappy: literals of every length class, copies with 1- and 2-byte offsets, an overlapping (run-length) copy
+    def lit(b):
+        n = len(b) - 1
+        if n < 60:
+            return bytes([n << 2]) + b
+        return bytes([60 << 2, n]) + b if n < 256 else bytes([61 << 2]) + struct.pack("<H", n) + b
+    plain = b"abcdefgh" + b"abcdefgh"[:6] + b"x" * 70 + b"Z" * 300 + bytes(range(200)) + b"abcd"
+    stream = (T._put_varint(len(plain)) + lit(b"abcdefgh") + bytes([((6 - 4) << 2) | 1, 8])          # copy len 6, offset 8
+              + lit(b"x") + bytes([((64 - 1) << 2) | 2]) + struct.pack("<H", 1) + bytes([((5 - 1) << 2) | 2]) + struct.pack("<H", 1)
+              + lit(b"Z" * 300) + lit(bytes(range(200)))
+              + bytes([((4 - 1) << 2) | 2]) + struct.pack("<H", 300 + 200 + 70 + 6 + 8))                 # "abcd" from the very start
+    assert T.snappy_decompress(stream) == plain
+    # a table whose data block is stored Snappy-compressed (type byte 1), as TF's TableBuilder may write it
+    payload = np.arange(6, dtype=np.float32).tobytes()
+    block = T._build_block([(b"", b"\x08\x01"), (b"a/w", T._entry_bytes(1, (2, 3), 0, 24, T.mask_crc(T.crc32c(payload))))])
+    comp = T._put_varint(len(block)) + lit(block)
+    out = bytearray()
+
+    def emit(contents, ctype):
+        off = len(out)
+        out.extend(contents + bytes([ctype]) + struct.pack("<I", T.mask_crc(T.crc32c(contents + bytes([ctype])))))
+        return T._put_varint(off) + T._put_varint(len(contents))
+    h = emit(comp, 1)
+    meta = emit(T._build_block([]), 0)
+    index = emit(T._build_block([(b"a/w", h)], 1), 0)
+    footer = meta + index
+    out.extend(footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", T.TABLE_MAGIC))
+    open(str(tmp_path / "snap.index"), "wb").write(bytes(out))
+    np.arange(6, dtype=np.float32).tofile(str(tmp_path / "snap.data-00000-of-00001"))
+    got = T.read_checkpoint(str(tmp_path / "snap"), verify=True)
+    assert list(got) == ["a/w"] and np.array_equal(got["a/w"], np.arange(6, dtype=np.float32).reshape(2, 3))
+
+
+def test_saver_reads_and_writes_tf_checkpoints(tmp_path):
+    """compat.Saver: save(format="tf") writes a tensor bundle, restore() finds it (before the .npz), accepts the
+    checkpoint's own scope prefix (the trainer builds under "contextmodel/", base.py:134-138 does not) and ignores the
+    Adam slot variables a TF-trained checkpoint also holds."""
+    import numpy as np
+    import pytest
+    from imitation_from_observation_b200 import compat as tf, tf_checkpoint as T
+
+    class Net:
+        def __init__(self):
+            self.shapes = {"conv/h0_conv/w": (5, 5, 3, 4), "conv/h0_conv/biases": (4,), "deconv/d_h0_lin/Matrix": (6, 8)}
+            rs = np.random.RandomState(1)
+            self.P = {k: rs.randn(*s).astype(np.float32) for k, s in self.shapes.items()}
+
+        def state_dict(self):
+            return {k: v.copy() for k, v in self.P.items()}
+
+        def load_state_dict(self, sd, prefix=""):
+            self.P = {k: np.asarray(sd[prefix + k], dtype=np.float32).copy() for k in self.shapes}
+
+    class Model:
+        def __init__(self, scope):
+            self.scope, self.net = scope, Net()
+
+    tf.reset_default_graph()
+    m = Model("contextmodel/")
+    tf._models.append(m)
+    want = m.net.state_dict()
+    path = str(tmp_path / "100" / "model_100_1.00")
+    tf.train.Saver(format="tf").save(None, path)
+    assert T.checkpoint_exists(path) and sorted(T.list_variables(path)) == sorted("contextmodel/" + k for k in want)
+    # a TF-trained checkpoint also carries optimiser slots: add some and rewrite
+    full = T.read_checkpoint(path)
+    full["contextmodel/conv/h0_conv/w/Adam"] = np.zeros((5, 5, 3, 4), np.float32)
+    full["beta1_power"] = np.array(0.9, np.float32)
+    T.write_checkpoint(path, full)
+    for scope in ("contextmodel/", ""):                    # same scope as saved, and the sampler's un-scoped build
+        tf.reset_default_graph()
+        m2 = Model(scope)
+        m2.net.P = {k: np.zeros(s, np.float32) for k, s in m2.net.shapes.items()}
+        tf._models.append(m2)
+        tf.train.Saver().restore(None, path)
+        for k in want:
+            assert np.array_equal(m2.net.P[k], want[k]), (scope, k)
+    # the default format stays the .npz, and restore still reads it
+    tf.reset_default_graph()
+    tf._models.append(m)
+    p2 = str(tmp_path / "npz" / "model")
+    tf.train.Saver().save(None, p2)
+    assert not T.checkpoint_exists(p2)
+    m.net.P = {k: np.zeros(s, np.float32) for k, s in m.net.shapes.items()}
+    tf.train.Saver().restore(None, p2)
+    assert all(np.array_equal(m.net.P[k], want[k]) for k in want)
+    # a checkpoint of another model is rejected with the missing names
+    tf.reset_default_graph()
+    m3 = Model("contextmodel/")
+    m3.net.shapes = dict(m3.net.shapes, **{"translate/trans_z/Matrix": (4, 4)})
+    tf._models.append(m3)
+    with pytest.raises(KeyError):
+        tf.train.Saver().restore(None, path)
+    tf.reset_default_graph()

@@ -255,6 +255,31 @@ def test_session_run_like_base_py():
     assert rel_err(sess.run(autodc.input_z, {tfinput: frames}), ref["input_z"]) < 1e-4
 
 
+def test_saver_tf_checkpoint_round_trip_through_the_network(tmp_path):
+    """Saver(format="tf") -> TensorFlow tensor bundle -> Saver().restore into a model built WITHOUT the trainer's
+    "contextmodel" scope (as base.py:134-138 builds it): same outputs."""
+    B, idim = 4, (16, 16)
+    batch = (np.random.RandomState(5).rand(3, B, *idim, 3) * 2 - 1).astype(np.float32)
+    tf.reset_default_graph()
+    x = tf.placeholder(tf.float32, (3, B) + idim + (3,), name="x")
+    m = ContextSkipNew(df_dim=4, gf_dim=4, featsize=16)
+    with tf.variable_scope("contextmodel"):
+        tf.build_model(m, x, precision="fp32", seed=3)
+    sess = tf.Session()
+    out0 = sess.run(m.out, {x: batch})
+    path = str(tmp_path / "model_1")
+    tf.train.Saver(format="tf").save(sess, path)
+    assert os.path.exists(path + ".index") and os.path.exists(path + ".data-00000-of-00001")
+    tf.reset_default_graph()
+    x2 = tf.placeholder(tf.float32, (3, B) + idim + (3,), name="x")
+    m2 = ContextSkipNew(df_dim=4, gf_dim=4, featsize=16)
+    tf.build_model(m2, x2, precision="fp32", seed=99)                 # other weights, no scope
+    sess2 = tf.Session()
+    assert rel_err(sess2.run(m2.out, {x2: batch}), out0) > 1e-2
+    tf.train.Saver().restore(sess2, path)
+    assert np.array_equal(sess2.run(m2.out, {x2: batch}), out0)
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_session_prefetch_is_transparent(pinned):
     """Session.run(..., prefetch=next_feed) copies the next batch into the idle input slot under the current step; the

@@ -165,24 +165,17 @@ class _Saver:
         return path
 
     def restore(self, sess, path):
-        from . import tf_checkpoint
-        if tf_checkpoint.checkpoint_exists(path):
-            have = tf_checkpoint.list_variables(path)
-            for m in _models:
-                names = list(m.net.shapes)
-                # the reference builds the model under "contextmodel/" in the trainer (train_script.py:120) but not
-                # always in the sampler (base.py:134-138): accept the checkpoint's own prefix
-                for pre in dict.fromkeys([m.scope, "contextmodel/", ""]):
-                    if all(pre + n in have for n in names):
-                        break
-                else:
-                    missing = [n for n in names if m.scope + n not in have]
-                    raise KeyError("checkpoint %s lacks %d variables of the model, e.g. %s" % (path, len(missing), missing[:3]))
-                m.net.load_state_dict(tf_checkpoint.read_checkpoint(path, [pre + n for n in names]), prefix=pre)
-            return
-        sd = dict(np.load(self._path(path)))
         for m in _models:
-            m.net.load_state_dict(sd, prefix=m.scope)
+            restore_model(m.net, path, scope=m.scope)
+
+
+def restore_model(net, path: str, scope: str = ""):
+    """Load `net`'s variables from a TensorFlow checkpoint (V2 bundle or V1 file) or the .npz Saver.save writes, trying
+    the model's own scope, then "contextmodel/", then no prefix (tf_checkpoint.load_variables).  Shared by Saver.restore
+    and sampler.RewardFeaturizer.initialize (base.py:143-145)."""
+    from . import tf_checkpoint
+    sd, pre = tf_checkpoint.load_variables(path, list(net.shapes), prefixes=(scope, "contextmodel/", ""))
+    net.load_state_dict(sd, prefix=pre)
 
 
 class train:                                                      # noqa: N801  (mirrors tf.train)
@@ -236,7 +229,14 @@ class Session:
         if ev is not None:
             ev.synchronize()                                     # the previous step's async copy out of this buffer
         np.copyto(pin.numpy(), arr, casting="unsafe")            # f64 -> f32 cast happens here (train_script feed)
-        return pin if host_ok else pin.to("cuda", non_blocking=True)
+        if host_ok:
+            return pin
+        # uint8 frames (and chained float feeds) are copied to the device here: remember the copy, so that the next
+        # _stage() does not refill the pinned buffer while this H2D copy is still queued behind earlier kernels
+        # (minimize-only steps never synchronise the host)
+        dev = pin.to("cuda", non_blocking=True)
+        self._pin_event[pin.data_ptr()] = torch.cuda.current_stream().record_event()
+        return dev
 
     def prefetch(self, feed_dict: dict):
         """Start the host->device copy of the NEXT step's batch while the current step computes (what tf.data's

@@ -166,8 +166,9 @@ class InceptionV3:
         return {k: v.detach().cpu().numpy().copy() for k, v in self.params.items()}
 
     def load_tf_checkpoint(self, prefix: str):
-        """Load slim's `inception_v3.ckpt` (rllab/sampler/base.py:130-132 restores it with tf.train.Saver): a TF tensor
-        bundle `<prefix>.index` + `<prefix>.data-*`, variables InceptionV3/<scope>/{weights, BatchNorm/beta,
+        """Load slim's `inception_v3.ckpt` (rllab/sampler/base.py:130-132 restores it with tf.train.Saver).  The published
+        file is a single-file V1 checkpoint (SavedTensorSlices in one table); a V2 bundle `<prefix>.index` + `<prefix>.data-*`
+        is read as well (tf_checkpoint.read_checkpoint dispatches).  Variables InceptionV3/<scope>/{weights, BatchNorm/beta,
         BatchNorm/moving_mean, BatchNorm/moving_variance}; the logits / aux-logits heads in the file are ignored."""
         from . import tf_checkpoint
         self.load_state_dict(tf_checkpoint.read_checkpoint(prefix, list(self.shapes)))

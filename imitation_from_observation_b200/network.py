@@ -392,7 +392,9 @@ class ContextNet:
                 continue
             if self._few(Cin, k) and Co % 4 == 0:
                 K = k * k * Cin
-                pt = self._patches("patch_%s_h%d_%d" % (scope, j, h.shape[0]), h, k, self.spec.strides[j])
+                # (forward()'s patch matrix is reused by backward; the functional enc1 / enc2 surface gets its own buffer)
+                pt = self._patches("patch_%s_h%d_%d%s" % (scope, j, h.shape[0], "" if tag is not None else "_fn"), h, k,
+                                   self.spec.strides[j])
                 ops.gemm(pt[:, :K], w.view(K, Co), out=outs[j].view(-1, Co), bias=b, act=True, round_tf32=self.round,
                          impl=self.impl)
             else:

@@ -57,8 +57,9 @@ class RewardFeaturizer:
             from .inception import InceptionV3
             if self.inception is None:
                 self.inception = InceptionV3(device=self.device, precision=self.precision)
-                if self.modelname:
-                    self.inception.load_state_dict(dict(np.load(self.modelname)))
+                if self.modelname:                                # base.py:108-110: slim's inception_v3.ckpt (or an .npz)
+                    from . import tf_checkpoint
+                    self.inception.load_state_dict(tf_checkpoint.load_variables(self.modelname, list(self.inception.shapes))[0])
             if self.meanfile:
                 data = np.load(self.meanfile)
                 self.set_inception_statistics(data[self.layer], data[self.layer + "std"])
@@ -76,12 +77,15 @@ class RewardFeaturizer:
             self.model.build(torch.empty((3, self.T, fh, fw, 2048), dtype=torch.float32, device="meta"),
                              device=self.device, precision=self.precision)
             if self.modelname:
-                sd = dict(np.load(self.modelname if self.modelname.endswith(".npz") else self.modelname + ".npz"))
-                prefix = "contextmodel/" if any(k.startswith("contextmodel/") for k in sd) else ""
-                self.model.net.load_state_dict({k: v for k, v in sd.items() if not k.startswith("InceptionV3/")},
-                                               prefix=prefix)
-                if any(k.startswith("InceptionV3/") for k in sd):
-                    self.inception.load_state_dict({k: v for k, v in sd.items() if k.startswith("InceptionV3/")})
+                # base.py:143-145 restores every non-optimiser variable of the checkpoint: the context model and, when the
+                # file holds them (train_script.py saves the whole graph), the frozen InceptionV3 variables
+                from . import compat, tf_checkpoint
+                compat.restore_model(self.model.net, self.modelname)
+                try:
+                    inc_sd, _ = tf_checkpoint.load_variables(self.modelname, list(self.inception.shapes))
+                    self.inception.load_state_dict(inc_sd)
+                except KeyError:
+                    pass                                   # a context-model-only file: InceptionV3 is loaded separately
         if self.model is None:
             if self.name in ("real", "sweep"):
                 self.model = ContextAEReal()                                   # base.py:134-135
@@ -93,9 +97,8 @@ class RewardFeaturizer:
             self.model.build(torch.empty(shape, dtype=torch.uint8, device="meta"), device=self.device,
                              precision=self.precision)
             if self.modelname:
-                sd = dict(np.load(self.modelname if self.modelname.endswith(".npz") else self.modelname + ".npz"))
-                prefix = "contextmodel/" if any(k.startswith("contextmodel/") for k in sd) else ""
-                self.model.net.load_state_dict(sd, prefix=prefix)
+                from . import compat
+                compat.restore_model(self.model.net, self.modelname)          # base.py:143-145
         self.initialized = True
 
     @staticmethod

@@ -1,18 +1,25 @@
-"""Reader / writer for TensorFlow "tensor bundle" checkpoints — what `tf.train.Saver()` (V2, the default since TF 0.12)
-writes in the reference: `saver.save(sess, 'model/.../model_...')` (scripts/train_script.py:189) and
-`tf.train.Saver(...).restore(sess, modelfile)` (rllab/sampler/base.py:144-145, 130-132 for `inception_v3.ckpt`).
+"""Reader / writer for TensorFlow checkpoints — what `tf.train.Saver()` writes in the reference:
+`saver.save(sess, 'model/.../model_...')` (scripts/train_script.py:189), `tf.train.Saver(...).restore(sess, modelfile)`
+(rllab/sampler/base.py:144-145) and the slim `inception_v3.ckpt` restored at base.py:130-132 / train_script.py:113-115.
 
+Two on-disk formats exist and both are read here:
+
+  V2 "tensor bundle" (Saver default since TF 0.12):
     <prefix>.index                    an SSTable (TensorFlow's copy of the LevelDB table format) mapping
                                       "" -> BundleHeaderProto and  <variable name> -> BundleEntryProto
     <prefix>.data-00000-of-00001      the raw little-endian tensor bytes, addressed by (shard, offset, size)
+  V1 (one file, e.g. slim's published `inception_v3.ckpt`):
+    <path>                            an SSTable mapping "" -> SavedTensorSlices{meta} (names, shapes, dtypes) and one
+                                      ordered-code key per stored slice -> SavedTensorSlices{data: SavedSlice{name, slice,
+                                      TensorProto}} with the values inline (tensor_content or the typed *_val fields)
 
 No TensorFlow here and no checkpoint ships with the reference, so this module is written from the published formats
-(tensorflow/core/util/tensor_bundle, tensorflow/core/lib/io/{table,block,format}, the protobuf wire format, Snappy's
-format description) and is **not validated against a TF-written file**; tests/test_host_logic.py holds it to its own
-writer, to hand-assembled tables with prefix-compressed keys, several data blocks and Snappy-compressed blocks, and to
-the CRC-32C check values of the published algorithm.  Only what a Saver checkpoint of dense float variables needs is
-implemented: DT_FLOAT / DT_DOUBLE / DT_INT32 / DT_INT64 / DT_UINT8 / DT_HALF / DT_BFLOAT16-as-uint16 tensors,
-unsliced entries, little-endian bundles.
+(tensorflow/core/util/{tensor_bundle,saved_tensor_slice.proto,tensor_slice_writer}, tensorflow/core/lib/io/{table,block,
+format}, the protobuf wire format, Snappy's format description) and is **not validated against a TF-written file**;
+tests/test_host_logic.py holds it to its own writers, to hand-assembled tables with prefix-compressed keys, several data
+blocks and Snappy-compressed blocks, and to the CRC-32C check values of the published algorithm.  Only what a Saver
+checkpoint of dense float variables needs is implemented: DT_FLOAT / DT_DOUBLE / DT_INT32 / DT_INT64 / DT_UINT8 / DT_HALF /
+DT_BFLOAT16-as-uint16 tensors, little-endian files; V2 entries must be unsliced, V1 slices are assembled.
 """
 from __future__ import annotations
 
@@ -296,11 +303,224 @@ def write_table(path: str, entries: List[Tuple[bytes, bytes]], block_size: int =
 
 
 # ---- the bundle ----------------------------------------------------------------------------------------------------------------
-def checkpoint_exists(prefix: str) -> bool:
+def _is_v2(prefix: str) -> bool:
     return os.path.exists(prefix + ".index")
 
 
+def _is_v1(path: str) -> bool:
+    """A single-file (Saver V1 / slim) checkpoint: a table file at `path` itself."""
+    if not os.path.isfile(path) or os.path.getsize(path) < 48:
+        return False
+    with open(path, "rb") as f:
+        f.seek(-8, os.SEEK_END)
+        return struct.unpack("<Q", f.read(8))[0] == TABLE_MAGIC
+
+
+def checkpoint_exists(prefix: str) -> bool:
+    return _is_v2(prefix) or _is_v1(prefix)
+
+
 def list_variables(prefix: str) -> Dict[str, Tuple[np.dtype, Tuple[int, ...]]]:
+    """{variable name: (dtype, shape)} of a V2 bundle `<prefix>.index` or a V1 single-file checkpoint `<prefix>`."""
+    if _is_v2(prefix):
+        return _list_variables_v2(prefix)
+    if _is_v1(prefix):
+        return {k: (dt, shp) for k, (dt, shp, _) in _v1_meta(read_table(prefix)).items()}
+    raise CheckpointError("%s is neither a TensorFlow V2 bundle (<prefix>.index) nor a V1 checkpoint file" % prefix)
+
+
+def read_checkpoint(prefix: str, names: Optional[List[str]] = None, verify: bool = True) -> Dict[str, np.ndarray]:
+    """{variable name: ndarray} of a Saver checkpoint: V2 bundle `<prefix>.index` + `<prefix>.data-*`, or the V1
+    single file `<prefix>` (slim's `inception_v3.ckpt`)."""
+    if _is_v2(prefix):
+        return _read_checkpoint_v2(prefix, names, verify)
+    if _is_v1(prefix):
+        return _read_checkpoint_v1(prefix, names, verify)
+    raise CheckpointError("%s is neither a TensorFlow V2 bundle (<prefix>.index) nor a V1 checkpoint file" % prefix)
+
+
+# ---- V1: SavedTensorSlices in one table ------------------------------------------------------------------------------------
+def _parse_shape(buf: bytes) -> List[int]:
+    dims = []
+    for n2, _, v2 in _fields(buf):                             # TensorShapeProto: dim = 2 { size = 1 }
+        if n2 == 2:
+            size = 0
+            for n3, _, v3 in _fields(v2):
+                if n3 == 1:
+                    size = _signed64(v3)
+            dims.append(size)
+    return dims
+
+
+def _parse_slice(buf: bytes) -> List[Tuple[int, Optional[int]]]:
+    """TensorSliceProto: extent = 1 { start = 1, length = 2 (absent = the full dimension) } -> [(start, length | None)]."""
+    out = []
+    for n, _, v in _fields(buf):
+        if n == 1:
+            start, length = 0, None
+            for n2, _, v2 in _fields(v):
+                if n2 == 1:
+                    start = _signed64(v2)
+                elif n2 == 2:
+                    length = _signed64(v2)
+            out.append((start, length))
+    return out
+
+
+def _v1_meta(table) -> Dict[str, Tuple[np.dtype, Tuple[int, ...], int]]:
+    if not table or table[0][0] != b"":
+        raise CheckpointError("V1 checkpoint has no SavedTensorSlices meta entry")
+    out = {}
+    for n, _, v in _fields(table[0][1]):
+        if n != 1:                                             # SavedTensorSlices.meta
+            continue
+        for n2, _, v2 in _fields(v):
+            if n2 != 1:                                        # SavedTensorSliceMeta.tensor
+                continue
+            name, shape, dtype = "", [], 0
+            for n3, _, v3 in _fields(v2):                      # SavedSliceMeta: name = 1, shape = 2, type = 3
+                if n3 == 1:
+                    name = v3.decode("utf-8")
+                elif n3 == 2:
+                    shape = _parse_shape(v3)
+                elif n3 == 3:
+                    dtype = v3
+            out[name] = (np.dtype(_DTYPES.get(dtype, np.uint8)), tuple(shape), dtype)
+    return out
+
+
+_V1_VAL_FIELDS = {5: "<f4", 6: "<f8", 7: "<i4", 10: "<i8", 11: "u1", 13: "<i4"}   # TensorProto *_val (13 = half_val as int32)
+
+
+def _tensor_proto_values(buf: bytes, dt: np.dtype, count: int) -> np.ndarray:
+    """Flat values of a TensorProto: tensor_content (4) or the typed, packed or repeated, *_val field."""
+    content, packed, scalars, field = None, [], [], None
+    for n, wt, v in _fields(buf):
+        if n == 4:
+            content = v
+        elif n in _V1_VAL_FIELDS:
+            field = n
+            if wt == 2:
+                packed.append(v)
+            else:
+                scalars.append(v)
+    if content is not None and len(content):
+        return np.frombuffer(content, dtype=dt.newbyteorder("<")).astype(dt)
+    if field is None:
+        return np.zeros(count, dtype=dt)
+    wire = np.dtype(_V1_VAL_FIELDS[field])
+    if packed:
+        raw = b"".join(packed)
+        if field in (7, 10, 11, 13):                           # varint-packed integer fields
+            vals, pos = [], 0
+            while pos < len(raw):
+                x, pos = _varint(raw, pos)
+                vals.append(_signed64(x))
+            arr = np.asarray(vals, dtype=np.int64)
+        else:
+            arr = np.frombuffer(raw, dtype=wire)
+    else:
+        if field in (5,):
+            arr = np.asarray(scalars, dtype=np.uint32).view("<f4")
+        elif field in (6,):
+            arr = np.asarray(scalars, dtype=np.uint64).view("<f8")
+        else:
+            arr = np.asarray([_signed64(x) for x in scalars], dtype=np.int64)
+    if field == 13:                                            # half_val: the 16 bits of each value in an int32
+        arr = arr.astype(np.uint16).view(np.float16)
+    if arr.size == 1 and count > 1:                            # TensorProto's "all elements equal" compression
+        arr = np.repeat(arr, count)
+    return arr.astype(dt)
+
+
+def _read_checkpoint_v1(path: str, names: Optional[List[str]], verify: bool) -> Dict[str, np.ndarray]:
+    table = read_table(path, verify)
+    meta = _v1_meta(table)
+    want = None if names is None else set(names)
+    out: Dict[str, np.ndarray] = {}
+    filled: Dict[str, int] = {}
+    for k, v in table[1:]:
+        for n, _, sv in _fields(v):
+            if n != 2:                                         # SavedTensorSlices.data = SavedSlice
+                continue
+            name, sl, tp = "", [], b""
+            for n2, _, v2 in _fields(sv):                      # SavedSlice: name = 1, slice = 2, data = 3
+                if n2 == 1:
+                    name = v2.decode("utf-8")
+                elif n2 == 2:
+                    sl = _parse_slice(v2)
+                elif n2 == 3:
+                    tp = v2
+            if want is not None and name not in want:
+                continue
+            if name not in meta:
+                raise CheckpointError("V1 checkpoint %s: slice of unknown tensor %s" % (path, name))
+            dt, shape, code = meta[name]
+            if code not in _DTYPES:
+                raise CheckpointError("variable %s has unsupported dtype enum %d" % (name, code))
+            if len(sl) not in (0, len(shape)):
+                raise CheckpointError("variable %s: slice rank %d does not match shape %s" % (name, len(sl), shape))
+            idx = tuple(slice(s, None if ln is None or ln < 0 else s + ln) for s, ln in sl) if sl else tuple(slice(None) for _ in shape)
+            if name not in out:
+                out[name] = np.zeros(shape, dtype=dt)
+                filled[name] = 0
+            view = out[name][idx] if shape else out[name]
+            vals = _tensor_proto_values(tp, dt, int(view.size))
+            if vals.size != view.size:
+                raise CheckpointError("variable %s: slice holds %d values, %d expected" % (name, vals.size, view.size))
+            if shape:
+                out[name][idx] = vals.reshape(view.shape)
+            else:
+                out[name] = vals.reshape(())
+            filled[name] += int(vals.size)
+    for name, arr in out.items():
+        if filled[name] != arr.size:
+            raise CheckpointError("variable %s: %d of %d values present in %s" % (name, filled[name], arr.size, path))
+    if want is not None and want - set(out):
+        raise KeyError("not in checkpoint %s: %s" % (path, sorted(want - set(out))))
+    return out
+
+
+def _ordered_name_slice_key(name: str, rank: int) -> bytes:
+    """Key of a full-extent slice as TensorSliceWriter encodes it (OrderedCode: 0, name, rank, (start, length) per
+    dimension with length = -1 for "full").  Readers here never decode keys; the writer needs them unique and sorted."""
+    esc = b"".join(b"\x00\xff" if c == 0 else b"\xff\x00" if c == 255 else bytes([c]) for c in name.encode("utf-8"))
+    num = lambda v: b"\x00" if v == 0 else bytes([len(v.to_bytes((v.bit_length() + 7) // 8, "big"))]) + v.to_bytes((v.bit_length() + 7) // 8, "big")
+    return num(0) + esc + b"\x00\x01" + num(rank) + (b"\x80" + b"\x7f") * rank
+
+
+def write_checkpoint_v1(path: str, variables: Dict[str, np.ndarray], use_tensor_content: bool = False):
+    """Single-file V1 checkpoint holding `variables` as full slices (float values in the packed float_val field, as
+    TensorSliceWriter::SaveData does, or in tensor_content)."""
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+
+    def ld(num: int, payload: bytes) -> bytes:                 # length-delimited field
+        return _put_varint(num << 3 | 2) + _put_varint(len(payload)) + payload
+
+    def shape_proto(shape) -> bytes:
+        return b"".join(ld(2, _put_varint(1 << 3) + _put_varint(int(d))) for d in shape)
+
+    metas, entries = b"", []
+    for name in sorted(variables, key=lambda s: s.encode("utf-8")):
+        a = np.ascontiguousarray(variables[name]) if np.ndim(variables[name]) else np.asarray(variables[name])
+        if a.dtype not in _DTYPE_OF:
+            raise CheckpointError("cannot store dtype %s (variable %s)" % (a.dtype, name))
+        code = _DTYPE_OF[a.dtype]
+        full = b"".join(ld(1, b"") for _ in a.shape)           # TensorSliceProto: one empty Extent per dimension
+        metas += ld(1, ld(1, name.encode("utf-8")) + ld(2, shape_proto(a.shape)) + _put_varint(3 << 3) + _put_varint(code) +
+                    ld(4, full))
+        if use_tensor_content or a.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            body = ld(4, a.astype(a.dtype.newbyteorder("<")).tobytes())
+        else:
+            body = ld(5 if a.dtype == np.float32 else 6, a.astype(a.dtype.newbyteorder("<")).tobytes())
+        tensor = _put_varint(1 << 3) + _put_varint(code) + ld(2, shape_proto(a.shape)) + body
+        entries.append((_ordered_name_slice_key(name, a.ndim),
+                        ld(2, ld(1, name.encode("utf-8")) + ld(2, full) + ld(3, tensor))))
+    entries.sort(key=lambda kv: kv[0])
+    write_table(path, [(b"", ld(1, metas))] + entries)
+
+
+def _list_variables_v2(prefix: str) -> Dict[str, Tuple[np.dtype, Tuple[int, ...]]]:
     out = {}
     for k, v in read_table(prefix + ".index"):
         if k:
@@ -309,7 +529,7 @@ def list_variables(prefix: str) -> Dict[str, Tuple[np.dtype, Tuple[int, ...]]]:
     return out
 
 
-def read_checkpoint(prefix: str, names: Optional[List[str]] = None, verify: bool = True) -> Dict[str, np.ndarray]:
+def _read_checkpoint_v2(prefix: str, names: Optional[List[str]] = None, verify: bool = True) -> Dict[str, np.ndarray]:
     """{variable name: ndarray} of a Saver V2 checkpoint `<prefix>.index` + `<prefix>.data-*`."""
     table = read_table(prefix + ".index", verify)
     if not table or table[0][0] != b"":
@@ -377,3 +597,29 @@ def write_checkpoint(prefix: str, variables: Dict[str, np.ndarray]):
     # BundleHeaderProto: num_shards = 1, endianness = LITTLE (default, omitted), version { producer = 1 }
     header = b"\x08\x01" + b"\x1a\x02\x08\x01"
     write_table(prefix + ".index", [(b"", header)] + entries)
+
+
+# ---- one restore path for every caller (compat.Saver.restore, sampler.RewardFeaturizer.initialize) ---------------------------
+def load_variables(path: str, names: List[str], prefixes=("",), verify: bool = True) -> Tuple[Dict[str, np.ndarray], str]:
+    """Values of `names` from whatever `path` is — a TensorFlow checkpoint (V2 bundle `<path>.index` or V1 single file),
+    else the `.npz` keyed by the same variable names that compat.Saver.save writes by default — under the first prefix of
+    `prefixes` for which every name is present.  The reference builds the model under "contextmodel/" in the trainer
+    (train_script.py:120) but not always in the sampler (base.py:134-138), hence the probing.
+    Returns ({prefix + name: array}, prefix)."""
+    if checkpoint_exists(path):
+        have = set(list_variables(path))
+        read = lambda keys: read_checkpoint(path, keys, verify)
+    else:
+        npz = path if path.endswith(".npz") else path + ".npz"
+        if not os.path.exists(npz):
+            raise FileNotFoundError("no checkpoint at %s (looked for %s.index, a V1 checkpoint file %s, and %s)"
+                                    % (path, path, path, npz))
+        data = np.load(npz)
+        have = set(data.files)
+        read = lambda keys: {k: data[k] for k in keys}
+    for pre in dict.fromkeys(prefixes):
+        if all(pre + n in have for n in names):
+            return read([pre + n for n in names]), pre
+    pre0 = next(iter(prefixes))
+    missing = [n for n in names if pre0 + n not in have]
+    raise KeyError("checkpoint %s lacks %d variables of the model, e.g. %s" % (path, len(missing), missing[:3]))

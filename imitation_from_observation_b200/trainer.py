@@ -121,8 +121,11 @@ class ModelTrainer:
                 self.log("%s %s %s %s %s %s E" % (itr, loss, sim, r1, r2, err))
                 validloss.append(loss)
                 if itr % self.save_every == 0:
-                    os.makedirs(os.path.join(self.basedir, str(itr)), exist_ok=True)
-                    saver.save(sess, "%s%d/model_%d_%.2f_%.2f_%.2f_%d" % (self.basedir, itr, itr, loss, r1, r2, err))
-                    np.save("%s%d/validloss" % (self.basedir, itr), validloss)
+                    # train_script.py:187-190 formats 'model/<itr>/model_...' with a basedir that ends in '/': one
+                    # normalised directory for both files, whatever the caller passed
+                    ckdir = os.path.join(self.basedir, str(itr))
+                    os.makedirs(ckdir, exist_ok=True)
+                    saver.save(sess, os.path.join(ckdir, "model_%d_%.2f_%.2f_%.2f_%d" % (itr, loss, r1, r2, err)))
+                    np.save(os.path.join(ckdir, "validloss"), validloss)
         self.sess, self.test = sess, test
         return allloss, validloss

@@ -240,3 +240,65 @@ def test_saver_reads_and_writes_tf_checkpoints(tmp_path):
     with pytest.raises(KeyError):
         tf.train.Saver().restore(None, path)
     tf.reset_default_graph()
+
+
+def test_tf_checkpoint_v1_single_file(tmp_path):
+    """The checkpoint the reference restores for InceptionV3 (slim's `inception_v3.ckpt`, base.py:130-132) is a single-file
+    V1 checkpoint: SavedTensorSlices protos in one table.  Reader vs our writer (float_val and tensor_content forms), a
+    hand-assembled variable stored in two slices, and the one restore path every caller uses (load_variables)."""
+    import numpy as np
+    import pytest
+    from imitation_from_observation_b200 import tf_checkpoint as T
+
+    rs = np.random.RandomState(3)
+    sd = {"InceptionV3/Conv2d_1a_3x3/weights": rs.randn(3, 3, 3, 32).astype(np.float32),
+          "InceptionV3/Conv2d_1a_3x3/BatchNorm/beta": rs.randn(32).astype(np.float32),
+          "InceptionV3/Logits/Conv2d_1c_1x1/biases": rs.randn(1001).astype(np.float32),
+          "global_step": np.asarray(7, dtype=np.int64), "f64": rs.randn(4, 5)}
+    for content in (False, True):
+        path = str(tmp_path / ("inception_v3_%d.ckpt" % content))
+        T.write_checkpoint_v1(path, sd, use_tensor_content=content)
+        assert T.checkpoint_exists(path) and not T._is_v2(path)
+        lv = T.list_variables(path)
+        assert lv["InceptionV3/Conv2d_1a_3x3/weights"] == (np.dtype(np.float32), (3, 3, 3, 32)) and lv["global_step"][1] == ()
+        got = T.read_checkpoint(path)
+        assert sorted(got) == sorted(sd)
+        for k in sd:
+            assert got[k].dtype == sd[k].dtype and np.array_equal(got[k], sd[k]), k
+        assert list(T.read_checkpoint(path, ["f64"])) == ["f64"]
+        with pytest.raises(KeyError):
+            T.read_checkpoint(path, ["nope"])
+
+    # a variable stored as two row slices ([0:2, :] and [2:5, :]) — what a partitioned save produces
+    def ld(num, payload):
+        return T._put_varint(num << 3 | 2) + T._put_varint(len(payload)) + payload
+
+    def vi(num, v):
+        return T._put_varint(num << 3) + T._put_varint(v)
+
+    full = rs.randn(5, 4).astype(np.float32)
+    shape = ld(2, vi(1, 5)) + ld(2, vi(1, 4))
+    meta = ld(1, ld(1, b"w") + ld(2, shape) + vi(3, 1))
+    entries = [(b"", ld(1, meta))]
+    for i, (r0, n) in enumerate(((0, 2), (2, 3))):
+        sl = ld(1, vi(1, r0) + vi(2, n)) + ld(1, b"")                 # extent rows [r0, r0+n), full columns
+        tensor = vi(1, 1) + ld(5, full[r0:r0 + n].tobytes())
+        entries.append((b"\x00w\x00\x01" + bytes([i]), ld(2, ld(1, b"w") + ld(2, sl) + ld(3, tensor))))
+    T.write_table(str(tmp_path / "sliced.ckpt"), entries)
+    assert np.array_equal(T.read_checkpoint(str(tmp_path / "sliced.ckpt"))["w"], full)
+    T.write_table(str(tmp_path / "half.ckpt"), entries[:2])            # a missing slice is an error, not zeros
+    with pytest.raises(T.CheckpointError):
+        T.read_checkpoint(str(tmp_path / "half.ckpt"))
+
+    # load_variables: V1 file, V2 bundle or .npz, under the first prefix that holds every name
+    names = ["Conv2d_1a_3x3/weights", "Conv2d_1a_3x3/BatchNorm/beta"]
+    v1 = str(tmp_path / "inception_v3_0.ckpt")
+    vals, pre = T.load_variables(v1, names, prefixes=("", "InceptionV3/"))
+    assert pre == "InceptionV3/" and np.array_equal(vals["InceptionV3/" + names[0]], sd["InceptionV3/" + names[0]])
+    np.savez(str(tmp_path / "m.npz"), **{"contextmodel/a": np.ones(3, np.float32)})
+    vals, pre = T.load_variables(str(tmp_path / "m"), ["a"], prefixes=("x/", "contextmodel/", ""))
+    assert pre == "contextmodel/" and np.array_equal(vals["contextmodel/a"], np.ones(3, np.float32))
+    with pytest.raises(KeyError):
+        T.load_variables(str(tmp_path / "m"), ["b"], prefixes=("", "contextmodel/"))
+    with pytest.raises(FileNotFoundError):
+        T.load_variables(str(tmp_path / "absent"), ["a"])

@@ -107,20 +107,23 @@ def test_inception_v3_endpoints_match_oracle():
 
 
 def test_inception_loads_a_tf_checkpoint(tmp_path):
-    """slim's inception_v3.ckpt is a TF tensor bundle (base.py:130-132): InceptionV3.load_tf_checkpoint reads the 4 x 94
-    variables by name and ignores the heads the file also holds."""
+    """slim's published inception_v3.ckpt is a single-file V1 checkpoint (base.py:130-132 restores it with tf.train.Saver;
+    a re-saved copy would be a V2 tensor bundle): InceptionV3.load_tf_checkpoint reads the 4 x 94 variables by name from
+    either format and ignores the heads the file also holds."""
     from imitation_from_observation_b200 import tf_checkpoint as T
     P = _inception_params(seed=14)
     sd = {k: v.numpy() for k, v in P.items()}
     sd["InceptionV3/Logits/Conv2d_1c_1x1/weights"] = np.zeros((1, 1, 2048, 1001), np.float32)      # unused head
     sd["InceptionV3/Logits/Conv2d_1c_1x1/biases"] = np.zeros((1001,), np.float32)
-    prefix = str(tmp_path / "inception_v3.ckpt")
-    T.write_checkpoint(prefix, sd)
-    a, b = I.InceptionV3(precision="mixed"), I.InceptionV3(precision="mixed")
+    a = I.InceptionV3(precision="mixed")
     a.load_state_dict(P)
-    b.load_tf_checkpoint(prefix)
-    for scope in a.folded:
-        assert torch.equal(a.folded[scope][0], b.folded[scope][0]) and torch.equal(a.folded[scope][1], b.folded[scope][1])
+    for fmt, writer in (("v1", T.write_checkpoint_v1), ("v2", T.write_checkpoint)):
+        prefix = str(tmp_path / fmt / "inception_v3.ckpt")
+        writer(prefix, sd)
+        b = I.InceptionV3(precision="mixed")
+        b.load_tf_checkpoint(prefix)
+        for scope in a.folded:
+            assert torch.equal(a.folded[scope][0], b.folded[scope][0]) and torch.equal(a.folded[scope][1], b.folded[scope][1])
 
 
 def test_inception_reward_kernel_matches_reference_loop():

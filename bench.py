@@ -99,6 +99,8 @@ class ClockSampler:
 def make_batches(spec, B, n, seed):
     """n distinct [3,B,H,W,C] float32 trainer batches drawn as scripts/train_script.py:154-159 does."""
     from imitation_from_observation_b200 import synthetic
+    if spec.c_dim != 3:
+        return make_feature_batches(spec, B, n, seed)
     bank = synthetic.to_float(synthetic.video_bank(25, 48, spec.height, spec.width, seed=1234 + seed)).astype(np.float32)
     rng = np.random.RandomState(seed)
     return [synthetic.trainer_batch(bank, B, 25, 48, rng) for _ in range(n)]
@@ -140,17 +142,74 @@ def cpu_reference_step_time(spec, sample_B, steps, warmup, threads, budget_s=Non
     return float(np.mean(times)), sample_B
 
 
+INC2 = dict(strides=(1, 2, 1, 2), kernels=(3, 3, 3, 3), filters=(1024, 1024, 512, 512))   # base.py:126
+
+
 def train_workload(args):
-    """(spec, model class name, label) of the training workload: the headline ContextSkipNew 64x64 (BASELINE
-    configs[1]) or, as a secondary line, configs[3]'s 6-layer 128x128 model."""
+    """(spec, model class name, label, BASELINE config) of the training workload: the headline ContextSkipNew 64x64
+    (BASELINE configs[1]); as secondary lines configs[3]'s 6-layer 128x128 model and the
+    full-size ContextAEInception2 on Mixed_7c feature maps (8x8x2048, 3x3 kernels, filters
+    1024/1024/512/512 — the layers north_star's ">= 70 % tensor-pipe on the 3x3 convs" is about)."""
     from imitation_from_observation_b200 import spec as S
     if args.workload == "striker6":
         return S.context_skip_deep(128, 128), "ContextSkipDeep", "ContextSkipDeep (6-layer) 128x128x3", "configs[3]"
+    if args.workload == "inception2":
+        return (S.context_ae_inception2(8, 8, 2048, INC2["strides"], INC2["kernels"], INC2["filters"]),
+                "ContextAEInception2", "ContextAEInception2 on 8x8x2048 Mixed_7c maps (3x3 convs, filters 1024/1024/512/512)",
+                "SURVEY 8a a9 / base.py:126")
     return S.context_skip_new(64, 64), "ContextSkipNew", "ContextSkipNew 64x64x3", "configs[1]"
 
 
+def make_feature_batches(spec, B, n, seed):
+    """n distinct [3,B,h,w,C] float32 feature-map batches (post-ReLU-like: non-negative, sparse) for the feature-map
+    models; frames of one triple are correlated the way consecutive video frames are."""
+    rs = np.random.RandomState(1234 + seed)
+    out = []
+    for _ in range(n):
+        base = rs.rand(1, B, spec.height, spec.width, spec.c_dim).astype(np.float32)
+        x = base + 0.25 * rs.rand(3, B, spec.height, spec.width, spec.c_dim).astype(np.float32) - 0.6
+        out.append(np.maximum(x, 0.0).astype(np.float32))
+    return out
+
+
 def metric_name(args, label):
-    return METRIC if args.workload == "train" else "frames/sec fwd+bwd+Adam, %s, B=%d triples per GPU" % (label, args.batch)
+    if args.workload == "train" and args.batch == 256 and not args.global_batch:
+        return METRIC
+    if args.global_batch:
+        return "frames/sec fwd+bwd+Adam, %s, global B=%d triples over all GPUs" % (label, args.global_batch)
+    return "frames/sec fwd+bwd+Adam, %s, B=%d triples per GPU" % (label, args.batch)
+
+
+def measure_tf32_peak(dev, seconds=0.4):
+    """cuBLAS TF32 GEMM 8192^3 on this GPU (torch.matmul with allow_tf32), burst = best of 5, sustained = back to back
+    for `seconds`: the measured stand-in for a TF32 roofline denominator (MEASURED_PEAKS.json only has bf16)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn((n, n), device=dev)
+        b = torch.randn((n, n), device=dev)
+        c = torch.empty((n, n), device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(5, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record(); torch.cuda.synchronize()
+        fl = 2.0 * n ** 3
+        return dict(burst=fl / (best * 1e-3) / 1e12, sustained=fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                    how="torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS), best of 5 / %d back to back" % reps)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def run_reference(args):
@@ -188,17 +247,35 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _lib.load()
+    # weak scaling: --batch triples on every GPU; strong scaling: --global-batch triples split over the GPUs
+    scaling = "strong" if args.global_batch else "weak"
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be divisible by the number of GPUs")
+        args.batch = args.global_batch // world
     B = args.batch
     spec, model_name, label, cfg_name = train_workload(args)
     peaks = load_peaks()
+    feature_model = spec.c_dim != 3                     # ContextAEInception2: the input is a Mixed_7c feature map
 
-    # the reference-facing object graph (train_script.py:118-129)
+    # the reference-facing object graph (train_script.py:100-129)
     tf.reset_default_graph()
-    tfinput = tf.placeholder(tf.float32, (3, B, spec.height, spec.width, 3), name="x")
-    model = MODEL_REGISTRY[model_name]()
+    inc_net = None
+    if feature_model:
+        # train_script.py:100-115: uint8 frames -> normalise -> frozen InceptionV3 -> Mixed_7c -> the context model
+        from imitation_from_observation_b200 import inception as I
+        inc_net = I.InceptionV3(device=dev, precision=args.precision, seed=0)
+        tfinput = tf.placeholder(tf.uint8, (3, B, 299, 299, 3), name="image")
+        image_trans = tf.multiply(tf.subtract(tf.image.convert_image_dtype(tfinput, dtype=tf.float32), 0.5), 2.0)
+        model_in = tf.inception_mixed_7c(image_trans, inc_net)
+        model = MODEL_REGISTRY[model_name](**INC2)
+    else:
+        tfinput = model_in = tf.placeholder(tf.float32, (3, B, spec.height, spec.width, 3), name="x")
+        model = MODEL_REGISTRY[model_name]()
     with tf.variable_scope("contextmodel"):
-        tf.build_model(model, tfinput, precision=args.precision, seed=0, global_batch=B * world, device=dev)
+        tf.build_model(model, model_in, precision=args.precision, seed=0, global_batch=B * world, device=dev)
     net = model.net
+    assert net.spec == spec, (net.spec, spec)
     if world > 1:
         net.attach_allreduce()
     lr_ph = tf.placeholder(tf.float32, shape=[])
@@ -206,8 +283,12 @@ def run_ours(args):
     sess = tf.Session()
 
     nb = 4
-    host = [torch.from_numpy(b).pin_memory() for b in make_batches(spec, B, nb, seed=rank)]
-    devb = [h.to(dev) for h in host]
+    devb = [torch.from_numpy(b).to(dev) for b in make_batches(spec, B, nb, seed=rank)]
+    if feature_model:
+        rs = np.random.RandomState(rank)
+        host = [torch.from_numpy(rs.randint(0, 256, size=(3, B, 299, 299, 3)).astype(np.uint8)).pin_memory() for _ in range(2)]
+    else:
+        host = [torch.from_numpy(b).pin_memory() for b in make_batches(spec, B, nb, seed=rank)]
 
     def barrier():
         if world > 1:
@@ -218,11 +299,15 @@ def run_ours(args):
         net.set_input(devb[i % nb])
         net.train_step(1e-4)
 
-    def step_e2e(i):
-        # the next step's batch is named so that its host->device copy runs under this step's kernels (Session.prefetch:
-        # input double buffering); the copy is still inside the timed region, once per step
-        _, loss = sess.run([optimizer, model.loss], {tfinput: host[i % nb], lr_ph: 1e-4},
-                           prefetch={tfinput: host[(i + 1) % nb]})
+    def step_e2e(i, prefetch):
+        # prefetch: the next step's batch is named so that its host->device copy runs under this step's kernels
+        # (Session.prefetch: input double buffering); the copy is still inside the timed region, once per step.
+        # Without it this is the reference's call site verbatim (train_script.py:163).
+        feed = {tfinput: host[i % len(host)], lr_ph: 1e-4}
+        if prefetch and not feature_model:
+            _, loss = sess.run([optimizer, model.loss], feed, prefetch={tfinput: host[(i + 1) % len(host)]})
+        else:
+            _, loss = sess.run([optimizer, model.loss], feed)
         return loss
 
     # ---- device-resident timing --------------------------------------------------------------------------------
@@ -234,10 +319,12 @@ def run_ours(args):
         sampler.start()
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         step_resident(args.warmup + i)
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps    # CPU time to enqueue one step (no sync inside)
     barrier()
     clocks = sampler.stop() if rank == 0 else {}
     launches = ops.launch_count() - l0
@@ -248,20 +335,26 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = 3.0 * B * world / (ms_step * 1e-3)
 
-    # ---- end to end through Session.run with host batches -------------------------------------------------------
-    for i in range(max(2, args.warmup // 2)):
-        step_e2e(i)
-    barrier()
-    e0.record()
-    last_loss = None
-    for i in range(args.steps):
-        last_loss = step_e2e(i)
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = 3.0 * B * world / (float(ms2.item()) / args.steps * 1e-3)
+    # ---- end to end through Session.run with host batches: with input prefetch, and the unmodified call site ------
+    def time_e2e(prefetch):
+        for i in range(max(2, args.warmup // 2)):
+            step_e2e(i, prefetch)
+        barrier()
+        e0.record()
+        loss = None
+        for i in range(args.steps):
+            loss = step_e2e(i, prefetch)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return 3.0 * B * world / (float(t.item()) / args.steps * 1e-3), loss
+
+    e2e_plain, last_loss = time_e2e(False)
+    e2e_value = e2e_plain
+    if not feature_model:
+        e2e_value, last_loss = time_e2e(True)
     h2d = int(host[0].numel() * host[0].element_size())
 
     # ---- roofline of the dominant kernel (tc_igemm_kernel), timed per launch with events on the launch stream ---
@@ -303,6 +396,16 @@ def run_ours(args):
                             tensor_passes=passes if dom == "tc" else 0,
                             frac_of_issued_tensor_flops=(ach * passes / peak) if dom == "tc" else None,
                             share_of_step=agg[dom]["s"] * 1e3 / ms_step)
+            try:                                   # a measured TF32 rate for context (cuBLAS, this GPU, now)
+                roofline["tf32_cublas_measured"] = measure_tf32_peak(dev)
+            except Exception as ex:                # noqa: BLE001  (diagnostic only)
+                roofline["tf32_cublas_measured"] = dict(error=str(ex)[:200])
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tpath):              # dram bytes per launch of the dominant kernel from the committed ncu capture
+                with open(tpath) as f:
+                    tr = json.load(f)
+                roofline["traffic"] = tr.get("dominant_kernel_dram_bytes_per_launch")
+                roofline["traffic_source"] = tr.get("source")
 
     # ---- CPU baseline: the restated reference on this box's host cores, bounded sample ---------------------------
     cpu = None
@@ -315,7 +418,7 @@ def run_ours(args):
 
     if rank == 0:
         line = dict(metric=metric_name(args, label), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    ms_per_step=ms_step, higher_is_better=True, scaling=scaling, vs_baseline=None,
                     dtype="f32 (%s)" % {"tf32x3": "tensor-core operands tf32, 3-pass split, fp32 accumulate",
                                         "mixed": "tensor cores, fp32 accumulate: forward fp32-grade (bf16 hi/lo planes, three "
                                                  "products; 3-pass tf32 split where planes do not apply), backward "
@@ -330,8 +433,12 @@ def run_ours(args):
                                    "%d distinct input batches rotate" % (16e-9 * spec.num_params(), nb)),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                             api="compat.Session.run([optimizer, loss], feed_dict, prefetch=next_feed) with pinned host batches",
-                             last_loss=float(last_loss)),
+                             api=("compat.Session.run([optimizer, loss], {uint8 frames}) through the frozen InceptionV3 "
+                                  "front-end (train_script.py:100-115), pinned host batches" if feature_model else
+                                  "compat.Session.run([optimizer, loss], feed_dict, prefetch=next_feed) with pinned host "
+                                  "batches; value_unmodified_call_site = the same without prefetch= (train_script.py:163 verbatim)"),
+                             value_unmodified_call_site=e2e_plain, last_loss=float(last_loss)),
+                    host_enqueue_ms_per_step=host_enqueue_ms,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, kernel_breakdown=breakdown,
                     gflop_per_step=3 * 2.0 * spec.fwd_macs_per_triple() * B / 1e9,
                     step_tflops=3 * 2.0 * spec.fwd_macs_per_triple() * B * world / (ms_step * 1e-3) / 1e12)
@@ -473,9 +580,12 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="triples per GPU")
     ap.add_argument("--ref-batch", type=int, default=256, help="max triples per step of the CPU reference (reduced to fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "striker6", "inception"],
-                    help="train = the headline metric (default); striker6 = BASELINE configs[3] (6-layer 128x128 model) "
-                         "and inception = configs[4], secondary lines")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: this many triples in total, split evenly over the GPUs (overrides --batch)")
+    ap.add_argument("--workload", default="train", choices=["train", "striker6", "inception", "inception2"],
+                    help="train = the headline metric (default); striker6 = BASELINE configs[3] (6-layer 128x128 model), "
+                         "inception = configs[4] and inception2 = the full-size ContextAEInception2 (3x3 convs on Mixed_7c "
+                         "maps), secondary lines")
     args = ap.parse_args()
     if args.workload == "inception":
         run_inception(args)

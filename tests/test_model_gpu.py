@@ -117,6 +117,35 @@ def test_striker_128x128_four_layer_vs_oracle():
         assert rel_l2(net.G[k].cpu(), G[k]) < GBAR["mixed"][0], k
 
 
+@pytest.mark.parametrize("B", [25, 32])
+def test_inception2_full_size_vs_oracle(B):
+    """SURVEY.md §8a a9 at the reference's size: ContextAEInception2 on Mixed_7c maps [3,B,8,8,2048], 3x3 kernels, strides
+    1/2/1/2, filters 1024/1024/512/512 (rllab/sampler/base.py:126; run_train_strike_inception.py:39-43), residual output
+    (arm_shaping.py:1890-1891).  B = 25 is the reference's batch (base.py:115); 32 tiles the 2x2 / 4x4 / 8x8 grids exactly.
+    Loss, outputs and every gradient against the fp64 oracle, default precision."""
+    spec = S.context_ae_inception2(8, 8, 2048, (1, 2, 1, 2), (3, 3, 3, 3), (1024, 1024, 512, 512))
+    assert spec.enc_sizes() == [(8, 8), (4, 4), (4, 4), (2, 2)] and spec.flat_dim() == 2048
+    assert 2 * spec.fwd_macs_per_triple() == pytest.approx(20.25e9, rel=1e-3)          # SURVEY.md §8d
+    P = O.init_params(spec, seed=12)
+    gen = torch.Generator().manual_seed(13)
+    for k in P:
+        if k.endswith("bias") or k.endswith("biases"):
+            P[k] = torch.randn(P[k].shape, generator=gen) * 0.01
+    # Mixed_7c is a concat of ReLU outputs: non-negative, about half of the entries zero
+    image = torch.relu(torch.randn((3, B, 8, 8, 2048), generator=gen) * 0.5)
+    ref, G = O.loss_and_grads(spec, {k: v.double() for k, v in P.items()}, image.double())
+    net = run_net(spec, B, P, image, "mixed")
+    for k in ("input_z", "translated_z", "out", "out2", "simloss", "recon1", "recon2", "loss"):
+        assert rel_err(net.fetch(k).cpu(), ref[k]) < TOL["mixed"], k
+    bar, median_bar = GBAR["mixed"]
+    errs = {k: rel_l2(net.G[k].cpu(), G[k]) for k in spec.param_shapes()}
+    print("inception2 B=%d gradient rel-L2: worst %.2e (%s), median %.2e" %
+          (B, max(errs.values()), max(errs, key=errs.get), float(np.median(list(errs.values())))))
+    for k, e in errs.items():
+        assert e < bar, (k, e)
+    assert float(np.median(list(errs.values()))) < median_bar, errs
+
+
 def test_legacy_context_ae_inception_on_mixed_5d_shape():
     """arm_shaping.py:1687-1783 on the strike-inception notebook's 35x35x288 feature map: odd extents at every level
     (35 -> 18 -> 9 -> 5 -> 3), residual output, linear context hz."""
@@ -253,6 +282,34 @@ def test_session_run_like_base_py():
         autodc.net.flat_p.zero_()
         saver.restore(sess, os.path.join(td, "m"))
     assert rel_err(sess.run(autodc.input_z, {tfinput: frames}), ref["input_z"]) < 1e-4
+
+
+def test_uint8_feeds_through_minimize_only_steps():
+    """Several optimiser steps with NO fetch (3 of 4 trainer steps, train_script.py:163-167) fed with distinct uint8
+    batches through the pinned staging buffer: nothing synchronises the host between steps, so the staging buffer must
+    not be refilled while the previous step's host->device copy is still queued.  Held against the same steps fed with
+    the normalised frames already on the device."""
+    B, idim, steps = 64, (32, 32), 8
+    rs = np.random.RandomState(11)
+    frames = [rs.randint(0, 256, size=(3, B) + idim + (3,)).astype(np.uint8) for _ in range(steps)]
+    finals = []
+    for mode in ("u8_host", "f32_device"):
+        tf.reset_default_graph()
+        if mode == "u8_host":
+            ph = tf.placeholder(tf.uint8, (3, B) + idim + (3,), name="x")
+            x = tf.multiply(tf.subtract(tf.image.convert_image_dtype(ph, dtype=tf.float32), 0.5), 2.0)
+        else:
+            ph = x = tf.placeholder(tf.float32, (3, B) + idim + (3,), name="x")
+        m = ContextSkipNew(df_dim=16, gf_dim=16, featsize=64)
+        tf.build_model(m, x, precision="fp32", seed=4)
+        opt = tf.train.AdamOptimizer(1e-3).minimize(m.loss)
+        sess = tf.Session()
+        for f in frames:
+            feed = f if mode == "u8_host" else ops.u8_normalize(torch.from_numpy(f).cuda())
+            sess.run(opt, {ph: feed})
+        torch.cuda.synchronize()
+        finals.append(m.net.flat_p.clone())
+    assert rel_l2(finals[0].cpu(), finals[1].cpu()) < 1e-5
 
 
 def test_saver_tf_checkpoint_round_trip_through_the_network(tmp_path):

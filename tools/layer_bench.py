@@ -21,6 +21,9 @@ ap.add_argument("--impl", default="x3,x1")
 ap.add_argument("--only", default="")
 ap.add_argument("--one", default="")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--model", default="skipnew", choices=["skipnew", "inception2"],
+                help="skipnew = the bench workload (ContextSkipNew 64x64x3); inception2 = ContextAEInception2 on 8x8x2048 "
+                     "Mixed_7c maps, 3x3 kernels, filters 1024/1024/512/512 (base.py:126)")
 a = ap.parse_args()
 B = a.batch
 dev = "cuda"
@@ -105,40 +108,60 @@ def add_gemm(name, M, N, K, tA=False, tB=False, bias=True, accumulate=False, pad
 
 E = 2 * B   # images through scope "conv" (src, tgt); ctx encoder has B
 D = 2 * B   # decoder passes
+if a.model == "inception2":
+    # encoder (scope "conv", 2B images): 3x3, strides 1/2/1/2 on 8x8x2048
+    add_fprop("h0", E, 8, 2048, 1024, k=3, st=1)
+    add_fprop("h1", E, 8, 1024, 1024, k=3, st=2)
+    add_fprop("h2", E, 4, 1024, 512, k=3, st=1)
+    add_fprop("h3", E, 4, 512, 512, k=3, st=2)
+    # decoder (2B passes, skips from the B context images)
+    add_trans("d_h1", D, 2, 512, 512, B, 512, k=3, st=2)
+    add_trans("d_h2", D, 4, 512, 512, B, 1024, k=3, st=1)
+    add_trans("d_h3", D, 4, 1024, 1024, B, 1024, k=3, st=2)
+    add_trans("d_h4", D, 8, 1024, 1024, B, 2048, k=3, st=1, act=False)
+    # backward of the two big layers
+    add_wgrad("d_h4.wgrad", D, 8, 2048, 1024, 1024, B, k=3, st=1)
+    add_fprop("d_h4.dgrad", D, 8, 2048, 2048, k=3, st=1)
+    add_wgrad("h0.wgrad", E, 8, 2048, 1024, 0, 0, k=3, st=1)
+    add_trans("h0.dgrad", E, 8, 1024, 0, 0, 2048, k=3, st=1)
+    cases_done = True
+else:
+    cases_done = False
 # forward
-add_im2col("h0.im2col", E, 64, 3)
-add_gemm("h0.gemm (K=75)", E * 1024, 64, 75, pad=1)
-add_fprop("h1", E, 32, 64, 128)
-add_fprop("h2", E, 16, 128, 256)
-add_fprop("h3", E, 8, 256, 512)
-add_gemm("h4_lin", E, 1024, 8192)
-add_gemm("hz_lin", B, 1024, 1024)
-add_gemm("d_h0_lin", D, 8192, 1024)
-add_trans("d_h1", D, 4, 512, 512, B, 256)
-add_trans("d_h2", D, 8, 256, 256, B, 128)
-add_trans("d_h3", D, 16, 128, 128, B, 64)
-add_trans("d_h4 (128->3 @64)", D, 32, 64, 64, B, 3, act=False)
-# backward: decoder
-add_gemm("d_h4.wgrad (M=75)", 75, 64, D * 1024, tA=True, bias=False, accumulate=True, pad=1)
-add_gemm("d_h4.dgrad (K=75)", D * 1024, 128, 75, bias=False, pad=1)
-add_wgrad("d_h3.wgrad", D, 32, 64, 128, 128, B)
-add_fprop("d_h3.dgrad", D, 32, 64, 256)
-add_wgrad("d_h2.wgrad", D, 16, 128, 256, 256, B)
-add_fprop("d_h2.dgrad", D, 16, 128, 512)
-add_wgrad("d_h1.wgrad", D, 8, 256, 512, 512, B)
-add_fprop("d_h1.dgrad", D, 8, 256, 1024)
-add_gemm("d_h0_lin.wgrad", 1024, 8192, D, tA=True, bias=False, accumulate=True)
-add_gemm("d_h0_lin.dgrad", D, 1024, 8192, tB=True, bias=False)
-# backward: encoder
-add_gemm("h4_lin.wgrad", 8192, 1024, E, tA=True, bias=False, accumulate=True)
-add_gemm("h4_lin.dgrad", E, 8192, 1024, tB=True, bias=False)
-add_wgrad("h3.wgrad", E, 8, 256, 512, 0, 0)
-add_trans("h3.dgrad", E, 4, 512, 0, 0, 256)
-add_wgrad("h2.wgrad", E, 16, 128, 256, 0, 0)
-add_trans("h2.dgrad", E, 8, 256, 0, 0, 128)
-add_wgrad("h1.wgrad", E, 32, 64, 128, 0, 0)
-add_trans("h1.dgrad", E, 16, 128, 0, 0, 64)
-add_gemm("h0.wgrad (M=75)", 75, 64, E * 1024, tA=True, bias=False, accumulate=True, pad=1)
+if not cases_done:
+  add_im2col("h0.im2col", E, 64, 3)
+  add_gemm("h0.gemm (K=75)", E * 1024, 64, 75, pad=1)
+  add_fprop("h1", E, 32, 64, 128)
+  add_fprop("h2", E, 16, 128, 256)
+  add_fprop("h3", E, 8, 256, 512)
+  add_gemm("h4_lin", E, 1024, 8192)
+  add_gemm("hz_lin", B, 1024, 1024)
+  add_gemm("d_h0_lin", D, 8192, 1024)
+  add_trans("d_h1", D, 4, 512, 512, B, 256)
+  add_trans("d_h2", D, 8, 256, 256, B, 128)
+  add_trans("d_h3", D, 16, 128, 128, B, 64)
+  add_trans("d_h4 (128->3 @64)", D, 32, 64, 64, B, 3, act=False)
+  # backward: decoder
+  add_gemm("d_h4.wgrad (M=75)", 75, 64, D * 1024, tA=True, bias=False, accumulate=True, pad=1)
+  add_gemm("d_h4.dgrad (K=75)", D * 1024, 128, 75, bias=False, pad=1)
+  add_wgrad("d_h3.wgrad", D, 32, 64, 128, 128, B)
+  add_fprop("d_h3.dgrad", D, 32, 64, 256)
+  add_wgrad("d_h2.wgrad", D, 16, 128, 256, 256, B)
+  add_fprop("d_h2.dgrad", D, 16, 128, 512)
+  add_wgrad("d_h1.wgrad", D, 8, 256, 512, 512, B)
+  add_fprop("d_h1.dgrad", D, 8, 256, 1024)
+  add_gemm("d_h0_lin.wgrad", 1024, 8192, D, tA=True, bias=False, accumulate=True)
+  add_gemm("d_h0_lin.dgrad", D, 1024, 8192, tB=True, bias=False)
+  # backward: encoder
+  add_gemm("h4_lin.wgrad", 8192, 1024, E, tA=True, bias=False, accumulate=True)
+  add_gemm("h4_lin.dgrad", E, 8192, 1024, tB=True, bias=False)
+  add_wgrad("h3.wgrad", E, 8, 256, 512, 0, 0)
+  add_trans("h3.dgrad", E, 4, 512, 0, 0, 256)
+  add_wgrad("h2.wgrad", E, 16, 128, 256, 0, 0)
+  add_trans("h2.dgrad", E, 8, 256, 0, 0, 128)
+  add_wgrad("h1.wgrad", E, 32, 64, 128, 0, 0)
+  add_trans("h1.dgrad", E, 16, 128, 0, 0, 64)
+  add_gemm("h0.wgrad (M=75)", 75, 64, E * 1024, tA=True, bias=False, accumulate=True, pad=1)
 
 only = set(x for x in a.only.split(",") if x)
 tot = {}

@@ -12,7 +12,9 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_i
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctx_b200.so")
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC3, IMPL_FAST, IMPL_BF16X3 = 0, 1, 2, 3, 4, 5
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC3, IMPL_FAST, IMPL_BF16X3, IMPL_P16X1 = 0, 1, 2, 3, 4, 5, 6
+IMPL_P16X3 = IMPL_BF16X3
+P16_BF16, P16_F16 = 0, 1
 
 
 class CtxError(RuntimeError):
@@ -27,6 +29,11 @@ class ConvGeom(Structure):
 class Epilogue(Structure):
     _fields_ = [("bias", c_void_p), ("act_ref", c_void_p), ("slope", c_float), ("act", c_int32),
                 ("accumulate", c_int32), ("round_tf32", c_int32)]
+
+
+class P16(Structure):
+    """ctx_p16: element type and arithmetic mode of a 16-bit-planes call (include/ctx_b200.h)."""
+    _fields_ = [("dtype", c_int32), ("nprod", c_int32), ("a_scale", c_void_p), ("amax_bits", c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/ctx_b200.h
@@ -61,6 +68,28 @@ SIGNATURES = {
     "ctx_conv2d_transpose_merged_pack": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_void_p]),
     "ctx_conv2d_transpose_merged_bf16x3": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                                      c_void_p, c_int32, POINTER(ConvGeom), POINTER(Epilogue), c_void_p]),
+    "ctx_split_planes": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p]),
+    "ctx_split_planes_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "ctx_conv2d_fprop_p16_eligible": (c_int32, [c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_fprop_p16": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, POINTER(ConvGeom),
+                                       POINTER(Epilogue), POINTER(P16), c_void_p]),
+    "ctx_conv2d_transpose_p16_eligible": (c_int32, [c_int32, c_int32, c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_transpose_p16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                           c_int32, c_int32, POINTER(ConvGeom), POINTER(Epilogue), POINTER(P16), c_void_p]),
+    "ctx_conv2d_transpose_merged_p16_eligible": (c_int32, [c_int32, c_int32, c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_transpose_merged_pack_p16": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_int32,
+                                                       c_int32, c_void_p]),
+    "ctx_conv2d_transpose_merged_p16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                                  c_void_p, c_int32, c_int32, POINTER(ConvGeom), POINTER(Epilogue),
+                                                  POINTER(P16), c_void_p]),
+    "ctx_conv2d_wgrad_p16_eligible": (c_int32, [c_int32, c_int32, c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_wgrad_p16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p,
+                                       POINTER(ConvGeom), POINTER(P16), c_void_p]),
+    "ctx_grad_planes": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                  c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "ctx_amax": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "ctx_skip_grad_sum": (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_float, c_void_p, c_int32,
+                                    c_void_p]),
     "ctx_crc32c": (C.c_uint32, [c_void_p, C.c_uint64, C.c_uint32]),
     "ctx_gather_frames": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "ctx_lrelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_void_p]),

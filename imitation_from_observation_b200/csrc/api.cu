@@ -186,88 +186,169 @@ extern "C" int ctx_conv2d_transpose(const float* x1, int32_t C1, const float* x2
   return simt_conv2d_transpose(x1, C1, x2, C2, x2_batch, w, y, Cn, *g, e, (cudaStream_t)stream);
 }
 
-// ---- forward convolutions from bf16 (hi, lo) planes (tc_bf16x3.cu) ------------------------------------------------------------
-extern "C" int ctx_conv2d_fprop_bf16x3_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g) {
-  if (!g || check_geom(g, "conv2d_fprop_bf16x3")) return 0;
-  return (ctx_tc_available() && bf3_conv2d_fprop_eligible(C, Co, *g)) ? 1 : 0;
+// ---- convolutions on 16-bit operand planes (tc_h16.cu) ---------------------------------------------------------------------
+static int p16_cfg(const ctx_p16* c, H16Cfg* out, const char* who) {
+  CTX_REQUIRE(c != nullptr, "%s: null ctx_p16", who);
+  CTX_REQUIRE(c->dtype == CTX_P16_F16 || c->dtype == CTX_P16_BF16, "%s: dtype must be CTX_P16_F16 or CTX_P16_BF16", who);
+  CTX_REQUIRE(c->nprod == 1 || c->nprod == 3, "%s: nprod must be 1 or 3", who);
+  CTX_REQUIRE(c->nprod == 3 || c->dtype == CTX_P16_F16, "%s: the single-product mode needs fp16 planes", who);
+  out->f16 = c->dtype == CTX_P16_F16 ? 1 : 0;
+  out->nprod = c->nprod;
+  out->a_scale = c->a_scale;
+  out->amax_bits = c->amax_bits;
+  return CTX_OK;
+}
+static const ctx_p16 kBf16x3 = {CTX_P16_BF16, 3, nullptr, nullptr};
+
+extern "C" int ctx_conv2d_fprop_p16_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g) {
+  if (!g || check_geom(g, "conv2d_fprop_p16")) return 0;
+  return (ctx_tc_available() && h16_conv2d_fprop_eligible(C, Co, *g)) ? 1 : 0;
 }
 
-extern "C" int ctx_conv2d_fprop_bf16x3(const void* x_planes, int32_t C, const void* w_planes, float* y, void* y_planes,
-                                       int32_t Co, const ctx_conv_geom* g, const ctx_epilogue* epi, void* stream) {
-  int rc = check_geom(g, "conv2d_fprop_bf16x3");
+extern "C" int ctx_conv2d_fprop_p16(const void* x_planes, int32_t C, const void* w_planes, float* y, void* y_planes,
+                                    int32_t y_planes_n, int32_t Co, const ctx_conv_geom* g, const ctx_epilogue* epi,
+                                    const ctx_p16* cfg, void* stream) {
+  int rc = check_geom(g, "conv2d_fprop_p16");
+  if (rc) return rc;
+  H16Cfg c;
+  rc = p16_cfg(cfg, &c, "conv2d_fprop_p16");
   if (rc) return rc;
   if (g->N == 0) return CTX_OK;
-  CTX_REQUIRE(x_planes && w_planes && y, "conv2d_fprop_bf16x3: null pointer");
-  if (!ctx_tc_available() || !bf3_conv2d_fprop_eligible(C, Co, *g)) {
-    set_error("conv2d_fprop_bf16x3: shape not eligible (C, Co %% 64, exact 128-pixel tiling) or no sm_100 device");
+  CTX_REQUIRE(x_planes && w_planes && y, "conv2d_fprop_p16: null pointer");
+  if (!ctx_tc_available() || !h16_conv2d_fprop_eligible(C, Co, *g)) {
+    set_error("conv2d_fprop_p16: shape not eligible (C, Co %% 64, exact 128-pixel tiling) or no sm_100 device");
     return CTX_ERR_UNSUPPORTED;
   }
-  g_last_impl = CTX_IMPL_BF16X3;
-  return bf3_conv2d_fprop((const __nv_bfloat16*)x_planes, C, (const __nv_bfloat16*)w_planes, y, (__nv_bfloat16*)y_planes,
-                          Co, *g, make_epi(epi), (cudaStream_t)stream);
+  g_last_impl = c.nprod == 3 ? CTX_IMPL_P16X3 : CTX_IMPL_P16X1;
+  return h16_conv2d_fprop(x_planes, C, w_planes, y, y_planes, y_planes_n, Co, *g, make_epi(epi), c, (cudaStream_t)stream);
 }
 
-extern "C" int ctx_conv2d_transpose_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
-                                                    const ctx_conv_geom* g) {
-  if (!g || check_geom(g, "conv2d_transpose_bf16x3")) return 0;
-  return (ctx_tc_available() && bf3_conv2d_transpose_eligible(C1, C2, x2_batch, Cn, *g)) ? 1 : 0;
+extern "C" int ctx_conv2d_transpose_p16_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
+                                                 const ctx_conv_geom* g) {
+  if (!g || check_geom(g, "conv2d_transpose_p16")) return 0;
+  return (ctx_tc_available() && h16_conv2d_transpose_eligible(C1, C2, x2_batch, Cn, *g)) ? 1 : 0;
 }
 
-extern "C" int ctx_conv2d_transpose_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
-                                           int32_t x2_batch, const void* w_planes, float* y, void* y_planes, int32_t Cn,
-                                           const ctx_conv_geom* g, const ctx_epilogue* epi, void* stream) {
-  int rc = check_geom(g, "conv2d_transpose_bf16x3");
+extern "C" int ctx_conv2d_transpose_p16(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2, int32_t x2_batch,
+                                        const void* w_planes, float* y, void* y_planes, int32_t y_planes_n, int32_t Cn,
+                                        const ctx_conv_geom* g, const ctx_epilogue* epi, const ctx_p16* cfg, void* stream) {
+  int rc = check_geom(g, "conv2d_transpose_p16");
+  if (rc) return rc;
+  H16Cfg c;
+  rc = p16_cfg(cfg, &c, "conv2d_transpose_p16");
   if (rc) return rc;
   if (g->N == 0) return CTX_OK;
-  CTX_REQUIRE(x1_planes && w_planes && y, "conv2d_transpose_bf16x3: null pointer");
-  CTX_REQUIRE((C2 == 0) == (x2_planes == nullptr), "conv2d_transpose_bf16x3: x2 and C2 must both be set or both be empty");
-  if (!ctx_tc_available() || !bf3_conv2d_transpose_eligible(C1, C2, x2_batch, Cn, *g)) {
-    set_error("conv2d_transpose_bf16x3: shape not eligible (channels %% 64, exact 128-pixel phase tiling) or no sm_100 device");
+  CTX_REQUIRE(x1_planes && w_planes && y, "conv2d_transpose_p16: null pointer");
+  CTX_REQUIRE((C2 == 0) == (x2_planes == nullptr), "conv2d_transpose_p16: x2 and C2 must both be set or both be empty");
+  if (!ctx_tc_available() || !h16_conv2d_transpose_eligible(C1, C2, x2_batch, Cn, *g)) {
+    set_error("conv2d_transpose_p16: shape not eligible (channels %% 64, exact 128-pixel phase tiling) or no sm_100 device");
     return CTX_ERR_UNSUPPORTED;
   }
-  g_last_impl = CTX_IMPL_BF16X3;
-  return bf3_conv2d_transpose((const __nv_bfloat16*)x1_planes, C1, (const __nv_bfloat16*)x2_planes, C2, x2_batch,
-                              (const __nv_bfloat16*)w_planes, y, (__nv_bfloat16*)y_planes, Cn, *g, make_epi(epi),
-                              (cudaStream_t)stream);
+  g_last_impl = c.nprod == 3 ? CTX_IMPL_P16X3 : CTX_IMPL_P16X1;
+  return h16_conv2d_transpose(x1_planes, C1, x2_planes, C2, x2_batch, w_planes, y, y_planes, y_planes_n, Cn, *g, make_epi(epi),
+                              c, (cudaStream_t)stream);
 }
 
-extern "C" int ctx_conv2d_transpose_merged_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
-                                                           const ctx_conv_geom* g) {
-  if (!g || check_geom(g, "conv2d_transpose_merged_bf16x3")) return 0;
-  return (ctx_tc_available() && bf3_conv2d_transpose_merged_eligible(C1, C2, x2_batch, Cn, *g)) ? 1 : 0;
+extern "C" int ctx_conv2d_transpose_merged_p16_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
+                                                        const ctx_conv_geom* g) {
+  if (!g || check_geom(g, "conv2d_transpose_merged_p16")) return 0;
+  return (ctx_tc_available() && h16_conv2d_transpose_merged_eligible(C1, C2, x2_batch, Cn, *g)) ? 1 : 0;
 }
 
 extern "C" int64_t ctx_conv2d_transpose_merged_rows(int32_t Cn, const ctx_conv_geom* g) {
   if (!g || check_geom(g, "conv2d_transpose_merged_rows")) return 0;
-  return bf3_conv2d_transpose_merged_rows(Cn, *g);
+  return h16_conv2d_transpose_merged_rows(Cn, *g);
 }
 
-extern "C" int ctx_conv2d_transpose_merged_pack(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g,
-                                                void* wm_planes, void* stream) {
+extern "C" int ctx_conv2d_transpose_merged_pack_p16(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g,
+                                                    void* wm_planes, int32_t nplanes, int32_t dtype, void* stream) {
   int rc = check_geom(g, "conv2d_transpose_merged_pack");
   if (rc) return rc;
   CTX_REQUIRE(w && wm_planes && Ck > 0 && Cn > 0, "conv2d_transpose_merged_pack: bad arguments");
-  return bf3_conv2d_transpose_merged_pack(w, Ck, Cn, *g, (__nv_bfloat16*)wm_planes, (cudaStream_t)stream);
+  CTX_REQUIRE(dtype == CTX_P16_F16 || dtype == CTX_P16_BF16, "conv2d_transpose_merged_pack: bad dtype");
+  return h16_conv2d_transpose_merged_pack(w, Ck, Cn, *g, wm_planes, nplanes, dtype == CTX_P16_F16, (cudaStream_t)stream);
 }
 
+extern "C" int ctx_conv2d_transpose_merged_p16(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
+                                               int32_t x2_batch, const void* wm_planes, float* y, void* y_planes,
+                                               int32_t y_planes_n, int32_t Cn, const ctx_conv_geom* g,
+                                               const ctx_epilogue* epi, const ctx_p16* cfg, void* stream) {
+  int rc = check_geom(g, "conv2d_transpose_merged_p16");
+  if (rc) return rc;
+  H16Cfg c;
+  rc = p16_cfg(cfg, &c, "conv2d_transpose_merged_p16");
+  if (rc) return rc;
+  if (g->N == 0) return CTX_OK;
+  CTX_REQUIRE(x1_planes && wm_planes && y, "conv2d_transpose_merged_p16: null pointer");
+  CTX_REQUIRE((C2 == 0) == (x2_planes == nullptr), "conv2d_transpose_merged_p16: x2 and C2 must both be set or both be empty");
+  if (!ctx_tc_available() || !h16_conv2d_transpose_merged_eligible(C1, C2, x2_batch, Cn, *g)) {
+    set_error("conv2d_transpose_merged_p16: shape not eligible (stride 2, 4 * Cn == 256 or 512, channels %% 64, even output, "
+              "input grid tiling into 128 pixels) or no sm_100 device");
+    return CTX_ERR_UNSUPPORTED;
+  }
+  g_last_impl = c.nprod == 3 ? CTX_IMPL_P16X3 : CTX_IMPL_P16X1;
+  return h16_conv2d_transpose_merged(x1_planes, C1, x2_planes, C2, x2_batch, wm_planes, y, y_planes, y_planes_n, Cn, *g,
+                                     make_epi(epi), c, (cudaStream_t)stream);
+}
+
+extern "C" int ctx_conv2d_wgrad_p16_eligible(int32_t Ca, int32_t Cb1, int32_t Cb2, int32_t small2_batch,
+                                             const ctx_conv_geom* g) {
+  if (!g || check_geom(g, "conv2d_wgrad_p16")) return 0;
+  return (ctx_tc_available() && h16_conv2d_wgrad_eligible(Ca, Cb1, Cb2, small2_batch, *g)) ? 1 : 0;
+}
+
+extern "C" int ctx_conv2d_wgrad_p16(const void* big_planes, int32_t Ca, const void* small1_planes, int32_t Cb1,
+                                    const void* small2_planes, int32_t Cb2, int32_t small2_batch, float* dw,
+                                    const ctx_conv_geom* g, const ctx_p16* cfg, void* stream) {
+  int rc = check_geom(g, "conv2d_wgrad_p16");
+  if (rc) return rc;
+  H16Cfg c;
+  rc = p16_cfg(cfg, &c, "conv2d_wgrad_p16");
+  if (rc) return rc;
+  CTX_REQUIRE(Ca > 0 && Cb1 > 0 && Cb2 >= 0, "conv2d_wgrad_p16: bad channel count");
+  if (g->N == 0) return CTX_OK;
+  CTX_REQUIRE(big_planes && small1_planes && dw, "conv2d_wgrad_p16: null pointer");
+  CTX_REQUIRE((Cb2 == 0) == (small2_planes == nullptr), "conv2d_wgrad_p16: small2 and Cb2 must both be set or both be empty");
+  CTX_REQUIRE(Cb2 == 0 || small2_batch > 0, "conv2d_wgrad_p16: small2_batch must be positive");
+  if (!ctx_tc_available() || !h16_conv2d_wgrad_eligible(Ca, Cb1, Cb2, small2_batch, *g)) {
+    set_error("conv2d_wgrad_p16: shape not eligible (channels %% 64, small grid tiling into 64 pixels) or no sm_100 device");
+    return CTX_ERR_UNSUPPORTED;
+  }
+  g_last_impl = c.nprod == 3 ? CTX_IMPL_P16X3 : CTX_IMPL_P16X1;
+  return h16_conv2d_wgrad(big_planes, Ca, small1_planes, Cb1, small2_planes, Cb2, small2_batch, dw, *g, c, (cudaStream_t)stream);
+}
+
+// the round-1 names: bf16 planes, three products, two result planes
+extern "C" int ctx_conv2d_fprop_bf16x3_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g) {
+  return ctx_conv2d_fprop_p16_eligible(C, Co, g);
+}
+extern "C" int ctx_conv2d_fprop_bf16x3(const void* x_planes, int32_t C, const void* w_planes, float* y, void* y_planes,
+                                       int32_t Co, const ctx_conv_geom* g, const ctx_epilogue* epi, void* stream) {
+  return ctx_conv2d_fprop_p16(x_planes, C, w_planes, y, y_planes, 2, Co, g, epi, &kBf16x3, stream);
+}
+extern "C" int ctx_conv2d_transpose_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
+                                                    const ctx_conv_geom* g) {
+  return ctx_conv2d_transpose_p16_eligible(C1, C2, x2_batch, Cn, g);
+}
+extern "C" int ctx_conv2d_transpose_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
+                                           int32_t x2_batch, const void* w_planes, float* y, void* y_planes, int32_t Cn,
+                                           const ctx_conv_geom* g, const ctx_epilogue* epi, void* stream) {
+  return ctx_conv2d_transpose_p16(x1_planes, C1, x2_planes, C2, x2_batch, w_planes, y, y_planes, 2, Cn, g, epi, &kBf16x3, stream);
+}
+extern "C" int ctx_conv2d_transpose_merged_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
+                                                           const ctx_conv_geom* g) {
+  return ctx_conv2d_transpose_merged_p16_eligible(C1, C2, x2_batch, Cn, g);
+}
+extern "C" int ctx_conv2d_transpose_merged_pack(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g,
+                                                void* wm_planes, void* stream) {
+  return ctx_conv2d_transpose_merged_pack_p16(w, Ck, Cn, g, wm_planes, 2, CTX_P16_BF16, stream);
+}
 extern "C" int ctx_conv2d_transpose_merged_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
                                                   int32_t x2_batch, const void* wm_planes, float* y, void* y_planes,
                                                   int32_t Cn, const ctx_conv_geom* g, const ctx_epilogue* epi,
                                                   void* stream) {
-  int rc = check_geom(g, "conv2d_transpose_merged_bf16x3");
-  if (rc) return rc;
-  if (g->N == 0) return CTX_OK;
-  CTX_REQUIRE(x1_planes && wm_planes && y, "conv2d_transpose_merged_bf16x3: null pointer");
-  CTX_REQUIRE((C2 == 0) == (x2_planes == nullptr), "conv2d_transpose_merged_bf16x3: x2 and C2 must both be set or both be empty");
-  if (!ctx_tc_available() || !bf3_conv2d_transpose_merged_eligible(C1, C2, x2_batch, Cn, *g)) {
-    set_error("conv2d_transpose_merged_bf16x3: shape not eligible (stride 2, 4 * Cn == 256, channels %% 64, even output, "
-              "input grid tiling into 128 pixels) or no sm_100 device");
-    return CTX_ERR_UNSUPPORTED;
-  }
-  g_last_impl = CTX_IMPL_BF16X3;
-  return bf3_conv2d_transpose_merged((const __nv_bfloat16*)x1_planes, C1, (const __nv_bfloat16*)x2_planes, C2, x2_batch,
-                                     (const __nv_bfloat16*)wm_planes, y, (__nv_bfloat16*)y_planes, Cn, *g, make_epi(epi),
-                                     (cudaStream_t)stream);
+  return ctx_conv2d_transpose_merged_p16(x1_planes, C1, x2_planes, C2, x2_batch, wm_planes, y, y_planes, 2, Cn, g, epi,
+                                         &kBf16x3, stream);
 }
 
 extern "C" int ctx_conv2d_wgrad(const float* big, int32_t Ca, const float* small1, int32_t Cb1, const float* small2,

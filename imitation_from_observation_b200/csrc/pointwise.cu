@@ -104,64 +104,6 @@ __global__ void gather_frames_kernel(const void* __restrict__ bank, const float*
   }
 }
 
-// ---- fp32 -> bf16 (hi, lo) planes: hi = bf16_rn(x), lo = bf16_rn(x - hi) ------------------------------------------------------
-// Operand preparation for tc_bf16x3.cu.  x - hi is exact in fp32, so hi + lo carries 16 significant bits of x.
-__device__ __forceinline__ void split_bf16_4(const float4 v, uint2& hi, uint2& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                      h3 = __float2bfloat16_rn(v.w);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                      l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
-}
-
-__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ planes) {
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
-  __nv_bfloat16* hi = planes;
-  __nv_bfloat16* lo = planes + n;
-  if (n % 4 == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)planes) & 7) == 0) {
-    for (int64_t j = i0; j < n / 4; j += step) {
-      uint2 h, l;
-      split_bf16_4(reinterpret_cast<const float4*>(x)[j], h, l);
-      reinterpret_cast<uint2*>(hi)[j] = h;
-      reinterpret_cast<uint2*>(lo)[j] = l;
-    }
-  } else {
-    for (int64_t j = i0; j < n; j += step) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(x[j]);
-      hi[j] = h;
-      lo[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h));
-    }
-  }
-}
-
-// w [T][R][Cc] fp32 -> planes [2][T][Cc][R]: the conv filter [kh*kw][Cin][Cout] becomes per-tap K-major rows [Cout][Cin].
-// 32 x 32 tiles through shared memory, both global accesses coalesced.
-__global__ void split_bf16_transpose_kernel(const float* __restrict__ w, int T, int R, int Cc,
-                                            __nv_bfloat16* __restrict__ planes) {
-  __shared__ float tile[32][33];
-  const int t = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const float* src = w + (int64_t)t * R * Cc;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < Cc) ? src[(int64_t)r * Cc + c] : 0.f;
-  }
-  __syncthreads();
-  const int64_t plane = (int64_t)T * R * Cc;
-  __nv_bfloat16* hi = planes + (int64_t)t * R * Cc;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < Cc && r < R) {
-      const float v = tile[threadIdx.x][i];
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      hi[(int64_t)c * R + r] = h;
-      hi[plane + (int64_t)c * R + r] = __float2bfloat16_rn(v - __bfloat162float(h));
-    }
-  }
-}
-
 // ---- lrelu backward ------------------------------------------------------------------------------------------
 __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yref, float* out,
                                  int64_t n, float slope, int accumulate) {
@@ -646,26 +588,6 @@ extern "C" int ctx_gather_frames(const void* bank, int32_t bank_is_u8, const flo
   else
     gather_frames_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(bank, lut256, bank_frames, frame_elems, frame_idx, out);
   CTX_LAUNCH_CHECK("gather_frames");
-  return CTX_OK;
-}
-
-extern "C" int ctx_split_bf16(const float* x, int64_t n, void* planes, void* stream) {
-  CTX_REQUIRE(n >= 0, "split_bf16: negative size");
-  if (n == 0) return CTX_OK;
-  CTX_REQUIRE(x && planes, "split_bf16: null pointer");
-  split_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, n, (__nv_bfloat16*)planes);
-  CTX_LAUNCH_CHECK("split_bf16");
-  return CTX_OK;
-}
-
-extern "C" int ctx_split_bf16_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, void* planes, void* stream) {
-  CTX_REQUIRE(T >= 0 && R >= 0 && Cc >= 0, "split_bf16_transpose: negative size");
-  if (T == 0 || R == 0 || Cc == 0) return CTX_OK;
-  CTX_REQUIRE(w && planes, "split_bf16_transpose: null pointer");
-  CTX_REQUIRE(T <= 65535 && cdiv(R, 32) <= 65535, "split_bf16_transpose: grid too large");
-  dim3 grid((unsigned)cdiv(Cc, 32), (unsigned)cdiv(R, 32), (unsigned)T);
-  split_bf16_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, T, R, Cc, (__nv_bfloat16*)planes);
-  CTX_LAUNCH_CHECK("split_bf16_transpose");
   return CTX_OK;
 }
 

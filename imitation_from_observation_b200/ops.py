@@ -131,133 +131,253 @@ def conv2d_transpose(x1, w, out_hw, bias=None, stride: int = 2, x2=None, act: bo
     return out
 
 
-# ---- forward convolutions from bf16 (hi, lo) planes ----------------------------------------------------------------
-# A planes tensor is torch.bfloat16 of shape (2,) + shape: [0] = hi = bf16(x), [1] = lo = bf16(x - hi).
-def split_bf16(x, out=None):
-    """fp32 tensor -> (hi, lo) bf16 planes (2, *x.shape)."""
+# ---- convolutions on 16-bit operand planes (csrc/tc_h16.cu) ---------------------------------------------------------------
+# A planes tensor is torch.float16 or torch.bfloat16 of shape (nplanes,) + shape: [0] = hi = rn16(s*x), [1] = lo = rn16(s*x - hi).
+PLANES_DTYPE = torch.float16          # default element type of the planes (fp16: 22 significant bits in hi + lo, and the
+#                                       hi plane alone is a TF32-grade operand for the single-product backward GEMMs)
+
+
+def _p16_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return _lib.P16_F16
+    if t.dtype == torch.bfloat16:
+        return _lib.P16_BF16
+    raise _lib.CtxError("a planes tensor must be float16 or bfloat16, got %s" % t.dtype)
+
+
+def _reqp(t: torch.Tensor, name: str, like: Optional[torch.Tensor] = None) -> int:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype not in (torch.float16, torch.bfloat16):
+        raise _lib.CtxError("%s must be a CUDA float16 / bfloat16 planes tensor" % name)
+    if like is not None and t.dtype != like.dtype:
+        raise _lib.CtxError("%s: every planes operand of a call must have the same element type" % name)
+    if not t.is_contiguous():
+        raise _lib.CtxError("%s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def _p16(planes: torch.Tensor, nprod: int, a_scale=None, amax=None) -> "_lib.P16":
+    if nprod == 3 and planes.shape[0] < 2:
+        raise _lib.CtxError("three-product mode needs (hi, lo) planes")
+    return _lib.P16(_p16_dtype(planes), int(nprod), None if a_scale is None else _req(a_scale, "a_scale"),
+                    None if amax is None else _req(amax, "amax", torch.int32))
+
+
+def split_planes(x, out=None, nplanes: int = 2, dtype=None):
+    """fp32 tensor -> planes (nplanes, *x.shape)."""
     p = _req(x, "x")
     if out is None:
-        out = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.bfloat16)
-    elif out.numel() != 2 * x.numel():
-        raise _lib.CtxError("split_bf16: out has the wrong size")
-    check(_lib.load().ctx_split_bf16(p, x.numel(), _req(out, "out", torch.bfloat16), _stream()), "ctx_split_bf16")
+        out = torch.empty((nplanes,) + tuple(x.shape), device=x.device, dtype=dtype or PLANES_DTYPE)
+    elif out.numel() != nplanes * x.numel():
+        raise _lib.CtxError("split_planes: out has the wrong size")
+    check(_lib.load().ctx_split_planes(p, x.numel(), _reqp(out, "out"), nplanes, _p16_dtype(out), _stream()), "ctx_split_planes")
     return out
+
+
+def split_planes_transpose(w, out=None, nplanes: int = 2, dtype=None):
+    """w [kh,kw,R,Cc] -> planes (nplanes, kh*kw*Cc, R): a conv filter [kh,kw,Cin,Cout] becomes the per-tap K-major rows
+    [Cout][Cin] conv2d_planes reads; a transposed-conv filter [kh,kw,Cout,Cin] becomes the rows [Cin][Cout] its data
+    gradient reads."""
+    kh, kw, R, Cc = w.shape
+    if out is None:
+        out = torch.empty((nplanes, kh * kw * Cc, R), device=w.device, dtype=dtype or PLANES_DTYPE)
+    elif out.numel() != nplanes * w.numel():
+        raise _lib.CtxError("split_planes_transpose: out has the wrong size")
+    check(_lib.load().ctx_split_planes_transpose(_req(w, "w"), kh * kw, R, Cc, _reqp(out, "out"), nplanes, _p16_dtype(out),
+                                                 _stream()), "ctx_split_planes_transpose")
+    return out
+
+
+def split_bf16(x, out=None):
+    return split_planes(x, out=out, nplanes=2, dtype=torch.bfloat16)
 
 
 def split_bf16_conv_filter(w, out=None):
-    """conv filter [kh,kw,Cin,Cout] -> planes (2, kh*kw*Cout, Cin): per-tap K-major rows for conv2d_bf16x3."""
-    kh, kw, Cin, Co = w.shape
-    if out is None:
-        out = torch.empty((2, kh * kw * Co, Cin), device=w.device, dtype=torch.bfloat16)
-    check(_lib.load().ctx_split_bf16_transpose(_req(w, "w"), kh * kw, Cin, Co, _req(out, "out", torch.bfloat16),
-                                               _stream()), "ctx_split_bf16_transpose")
-    return out
+    return split_planes_transpose(w, out=out, nplanes=2, dtype=torch.bfloat16)
 
 
-def conv2d_bf16x3_eligible(n, in_hw, Cin, Co, k, stride) -> bool:
+def conv2d_planes_eligible(n, in_hw, Cin, Co, k, stride) -> bool:
     g = conv_geom(n, tuple(in_hw), k, stride)
-    return bool(_lib.load().ctx_conv2d_fprop_bf16x3_eligible(Cin, Co, C.byref(g)))
+    return bool(_lib.load().ctx_conv2d_fprop_p16_eligible(Cin, Co, C.byref(g)))
 
 
-def conv2d_bf16x3(xp, wp, k: int, bias=None, stride: int = 2, act: bool = False, out=None, out_planes=None):
-    """conv2d(SAME) + bias (+ lrelu) from planes: xp (2,N,H,W,C), wp (2,k*k*Co,C) -> out fp32 [N,P,Q,Co] (+ out_planes)."""
+def conv2d_planes(xp, wp, k: int, bias=None, stride: int = 2, act: bool = False, out=None, out_planes=None, nprod: int = 3,
+                  act_ref=None, accumulate: bool = False, a_scale=None, amax=None):
+    """conv2d(SAME) + bias (+ lrelu) from planes: xp (np,N,H,W,C), wp (np,k*k*Co,C) -> out fp32 [N,P,Q,Co] (+ out_planes).
+    nprod = 1 with a_scale / amax is the data gradient of a transposed conv (xp = planes of dY)."""
     _, N, H, W_, Cin = xp.shape
     Co = wp.shape[1] // (k * k)
     if wp.shape[2] != Cin or wp.shape[1] != k * k * Co:
-        raise _lib.CtxError("conv2d_bf16x3: filter planes %s do not match input planes %s" % (tuple(wp.shape), tuple(xp.shape)))
+        raise _lib.CtxError("conv2d_planes: filter planes %s do not match input planes %s" % (tuple(wp.shape), tuple(xp.shape)))
     g = conv_geom(N, (H, W_), k, stride)
     if out is None:
         out = torch.empty((N, g.P, g.Q, Co), device=xp.device, dtype=torch.float32)
-    if out_planes is not None and out_planes.numel() != 2 * out.numel():
-        raise _lib.CtxError("conv2d_bf16x3: out_planes has the wrong size")
-    epi = make_epilogue(bias, act)
+    if out_planes is not None and out_planes.numel() != out_planes.shape[0] * out.numel():
+        raise _lib.CtxError("conv2d_planes: out_planes has the wrong size")
+    epi = make_epilogue(bias, act, act_ref, accumulate)
+    cfg = _p16(xp, nprod, a_scale, amax)
     pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * k * k * Cin)
-    check(_lib.load().ctx_conv2d_fprop_bf16x3(_req(xp, "xp", torch.bfloat16), Cin, _req(wp, "wp", torch.bfloat16),
-                                              _req(out, "out"),
-                                              None if out_planes is None else _req(out_planes, "out_planes", torch.bfloat16),
-                                              Co, C.byref(g), C.byref(epi), _stream()), "ctx_conv2d_fprop_bf16x3")
+    check(_lib.load().ctx_conv2d_fprop_p16(_reqp(xp, "xp"), Cin, _reqp(wp, "wp", xp), _req(out, "out"),
+                                           None if out_planes is None else _reqp(out_planes, "out_planes", xp),
+                                           0 if out_planes is None else out_planes.shape[0], Co, C.byref(g), C.byref(epi),
+                                           C.byref(cfg), _stream()), "ctx_conv2d_fprop_p16")
     pr.done()
     return out
 
 
-def conv2d_transpose_bf16x3_eligible(n, out_hw, C1, C2, x2_batch, Cn, k, stride) -> bool:
+def conv2d_transpose_planes_eligible(n, out_hw, C1, C2, x2_batch, Cn, k, stride) -> bool:
     g = conv_geom(n, tuple(out_hw), k, stride)
-    return bool(_lib.load().ctx_conv2d_transpose_bf16x3_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
+    return bool(_lib.load().ctx_conv2d_transpose_p16_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
 
 
-def conv2d_transpose_bf16x3(x1p, wp, out_hw, k: int, bias=None, stride: int = 2, x2p=None, act: bool = False, out=None,
-                            out_planes=None):
-    """conv2d_transpose(SAME) + bias (+ lrelu) over concat([x1, x2], 3) from planes: x1p (2,N,P,Q,C1), x2p (2,N2,P,Q,C2),
-    wp (2, k*k*Cn, C1+C2) = split_bf16 of the filter [k,k,Cn,Ck] -> out fp32 [N,H,W,Cn] (+ out_planes)."""
+def conv2d_transpose_planes(x1p, wp, out_hw, k: int, bias=None, stride: int = 2, x2p=None, act: bool = False, out=None,
+                            out_planes=None, nprod: int = 3, act_ref=None, accumulate: bool = False, a_scale=None,
+                            amax=None):
+    """conv2d_transpose(SAME) + bias (+ lrelu) over concat([x1, x2], 3) from planes: x1p (np,N,P,Q,C1), x2p (np,N2,P,Q,C2),
+    wp (np, k*k*Cn, C1+C2) = planes of the filter [k,k,Cn,Ck] -> out fp32 [N,H,W,Cn] (+ out_planes).  nprod = 1 with
+    a_scale / amax / act_ref / accumulate is the data gradient of a conv (x1p = planes of dY, wp = planes of the HWIO filter)."""
     _, N, P, Q, C1 = x1p.shape
     C2 = 0 if x2p is None else x2p.shape[4]
     Ck = wp.shape[-1]
-    Cn = wp.numel() // (2 * k * k * Ck)
-    if Ck != C1 + C2:
-        raise _lib.CtxError("conv2d_transpose_bf16x3: filter planes do not match the inputs")
+    Cn = wp.shape[1] // (k * k)
+    if Ck != C1 + C2 or wp.shape[1] != k * k * Cn:
+        raise _lib.CtxError("conv2d_transpose_planes: filter planes do not match the inputs")
     g = conv_geom(N, tuple(out_hw), k, stride)
     if (g.P, g.Q) != (P, Q):
-        raise _lib.CtxError("conv2d_transpose_bf16x3: output %s inconsistent with input grid %s" % (tuple(out_hw), (P, Q)))
+        raise _lib.CtxError("conv2d_transpose_planes: output %s inconsistent with input grid %s" % (tuple(out_hw), (P, Q)))
     if out is None:
         out = torch.empty((N, g.H, g.W, Cn), device=x1p.device, dtype=torch.float32)
-    if out_planes is not None and out_planes.numel() != 2 * out.numel():
-        raise _lib.CtxError("conv2d_transpose_bf16x3: out_planes has the wrong size")
-    epi = make_epilogue(bias, act)
+    if out_planes is not None and out_planes.numel() != out_planes.shape[0] * out.numel():
+        raise _lib.CtxError("conv2d_transpose_planes: out_planes has the wrong size")
+    epi = make_epilogue(bias, act, act_ref, accumulate)
+    cfg = _p16(x1p, nprod, a_scale, amax)
     pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * Ck)
-    check(_lib.load().ctx_conv2d_transpose_bf16x3(
-        _req(x1p, "x1p", torch.bfloat16), C1, None if x2p is None else _req(x2p, "x2p", torch.bfloat16), C2,
-        0 if x2p is None else x2p.shape[1], _req(wp, "wp", torch.bfloat16), _req(out, "out"),
-        None if out_planes is None else _req(out_planes, "out_planes", torch.bfloat16), Cn, C.byref(g), C.byref(epi),
-        _stream()), "ctx_conv2d_transpose_bf16x3")
+    check(_lib.load().ctx_conv2d_transpose_p16(
+        _reqp(x1p, "x1p"), C1, None if x2p is None else _reqp(x2p, "x2p", x1p), C2, 0 if x2p is None else x2p.shape[1],
+        _reqp(wp, "wp", x1p), _req(out, "out"), None if out_planes is None else _reqp(out_planes, "out_planes", x1p),
+        0 if out_planes is None else out_planes.shape[0], Cn, C.byref(g), C.byref(epi), C.byref(cfg), _stream()),
+        "ctx_conv2d_transpose_p16")
     pr.done()
     return out
 
 
 def conv2d_transpose_merged_eligible(n, out_hw, C1, C2, x2_batch, Cn, k, stride) -> bool:
     g = conv_geom(n, tuple(out_hw), k, stride)
-    return bool(_lib.load().ctx_conv2d_transpose_merged_bf16x3_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
+    return bool(_lib.load().ctx_conv2d_transpose_merged_p16_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
 
 
-def conv2d_transpose_merged_pack(w, out_hw, stride: int = 2, out=None):
-    """Transposed-conv filter [k,k,Cn,Ck] -> packed planes (2, rows, Ck) for conv2d_transpose_merged_bf16x3."""
+def conv2d_transpose_merged_pack(w, out_hw, stride: int = 2, out=None, nplanes: int = 2, dtype=None):
+    """Transposed-conv filter [k,k,Cn,Ck] -> packed planes (nplanes, rows, Ck) for conv2d_transpose_merged_planes."""
     k, _, Cn, Ck = w.shape
     g = conv_geom(1, tuple(out_hw), k, stride)
     rows = int(_lib.load().ctx_conv2d_transpose_merged_rows(Cn, C.byref(g)))
     if rows <= 0:
         raise _lib.CtxError("conv2d_transpose_merged_pack: geometry not eligible")
     if out is None:
-        out = torch.empty((2, rows, Ck), device=w.device, dtype=torch.bfloat16)
-    elif tuple(out.shape) != (2, rows, Ck):
-        raise _lib.CtxError("conv2d_transpose_merged_pack: out must be (2, %d, %d)" % (rows, Ck))
-    check(_lib.load().ctx_conv2d_transpose_merged_pack(_req(w, "w"), Ck, Cn, C.byref(g), _req(out, "out", torch.bfloat16),
-                                                       _stream()), "ctx_conv2d_transpose_merged_pack")
+        out = torch.empty((nplanes, rows, Ck), device=w.device, dtype=dtype or PLANES_DTYPE)
+    elif tuple(out.shape) != (nplanes, rows, Ck):
+        raise _lib.CtxError("conv2d_transpose_merged_pack: out must be (%d, %d, %d)" % (nplanes, rows, Ck))
+    check(_lib.load().ctx_conv2d_transpose_merged_pack_p16(_req(w, "w"), Ck, Cn, C.byref(g), _reqp(out, "out"), nplanes,
+                                                           _p16_dtype(out), _stream()), "ctx_conv2d_transpose_merged_pack_p16")
     return out
 
 
-def conv2d_transpose_merged_bf16x3(x1p, wmp, out_hw, k: int, Cn: int, bias=None, stride: int = 2, x2p=None,
-                                   act: bool = False, out=None, out_planes=None):
+def conv2d_transpose_merged_planes(x1p, wmp, out_hw, k: int, Cn: int, bias=None, stride: int = 2, x2p=None,
+                                   act: bool = False, out=None, out_planes=None, nprod: int = 3, act_ref=None,
+                                   accumulate: bool = False, a_scale=None, amax=None):
     """conv2d_transpose(SAME, stride 2) + bias (+ lrelu) with the four stride phases merged into one GEMM; wmp from
     conv2d_transpose_merged_pack."""
     _, N, P, Q, C1 = x1p.shape
     C2 = 0 if x2p is None else x2p.shape[4]
     if wmp.shape[-1] != C1 + C2:
-        raise _lib.CtxError("conv2d_transpose_merged_bf16x3: packed filter does not match the inputs")
+        raise _lib.CtxError("conv2d_transpose_merged_planes: packed filter does not match the inputs")
     g = conv_geom(N, tuple(out_hw), k, stride)
     if (g.P, g.Q) != (P, Q):
-        raise _lib.CtxError("conv2d_transpose_merged_bf16x3: output %s inconsistent with input grid %s" % (tuple(out_hw), (P, Q)))
+        raise _lib.CtxError("conv2d_transpose_merged_planes: output %s inconsistent with input grid %s" % (tuple(out_hw), (P, Q)))
     if out is None:
         out = torch.empty((N, g.H, g.W, Cn), device=x1p.device, dtype=torch.float32)
-    if out_planes is not None and out_planes.numel() != 2 * out.numel():
-        raise _lib.CtxError("conv2d_transpose_merged_bf16x3: out_planes has the wrong size")
-    epi = make_epilogue(bias, act)
+    if out_planes is not None and out_planes.numel() != out_planes.shape[0] * out.numel():
+        raise _lib.CtxError("conv2d_transpose_merged_planes: out_planes has the wrong size")
+    epi = make_epilogue(bias, act, act_ref, accumulate)
+    cfg = _p16(x1p, nprod, a_scale, amax)
     pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * (C1 + C2))
-    check(_lib.load().ctx_conv2d_transpose_merged_bf16x3(
-        _req(x1p, "x1p", torch.bfloat16), C1, None if x2p is None else _req(x2p, "x2p", torch.bfloat16), C2,
-        0 if x2p is None else x2p.shape[1], _req(wmp, "wmp", torch.bfloat16), _req(out, "out"),
-        None if out_planes is None else _req(out_planes, "out_planes", torch.bfloat16), Cn, C.byref(g), C.byref(epi),
-        _stream()), "ctx_conv2d_transpose_merged_bf16x3")
+    check(_lib.load().ctx_conv2d_transpose_merged_p16(
+        _reqp(x1p, "x1p"), C1, None if x2p is None else _reqp(x2p, "x2p", x1p), C2, 0 if x2p is None else x2p.shape[1],
+        _reqp(wmp, "wmp", x1p), _req(out, "out"), None if out_planes is None else _reqp(out_planes, "out_planes", x1p),
+        0 if out_planes is None else out_planes.shape[0], Cn, C.byref(g), C.byref(epi), C.byref(cfg), _stream()),
+        "ctx_conv2d_transpose_merged_p16")
     pr.done()
     return out
+
+
+def conv2d_wgrad_planes_eligible(n, big_hw, Ca, Cb1, Cb2, small2_batch, k, stride) -> bool:
+    g = conv_geom(n, tuple(big_hw), k, stride)
+    return bool(_lib.load().ctx_conv2d_wgrad_p16_eligible(Ca, Cb1, Cb2, small2_batch, C.byref(g)))
+
+
+def conv2d_wgrad_planes(bigp, small1p, k: int, stride: int, small2p=None, dw=None, nprod: int = 1, a_scale=None):
+    """dw[k,k,Ca,Cb1+Cb2] += sum_pixels big[shifted] (x) [small1 ‖ small2] from planes: bigp (np,N,H,W,Ca), small*p
+    (np,.,P,Q,Cb*).  a_scale: device scalar the gradient operand's planes were scaled by."""
+    _, N, H, W_, Ca = bigp.shape
+    Cb1 = small1p.shape[4]
+    Cb2 = 0 if small2p is None else small2p.shape[4]
+    g = conv_geom(N, (H, W_), k, stride)
+    if tuple(small1p.shape[1:4]) != (N, g.P, g.Q):
+        raise _lib.CtxError("conv2d_wgrad_planes: small grid %s does not match geometry (%d,%d,%d)"
+                            % (tuple(small1p.shape), N, g.P, g.Q))
+    if dw is None:
+        dw = torch.zeros((k, k, Ca, Cb1 + Cb2), device=bigp.device, dtype=torch.float32)
+    cfg = _p16(bigp, nprod, a_scale, None)
+    if nprod == 3 and (small1p.shape[0] < 2 or (small2p is not None and small2p.shape[0] < 2)):
+        raise _lib.CtxError("conv2d_wgrad_planes: three-product mode needs (hi, lo) planes of every operand")
+    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Ca)
+    check(_lib.load().ctx_conv2d_wgrad_p16(_reqp(bigp, "bigp"), Ca, _reqp(small1p, "small1p", bigp), Cb1,
+                                           None if small2p is None else _reqp(small2p, "small2p", bigp), Cb2,
+                                           0 if small2p is None else small2p.shape[1], _req(dw, "dw"), C.byref(g),
+                                           C.byref(cfg), _stream()), "ctx_conv2d_wgrad_p16")
+    pr.done()
+    return dw
+
+
+def grad_planes(x, C_: int, planes=None, ref=None, amax=None, scale=None, db=None, out_f32=None, ldx: Optional[int] = None,
+                slope: float = LRELU_SLOPE):
+    """Raw fp32 gradient x (any shape, rows of `ldx` floats of which the first C_ are used) -> lrelu' mask from `ref`
+    -> planes scaled by the power of two written to `scale` (from `amax`, the bits of max |x|), + bias gradient db, +
+    optional fp32 copy.  planes: (np, rows, C_)-sized tensor."""
+    ldx = C_ if ldx is None else ldx
+    rows = x.numel() // ldx
+    if not x.is_contiguous() or x.numel() != rows * ldx:
+        raise _lib.CtxError("grad_planes: x must be dense rows of ldx floats")
+    if planes is not None and planes.numel() != planes.shape[0] * rows * C_:
+        raise _lib.CtxError("grad_planes: planes has the wrong size")
+    check(_lib.load().ctx_grad_planes(_req(x, "x"), rows, C_, ldx, _opt(ref, "ref"), float(slope),
+                                      None if amax is None else _req(amax, "amax", torch.int32), _opt(scale, "scale"),
+                                      None if planes is None else _reqp(planes, "planes"),
+                                      0 if planes is None else planes.shape[0],
+                                      _lib.P16_F16 if planes is None else _p16_dtype(planes), _opt(db, "db"),
+                                      _opt(out_f32, "out_f32"), _stream()), "ctx_grad_planes")
+    return planes
+
+
+def amax(x, slot):
+    """slot (int32[1], device) = max(slot, bits(max |x|))."""
+    check(_lib.load().ctx_amax(_req(x, "x"), x.numel(), _req(slot, "slot", torch.int32), _stream()), "ctx_amax")
+    return slot
+
+
+def skip_grad_sum(dcat, G: int, C1: int, C2: int, dskip, skip_ref=None, accumulate: bool = False, slope: float = LRELU_SLOPE):
+    """dskip[rows, C2] (+)= (sum over the G stacked passes of dcat[..., C1:]) * lrelu'(skip_ref)."""
+    rows = dcat.numel() // (G * (C1 + C2))
+    check(_lib.load().ctx_skip_grad_sum(_req(dcat, "dcat"), G, rows, C1, C2, _opt(skip_ref, "skip_ref"), float(slope),
+                                        _req(dskip, "dskip"), int(accumulate), _stream()), "ctx_skip_grad_sum")
+    return dskip
+
+
+# round-1 names (bf16 planes, three products)
+conv2d_bf16x3_eligible = conv2d_planes_eligible
+conv2d_bf16x3 = conv2d_planes
+conv2d_transpose_bf16x3_eligible = conv2d_transpose_planes_eligible
+conv2d_transpose_bf16x3 = conv2d_transpose_planes
+conv2d_transpose_merged_bf16x3 = conv2d_transpose_merged_planes
 
 
 def conv2d_wgrad(big, small1, k: int, stride: int, small2=None, dw=None, impl=IMPL_AUTO):

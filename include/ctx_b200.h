@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CTX_B200_VERSION 100
+#define CTX_B200_VERSION 200
 
 enum {
   CTX_OK = 0,
@@ -43,7 +43,9 @@ enum {
                          /* shape is not eligible                                                            */
   CTX_IMPL_TC3 = 3,      /* force tcgen05, 3-pass split; error if the shape is not eligible                  */
   CTX_IMPL_FAST = 4,     /* single-pass TF32 when the shape qualifies, else SIMT                             */
-  CTX_IMPL_BF16X3 = 5    /* reported by ctx_last_impl() after a ctx_*_bf16x3 call (not a selector)           */
+  CTX_IMPL_P16X3 = 5,    /* reported by ctx_last_impl() after a 16-bit-planes call with three products ...   */
+  CTX_IMPL_BF16X3 = 5,   /* ... (round-1 name)                                                               */
+  CTX_IMPL_P16X1 = 6     /* ... and with one product (fp16 planes); neither is a selector                    */
 };
 
 /* Geometry of one SAME conv / transposed conv.  "big" is the conv input (= transposed-conv output) grid,
@@ -128,47 +130,119 @@ int ctx_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
              const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
              const ctx_epilogue* epi, int32_t impl, void* stream);
 
-/* ---- forward convolutions from pre-split bf16 planes ------------------------------------------------------
- * A "planes" tensor is [2][shape] bf16: plane 0 = hi = bf16_rn(x), plane 1 = lo = bf16_rn(x - hi), so hi + lo carries
- * 16 significant bits of the fp32 value.  The kernels compute hi*hi + hi*lo + lo*hi on the bf16 tensor cores with fp32
- * accumulation: fp32-grade results (max-norm error 5e-6..9e-6 per GEMM, measured) at half the tensor-core time of the
- * 3-pass TF32 split, with no operand splitting inside the GEMM.  Same layer semantics as ctx_conv2d_fprop /
- * ctx_conv2d_transpose (arm_shaping.py:21-32, 62-85, 1323-1329); epilogue: bias and lrelu only.  y is written in fp32
- * and, when y_planes is not null, also as planes for the next layer.  Shapes: channels % 64 == 0, stride 1 or 2, output
- * (phase) grids that tile exactly into 128 pixels — ask ctx_*_bf16x3_eligible; ineligible shapes return
- * CTX_ERR_UNSUPPORTED (use the fp32-input entry points). */
+/* ---- convolutions on 16-bit operand planes (csrc/tc_h16.cu) ------------------------------------------------------
+ * A "planes" tensor is [nplanes][shape] of fp16 or bf16: plane 0 = hi = rn16(s*x), plane 1 = lo = rn16(s*x - hi), with s
+ * a power-of-two scale (1 unless stated).  hi + lo carries 22 (fp16) / 16 (bf16) significant bits of the fp32 value.
+ *   nprod = 3: hi*hi + hi*lo + lo*hi on the 16-bit tensor cores with fp32 accumulation — fp32-grade results (max-norm
+ *              error 5e-6..9e-6 per GEMM, measured) at half the tensor-core time of the 3-pass TF32 split and with no operand
+ *              splitting inside the GEMM: the FORWARD pass.
+ *   nprod = 1: hi*hi with fp16 planes — fp16 has the TF32 significand (1 + 10 bits), rounded to nearest by the producer of
+ *              the planes, so this is single-pass-TF32 accuracy at twice the tensor-core rate and half the operand bytes:
+ *              the BACKWARD pass.  Gradients are brought into fp16's range by a per-tensor power-of-two scale
+ *              (ctx_grad_planes); the GEMM divides its result by *a_scale.
+ * Same layer semantics as ctx_conv2d_fprop / ctx_conv2d_transpose / ctx_conv2d_wgrad (arm_shaping.py:21-32, 62-85,
+ * 1323-1329 and their autodiff).  Epilogue: bias, lrelu, act_ref mask, accumulate (no round_tf32).  y is written in fp32
+ * and, when y_planes is not null, also as y_planes_n planes for the next layer.  Shapes: channels % 64 == 0, stride 1 or
+ * 2, output (phase) grids that tile exactly into 128 pixels (64 for the filter gradient) — ask ctx_*_p16_eligible;
+ * ineligible shapes return CTX_ERR_UNSUPPORTED (use the fp32-input entry points). */
+enum { CTX_P16_BF16 = 0, CTX_P16_F16 = 1 };
+
+typedef struct ctx_p16 {
+  int32_t dtype;             /* CTX_P16_F16 | CTX_P16_BF16: element type of every planes operand of the call          */
+  int32_t nprod;             /* 3 | 1 (1 needs fp16)                                                                   */
+  const float* a_scale;      /* device scalar or NULL: the gradient operand's planes hold (*a_scale) * x; result /= it  */
+  uint32_t* amax_bits;       /* device word or NULL: atomicMax of the bit patterns of |y| (input of ctx_grad_planes)    */
+} ctx_p16;
+
+/* planes[0][i] = rn16(x[i]); planes[1][i] = rn16(x[i] - planes[0][i]) (nplanes == 2) for i < n; fp16 saturates. */
+int ctx_split_planes(const float* x, int64_t n, void* planes, int32_t nplanes, int32_t dtype, void* stream);
+
+/* w [T][R][Cc] fp32 -> planes [nplanes][T][Cc][R]: a conv filter [kh*kw][Cin][Cout] (arm_shaping.py:25) becomes the per-tap
+ * K-major matrix [kh*kw*Cout][Cin] ctx_conv2d_fprop_p16 reads; a transposed-conv filter [kh*kw][Cout][Cin] becomes the
+ * [kh*kw*Cin][Cout] matrix its data gradient (a conv fprop over dY) reads.  (Used as stored, a transposed-conv filter is
+ * already K-major for its forward pass and a conv filter for its data gradient: ctx_split_planes.) */
+int ctx_split_planes_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, void* planes, int32_t nplanes,
+                               int32_t dtype, void* stream);
+
+int ctx_conv2d_fprop_p16_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g);
+
+/* x_planes [.][N,H,W,C], w_planes [.][kh*kw*Co][C], y [N,P,Q,Co] fp32, y_planes [y_planes_n][N,P,Q,Co] or NULL.
+ * Also the data gradient of a transposed conv (x = planes of dY scaled by *cfg->a_scale, w from
+ * ctx_split_planes_transpose of the [kh,kw,Cout,Cin] filter). */
+int ctx_conv2d_fprop_p16(const void* x_planes, int32_t C, const void* w_planes, float* y, void* y_planes,
+                         int32_t y_planes_n, int32_t Co, const ctx_conv_geom* g, const ctx_epilogue* epi,
+                         const ctx_p16* cfg, void* stream);
+
+int ctx_conv2d_transpose_p16_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn, const ctx_conv_geom* g);
+
+/* x1_planes [.][N,P,Q,C1], x2_planes [.][x2_batch,P,Q,C2] or NULL (image n reads x2 image n % x2_batch: the fused
+ * skip concat), w_planes [.][kh*kw*Cn][C1+C2], y [N,H,W,Cn] fp32, y_planes [y_planes_n][N,H,W,Cn] or NULL.
+ * Also the data gradient of a conv (x1 = planes of dY, w = planes of the HWIO filter as stored). */
+int ctx_conv2d_transpose_p16(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2, int32_t x2_batch,
+                             const void* w_planes, float* y, void* y_planes, int32_t y_planes_n, int32_t Cn,
+                             const ctx_conv_geom* g, const ctx_epilogue* epi, const ctx_p16* cfg, void* stream);
+
+/* Stride-2 transposed conv with few output channels (4 * Cn == 256 or 512, e.g. d_h3: 256 -> 64 channels) as ONE GEMM over
+ * all four stride phases: rows = input pixels, columns = (phase, channel), K = (distinct input offset, source, channel) —
+ * the input is fetched once per distinct offset (9 for a 5x5 filter) instead of once per tap (25), in 256-wide CTA-pair
+ * tiles.  The filter must first be packed (per parameter update) into wm_planes
+ * [nplanes][ctx_conv2d_transpose_merged_rows(Cn, g)][Ck]: row (offset, phase, co) holds the weights of the one tap phase
+ * `phase` uses at that offset, or zeros.  Same semantics as ctx_conv2d_transpose_p16. */
+int ctx_conv2d_transpose_merged_p16_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
+                                             const ctx_conv_geom* g);
+int64_t ctx_conv2d_transpose_merged_rows(int32_t Cn, const ctx_conv_geom* g);
+int ctx_conv2d_transpose_merged_pack_p16(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g, void* wm_planes,
+                                         int32_t nplanes, int32_t dtype, void* stream);
+int ctx_conv2d_transpose_merged_p16(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
+                                    int32_t x2_batch, const void* wm_planes, float* y, void* y_planes, int32_t y_planes_n,
+                                    int32_t Cn, const ctx_conv_geom* g, const ctx_epilogue* epi, const ctx_p16* cfg,
+                                    void* stream);
+
+int ctx_conv2d_wgrad_p16_eligible(int32_t Ca, int32_t Cb1, int32_t Cb2, int32_t small2_batch, const ctx_conv_geom* g);
+
+/* ctx_conv2d_wgrad from planes: big_planes [.][N,H,W,Ca], small1_planes [.][N,P,Q,Cb1], small2_planes
+ * [.][small2_batch,P,Q,Cb2] or NULL; dw [kh,kw,Ca,Cb1+Cb2] fp32 +=.  Pixels are the GEMM's K dimension: both operands are
+ * MN-major tiles, split-K over 64-pixel blocks, fp32 vector reductions.  *cfg->a_scale is the scale of whichever operand
+ * is the gradient (big for a transposed-conv filter, small1 for a conv filter); the sums are divided by it. */
+int ctx_conv2d_wgrad_p16(const void* big_planes, int32_t Ca, const void* small1_planes, int32_t Cb1,
+                         const void* small2_planes, int32_t Cb2, int32_t small2_batch, float* dw,
+                         const ctx_conv_geom* g, const ctx_p16* cfg, void* stream);
+
+/* Gradient -> operand planes, one pass over a raw fp32 gradient x [rows, ldx] (columns 0..C-1 are used):
+ *   v[r,c] = x[r*ldx + c] * (ref ? (ref[r*C + c] >= 0 ? 1 : slope) : 1)          lrelu' from the saved output
+ *   s      = 2^k with amax * s in [2^14, 2^15), amax = the float whose bits are *amax_bits (0 -> s = 1; bf16: s = 1);
+ *            *scale = s                                                           (device scalar, read by the consumers)
+ *   planes[0][r*C + c] = rn16(s * v),  planes[1][...] = rn16(s * v - planes[0])   (nplanes == 2)
+ *   db[c]             += sum_r v[r,c]                                             if db      (tf.nn.bias_add's gradient)
+ *   out_f32[r*C + c]   = v                                                        if out_f32 (fp32 consumers: dense layers)
+ * Replaces lrelu' + bias gradient + operand rounding of the backward pass the reference gets from
+ * AdamOptimizer.minimize (scripts/train_script.py:128). */
+int ctx_grad_planes(const float* x, int64_t rows, int32_t C, int32_t ldx, const float* ref, float slope,
+                    const uint32_t* amax_bits, float* scale, void* planes, int32_t nplanes, int32_t dtype,
+                    float* db, float* out_f32, void* stream);
+
+/* *amax_bits = max(*amax_bits, bits(max_i |x[i]|)) — for gradients produced by kernels without the amax epilogue. */
+int ctx_amax(const float* x, int64_t n, uint32_t* amax_bits, void* stream);
+
+/* dskip[B*pix, C2] (+)= (sum_g dcat[(g*B*pix + row), C1 + c]) * lrelu'(skip_ref): the skip half of ctx_split_skip_grad
+ * (the state half goes through ctx_grad_planes). */
+int ctx_skip_grad_sum(const float* dcat, int32_t G, int64_t rows, int32_t C1, int32_t C2, const float* skip_ref,
+                      float slope, float* dskip, int32_t accumulate, void* stream);
+
+/* ---- round-1 names of the planes entry points: bf16 planes, three products, two result planes -------------------- */
 
 /* planes[0][i] = bf16_rn(x[i]); planes[1][i] = bf16_rn(x[i] - planes[0][i]) for i < n. */
 int ctx_split_bf16(const float* x, int64_t n, void* planes, void* stream);
-
-/* w [T][R][Cc] fp32 -> planes [2][T][Cc][R]: a conv filter [kh*kw][Cin][Cout] (arm_shaping.py:25) becomes the per-tap
- * K-major matrix [kh*kw*Cout][Cin] ctx_conv2d_fprop_bf16x3 reads.  (A transposed-conv filter [kh,kw,Cout,Cin] is already
- * K-major: use ctx_split_bf16.) */
 int ctx_split_bf16_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, void* planes, void* stream);
-
 int ctx_conv2d_fprop_bf16x3_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g);
-
-/* x_planes [2][N,H,W,C], w_planes [2][kh*kw*Co][C], y [N,P,Q,Co] fp32, y_planes [2][N,P,Q,Co] or NULL. */
 int ctx_conv2d_fprop_bf16x3(const void* x_planes, int32_t C, const void* w_planes, float* y, void* y_planes, int32_t Co,
                             const ctx_conv_geom* g, const ctx_epilogue* epi, void* stream);
-
 int ctx_conv2d_transpose_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn, const ctx_conv_geom* g);
-
-/* x1_planes [2][N,P,Q,C1], x2_planes [2][x2_batch,P,Q,C2] or NULL (image n reads x2 image n % x2_batch: the fused
- * skip concat), w_planes [2][kh*kw*Cn][C1+C2], y [N,H,W,Cn] fp32, y_planes [2][N,H,W,Cn] or NULL. */
 int ctx_conv2d_transpose_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2, int32_t x2_batch,
                                 const void* w_planes, float* y, void* y_planes, int32_t Cn, const ctx_conv_geom* g,
                                 const ctx_epilogue* epi, void* stream);
-
-/* Stride-2 transposed conv with few output channels (4 * Cn == 256, e.g. d_h3: 256 -> 64 channels) as ONE GEMM over all
- * four stride phases: rows = input pixels, columns = (phase, channel), K = (distinct input offset, source, channel) — the
- * input is fetched once per distinct offset (9 for a 5x5 filter) instead of once per tap (25), in 256-wide CTA-pair tiles.
- * The filter must first be packed (per parameter update) into wm_planes [2][ctx_conv2d_transpose_merged_rows(Cn, g)][Ck]:
- * row (offset, phase, co) holds the weights of the one tap phase `phase` uses at that offset, or zeros.  Same semantics as
- * ctx_conv2d_transpose_bf16x3. */
 int ctx_conv2d_transpose_merged_bf16x3_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
                                                 const ctx_conv_geom* g);
-int64_t ctx_conv2d_transpose_merged_rows(int32_t Cn, const ctx_conv_geom* g);
 int ctx_conv2d_transpose_merged_pack(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g, void* wm_planes,
                                      void* stream);
 int ctx_conv2d_transpose_merged_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,

@@ -37,7 +37,7 @@ def test_ctypes_table_matches_header():
 
 
 def test_version_and_error_string(lib):
-    assert lib.ctx_version() == 100
+    assert lib.ctx_version() == 200
     assert isinstance(_lib.last_error(), str)
 
 

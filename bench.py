@@ -368,30 +368,32 @@ def run_ours(args):
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
-        w_sum = 0.0                                  # tensor-core time units issued, in single-pass TF32 MMA equivalents
+        w_sum = 0.0                                  # tensor-core time units issued, in 16-bit (kind::f16) MMA equivalents
         for kind, impl, flops, a, b in prof:
-            key = {1: "simt", 2: "tc", 3: "tc", 5: "tc"}.get(impl, "simt")      # 5 = bf16x3 planes (tc_bf16x3.cu)
-            w_sum = w_sum + flops * {2: 1.0, 3: 3.0, 5: 1.5}.get(impl, 0.0) if key == "tc" else w_sum
+            # 2 / 3 = single-pass / 3-pass TF32 (tc_gemm.cu); 5 / 6 = three / one product on 16-bit planes (tc_h16.cu)
+            key = {1: "simt", 2: "tc", 3: "tc", 5: "tc", 6: "tc"}.get(impl, "simt")
+            w_sum = w_sum + flops * {2: 2.0, 3: 6.0, 5: 3.0, 6: 1.0}.get(impl, 0.0) if key == "tc" else w_sum
             t = a.elapsed_time(b) * 1e-3
             d = agg.setdefault(key, dict(flops=0.0, s=0.0, calls=0))
             d["flops"] += flops; d["s"] += t; d["calls"] += 1
-            d2 = agg.setdefault(key + ":" + ("bf16x3_" if impl == 5 else "") + kind, dict(flops=0.0, s=0.0, calls=0))
+            d2 = agg.setdefault(key + ":" + {5: "p16x3_", 6: "p16x1_"}.get(impl, "") + kind, dict(flops=0.0, s=0.0, calls=0))
             d2["flops"] += flops; d2["s"] += t; d2["calls"] += 1
         breakdown = {k: dict(tflops=v["flops"] / max(v["s"], 1e-12) / 1e12, ms=v["s"] * 1e3, calls=v["calls"])
                      for k, v in sorted(agg.items())}
         dom = "tc" if "tc" in agg and agg["tc"]["s"] >= agg.get("simt", dict(s=0))["s"] * 0.5 else "simt"
         if dom in agg:
             ach = agg[dom]["flops"] / agg[dom]["s"] / 1e12
-            # mean tensor-core time per product in single-pass TF32 units: 1 (single pass), 3 (3-pass TF32 split),
-            # 1.5 (three bf16 MMAs at twice the TF32 rate), weighted by each launch's algorithmic flops
+            # mean tensor-core time per algorithmic product in 16-bit-MMA units: 1 (one fp16 product), 3 (three products on
+            # (hi, lo) planes), 2 (single-pass TF32: half the 16-bit rate), 6 (3-pass TF32 split), weighted by each
+            # launch's algorithmic flops
             passes = w_sum / agg["tc"]["flops"] if dom == "tc" else 0.0
             if dom == "tc":
-                peak = peaks["bf16_tflops_sustained"] / 2.0
-                basis = ("TF32 dense = %s bf16 sustained %.1f TFLOP/s / 2" % (peaks["source"], peaks["bf16_tflops_sustained"]))
+                peak = peaks["bf16_tflops_sustained"]
+                basis = ("16-bit dense (kind::f16) = %s bf16 sustained %.1f TFLOP/s" % (peaks["source"], peaks["bf16_tflops_sustained"]))
             else:
                 peak, basis = 80.0, "nominal fp32 CUDA-core peak (no measured figure)"
             roofline = dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
-                            kernel="tc_igemm_kernel + bf3_kernel (tcgen05)" if dom == "tc" else "simt_gemm_kernel",
+                            kernel="h16_kernel + tc_igemm_kernel (tcgen05)" if dom == "tc" else "simt_gemm_kernel",
                             peak_basis=basis,
                             tensor_passes=passes if dom == "tc" else 0,
                             frac_of_issued_tensor_flops=(ach * passes / peak) if dom == "tc" else None,
@@ -420,9 +422,10 @@ def run_ours(args):
         line = dict(metric=metric_name(args, label), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling=scaling, vs_baseline=None,
                     dtype="f32 (%s)" % {"tf32x3": "tensor-core operands tf32, 3-pass split, fp32 accumulate",
-                                        "mixed": "tensor cores, fp32 accumulate: forward fp32-grade (bf16 hi/lo planes, three "
-                                                 "products; 3-pass tf32 split where planes do not apply), backward "
-                                                 "single-pass tf32",
+                                        "mixed": "tensor cores, fp32 accumulate: forward fp32-grade (fp16 hi/lo planes, three "
+                                                 "products; 3-pass tf32 split where planes do not apply), backward one "
+                                                 "product on fp16 hi planes = tf32's significand rounded to nearest "
+                                                 "(single-pass tf32 for dense / 3-channel layers)",
                                         "tf32": "tensor-core operands tf32, single pass, fp32 accumulate",
                                         "fp32": "exact fp32 SIMT"}[args.precision],
                     data="synthetic",

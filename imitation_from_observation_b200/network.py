@@ -43,10 +43,13 @@ def _numel(shape) -> int:
 class ContextNet:
     """One network instance bound to a device, a per-rank batch size and a precision mode.
 
-    precision = "mixed" (default): forward in the 3-pass TF32 split (below), backward (data and filter gradients)
-                        in single-pass TF32 with gradients rounded to nearest by the producing epilogue.  The forward
-                        pass decides every lrelu mask, so it keeps fp32-grade accuracy; the backward GEMMs are smooth
-                        in their operands, where TF32's unbiased 2^-12 rounding averages out.
+    precision = "mixed" (default): forward fp32-grade — convolutions on fp16 (hi, lo) operand planes, three products
+                        (csrc/tc_h16.cu), the 3-pass TF32 split where planes do not apply; backward (data and filter
+                        gradients) single-product on the fp16 hi planes = TF32's 11-bit significand ROUNDED TO NEAREST
+                        by the producer (gradients scaled per tensor into fp16's range), single-pass TF32 for the dense
+                        and few-channel layers.  The forward pass decides every lrelu mask, so it keeps fp32-grade
+                        accuracy; the backward GEMMs are smooth in their operands, where the unbiased 2^-12 rounding
+                        averages out.
     precision = "tf32x3": tcgen05 kernels with the 3-pass TF32 split (hi*hi + hi*lo + lo*hi, fp32
                         accumulate; ~2^-21 per product, i.e. fp32-faithful) wherever the shape qualifies, the exact
                         fp32 SIMT kernels elsewhere.  The strictest tensor-core mode.
@@ -131,11 +134,20 @@ class ContextNet:
         self.dec = spec.dec_layers()
         self.L = spec.depth                              # encoder convs = decoder transposed convs (4 in the reference)
         self.lin = spec.lin_name                         # "h4_lin" at the reference's depth
-        # Forward convolutions on pre-split bf16 planes (csrc/tc_bf16x3.cu): the fp32-grade forward of "mixed" runs
-        # hi*hi + hi*lo + lo*hi on the bf16 tensor cores wherever channels % 64 == 0 and the pixel grid tiles exactly;
+        # Forward convolutions on pre-split 16-bit planes (csrc/tc_h16.cu): the fp32-grade forward of "mixed" runs
+        # hi*hi + hi*lo + lo*hi on the 16-bit tensor cores wherever channels % 64 == 0 and the pixel grid tiles exactly;
         # the other layers (3-channel image side, dense layers) stay on the 3-pass TF32 kernel.  CTX_FWD_BF3=0 disables.
+        # Planes are fp16 (22 significant bits in hi + lo; CTX_PLANES=bf16 selects bf16: 16 bits, fp32's range); the hi
+        # plane alone is the backward pass's operand (_enc_p1 / _dec_p1 below, fp16 only).
+        self.pdt = torch.bfloat16 if os.environ.get("CTX_PLANES", "fp16") == "bf16" else torch.float16
         self._enc_bf3 = [False] * self.L
         self._dec_bf3 = [False] * self.L
+        self._enc_p1 = [False] * self.L                  # backward of encoder conv j on fp16 hi planes (one product)
+        self._enc_p1_merged = [False] * self.L           # ... its data gradient in the phase-merged form (Cin = 64 / 128)
+        self._dec_p1 = [False] * self.L                  # backward of decoder level i on fp16 hi planes
+        self._wb: Dict[str, torch.Tensor] = {}           # backward weight planes (one fp16 plane), refreshed with _wp
+        self._in_planes: Dict[tuple, torch.Tensor] = {}  # (tag, j) -> planes of the input of encoder conv j (forward)
+        self._dec_planes: Dict[int, tuple] = {}          # i -> (state planes, skip planes) of decoder level i (forward)
         self._dec_merged = [False] * self.L              # stride-2 levels with 64 output channels: phases merged along N
         self._wp: Dict[str, torch.Tensor] = {}           # weight planes, refreshed after every parameter update
         self._wp_stale = True
@@ -150,7 +162,23 @@ class ContextNet:
                     self._dec_merged[i] = (os.environ.get("CTX_BF3_MERGE", "1") != "0" and
                                            ops.conv2d_transpose_merged_eligible(*args))
                     self._dec_bf3[i] = self._dec_merged[i] or ops.conv2d_transpose_bf16x3_eligible(*args)
+            if (spec.separate_ctx_encoder and self.pdt == torch.float16 and os.environ.get("CTX_BWD_P16", "1") != "0"):
+                for j in range(1, self.L):
+                    Cin, Co, k, st = self.chans[j], self.chans[j + 1], spec.kernels[j], spec.strides[j]
+                    rows = (2 * self.B, self.B)          # scope "conv" rows / context rows
+                    mg = all(ops.conv2d_transpose_merged_eligible(n, self.sizes[j], Co, 0, 0, Cin, k, st) for n in rows) \
+                        and os.environ.get("CTX_BF3_MERGE", "1") != "0"
+                    dg = mg or all(ops.conv2d_transpose_planes_eligible(n, self.sizes[j], Co, 0, 0, Cin, k, st) for n in rows)
+                    wg = all(ops.conv2d_wgrad_planes_eligible(n, self.sizes[j], Cin, Co, 0, 0, k, st) for n in rows)
+                    self._enc_p1[j] = self._enc_bf3[j] and dg and wg
+                    self._enc_p1_merged[j] = self._enc_p1[j] and mg
+                for i, Ld in enumerate(self.dec):
+                    Cs, Csk, Co, k, st = Ld["c_state"], Ld["c_skip"], Ld["c_out"], Ld["k"], Ld["stride"]
+                    self._dec_p1[i] = (self._dec_bf3[i] and
+                                       ops.conv2d_planes_eligible(2 * self.B, Ld["out_hw"], Co, Cs + Csk, k, st) and
+                                       ops.conv2d_wgrad_planes_eligible(2 * self.B, Ld["out_hw"], Co, Cs, Csk, self.B, k, st))
         self.bf3 = any(self._enc_bf3) or any(self._dec_bf3)
+        self.p1 = any(self._enc_p1) or any(self._dec_p1)
         self._level = 0
 
     # ---- second stream -----------------------------------------------------------------------------------------
@@ -334,12 +362,16 @@ class ContextNet:
         if self._in_events is not None:
             torch.cuda.current_stream(self.device).wait_event(self._in_events[which])
 
-    # ---- bf16 (hi, lo) planes ----------------------------------------------------------------------------------------
-    def _planes(self, name: str, shape) -> torch.Tensor:
-        return self._buf(name, (2,) + tuple(shape), dtype=torch.bfloat16)
+    # ---- 16-bit (hi, lo) planes --------------------------------------------------------------------------------------
+    def _planes(self, name: str, shape, n: int = 2) -> torch.Tensor:
+        return self._buf(name, (n,) + tuple(shape), dtype=self.pdt)
+
+    def _split(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        return ops.split_planes(x, out=out, nplanes=out.shape[0])
 
     def _refresh_weight_planes(self, scope: Optional[str] = None):
-        """(hi, lo) planes of the filters the bf16x3 layers read, from the fp32 masters (one small launch per filter)."""
+        """Operand planes of the filters, from the fp32 masters (one small launch per filter and layout): (hi, lo) planes
+        for the three-product forward layers, one hi plane in the data gradient's layout for the backward layers."""
         if not self.bf3:
             return
         sp = self.spec
@@ -348,22 +380,37 @@ class ContextNet:
             if scope not in (None, sc):
                 continue
             for j in range(self.L):
+                name = "%s/h%d_conv/w" % (sc, j)
+                k = sp.kernels[j]
                 if self._enc_bf3[j]:
-                    name = "%s/h%d_conv/w" % (sc, j)
-                    k = sp.kernels[j]
                     buf = self._planes("wp:" + name, (k * k * self.chans[j + 1], self.chans[j]))
-                    self._wp[name] = ops.split_bf16_conv_filter(self.P[name], out=buf)
+                    self._wp[name] = ops.split_planes_transpose(self.P[name], out=buf)
+                if self._enc_p1[j]:
+                    # data gradient = transposed conv of dY with the HWIO filter as stored: rows (tap, Cin), K = Cout
+                    if self._enc_p1_merged[j]:
+                        self._wb[name] = ops.conv2d_transpose_merged_pack(self.P[name], self.sizes[j], sp.strides[j],
+                                                                          out=self._bufs.get("wb:" + name), nplanes=1,
+                                                                          dtype=self.pdt)
+                        self._bufs["wb:" + name] = self._wb[name]
+                    else:
+                        buf = self._planes("wb:" + name, (k * k * self.chans[j], self.chans[j + 1]), n=1)
+                        self._wb[name] = ops.split_planes(self.P[name], out=buf, nplanes=1)
         if scope in (None, "deconv"):
             for i, Ld in enumerate(self.dec):
+                name = "deconv/%s/w" % Ld["name"]
+                Ck = Ld["c_state"] + Ld["c_skip"]
                 if self._dec_bf3[i]:
-                    name = "deconv/%s/w" % Ld["name"]
                     if self._dec_merged[i]:
                         self._wp[name] = ops.conv2d_transpose_merged_pack(self.P[name], Ld["out_hw"], Ld["stride"],
-                                                                          out=self._bufs.get("wp:" + name))
+                                                                          out=self._bufs.get("wp:" + name), dtype=self.pdt)
                         self._bufs["wp:" + name] = self._wp[name]
-                        continue
-                    buf = self._planes("wp:" + name, (Ld["k"] * Ld["k"] * Ld["c_out"], Ld["c_state"] + Ld["c_skip"]))
-                    self._wp[name] = ops.split_bf16(self.P[name], out=buf)
+                    else:
+                        buf = self._planes("wp:" + name, (Ld["k"] * Ld["k"] * Ld["c_out"], Ck))
+                        self._wp[name] = ops.split_planes(self.P[name], out=buf)
+                if self._dec_p1[i]:
+                    # data gradient = conv of dY with the [kh,kw,Cout,Cin] filter read as HWIO: rows (tap, Cin), K = Cout
+                    buf = self._planes("wb:" + name, (Ld["k"] * Ld["k"] * Ck, Ld["c_out"]), n=1)
+                    self._wb[name] = ops.split_planes_transpose(self.P[name], out=buf, nplanes=1)
 
     # ---- forward pieces (also the functional enc1 / enc2 / translate / dec surface) ------------------------------
     def encode_convs(self, scope: str, x: torch.Tensor, outs: Sequence[torch.Tensor], tag: Optional[str] = None,
@@ -384,9 +431,10 @@ class ContextNet:
             op = self._planes("%s_h%d_p%d" % (tag, j, h.shape[0]), outs[j].shape) if want_p else None
             if use_bf:
                 if hp is None:
-                    hp = ops.split_bf16(h, out=self._planes("%s_in%d_p%d" % (tag, j, h.shape[0]), h.shape))
-                ops.conv2d_bf16x3(hp, self._wp["%s/h%d_conv/w" % (scope, j)], k, bias=b, stride=self.spec.strides[j],
-                                  act=True, out=outs[j], out_planes=op)
+                    hp = self._split(h, self._planes("%s_in%d_p%d" % (tag, j, h.shape[0]), h.shape))
+                self._in_planes[(tag, j)] = hp             # backward's filter gradient reads the hi plane
+                ops.conv2d_planes(hp, self._wp["%s/h%d_conv/w" % (scope, j)], k, bias=b, stride=self.spec.strides[j],
+                                  act=True, out=outs[j], out_planes=op, nprod=3, amax=self._fwd_amax())
                 h, hp = outs[j], op
                 produced[j] = op
                 continue
@@ -401,9 +449,14 @@ class ContextNet:
                 ops.conv2d(h, w, b, stride=self.spec.strides[j], act=True, out=outs[j], round_tf32=self.round,
                            impl=self.impl)
             h = outs[j]
-            hp = ops.split_bf16(h, out=op) if want_p else None
+            hp = self._split(h, op) if want_p else None
             produced[j] = hp
         return produced
+
+    def _fwd_amax(self) -> torch.Tensor:
+        """int32 word: bit pattern of the largest |activation| the plane layers produced this step (fp16 planes saturate at
+        65504: fetch('loss') turns NaN instead of training on clipped activations)."""
+        return self._buf("losses", (8,))[4:5].view(torch.int32)
 
     def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, bias=None, act=False, act_ref=None,
               accumulate=False, round_=None, bwd=False):
@@ -469,6 +522,7 @@ class ContextNet:
         n_e = xe.shape[0]
         e_hs, e_h4 = self._enc_buffers(n_e, "e")
         c_planes = None
+        self._buf("losses", (8,)).zero_()               # [recon1, recon2, simloss, -, bits of max |activation|, ...]
         cat = self._buf("cat", (B, 2 * F))
         z2 = self._buf("z2", (2 * B, F))
         f4 = 4  # bytes per float
@@ -537,22 +591,24 @@ class ContextNet:
             if tag is not None and self._dec_bf3[i] and skips[self.L - 1 - i].shape[0] == self.B:
                 j = self.L - 1 - i
                 if dp is None:
-                    dp = ops.split_bf16(d[i], out=self._planes("%s%d_in_p%d" % (tag, i, n), d[i].shape))
+                    dp = self._split(d[i], self._planes("%s%d_in_p%d" % (tag, i, n), d[i].shape))
                 sk = skip_planes[j] if skip_planes is not None else None
                 if sk is None:
-                    sk = ops.split_bf16(skips[j].contiguous(), out=self._planes("%s_skip%d_p" % (tag, j), skips[j].shape))
+                    sk = self._split(skips[j].contiguous(), self._planes("%s_skip%d_p" % (tag, j), skips[j].shape))
+                self._dec_planes[i] = (dp, sk)             # backward's filter gradient reads the hi planes
                 op = None
                 if not last and self._dec_bf3[i + 1]:
                     op = self._planes("%s%d_p%d" % (tag, i + 1, n), d[i + 1].shape)
                 if self._dec_merged[i]:
-                    ops.conv2d_transpose_merged_bf16x3(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
+                    ops.conv2d_transpose_merged_planes(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
                                                        L["c_out"], bias=self.P["deconv/%s/biases" % L["name"]],
                                                        stride=L["stride"], x2p=sk, act=not last, out=d[i + 1],
-                                                       out_planes=op)
+                                                       out_planes=op, nprod=3, amax=self._fwd_amax())
                 else:
-                    ops.conv2d_transpose_bf16x3(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
+                    ops.conv2d_transpose_planes(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
                                                 bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2p=sk,
-                                                act=not last, out=d[i + 1], out_planes=op)
+                                                act=not last, out=d[i + 1], out_planes=op, nprod=3,
+                                                amax=self._fwd_amax())
                 dp = op
                 continue
             dp = None
@@ -562,8 +618,7 @@ class ContextNet:
 
     def _fwd_losses(self, d4: torch.Tensor, tgt: torch.Tensor, ctx: torch.Tensor):
         B, F = self.B, self.F
-        losses = self._buf("losses", (4,))
-        losses.zero_()
+        losses = self._buf("losses", (8,))
         g_d4 = self._buf("g_out", tuple(d4.shape))
         w = self._bufs.get("w_recon")
         if w is None:
@@ -607,9 +662,39 @@ class ContextNet:
         else:
             gc_hs, gc_h4 = [g[2 * B:] for g in ge_hs], ge_h4[2 * B:]
 
+        # ---- gradients as fp16 operand planes (the one-product layers) ----------------------------------------------------
+        # A gradient tensor that feeds a one-product GEMM exists as ONE fp16 plane scaled by a power of two chosen from the
+        # tensor's max |.| (fp16 keeps TF32's significand but only 5 exponent bits).  The max comes from the epilogue of the
+        # kernel that produced the fp32 gradient (or one ctx_amax pass); ctx_grad_planes applies lrelu', rounds to nearest
+        # and forms the bias gradient in the same pass.
+        slots = scales = None
+        if self.p1:
+            slots = self._buf("g_amax", (64,), dtype=torch.int32)
+            slots.zero_()
+            scales = self._buf("g_scale", (64,))
+        nslot = [0]
+
+        def new_slot():
+            i = nslot[0]
+            nslot[0] += 1
+            return slots[i:i + 1], scales[i:i + 1]
+
+        def to_planes(x, C_, name, ldx=None, ref=None, db=None, slot=None):
+            """fp32 gradient rows -> (fp16 plane [1, rows, C_] holding scale * x * lrelu'(ref), scale); slot: (amax word the
+            producer of x filled, scale word) — without it one pass over x finds the max."""
+            if slot is None:
+                slot = new_slot()
+                ops.amax(x, slot[0])
+            rows = x.numel() // (ldx or C_)
+            gp = self._buf(name, (1, rows, C_), dtype=torch.float16)
+            ops.grad_planes(x, C_, planes=gp, ref=ref, amax=slot[0], scale=slot[1], db=db, ldx=ldx)
+            return gp, slot[1]
+
         # ---- decoder: d_h<L> .. d_h1 ----------------------------------------------------------------------------
         Ld = self.L
         g_out = bufs["g_out"]                             # d loss / d d4 (written by the loss kernel)
+        gp = None                                          # (plane, scale) of g_out when the level runs on planes
+        bias_done = False                                  # this level's bias gradient came with its planes
         ib, rb = self.impl_b, self.round_b
         for i in reversed(range(Ld)):
             L = self.dec[i]
@@ -617,7 +702,19 @@ class ContextNet:
             state, skip = d[i], c_hs[Ld - 1 - i]
             Cs, Ck, Co, k = L["c_state"], L["c_state"] + L["c_skip"], L["c_out"], L["k"]
             dcat = self._buf("dcat%d" % i, (2 * B,) + tuple(L["in_hw"]) + (Ck,))
-            if self._few(Co, k):
+            slot_d = None
+            if self._dec_p1[i]:
+                if gp is None:
+                    gp = to_planes(g_out, Co, "gp_d%d" % (i + 1), db=G["deconv/%s/biases" % L["name"]])
+                gp5 = gp[0].view((1,) + tuple(d[i + 1].shape))
+                dpl, skp = self._dec_planes[i]
+                with self._side():                         # filter gradient: big = dY planes, small = [state ‖ skip] hi planes
+                    ops.conv2d_wgrad_planes(gp5, dpl[:1], k, L["stride"], small2p=skp[:1], dw=G[wname], nprod=1,
+                                            a_scale=gp[1])
+                slot_d = new_slot()
+                ops.conv2d_planes(gp5, self._wb[wname], k, stride=L["stride"], out=dcat, nprod=1, a_scale=gp[1],
+                                  amax=slot_d[0])
+            elif self._few(Co, k):
                 # few output channels (the image): patch matrix of g_out, then three dense GEMMs
                 K = k * k * Co
                 pt = self._patches("patch_g_d%d" % (i + 1), g_out, k, L["stride"], round_tf32=rb)[:, :K]
@@ -628,19 +725,29 @@ class ContextNet:
                     for g_ in range(2):
                         ops.gemm(pt[g_ * rows:(g_ + 1) * rows], skip.view(-1, Ck - Cs), out=dw2[:, Cs:], transA=True,
                                  accumulate=True, impl=ib)
-                    ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+                    if not bias_done:
+                        ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
                 ops.gemm(pt, Wb[wname].view(K, Ck), out=dcat.view(-1, Ck), impl=ib)
             else:
                 # filter gradient: big = g_out [2B, out_hw, Cout], small = [state ‖ skip] (side stream)
                 with self._side():
                     ops.conv2d_wgrad(g_out, state, k, L["stride"], small2=skip, dw=G[wname], impl=ib)
-                    ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+                    if not bias_done:
+                        ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
                 # data gradient of the concatenated input = SAME conv of g_out with the [kh,kw,Cout,Cin] filter as HWIO
                 ops.conv2d(g_out, Wb[wname], None, stride=L["stride"], act=False, out=dcat, impl=ib)
+            if i > 0 and self._dec_p1[i - 1]:
+                # the level below runs on planes: state half -> lrelu' -> scaled fp16 plane + its bias gradient in one
+                # pass; skip half -> sum of the two decoder passes -> lrelu' -> the context encoder's fp32 gradient
+                gp = to_planes(dcat, Cs, "gp_d%d" % i, ldx=Ck, ref=state, slot=slot_d,
+                               db=G["deconv/%s/biases" % self.dec[i - 1]["name"]])
+                ops.skip_grad_sum(dcat, 2, Cs, Ck - Cs, gc_hs[Ld - 1 - i], skip_ref=skip)
+                g_out, bias_done = None, True
+                continue
             g_state = self._buf("g_d%d" % i, tuple(state.shape))
             ops.split_skip_grad(dcat, 2, B, Cs, Ck - Cs, g_state, gc_hs[Ld - 1 - i],
                                 state_ref=state, skip_ref=skip, accumulate_skip=False, round_tf32=rb)
-            g_out = g_state
+            g_out, gp, bias_done = g_state, None, False
         # ---- d_h0_lin ------------------------------------------------------------------------------------------------
         g_d0 = g_out                                       # [2B, flat], lrelu' applied
         Wd0 = Wb["deconv/d_h0_lin/Matrix"]
@@ -705,8 +812,9 @@ class ContextNet:
         # finer all-reduce stages (data parallel): issued from the stream that wrote the gradients, no join needed
         fine = on_stage is not None and getattr(getattr(on_stage, "__self__", None), "fine", False)
 
-        def encoder_backward(scope, x, hs, h4, g_hs, g_h4, groups):
-            """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate."""
+        def encoder_backward(scope, x, hs, h4, g_hs, g_h4, groups, tag):
+            """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate.
+            tag: forward()'s buffer tag of this encoder pass (its operand planes)."""
             n = x.shape[0]
             with self._side():
                 self._gemm(True, False, flat, F, n, hs[-1].data_ptr(), flat, g_h4.data_ptr(), F,
@@ -718,10 +826,38 @@ class ContextNet:
                 self._gemm(False, True, nr, flat, F, g_h4[r0:r0 + nr].data_ptr(), F,
                            Wb["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), F, g_hs[-1][r0:r0 + nr].data_ptr(), flat,
                            act_ref=hs[-1][r0:r0 + nr].data_ptr(), accumulate=acc, bwd=True)
+            gp, bias_done = None, False                    # (plane, scale) of g_hs[j] when conv j runs on planes
             for j in reversed(range(Ld)):
                 wname = "%s/h%d_conv/w" % (scope, j)
                 src = hs[j - 1] if j > 0 else x
                 kj, Cin = sp.kernels[j], src.shape[3]
+                if self._enc_p1[j]:                        # (j >= 1, one row group: separate context encoder)
+                    if gp is None:
+                        gp = to_planes(g_hs[j], g_hs[j].shape[3], "gp_%s_h%d" % (tag, j),
+                                       db=G["%s/h%d_conv/biases" % (scope, j)])
+                    gp5 = gp[0].view((1,) + tuple(g_hs[j].shape))
+                    with self._side():                     # filter gradient: big = the conv's input (hi plane), small = dY
+                        ops.conv2d_wgrad_planes(self._in_planes[(tag, j)][:1], gp5, kj, sp.strides[j], dw=G[wname],
+                                                nprod=1, a_scale=gp[1])
+                        if fine and j == Ld - 1:
+                            on_stage(scope + "/top")
+                    slot = new_slot()
+                    acc = groups[0][2]
+                    if self._enc_p1_merged[j]:
+                        ops.conv2d_transpose_merged_planes(gp5, self._wb[wname], self.sizes[j], kj, Cin,
+                                                           stride=sp.strides[j], out=g_hs[j - 1], nprod=1,
+                                                           act_ref=hs[j - 1], accumulate=acc, a_scale=gp[1], amax=slot[0])
+                    else:
+                        ops.conv2d_transpose_planes(gp5, self._wb[wname], self.sizes[j], kj, stride=sp.strides[j],
+                                                    out=g_hs[j - 1], nprod=1, act_ref=hs[j - 1], accumulate=acc,
+                                                    a_scale=gp[1], amax=slot[0])
+                    if self._enc_p1[j - 1]:
+                        gp = to_planes(g_hs[j - 1], Cin, "gp_%s_h%d" % (tag, j - 1), slot=slot,
+                                       db=G["%s/h%d_conv/biases" % (scope, j - 1)])
+                        bias_done = True
+                    else:
+                        gp, bias_done = None, False
+                    continue
                 with self._side():                         # filter + bias gradient beside the data gradient below
                     if self._few(Cin, kj) and g_hs[j].shape[3] % 4 == 0:
                         K = kj * kj * Cin
@@ -730,9 +866,11 @@ class ContextNet:
                                  accumulate=True, impl=self.impl_b)
                     else:
                         ops.conv2d_wgrad(src, g_hs[j], kj, sp.strides[j], dw=G[wname], impl=self.impl_b)
-                    ops.bias_grad(g_hs[j], G["%s/h%d_conv/biases" % (scope, j)])
+                    if not bias_done:
+                        ops.bias_grad(g_hs[j], G["%s/h%d_conv/biases" % (scope, j)])
                     if fine and j == Ld - 1:
                         on_stage(scope + "/top")
+                bias_done = False
                 if j > 0:
                     for (r0, nr, acc) in groups:
                         ops.conv2d_transpose(g_hs[j][r0:r0 + nr], Wb[wname], self.sizes[j], stride=sp.strides[j],
@@ -740,16 +878,16 @@ class ContextNet:
                                              accumulate=acc, round_tf32=self.round_b, impl=self.impl_b)
 
         if sp.separate_ctx_encoder:
-            encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False)])
+            encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False)], "e")
             if on_stage:
                 self._join()
                 on_stage("conv")
-            encoder_backward("conv_context", xc, c_hs, c_h4, gc_hs, gc_h4, [(0, B, True)])
+            encoder_backward("conv_context", xc, c_hs, c_h4, gc_hs, gc_h4, [(0, B, True)], "c")
             if on_stage:
                 self._join()
                 on_stage("conv_context")
         else:
-            encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False), (2 * B, B, True)])
+            encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False), (2 * B, B, True)], "e")
             if on_stage:
                 self._join()
                 on_stage("conv")
@@ -878,7 +1016,11 @@ class ContextNet:
             return bufs["losses"][2]
         if name == "loss":
             l = bufs["losses"]
-            return self._w_recon[0] * l[0] + self._w_recon[1] * l[1] + self._w_sim * l[2]
+            loss = self._w_recon[0] * l[0] + self._w_recon[1] * l[1] + self._w_sim * l[2]
+            if self.bf3 and self.pdt == torch.float16:
+                # an activation beyond fp16's range was clipped in its operand planes: not a loss worth reporting
+                loss = torch.where(l[4:5].view(torch.int32)[0] >= 0x477FE000, torch.full_like(loss, float("nan")), loss)
+            return loss
         if name == "image_trans":
             xe, xc = self._input_buffers()
             return torch.stack([xe[:B], xc, xe[B:2 * B]])

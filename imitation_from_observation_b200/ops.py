@@ -238,6 +238,7 @@ def conv2d_transpose_planes(x1p, wp, out_hw, k: int, bias=None, stride: int = 2,
     _, N, P, Q, C1 = x1p.shape
     C2 = 0 if x2p is None else x2p.shape[4]
     Ck = wp.shape[-1]
+    wp = wp.view(wp.shape[0], -1, Ck)                     # (np, k, k, Cn, Ck) planes of the filter as stored are fine too
     Cn = wp.shape[1] // (k * k)
     if Ck != C1 + C2 or wp.shape[1] != k * k * Cn:
         raise _lib.CtxError("conv2d_transpose_planes: filter planes do not match the inputs")

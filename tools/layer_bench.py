@@ -27,7 +27,15 @@ ap.add_argument("--model", default="skipnew", choices=["skipnew", "inception2"],
 a = ap.parse_args()
 B = a.batch
 dev = "cuda"
-IMPLS = {"x3": IMPL_AUTO, "x1": IMPL_FAST, "simt": IMPL_SIMT, "bf3": "bf3"}     # bf3 = bf16 (hi, lo) planes, forward layers
+# bf3 = bf16 (hi, lo) planes, three products (round 1's forward); p3 = fp16 (hi, lo) planes, three products; p1 = fp16 hi
+# planes, one product (the backward pass: TF32-grade operands rounded to nearest)
+IMPLS = {"x3": IMPL_AUTO, "x1": IMPL_FAST, "simt": IMPL_SIMT, "bf3": "bf3", "p3": "p3", "p1": "p1"}
+PL = {"bf3": (torch.bfloat16, 3, 2), "p3": (torch.float16, 3, 2), "p1": (torch.float16, 1, 1)}   # dtype, nprod, planes
+
+
+def planes_of(x, tag, transpose=False):
+    dt, _, npl = PL[tag]
+    return (ops.split_planes_transpose if transpose else ops.split_planes)(x, nplanes=npl, dtype=dt)
 
 
 def rnd(*shape):
@@ -41,13 +49,18 @@ def add_fprop(name, N, H, C, Co, k=5, st=2):
     x, w, b = rnd(N, H, H, C), rnd(k, k, C, Co), rnd(Co)
     P = -(-H // st)
     y = torch.empty((N, P, P, Co), device=dev)
-    bf = ops.conv2d_bf16x3_eligible(N, (H, H), C, Co, k, st)
-    xp, wp = (ops.split_bf16(x), ops.split_bf16_conv_filter(w)) if bf else (None, None)
-    yp = torch.empty((2, N, P, P, Co), device=dev, dtype=torch.bfloat16) if bf else None
+    bf = ops.conv2d_planes_eligible(N, (H, H), C, Co, k, st)
+    cache = {}
 
     def run(impl):
-        if impl == "bf3":
-            return ops.conv2d_bf16x3(xp, wp, k, bias=b, stride=st, act=True, out=y, out_planes=yp) if bf else None
+        if impl in PL:
+            if not bf:
+                return None
+            if impl not in cache:
+                cache[impl] = (planes_of(x, impl), planes_of(w, impl, True),
+                               torch.empty((PL[impl][2], N, P, P, Co), device=dev, dtype=PL[impl][0]))
+            xp, wp, yp = cache[impl]
+            return ops.conv2d_planes(xp, wp, k, bias=b, stride=st, act=True, out=y, out_planes=yp, nprod=PL[impl][1])
         return ops.conv2d(x, w, b, stride=st, act=True, out=y, impl=impl)
     cases.append(("fprop", name, 2.0 * N * P * P * Co * k * k * C, run))
 
@@ -65,21 +78,27 @@ def add_trans(name, N, P, C1, C2, NB, Cn, k=5, st=2, act=True):
     x2 = rnd(NB, P, P, C2) if C2 else None
     w, b = rnd(k, k, Cn, C1 + C2), rnd(Cn)
     y = torch.empty((N, P * st, P * st, Cn), device=dev)
-    bf = ops.conv2d_transpose_bf16x3_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
-    merged = bf and os.environ.get("CTX_BF3_MERGE", "1") != "0" and \
+    bf = ops.conv2d_transpose_planes_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
+    merged = os.environ.get("CTX_BF3_MERGE", "1") != "0" and \
         ops.conv2d_transpose_merged_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
-    x1p, wp = (ops.split_bf16(x1), ops.split_bf16(w)) if bf else (None, None)
-    wm = ops.conv2d_transpose_merged_pack(w, (P * st, P * st), st) if merged else None
-    x2p = ops.split_bf16(x2) if bf and C2 else None
-    yp = torch.empty((2, N, P * st, P * st, Cn), device=dev, dtype=torch.bfloat16) if bf else None
+    cache = {}
 
     def run(impl):
-        if impl == "bf3" and merged:
-            return ops.conv2d_transpose_merged_bf16x3(x1p, wm, (P * st, P * st), k, Cn, bias=b, stride=st, x2p=x2p, act=act,
-                                                      out=y, out_planes=yp)
-        if impl == "bf3":
-            return ops.conv2d_transpose_bf16x3(x1p, wp, (P * st, P * st), k, bias=b, stride=st, x2p=x2p, act=act, out=y,
-                                               out_planes=yp) if bf else None
+        if impl in PL:
+            if not (bf or merged):
+                return None
+            dt, nprod, npl = PL[impl]
+            if impl not in cache:
+                cache[impl] = (planes_of(x1, impl), planes_of(x2, impl) if C2 else None,
+                               ops.conv2d_transpose_merged_pack(w, (P * st, P * st), st, nplanes=npl, dtype=dt) if merged
+                               else planes_of(w, impl).view(npl, k * k * Cn, C1 + C2),
+                               torch.empty((npl, N, P * st, P * st, Cn), device=dev, dtype=dt))
+            x1p, x2p, wp, yp = cache[impl]
+            if merged:
+                return ops.conv2d_transpose_merged_planes(x1p, wp, (P * st, P * st), k, Cn, bias=b, stride=st, x2p=x2p,
+                                                          act=act, out=y, out_planes=yp, nprod=nprod)
+            return ops.conv2d_transpose_planes(x1p, wp, (P * st, P * st), k, bias=b, stride=st, x2p=x2p, act=act, out=y,
+                                               out_planes=yp, nprod=nprod)
         return ops.conv2d_transpose(x1, w, (P * st, P * st), bias=b, stride=st, x2=x2, act=act, out=y, impl=impl)
     cases.append(("transpose", name, 2.0 * N * P * P * Cn * k * k * (C1 + C2), run))
 
@@ -89,8 +108,19 @@ def add_wgrad(name, N, H, Ca, Cb1, Cb2, NB, k=5, st=2):
     big, s1 = rnd(N, H, H, Ca), rnd(N, P, P, Cb1)
     s2 = rnd(NB, P, P, Cb2) if Cb2 else None
     dw = torch.zeros((k, k, Ca, Cb1 + Cb2), device=dev)
-    cases.append(("wgrad", name, 2.0 * N * P * P * (Cb1 + Cb2) * k * k * Ca,
-                  lambda impl: ops.conv2d_wgrad(big, s1, k, st, small2=s2, dw=dw, impl=impl)))
+    ok = ops.conv2d_wgrad_planes_eligible(N, (H, H), Ca, Cb1, Cb2, NB, k, st)
+    cache = {}
+
+    def run(impl):
+        if impl in PL:
+            if not ok:
+                return None
+            if impl not in cache:
+                cache[impl] = (planes_of(big, impl), planes_of(s1, impl), planes_of(s2, impl) if Cb2 else None)
+            bp, s1p, s2p = cache[impl]
+            return ops.conv2d_wgrad_planes(bp, s1p, k, st, small2p=s2p, dw=dw, nprod=PL[impl][1])
+        return ops.conv2d_wgrad(big, s1, k, st, small2=s2, dw=dw, impl=impl)
+    cases.append(("wgrad", name, 2.0 * N * P * P * (Cb1 + Cb2) * k * k * Ca, run))
 
 
 def add_gemm(name, M, N, K, tA=False, tB=False, bias=True, accumulate=False, pad=0):
@@ -173,8 +203,8 @@ for kind, name, flops, fn in cases:
     line = "%-10s %-22s %8.2f GF " % (kind, name, flops / 1e9)
     for tag in a.impl.split(","):
         impl = IMPLS[tag]
-        if impl == "bf3" and (kind not in ("fprop", "transpose") or fn(impl) is None):
-            line += "| bf3      n/a                    "
+        if impl in PL and (kind not in ("fprop", "transpose", "wgrad") or fn(impl) is None):
+            line += "| %-3s      n/a                    " % tag
             continue
         for _ in range(2):
             fn(impl)
@@ -186,7 +216,7 @@ for kind, name, flops, fn in cases:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
-        used = {1: "simt", 2: "tc1", 3: "tc3", 5: "bf3"}.get(int(ops._lib.load().ctx_last_impl()), "?")
+        used = {1: "simt", 2: "tc1", 3: "tc3", 5: "p3", 6: "p1"}.get(int(ops._lib.load().ctx_last_impl()), "?")
         tot[tag] = tot.get(tag, 0.0) + ms
         line += "| %s(%s) %8.1f us %7.1f TF/s " % (tag, used, ms * 1e3, flops / ms / 1e9)
     print(line, flush=True)

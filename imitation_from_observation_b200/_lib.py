@@ -31,6 +31,12 @@ class Epilogue(Structure):
                 ("accumulate", c_int32), ("round_tf32", c_int32)]
 
 
+class L2Fused(Structure):
+    """ctx_l2_fused: the reconstruction loss evaluated inside ctx_conv2d_transpose_few (include/ctx_b200.h)."""
+    _fields_ = [("tgt", c_void_p), ("resid", c_void_p), ("weight", c_void_p), ("loss", c_void_p), ("dpred", c_void_p),
+                ("dpred_amax", c_void_p), ("pass_images", c_int32)]
+
+
 class P16(Structure):
     """ctx_p16: element type and arithmetic mode of a 16-bit-planes call (include/ctx_b200.h)."""
     _fields_ = [("dtype", c_int32), ("nprod", c_int32), ("a_scale", c_void_p), ("amax_bits", c_void_p)]
@@ -68,8 +74,9 @@ SIGNATURES = {
     "ctx_conv2d_transpose_merged_pack": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_void_p]),
     "ctx_conv2d_transpose_merged_bf16x3": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                                      c_void_p, c_int32, POINTER(ConvGeom), POINTER(Epilogue), c_void_p]),
-    "ctx_split_planes": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p]),
-    "ctx_split_planes_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "ctx_split_planes": (c_int32, [c_void_p, c_int64, c_float, c_void_p, c_int32, c_int32, c_void_p]),
+    "ctx_split_planes_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_int32, c_int32,
+                                             c_void_p]),
     "ctx_conv2d_fprop_p16_eligible": (c_int32, [c_int32, c_int32, POINTER(ConvGeom)]),
     "ctx_conv2d_fprop_p16": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, POINTER(ConvGeom),
                                        POINTER(Epilogue), POINTER(P16), c_void_p]),
@@ -77,7 +84,7 @@ SIGNATURES = {
     "ctx_conv2d_transpose_p16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                            c_int32, c_int32, POINTER(ConvGeom), POINTER(Epilogue), POINTER(P16), c_void_p]),
     "ctx_conv2d_transpose_merged_p16_eligible": (c_int32, [c_int32, c_int32, c_int32, c_int32, POINTER(ConvGeom)]),
-    "ctx_conv2d_transpose_merged_pack_p16": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_int32,
+    "ctx_conv2d_transpose_merged_pack_p16": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_float, c_void_p, c_int32,
                                                        c_int32, c_void_p]),
     "ctx_conv2d_transpose_merged_p16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                                   c_void_p, c_int32, c_int32, POINTER(ConvGeom), POINTER(Epilogue),
@@ -90,6 +97,18 @@ SIGNATURES = {
     "ctx_amax": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ctx_skip_grad_sum": (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_float, c_void_p, c_int32,
                                     c_void_p]),
+    "ctx_conv2d_few_eligible": (c_int32, [c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_few_pack_bytes": (c_int64, [c_int32, POINTER(ConvGeom), c_int32]),
+    "ctx_conv2d_few_pack": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_int32, c_void_p]),
+    "ctx_conv2d_few_fprop": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                       POINTER(ConvGeom), POINTER(Epilogue), c_int32, c_void_p, c_void_p, c_void_p]),
+    "ctx_conv2d_few_wgrad": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p,
+                                       POINTER(ConvGeom), c_void_p, c_void_p, c_void_p]),
+    "ctx_conv2d_transpose_few_eligible": (c_int32, [c_int32, c_int32, c_int32, c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_transpose_few_pack_bytes": (c_int64, [c_int32, POINTER(ConvGeom)]),
+    "ctx_conv2d_transpose_few_pack": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_void_p]),
+    "ctx_conv2d_transpose_few": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                           POINTER(ConvGeom), POINTER(Epilogue), POINTER(L2Fused), c_void_p]),
     "ctx_crc32c": (C.c_uint32, [c_void_p, C.c_uint64, C.c_uint32]),
     "ctx_gather_frames": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "ctx_lrelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_void_p]),

@@ -260,13 +260,13 @@ extern "C" int64_t ctx_conv2d_transpose_merged_rows(int32_t Cn, const ctx_conv_g
   return h16_conv2d_transpose_merged_rows(Cn, *g);
 }
 
-extern "C" int ctx_conv2d_transpose_merged_pack_p16(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g,
+extern "C" int ctx_conv2d_transpose_merged_pack_p16(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g, float scale,
                                                     void* wm_planes, int32_t nplanes, int32_t dtype, void* stream) {
   int rc = check_geom(g, "conv2d_transpose_merged_pack");
   if (rc) return rc;
   CTX_REQUIRE(w && wm_planes && Ck > 0 && Cn > 0, "conv2d_transpose_merged_pack: bad arguments");
   CTX_REQUIRE(dtype == CTX_P16_F16 || dtype == CTX_P16_BF16, "conv2d_transpose_merged_pack: bad dtype");
-  return h16_conv2d_transpose_merged_pack(w, Ck, Cn, *g, wm_planes, nplanes, dtype == CTX_P16_F16, (cudaStream_t)stream);
+  return h16_conv2d_transpose_merged_pack(w, Ck, Cn, *g, scale, wm_planes, nplanes, dtype == CTX_P16_F16, (cudaStream_t)stream);
 }
 
 extern "C" int ctx_conv2d_transpose_merged_p16(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
@@ -341,7 +341,7 @@ extern "C" int ctx_conv2d_transpose_merged_bf16x3_eligible(int32_t C1, int32_t C
 }
 extern "C" int ctx_conv2d_transpose_merged_pack(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g,
                                                 void* wm_planes, void* stream) {
-  return ctx_conv2d_transpose_merged_pack_p16(w, Ck, Cn, g, wm_planes, 2, CTX_P16_BF16, stream);
+  return ctx_conv2d_transpose_merged_pack_p16(w, Ck, Cn, g, 1.f, wm_planes, 2, CTX_P16_BF16, stream);
 }
 extern "C" int ctx_conv2d_transpose_merged_bf16x3(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
                                                   int32_t x2_batch, const void* wm_planes, float* y, void* y_planes,

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared between the translation units of libctx_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include "common.cuh"
@@ -44,6 +45,10 @@ struct H16Cfg {
   const float* a_scale;     // device scalar or null: the (gradient) operand planes hold s * x; the result is divided by s
   uint32_t* amax_bits;      // device word or null: atomicMax of the bit patterns of |result|
 };
+// tensor map (f16: 0 = bf16, 1 = fp16, 2 = fp32), zero fill, 128-byte swizzle; dims / box innermost first; strides in ELEMENTS
+// for dims 1..rank-1
+int h16_make_map(CUtensorMap* out, int f16, const void* base, int rank, const int64_t* dims, const int64_t* strides,
+                 const int* box);
 int h16_conv2d_fprop_eligible(int C, int Co, const ctx_conv_geom& g);
 int h16_conv2d_fprop(const void* xp, int C, const void* wp, float* y, void* yp, int yp_n, int Co, const ctx_conv_geom& g,
                      const Epi& epi, const H16Cfg& cfg, cudaStream_t stream);
@@ -52,8 +57,8 @@ int h16_conv2d_transpose(const void* x1p, int C1, const void* x2p, int C2, int x
                          int yp_n, int Cn, const ctx_conv_geom& g, const Epi& epi, const H16Cfg& cfg, cudaStream_t stream);
 int h16_conv2d_transpose_merged_eligible(int C1, int C2, int x2_batch, int Cn, const ctx_conv_geom& g);
 int64_t h16_conv2d_transpose_merged_rows(int Cn, const ctx_conv_geom& g);
-int h16_conv2d_transpose_merged_pack(const float* w, int Ck, int Cn, const ctx_conv_geom& g, void* planes, int nplanes,
-                                     int f16, cudaStream_t stream);
+int h16_conv2d_transpose_merged_pack(const float* w, int Ck, int Cn, const ctx_conv_geom& g, float scale, void* planes,
+                                     int nplanes, int f16, cudaStream_t stream);
 int h16_conv2d_transpose_merged(const void* x1p, int C1, const void* x2p, int C2, int x2_batch, const void* wmp, float* y,
                                 void* yp, int yp_n, int Cn, const ctx_conv_geom& g, const Epi& epi, const H16Cfg& cfg,
                                 cudaStream_t stream);

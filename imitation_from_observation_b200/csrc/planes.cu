@@ -43,7 +43,8 @@ __device__ __forceinline__ void p_split4(const float4 v, bool f16, uint2& hi, ui
 }
 
 // ---- x -> planes ---------------------------------------------------------------------------------------------------------------
-__global__ void split_planes_kernel(const float* __restrict__ x, int64_t n, uint16_t* __restrict__ planes, int nplanes, int f16) {
+__global__ void split_planes_kernel(const float* __restrict__ x, int64_t n, uint16_t* __restrict__ planes, int nplanes, int f16,
+                                    float scale) {
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
   uint16_t* hi = planes;
   uint16_t* lo = planes + n;
@@ -51,28 +52,31 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int64_t n, uint
   if (n % 4 == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)planes) & 7) == 0) {
     for (int64_t j = i0; j < n / 4; j += step) {
       uint2 a, b;
-      p_split4(reinterpret_cast<const float4*>(x)[j], h, a, b);
+      float4 v = reinterpret_cast<const float4*>(x)[j];
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      p_split4(v, h, a, b);
       reinterpret_cast<uint2*>(hi)[j] = a;
       if (nplanes == 2) reinterpret_cast<uint2*>(lo)[j] = b;
     }
   } else {
     for (int64_t j = i0; j < n; j += step) {
-      const uint16_t a = p_one16(x[j], h);
+      const float v = x[j] * scale;
+      const uint16_t a = p_one16(v, h);
       hi[j] = a;
-      if (nplanes == 2) lo[j] = p_one16(x[j] - p_lo16(a, h), h);
+      if (nplanes == 2) lo[j] = p_one16(v - p_lo16(a, h), h);
     }
   }
 }
 
 // w [T][R][Cc] fp32 -> planes [nplanes][T][Cc][R]; 32 x 32 tiles through shared memory, both global accesses coalesced
 __global__ void split_planes_transpose_kernel(const float* __restrict__ w, int T, int R, int Cc, uint16_t* __restrict__ planes,
-                                              int nplanes, int f16) {
+                                              int nplanes, int f16, float scale) {
   __shared__ float tile[32][33];
   const int t = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const float* src = w + (int64_t)t * R * Cc;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < Cc) ? src[(int64_t)r * Cc + c] : 0.f;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? src[(int64_t)r * Cc + c] * scale : 0.f;
   }
   __syncthreads();
   const int64_t plane = (int64_t)T * R * Cc;
@@ -203,19 +207,20 @@ using namespace ctx;
 
 static int dtype_ok(int32_t dtype) { return dtype == CTX_P16_F16 || dtype == CTX_P16_BF16; }
 
-extern "C" int ctx_split_planes(const float* x, int64_t n, void* planes, int32_t nplanes, int32_t dtype, void* stream) {
+extern "C" int ctx_split_planes(const float* x, int64_t n, float scale, void* planes, int32_t nplanes, int32_t dtype,
+                                void* stream) {
   CTX_REQUIRE(n >= 0, "split_planes: negative size");
   CTX_REQUIRE((nplanes == 1 || nplanes == 2) && dtype_ok(dtype), "split_planes: nplanes must be 1 or 2, dtype F16 or BF16");
   if (n == 0) return CTX_OK;
   CTX_REQUIRE(x && planes, "split_planes: null pointer");
   split_planes_kernel<<<planes_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, n, (uint16_t*)planes, nplanes,
-                                                                                   dtype == CTX_P16_F16);
+                                                                                   dtype == CTX_P16_F16, scale);
   CTX_LAUNCH_CHECK("split_planes");
   return CTX_OK;
 }
 
-extern "C" int ctx_split_planes_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, void* planes, int32_t nplanes,
-                                          int32_t dtype, void* stream) {
+extern "C" int ctx_split_planes_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, float scale, void* planes,
+                                          int32_t nplanes, int32_t dtype, void* stream) {
   CTX_REQUIRE(T >= 0 && R >= 0 && Cc >= 0, "split_planes_transpose: negative size");
   CTX_REQUIRE((nplanes == 1 || nplanes == 2) && dtype_ok(dtype), "split_planes_transpose: nplanes must be 1 or 2, dtype F16 or BF16");
   if (T == 0 || R == 0 || Cc == 0) return CTX_OK;
@@ -223,17 +228,17 @@ extern "C" int ctx_split_planes_transpose(const float* w, int32_t T, int32_t R, 
   CTX_REQUIRE(T <= 65535 && cdiv(R, 32) <= 65535, "split_planes_transpose: grid too large");
   dim3 grid((unsigned)cdiv(Cc, 32), (unsigned)cdiv(R, 32), (unsigned)T);
   split_planes_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, T, R, Cc, (uint16_t*)planes, nplanes,
-                                                                               dtype == CTX_P16_F16);
+                                                                               dtype == CTX_P16_F16, scale);
   CTX_LAUNCH_CHECK("split_planes_transpose");
   return CTX_OK;
 }
 
 extern "C" int ctx_split_bf16(const float* x, int64_t n, void* planes, void* stream) {
-  return ctx_split_planes(x, n, planes, 2, CTX_P16_BF16, stream);
+  return ctx_split_planes(x, n, 1.f, planes, 2, CTX_P16_BF16, stream);
 }
 
 extern "C" int ctx_split_bf16_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, void* planes, void* stream) {
-  return ctx_split_planes_transpose(w, T, R, Cc, planes, 2, CTX_P16_BF16, stream);
+  return ctx_split_planes_transpose(w, T, R, Cc, 1.f, planes, 2, CTX_P16_BF16, stream);
 }
 
 extern "C" int ctx_grad_planes(const float* x, int64_t rows, int32_t C, int32_t ldx, const float* ref, float slope,

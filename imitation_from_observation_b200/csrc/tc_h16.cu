@@ -504,8 +504,8 @@ static HEncodeFn h_get_encode() {
 }
 
 // 16-bit tensor map, zero fill, 128-byte swizzle; dims / box innermost first; strides in ELEMENTS for dims 1..rank-1
-static int h_make_map(CUtensorMap* out, int f16, const void* base, int rank, const int64_t* dims, const int64_t* strides,
-                      const int* box) {
+int h16_make_map(CUtensorMap* out, int f16, const void* base, int rank, const int64_t* dims, const int64_t* strides,
+                 const int* box) {
   HEncodeFn enc = h_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return CTX_ERR_CUDA; }
   cuuint64_t gd[5], gs[4];
@@ -515,11 +515,13 @@ static int h_make_map(CUtensorMap* out, int f16, const void* base, int rank, con
     if (dims[i] <= 0 || box[i] <= 0 || box[i] > 256) { set_error("16-bit tensor map: bad dim/box %d: %lld/%d", i, (long long)dims[i], box[i]); return CTX_ERR_ARG; }
   }
   for (int i = 1; i < rank; ++i) {
-    gs[i - 1] = (cuuint64_t)strides[i] * 2u;
+    gs[i - 1] = (cuuint64_t)strides[i] * (f16 == 2 ? 4u : 2u);
     if (gs[i - 1] % 16 != 0) { set_error("16-bit tensor map: stride %d (%lld elements) is not 16-byte aligned", i, (long long)strides[i]); return CTX_ERR_ARG; }
   }
   if (((uintptr_t)base & 15) != 0) { set_error("16-bit tensor map: base pointer is not 16-byte aligned"); return CTX_ERR_ARG; }
-  CUresult r = enc(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base,
+  const CUtensorMapDataType dt = f16 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                          : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(out, dt, (cuuint32_t)rank, (void*)base,
                    gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (16-bit) failed with CUresult %d", (int)r); return CTX_ERR_CUDA; }
@@ -659,7 +661,7 @@ int h16_conv2d_fprop(const void* xp, int C, const void* wp, float* y, void* yp, 
   if (g.stride == 1) {
     int64_t dims[5] = {C, g.W, g.H, g.N, np}, str[5] = {1, C, (int64_t)g.W * C, (int64_t)g.H * g.W * C, x_plane};
     int box[5] = {64, g.Q, p.BP, p.NB, np};
-    rc = h_make_map(&p.mapA[0], cfg.f16, xp, 5, dims, str, box);
+    rc = h16_make_map(&p.mapA[0], cfg.f16, xp, 5, dims, str, box);
     if (rc) return rc;
   } else {
     for (int hp = 0; hp < 2; ++hp)
@@ -668,7 +670,7 @@ int h16_conv2d_fprop(const void* xp, int C, const void* wp, float* y, void* yp, 
         int64_t dims[5] = {C, Wh, Hh, g.N, np};
         int64_t str[5] = {1, 2 * (int64_t)C, 2 * (int64_t)g.W * C, (int64_t)g.H * g.W * C, x_plane};
         int box[5] = {64, g.Q, p.BP, p.NB, np};
-        rc = h_make_map(&p.mapA[hp * 2 + wq], cfg.f16, (const uint16_t*)xp + ((int64_t)hp * g.W + wq) * C, 5, dims, str, box);
+        rc = h16_make_map(&p.mapA[hp * 2 + wq], cfg.f16, (const uint16_t*)xp + ((int64_t)hp * g.W + wq) * C, 5, dims, str, box);
         if (rc) return rc;
       }
   }
@@ -676,7 +678,7 @@ int h16_conv2d_fprop(const void* xp, int C, const void* wp, float* y, void* yp, 
     const int64_t rows = (int64_t)g.kh * g.kw * Co;
     int64_t dims[3] = {C, rows, np}, str[3] = {1, C, rows * C};
     int box[3] = {64, pair ? 128 : p.BN, np};
-    rc = h_make_map(&p.mapB[0], cfg.f16, wp, 3, dims, str, box);
+    rc = h16_make_map(&p.mapB[0], cfg.f16, wp, 3, dims, str, box);
     if (rc) return rc;
   }
   const int cblk = C / 64;
@@ -766,21 +768,21 @@ int h16_conv2d_transpose(const void* x1p, int C1, const void* x2p, int C2, int x
     const int64_t plane = (int64_t)g.N * g.P * g.Q * C1;
     int64_t dims[5] = {C1, g.Q, g.P, g.N, np}, str[5] = {1, C1, (int64_t)g.Q * C1, (int64_t)g.P * g.Q * C1, plane};
     int box[5] = {64, phs[0].Wp, p.BP, p.NB, np};
-    rc = h_make_map(&p.mapA[0], cfg.f16, x1p, 5, dims, str, box);
+    rc = h16_make_map(&p.mapA[0], cfg.f16, x1p, 5, dims, str, box);
     if (rc) return rc;
   }
   if (C2 > 0) {
     const int64_t plane = (int64_t)x2_batch * g.P * g.Q * C2;
     int64_t dims[5] = {C2, g.Q, g.P, x2_batch, np}, str[5] = {1, C2, (int64_t)g.Q * C2, (int64_t)g.P * g.Q * C2, plane};
     int box[5] = {64, phs[0].Wp, p.BP, p.NB, np};
-    rc = h_make_map(&p.mapA[1], cfg.f16, x2p, 5, dims, str, box);
+    rc = h16_make_map(&p.mapA[1], cfg.f16, x2p, 5, dims, str, box);
     if (rc) return rc;
   }
   {
     const int64_t rows = (int64_t)g.kh * g.kw * Cn;
     int64_t dims[3] = {Ck, rows, np}, str[3] = {1, Ck, rows * Ck};
     int box[3] = {64, pair ? 128 : p.BN, np};
-    rc = h_make_map(&p.mapB[0], cfg.f16, wp, 3, dims, str, box);
+    rc = h16_make_map(&p.mapB[0], cfg.f16, wp, 3, dims, str, box);
     if (rc) return rc;
   }
   int seg0 = 0;
@@ -857,7 +859,7 @@ int h16_conv2d_transpose_merged_eligible(int C1, int C2, int x2_batch, int Cn, c
 }
 
 __global__ void h16_merged_pack_kernel(const float* __restrict__ w, int kw, int Cn, int Ck, HMergedPlan mp, void* planes,
-                                       int nplanes, int f16) {
+                                       int nplanes, int f16, float scale) {
   // planes [nplanes][noff * 4 * Cn][Ck]; one thread per (row, 4 channels)
   const int64_t rows = (int64_t)mp.nh * mp.nw * 4 * Cn, total = rows * (Ck / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -868,6 +870,7 @@ __global__ void h16_merged_pack_kernel(const float* __restrict__ w, int kw, int 
     const int r = mp.tap_r[phase >> 1][off / mp.nw], s_ = mp.tap_s[phase & 1][off % mp.nw];
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r >= 0 && s_ >= 0) v = *reinterpret_cast<const float4*>(w + (((int64_t)r * kw + s_) * Cn + co) * Ck + c4);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     const uint32_t h0 = h16::pack16(v.x, v.y, f16 != 0), h1 = h16::pack16(v.z, v.w, f16 != 0);
     uint16_t* hi = reinterpret_cast<uint16_t*>(planes) + row * Ck + c4;
     *reinterpret_cast<uint2*>(hi) = make_uint2(h0, h1);
@@ -886,15 +889,15 @@ int64_t h16_conv2d_transpose_merged_rows(int Cn, const ctx_conv_geom& g) {
 }
 
 // w [kh,kw,Cn,Ck] fp32 -> packed planes [nplanes][rows][Ck], rows = h16_conv2d_transpose_merged_rows
-int h16_conv2d_transpose_merged_pack(const float* w, int Ck, int Cn, const ctx_conv_geom& g, void* planes, int nplanes,
-                                     int f16, cudaStream_t stream) {
+int h16_conv2d_transpose_merged_pack(const float* w, int Ck, int Cn, const ctx_conv_geom& g, float scale, void* planes,
+                                     int nplanes, int f16, cudaStream_t stream) {
   HMergedPlan mp;
   CTX_REQUIRE(h_merged_plan(g, &mp) && Ck % 4 == 0, "conv2d_transpose_merged_pack: geometry not eligible");
   CTX_REQUIRE(h_aligned16(w) && h_aligned16(planes), "conv2d_transpose_merged_pack: pointers must be 16-byte aligned");
   CTX_REQUIRE(nplanes == 1 || nplanes == 2, "conv2d_transpose_merged_pack: nplanes must be 1 or 2");
   const int64_t total = (int64_t)mp.nh * mp.nw * 4 * Cn * (Ck / 4);
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  h16_merged_pack_kernel<<<blocks, 256, 0, stream>>>(w, g.kw, Cn, Ck, mp, planes, nplanes, f16);
+  h16_merged_pack_kernel<<<blocks, 256, 0, stream>>>(w, g.kw, Cn, Ck, mp, planes, nplanes, f16, scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "merged_pack");
   count_launch();
@@ -929,21 +932,21 @@ int h16_conv2d_transpose_merged(const void* x1p, int C1, const void* x2p, int C2
     const int64_t plane = (int64_t)g.N * g.P * g.Q * C1;
     int64_t dims[5] = {C1, g.Q, g.P, g.N, np}, str[5] = {1, C1, (int64_t)g.Q * C1, (int64_t)g.P * g.Q * C1, plane};
     int box[5] = {64, g.Q, p.BP, p.NB, np};
-    rc = h_make_map(&p.mapA[0], cfg.f16, x1p, 5, dims, str, box);
+    rc = h16_make_map(&p.mapA[0], cfg.f16, x1p, 5, dims, str, box);
     if (rc) return rc;
   }
   if (C2 > 0) {
     const int64_t plane = (int64_t)x2_batch * g.P * g.Q * C2;
     int64_t dims[5] = {C2, g.Q, g.P, x2_batch, np}, str[5] = {1, C2, (int64_t)g.Q * C2, (int64_t)g.P * g.Q * C2, plane};
     int box[5] = {64, g.Q, p.BP, p.NB, np};
-    rc = h_make_map(&p.mapA[1], cfg.f16, x2p, 5, dims, str, box);
+    rc = h16_make_map(&p.mapA[1], cfg.f16, x2p, 5, dims, str, box);
     if (rc) return rc;
   }
   {
     const int64_t rows = (int64_t)mp.nh * mp.nw * 4 * Cn;
     int64_t dims[3] = {Ck, rows, np}, str[3] = {1, Ck, rows * Ck};
     int box[3] = {64, pair ? 128 : 256, np};
-    rc = h_make_map(&p.mapB[0], cfg.f16, wmp, 3, dims, str, box);
+    rc = h16_make_map(&p.mapB[0], cfg.f16, wmp, 3, dims, str, box);
     if (rc) return rc;
   }
   int nseg = 0, kblocks = 0;
@@ -1032,7 +1035,7 @@ int h16_conv2d_wgrad(const void* big, int Ca, const void* s1, int Cb1, const voi
     if (g.stride == 1) {
       int64_t dims[5] = {64, g.W, g.H, g.N, Ca / 64}, str[5] = {1, Ca, (int64_t)g.W * Ca, (int64_t)g.H * g.W * Ca, 64};
       int box[5] = {64, g.Q, p.kBP, p.kNB, p.a_box};
-      rc = h_make_map(&p.mapA[4 * pl], cfg.f16, base0, 5, dims, str, box);
+      rc = h16_make_map(&p.mapA[4 * pl], cfg.f16, base0, 5, dims, str, box);
       if (rc) return rc;
     } else {
       for (int hp = 0; hp < 2; ++hp)
@@ -1041,7 +1044,7 @@ int h16_conv2d_wgrad(const void* big, int Ca, const void* s1, int Cb1, const voi
           int64_t dims[5] = {64, Wh, Hh, g.N, Ca / 64};
           int64_t str[5] = {1, 2 * (int64_t)Ca, 2 * (int64_t)g.W * Ca, (int64_t)g.H * g.W * Ca, 64};
           int box[5] = {64, g.Q, p.kBP, p.kNB, p.a_box};
-          rc = h_make_map(&p.mapA[4 * pl + hp * 2 + wq], cfg.f16, base0 + ((int64_t)hp * g.W + wq) * Ca, 5, dims, str, box);
+          rc = h16_make_map(&p.mapA[4 * pl + hp * 2 + wq], cfg.f16, base0 + ((int64_t)hp * g.W + wq) * Ca, 5, dims, str, box);
           if (rc) return rc;
         }
     }
@@ -1051,14 +1054,14 @@ int h16_conv2d_wgrad(const void* big, int Ca, const void* s1, int Cb1, const voi
     const int64_t rows = (int64_t)g.N * g.P * g.Q;
     int64_t dims[4] = {64, rows, Cb1 / 64, np}, str[4] = {1, Cb1, 64, rows * Cb1};
     int box[4] = {64, 64, p.b_box, 1};
-    rc = h_make_map(&p.mapB[0], cfg.f16, s1, 4, dims, str, box);
+    rc = h16_make_map(&p.mapB[0], cfg.f16, s1, 4, dims, str, box);
     if (rc) return rc;
   }
   if (Cb2 > 0) {
     const int64_t rows = (int64_t)s2_batch * g.P * g.Q;
     int64_t dims[4] = {64, rows, Cb2 / 64, np}, str[4] = {1, Cb2, 64, rows * Cb2};
     int box[4] = {64, 64, p.b_box, 1};
-    rc = h_make_map(&p.mapB[1], cfg.f16, s2, 4, dims, str, box);
+    rc = h16_make_map(&p.mapB[1], cfg.f16, s2, 4, dims, str, box);
     if (rc) return rc;
   }
   for (int r = 0; r < g.kh; ++r)

@@ -4,8 +4,8 @@
     demo bank layout                scripts/train_script.py:83-97: vdata [nlen, N, H, W, 3]
 
 `scipy.misc.imresize` (removed from SciPy long ago) was a PIL resize with bilinear interpolation of the uint8 image;
-it is restated here with Pillow.  The mp4 / ffmpeg front-end of the trainer (train_script.py:59-82) is out of scope:
-ModelTrainer takes the `.npy` bank the reference saves.
+it is restated here with Pillow.  The mp4 front-end of the trainer (train_script.py:59-96, imageio + ffmpeg there) is
+`read_video` / `videos_to_bank` on OpenCV's FFMPEG reader; ModelTrainer also takes the `.npy` bank the reference saves.
 
 `DeviceBank` keeps that bank in HBM and answers the trainer's own indexing expressions (train_script.py:150-173) with
 device batches assembled by `ctx_gather_frames`, which removes the per-step host gather, float64->float32 cast and H2D
@@ -51,6 +51,66 @@ def frames_to_bank(videos, nlen: int, nskip: int, idims, rescale: bool = True) -
             continue
         for j, f in enumerate(frames):
             idata[j].append(f)
+    return np.array(idata)
+
+
+def read_video(path: str):
+    """All frames of a video file as RGB uint8 arrays — imageio.get_reader(name, 'ffmpeg') of train_script.py:66 (same
+    FFMPEG decoder underneath; OpenCV hands frames back as BGR)."""
+    import cv2
+    cap = cv2.VideoCapture(path)
+    if not cap.isOpened():
+        raise IOError("cannot open video %s" % path)
+    frames = []
+    try:
+        while True:
+            ok, frame = cap.read()
+            if not ok:
+                break
+            frames.append(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB))
+    finally:
+        cap.release()
+    return frames
+
+
+def videos_to_bank(paths, nlen: int, nskip: int, idims, rescale: bool = True, nvideos: int = 1 << 30,
+                   inception: bool = False, rng=None, log=None) -> np.ndarray:
+    """train_script.py:58-96: shuffle the demo videos, keep those with exactly 51 frames, take frames 1, 1 + nskip, ... < 51,
+    transform each (resize, x / 127.5 - 1 unless `rescale` is off), drop a video with an all-black frame (unless
+    `inception`: uint8 frames go to the feature extractor), stop after `nvideos` videos or more than 10 unreadable files.
+    Returns vdata [nlen, N, H, W, 3] — the array the reference saves as vdata_strike<N>.npy."""
+    paths = list(paths)
+    (rng or np.random).shuffle(paths)                          # :63
+    idata = [[] for _ in range(nlen)]
+    nfail = itr = 0
+    for name in paths:
+        try:
+            vid = read_video(name)
+            if len(vid) == 51:                                 # :69
+                frames = []
+                for j in range(1, 51, nskip):
+                    frame = transform(vid[j], idims[0], idims[1], rescale)
+                    if not inception and np.max(frame) == -1:  # :73-76
+                        if log:
+                            log("rip %s %s" % (itr, name))
+                        frames = []
+                        break
+                    frames.append(frame)
+                if len(frames) != nlen:
+                    continue                                   # (:78-79: such a video does not count towards nvideos)
+                for j, f in enumerate(frames):
+                    idata[j].append(f)
+            elif log:
+                log("%s %s" % (name, len(vid)))
+            itr += 1
+        except Exception as ex:                                # noqa: BLE001  (:84-89: log, give up after 10 failures)
+            nfail += 1
+            if log:
+                log("Unexpected error: %r %s" % (ex, name))
+            if nfail > 10:
+                break
+        if itr >= nvideos:
+            break
     return np.array(idata)
 
 

@@ -140,11 +140,15 @@ class ContextNet:
         # Planes are fp16 (22 significant bits in hi + lo; CTX_PLANES=bf16 selects bf16: 16 bits, fp32's range); the hi
         # plane alone is the backward pass's operand (_enc_p1 / _dec_p1 below, fp16 only).
         self.pdt = torch.bfloat16 if os.environ.get("CTX_PLANES", "fp16") == "bf16" else torch.float16
+        self._wsc = 256.0 if self.pdt == torch.float16 else 1.0
         self._enc_bf3 = [False] * self.L
         self._dec_bf3 = [False] * self.L
         self._enc_p1 = [False] * self.L                  # backward of encoder conv j on fp16 hi planes (one product)
         self._enc_p1_merged = [False] * self.L           # ... its data gradient in the phase-merged form (Cin = 64 / 128)
         self._dec_p1 = [False] * self.L                  # backward of decoder level i on fp16 hi planes
+        self._enc_few = [False] * self.L                 # few-channel-input conv (the image): patches built on chip
+        self._dec_few = [False] * self.L                 # few-channel-output level (the reconstruction): its backward
+        self._dec_fewt = [False] * self.L                # ... and its forward (channel GEMM + col2im gather, fused loss)
         self._wb: Dict[str, torch.Tensor] = {}           # backward weight planes (one fp16 plane), refreshed with _wp
         self._in_planes: Dict[tuple, torch.Tensor] = {}  # (tag, j) -> planes of the input of encoder conv j (forward)
         self._dec_planes: Dict[int, tuple] = {}          # i -> (state planes, skip planes) of decoder level i (forward)
@@ -163,9 +167,15 @@ class ContextNet:
                                            ops.conv2d_transpose_merged_eligible(*args))
                     self._dec_bf3[i] = self._dec_merged[i] or ops.conv2d_transpose_bf16x3_eligible(*args)
             if (spec.separate_ctx_encoder and self.pdt == torch.float16 and os.environ.get("CTX_BWD_P16", "1") != "0"):
-                for j in range(1, self.L):
+                few_on = os.environ.get("CTX_FEW", "1") != "0"
+                for j in range(self.L):
                     Cin, Co, k, st = self.chans[j], self.chans[j + 1], spec.kernels[j], spec.strides[j]
                     rows = (2 * self.B, self.B)          # scope "conv" rows / context rows
+                    if j == 0:                           # no data gradient below the first layer
+                        self._enc_few[0] = few_on and ops.conv2d_few_eligible(2 * self.B, self.sizes[0], Cin, Co, k, st)
+                        self._enc_p1[0] = self._enc_bf3[0] and all(
+                            ops.conv2d_wgrad_planes_eligible(n, self.sizes[0], Cin, Co, 0, 0, k, st) for n in rows)
+                        continue
                     mg = all(ops.conv2d_transpose_merged_eligible(n, self.sizes[j], Co, 0, 0, Cin, k, st) for n in rows) \
                         and os.environ.get("CTX_BF3_MERGE", "1") != "0"
                     dg = mg or all(ops.conv2d_transpose_planes_eligible(n, self.sizes[j], Co, 0, 0, Cin, k, st) for n in rows)
@@ -177,9 +187,14 @@ class ContextNet:
                     self._dec_p1[i] = (self._dec_bf3[i] and
                                        ops.conv2d_planes_eligible(2 * self.B, Ld["out_hw"], Co, Cs + Csk, k, st) and
                                        ops.conv2d_wgrad_planes_eligible(2 * self.B, Ld["out_hw"], Co, Cs, Csk, self.B, k, st))
-        self.bf3 = any(self._enc_bf3) or any(self._dec_bf3)
-        self.p1 = any(self._enc_p1) or any(self._dec_p1)
+                    self._dec_few[i] = (few_on and not self._dec_bf3[i] and Cs % 64 == 0 and Csk % 64 == 0 and
+                                        ops.conv2d_few_eligible(2 * self.B, Ld["out_hw"], Co, Cs + Csk, k, st))
+                    self._dec_fewt[i] = (self._dec_few[i] and os.environ.get("CTX_FEW_T", "1") != "0" and
+                                         ops.conv2d_transpose_few_eligible(2 * self.B, Ld["out_hw"], Cs, Csk, self.B, Co, k, st))
+        self.bf3 = any(self._enc_bf3) or any(self._dec_bf3) or any(self._enc_few) or any(self._dec_few)
+        self.p1 = any(self._enc_p1) or any(self._dec_p1) or any(self._enc_few) or any(self._dec_few)
         self._level = 0
+        self._l2_fused = False                           # the last forward evaluated the reconstruction loss inside d_h<L>
 
     # ---- second stream -----------------------------------------------------------------------------------------
     # Independent launches run on a side stream so that one kernel's last, partly filled wave overlaps another
@@ -366,6 +381,16 @@ class ContextNet:
     def _planes(self, name: str, shape, n: int = 2) -> torch.Tensor:
         return self._buf(name, (n,) + tuple(shape), dtype=self.pdt)
 
+    def _wscale(self) -> Optional[torch.Tensor]:
+        """Device scalar the forward plane layers divide their result by: the (hi, lo) filter planes hold 2^8 * w when the
+        planes are fp16 — filters are ~N(0, 0.02), whose lo parts would otherwise fall into fp16's subnormals (19 bits)."""
+        if self._wsc == 1.0:
+            return None
+        t = self._bufs.get("wscale")
+        if t is None:
+            t = self._bufs["wscale"] = torch.full((1,), self._wsc, device=self.device, dtype=torch.float32)
+        return t
+
     def _split(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         return ops.split_planes(x, out=out, nplanes=out.shape[0])
 
@@ -382,9 +407,12 @@ class ContextNet:
             for j in range(self.L):
                 name = "%s/h%d_conv/w" % (sc, j)
                 k = sp.kernels[j]
+                if self._enc_few[j]:
+                    self._wp[name] = self._bufs["wp:" + name] = ops.conv2d_few_pack(self.P[name], 2,
+                                                                                     out=self._bufs.get("wp:" + name))
                 if self._enc_bf3[j]:
                     buf = self._planes("wp:" + name, (k * k * self.chans[j + 1], self.chans[j]))
-                    self._wp[name] = ops.split_planes_transpose(self.P[name], out=buf)
+                    self._wp[name] = ops.split_planes_transpose(self.P[name], out=buf, scale=self._wsc)
                 if self._enc_p1[j]:
                     # data gradient = transposed conv of dY with the HWIO filter as stored: rows (tap, Cin), K = Cout
                     if self._enc_p1_merged[j]:
@@ -402,11 +430,18 @@ class ContextNet:
                 if self._dec_bf3[i]:
                     if self._dec_merged[i]:
                         self._wp[name] = ops.conv2d_transpose_merged_pack(self.P[name], Ld["out_hw"], Ld["stride"],
-                                                                          out=self._bufs.get("wp:" + name), dtype=self.pdt)
+                                                                          out=self._bufs.get("wp:" + name), dtype=self.pdt,
+                                                                          scale=self._wsc)
                         self._bufs["wp:" + name] = self._wp[name]
                     else:
                         buf = self._planes("wp:" + name, (Ld["k"] * Ld["k"] * Ld["c_out"], Ck))
-                        self._wp[name] = ops.split_planes(self.P[name], out=buf)
+                        self._wp[name] = ops.split_planes(self.P[name], out=buf, scale=self._wsc)
+                if self._dec_fewt[i]:
+                    self._wp[name] = self._bufs["wp:" + name] = ops.conv2d_transpose_few_pack(
+                        self.P[name], out=self._bufs.get("wp:" + name))
+                if self._dec_few[i]:                      # data gradient: few-channel-input conv of dY, filter read as HWIO
+                    self._wb[name] = self._bufs["wb:" + name] = ops.conv2d_few_pack(self.P[name], 1,
+                                                                                     out=self._bufs.get("wb:" + name))
                 if self._dec_p1[i]:
                     # data gradient = conv of dY with the [kh,kw,Cout,Cin] filter read as HWIO: rows (tap, Cin), K = Cout
                     buf = self._planes("wb:" + name, (Ld["k"] * Ld["k"] * Ck, Ld["c_out"]), n=1)
@@ -427,14 +462,22 @@ class ContextNet:
             k, Cin, Co = self.spec.kernels[j], h.shape[3], w.shape[3]
             use_bf = tag is not None and self._enc_bf3[j]
             want_p = tag is not None and ((j + 1 < L and self._enc_bf3[j + 1]) or
-                                          (skip_planes and self._dec_bf3[L - 1 - j]))
+                                          (skip_planes and (self._dec_bf3[L - 1 - j] or self._dec_few[L - 1 - j])))
             op = self._planes("%s_h%d_p%d" % (tag, j, h.shape[0]), outs[j].shape) if want_p else None
+            if tag is not None and self._enc_few[j]:
+                # the image: patch matrix built in shared memory, three products, result + its planes in one pass
+                ops.conv2d_few(h, self._wp["%s/h%d_conv/w" % (scope, j)], k, Co, bias=b, stride=self.spec.strides[j],
+                               act=True, out=outs[j], out_planes=op, nprod=3, amax=self._fwd_amax())
+                h, hp = outs[j], op
+                produced[j] = op
+                continue
             if use_bf:
                 if hp is None:
                     hp = self._split(h, self._planes("%s_in%d_p%d" % (tag, j, h.shape[0]), h.shape))
                 self._in_planes[(tag, j)] = hp             # backward's filter gradient reads the hi plane
                 ops.conv2d_planes(hp, self._wp["%s/h%d_conv/w" % (scope, j)], k, bias=b, stride=self.spec.strides[j],
-                                  act=True, out=outs[j], out_planes=op, nprod=3, amax=self._fwd_amax())
+                                  act=True, out=outs[j], out_planes=op, nprod=3, amax=self._fwd_amax(),
+                                  a_scale=self._wscale())
                 h, hp = outs[j], op
                 produced[j] = op
                 continue
@@ -564,7 +607,13 @@ class ContextNet:
                 self._fwd_hz("conv", e_h4[B:2 * B], z2.data_ptr() + B * F * f4, F, act=True)  # tgt z -> z2[B:]
                 nd = 2 * B
             d = self._dec_buffers()
-            self._fwd_decoder(z2[:nd], [c[:B] for c in c_hs], [t[:nd] for t in d], skip_planes=c_planes, tag="d")
+            l2 = None
+            if level == FWD_ALL:                           # the reconstruction loss can ride on the last decoder layer
+                losses = self._buf("losses", (8,))
+                l2 = dict(tgt=xe[B:2 * B], resid=xc if sp.residual_out else None, weight=self._recon_weights(),
+                          loss=losses[0:2], dpred=self._buf("g_out", tuple(d[self.L].shape)),
+                          amax=losses[5:6].view(torch.int32), pass_images=B)
+            self._fwd_decoder(z2[:nd], [c[:B] for c in c_hs], [t[:nd] for t in d], skip_planes=c_planes, tag="d", l2=l2)
             if level == FWD_ALL:
                 self._fwd_losses(d[self.L], xe[B:2 * B], xc)
         self._level = level
@@ -577,11 +626,13 @@ class ContextNet:
         return d
 
     def _fwd_decoder(self, z: torch.Tensor, skips: Sequence[torch.Tensor], d: Sequence[torch.Tensor],
-                     skip_planes: Optional[Sequence[Optional[torch.Tensor]]] = None, tag: Optional[str] = None):
+                     skip_planes: Optional[Sequence[Optional[torch.Tensor]]] = None, tag: Optional[str] = None,
+                     l2: Optional[dict] = None):
         """arm_shaping.py:1314-1329 for all stacked passes at once; skips = ctx (h0..h_{L-1}), batch B.
         tag (forward() only) enables the bf16-plane levels; skip_planes[j] = planes of skips[j] where the context
         encoder produced them."""
         n = z.shape[0]
+        self._l2_fused = False
         dp = None                                          # planes of the running decoder state
         self._gemm(False, False, n, self.flat, self.F, z.data_ptr(), self.F,
                    self.Wf["deconv/d_h0_lin/Matrix"].data_ptr(), self.flat, d[0].data_ptr(), self.flat,
@@ -597,34 +648,56 @@ class ContextNet:
                     sk = self._split(skips[j].contiguous(), self._planes("%s_skip%d_p" % (tag, j), skips[j].shape))
                 self._dec_planes[i] = (dp, sk)             # backward's filter gradient reads the hi planes
                 op = None
-                if not last and self._dec_bf3[i + 1]:
+                if not last and (self._dec_bf3[i + 1] or self._dec_few[i + 1]):
                     op = self._planes("%s%d_p%d" % (tag, i + 1, n), d[i + 1].shape)
                 if self._dec_merged[i]:
                     ops.conv2d_transpose_merged_planes(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
                                                        L["c_out"], bias=self.P["deconv/%s/biases" % L["name"]],
                                                        stride=L["stride"], x2p=sk, act=not last, out=d[i + 1],
-                                                       out_planes=op, nprod=3, amax=self._fwd_amax())
+                                                       out_planes=op, nprod=3, amax=self._fwd_amax(),
+                                                       a_scale=self._wscale())
                 else:
                     ops.conv2d_transpose_planes(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"],
                                                 bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2p=sk,
                                                 act=not last, out=d[i + 1], out_planes=op, nprod=3,
-                                                amax=self._fwd_amax())
+                                                amax=self._fwd_amax(), a_scale=self._wscale())
                 dp = op
                 continue
+            if tag is not None and self._dec_few[i] and skips[self.L - 1 - i].shape[0] == self.B:
+                j = self.L - 1 - i                         # backward's filter gradient reads the hi planes of [state ‖ skip]
+                if dp is None:
+                    dp = self._split(d[i], self._planes("%s%d_in_p%d" % (tag, i, n), d[i].shape))
+                sk = skip_planes[j] if skip_planes is not None else None
+                if sk is None:
+                    sk = self._split(skips[j].contiguous(), self._planes("%s_skip%d_p" % (tag, j), skips[j].shape))
+                self._dec_planes[i] = (dp, sk)
+                if self._dec_fewt[i]:
+                    # few output channels: channel contraction on the tensor cores, col2im as a gather from shared memory,
+                    # and (training) the reconstruction loss + d loss / d out in the same pass
+                    ops.conv2d_transpose_few(dp, self._wp["deconv/%s/w" % L["name"]], L["out_hw"], L["k"], L["c_out"],
+                                             bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2p=sk,
+                                             act=not last, out=d[i + 1], l2=l2 if last else None)
+                    self._l2_fused = last and l2 is not None
+                    dp = None
+                    continue
             dp = None
             ops.conv2d_transpose(d[i], self.Wf["deconv/%s/w" % L["name"]], L["out_hw"],
                                  bias=self.P["deconv/%s/biases" % L["name"]], stride=L["stride"], x2=skips[self.L - 1 - i],
                                  act=not last, out=d[i + 1], round_tf32=self.round and not last, impl=self.impl)
 
-    def _fwd_losses(self, d4: torch.Tensor, tgt: torch.Tensor, ctx: torch.Tensor):
-        B, F = self.B, self.F
-        losses = self._buf("losses", (8,))
-        g_d4 = self._buf("g_out", tuple(d4.shape))
+    def _recon_weights(self) -> torch.Tensor:
         w = self._bufs.get("w_recon")
         if w is None:
             w = self._bufs["w_recon"] = torch.tensor(self._w_recon, device=self.device, dtype=torch.float32)
-        ops.l2_loss_fwd_bwd(d4, tgt, losses[0:2], dpred=g_d4, resid=ctx if self.spec.residual_out else None,
-                            weight=w)
+        return w
+
+    def _fwd_losses(self, d4: torch.Tensor, tgt: torch.Tensor, ctx: torch.Tensor):
+        B, F = self.B, self.F
+        losses = self._buf("losses", (8,))
+        if not self._l2_fused:
+            g_d4 = self._buf("g_out", tuple(d4.shape))
+            ops.l2_loss_fwd_bwd(d4, tgt, losses[0:2], dpred=g_d4, resid=ctx if self.spec.residual_out else None,
+                                weight=self._recon_weights())
         z2 = self._bufs["z2"]
         ops.mse_scaled_fwd_bwd(z2[:B], z2[B:], 1e3, 1.0 / (B * F), loss=losses[2:3])      # reported: local mean
 
@@ -661,6 +734,16 @@ class ContextNet:
             gc_h4 = self._buf("g_c_lin", tuple(c_h4.shape))
         else:
             gc_hs, gc_h4 = [g[2 * B:] for g in ge_hs], ge_h4[2 * B:]
+
+        # ---- activations read by the single-pass TF32 dense filter gradients ----------------------------------------------------
+        # The tensor core TRUNCATES fp32 operands to TF32: gradients and weights reach it rounded to nearest (producer
+        # epilogues, shadow parameters), but the forward activations are exact fp32, and truncating them shrinks every dense
+        # filter gradient by ~6e-4 (profiles/r2_grad_check_p16_v1.txt).  A rounded copy costs one pass over a few MB.
+        def rn(t):
+            if not self.round_b or self.round:
+                return t
+            buf = self._buf("rn:%x" % t.data_ptr(), tuple(t.shape))
+            return ops.round_tf32(t, out=buf)
 
         # ---- gradients as fp16 operand planes (the one-product layers) ----------------------------------------------------
         # A gradient tensor that feeds a one-product GEMM exists as ONE fp16 plane scaled by a power of two chosen from the
@@ -714,6 +797,22 @@ class ContextNet:
                 slot_d = new_slot()
                 ops.conv2d_planes(gp5, self._wb[wname], k, stride=L["stride"], out=dcat, nprod=1, a_scale=gp[1],
                                   amax=slot_d[0])
+            elif self._dec_few[i] and i in self._dec_planes:
+                # few output channels (the reconstruction): both gradients are few-channel-INPUT convolutions over dY, patch
+                # matrix built on chip; dY is scaled into fp16's range from its max
+                slot_g = new_slot()
+                if i == Ld - 1 and self._l2_fused:         # max |d loss / d out| came with the fused loss
+                    slot_g = (bufs["losses"][5:6].view(torch.int32), slot_g[1])
+                else:
+                    ops.amax(g_out, slot_g[0])
+                dpl, skp = self._dec_planes[i]
+                with self._side():
+                    ops.conv2d_few_wgrad(g_out, dpl[:1], k, L["stride"], small2p=skp[:1], dw=G[wname], x_amax=slot_g[0])
+                    if not bias_done:
+                        ops.bias_grad(g_out, G["deconv/%s/biases" % L["name"]])
+                slot_d = new_slot()
+                ops.conv2d_few(g_out, self._wb[wname], k, Ck, stride=L["stride"], out=dcat, nprod=1, x_amax=slot_g[0],
+                               amax=slot_d[0])
             elif self._few(Co, k):
                 # few output channels (the image): patch matrix of g_out, then three dense GEMMs
                 K = k * k * Co
@@ -752,7 +851,7 @@ class ContextNet:
         g_d0 = g_out                                       # [2B, flat], lrelu' applied
         Wd0 = Wb["deconv/d_h0_lin/Matrix"]
         with self._side():
-            self._gemm(True, False, F, flat, 2 * B, z2.data_ptr(), F, g_d0.data_ptr(), flat,
+            self._gemm(True, False, F, flat, 2 * B, rn(z2).data_ptr(), F, g_d0.data_ptr(), flat,
                        G["deconv/d_h0_lin/Matrix"].data_ptr(), flat, accumulate=True, round_=False, bwd=True)
             ops.bias_grad(g_d0.view(2 * B, flat), G["deconv/d_h0_lin/bias"])
         g_z2 = self._buf("g_z2", (2 * B, F))
@@ -771,14 +870,14 @@ class ContextNet:
         # (every filter / bias gradient of these small layers goes to the side stream: the data-gradient chain below is
         # a sequence of ~20 us launches that leave most SMs idle)
         with self._side():
-            self._gemm(True, False, F, F, B, th0.data_ptr(), F, g_transz.data_ptr(), F,
+            self._gemm(True, False, F, F, B, rn(th0).data_ptr(), F, g_transz.data_ptr(), F,
                        G["translate/trans_z/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
             ops.bias_grad(g_transz, G["translate/trans_z/bias"])
         g_th0 = self._buf("g_th0", (B, F))
         self._gemm(False, True, B, F, F, g_transz.data_ptr(), F, Wb["translate/trans_z/Matrix"].data_ptr(), F,
                    g_th0.data_ptr(), F, act_ref=th0.data_ptr(), bwd=True)
         with self._side():
-            self._gemm(True, False, 2 * F, F, B, cat.data_ptr(), 2 * F, g_th0.data_ptr(), F,
+            self._gemm(True, False, 2 * F, F, B, rn(cat).data_ptr(), 2 * F, g_th0.data_ptr(), F,
                        G["translate/trans_h0/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
             ops.bias_grad(g_th0, G["translate/trans_h0/bias"])
         g_cat = self._buf("g_cat", (B, 2 * F))
@@ -796,7 +895,7 @@ class ContextNet:
         def hz_backward(scope, g_ptr, ldg, h4_rows, gh4_rows):
             n = h4_rows.shape[0]
             with self._side():
-                self._gemm(True, False, F, F, n, h4_rows.data_ptr(), F, g_ptr, ldg,
+                self._gemm(True, False, F, F, n, rn(h4_rows).data_ptr(), F, g_ptr, ldg,
                            G[scope + "/hz_lin/Matrix"].data_ptr(), F, accumulate=True, round_=False, bwd=True)
                 check = _lib.check
                 check(_lib.load().ctx_bias_grad(g_ptr, n, F, ldg, G[scope + "/hz_lin/bias"].data_ptr(), ops._stream()),
@@ -817,7 +916,7 @@ class ContextNet:
             tag: forward()'s buffer tag of this encoder pass (its operand planes)."""
             n = x.shape[0]
             with self._side():
-                self._gemm(True, False, flat, F, n, hs[-1].data_ptr(), flat, g_h4.data_ptr(), F,
+                self._gemm(True, False, flat, F, n, rn(hs[-1]).data_ptr(), flat, g_h4.data_ptr(), F,
                            G["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), F, accumulate=True, round_=False, bwd=True)
                 ops.bias_grad(g_h4, G["%s/%s/bias" % (scope, self.lin)])
                 if fine:                                   # hz_lin + h<L>_lin gradients are final (both on this stream)
@@ -831,7 +930,13 @@ class ContextNet:
                 wname = "%s/h%d_conv/w" % (scope, j)
                 src = hs[j - 1] if j > 0 else x
                 kj, Cin = sp.kernels[j], src.shape[3]
-                if self._enc_p1[j]:                        # (j >= 1, one row group: separate context encoder)
+                if j == 0 and self._enc_few[0]:            # the image: filter gradient with the patch matrix built on chip
+                    if gp is None:
+                        gp = to_planes(g_hs[0], g_hs[0].shape[3], "gp_%s_h0" % tag, db=G["%s/h0_conv/biases" % scope])
+                    with self._side():
+                        ops.conv2d_few_wgrad(src, gp[0], kj, sp.strides[0], dw=G[wname], r_scale=gp[1])
+                    continue
+                if self._enc_p1[j]:                        # (one row group: separate context encoder)
                     if gp is None:
                         gp = to_planes(g_hs[j], g_hs[j].shape[3], "gp_%s_h%d" % (tag, j),
                                        db=G["%s/h%d_conv/biases" % (scope, j)])
@@ -841,6 +946,8 @@ class ContextNet:
                                                 nprod=1, a_scale=gp[1])
                         if fine and j == Ld - 1:
                             on_stage(scope + "/top")
+                    if j == 0:
+                        continue
                     slot = new_slot()
                     acc = groups[0][2]
                     if self._enc_p1_merged[j]:
@@ -851,7 +958,7 @@ class ContextNet:
                         ops.conv2d_transpose_planes(gp5, self._wb[wname], self.sizes[j], kj, stride=sp.strides[j],
                                                     out=g_hs[j - 1], nprod=1, act_ref=hs[j - 1], accumulate=acc,
                                                     a_scale=gp[1], amax=slot[0])
-                    if self._enc_p1[j - 1]:
+                    if self._enc_p1[j - 1] or (j == 1 and self._enc_few[0]):
                         gp = to_planes(g_hs[j - 1], Cin, "gp_%s_h%d" % (tag, j - 1), slot=slot,
                                        db=G["%s/h%d_conv/biases" % (scope, j - 1)])
                         bias_done = True
@@ -930,18 +1037,26 @@ class ContextNet:
                 self._s3 = torch.cuda.Stream(device=self.device)
             cur = torch.cuda.current_stream(self.device)
 
+            from . import parallel
+            scopes = parallel.scope_ranges(self.offsets, self.flat_size)
+
             def adam_range(a, b):                          # runs with the optimiser stream current, after the bucket
                 # every kernel that READS these parameters (the data gradients of their layers) is already enqueued on
                 # the main stream when a later bucket is launched: the update must not overtake it
                 self._s3.wait_stream(cur)
                 ops.adam_step(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr_t, b1, b2, eps,
                               p_tf32=None if self.flat_pr is None else self.flat_pr[a:b])
+                # next step's operand planes of every scope this bucket completes, under the remaining backward /
+                # reductions (as the single-GPU branch does) instead of serially at the start of the next forward
+                for sc, sa, sb in scopes:
+                    if a < sb <= b:                        # the bucket holds the END of the scope: its last part
+                        self._refresh_weight_planes(sc)
 
             ar.on_reduced, ar.reduced_stream = adam_range, self._s3
             self.backward(on_stage=ar.stage_done)
             ar.finish()
             cur.wait_stream(self._s3)
-            self._wp_stale = True
+            self._wp_stale = False
             return
         if self.allreduce is not None:
             self.backward(on_stage=self.allreduce.stage_done)

@@ -32,11 +32,11 @@ class _Prof:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
 
-    def done(self):
+    def done(self, impl=None):
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.kind, int(_lib.load().ctx_last_impl()), self.flops, self.e0, e1))
+            PROFILE.append((self.kind, int(_lib.load().ctx_last_impl()) if impl is None else impl, self.flops, self.e0, e1))
 
 
 def _stream() -> int:
@@ -162,18 +162,19 @@ def _p16(planes: torch.Tensor, nprod: int, a_scale=None, amax=None) -> "_lib.P16
                     None if amax is None else _req(amax, "amax", torch.int32))
 
 
-def split_planes(x, out=None, nplanes: int = 2, dtype=None):
-    """fp32 tensor -> planes (nplanes, *x.shape)."""
+def split_planes(x, out=None, nplanes: int = 2, dtype=None, scale: float = 1.0):
+    """fp32 tensor -> planes (nplanes, *x.shape) of scale * x (scale: a power of two)."""
     p = _req(x, "x")
     if out is None:
         out = torch.empty((nplanes,) + tuple(x.shape), device=x.device, dtype=dtype or PLANES_DTYPE)
     elif out.numel() != nplanes * x.numel():
         raise _lib.CtxError("split_planes: out has the wrong size")
-    check(_lib.load().ctx_split_planes(p, x.numel(), _reqp(out, "out"), nplanes, _p16_dtype(out), _stream()), "ctx_split_planes")
+    check(_lib.load().ctx_split_planes(p, x.numel(), float(scale), _reqp(out, "out"), nplanes, _p16_dtype(out), _stream()),
+          "ctx_split_planes")
     return out
 
 
-def split_planes_transpose(w, out=None, nplanes: int = 2, dtype=None):
+def split_planes_transpose(w, out=None, nplanes: int = 2, dtype=None, scale: float = 1.0):
     """w [kh,kw,R,Cc] -> planes (nplanes, kh*kw*Cc, R): a conv filter [kh,kw,Cin,Cout] becomes the per-tap K-major rows
     [Cout][Cin] conv2d_planes reads; a transposed-conv filter [kh,kw,Cout,Cin] becomes the rows [Cin][Cout] its data
     gradient reads."""
@@ -182,8 +183,8 @@ def split_planes_transpose(w, out=None, nplanes: int = 2, dtype=None):
         out = torch.empty((nplanes, kh * kw * Cc, R), device=w.device, dtype=dtype or PLANES_DTYPE)
     elif out.numel() != nplanes * w.numel():
         raise _lib.CtxError("split_planes_transpose: out has the wrong size")
-    check(_lib.load().ctx_split_planes_transpose(_req(w, "w"), kh * kw, R, Cc, _reqp(out, "out"), nplanes, _p16_dtype(out),
-                                                 _stream()), "ctx_split_planes_transpose")
+    check(_lib.load().ctx_split_planes_transpose(_req(w, "w"), kh * kw, R, Cc, float(scale), _reqp(out, "out"), nplanes,
+                                                 _p16_dtype(out), _stream()), "ctx_split_planes_transpose")
     return out
 
 
@@ -266,7 +267,7 @@ def conv2d_transpose_merged_eligible(n, out_hw, C1, C2, x2_batch, Cn, k, stride)
     return bool(_lib.load().ctx_conv2d_transpose_merged_p16_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
 
 
-def conv2d_transpose_merged_pack(w, out_hw, stride: int = 2, out=None, nplanes: int = 2, dtype=None):
+def conv2d_transpose_merged_pack(w, out_hw, stride: int = 2, out=None, nplanes: int = 2, dtype=None, scale: float = 1.0):
     """Transposed-conv filter [k,k,Cn,Ck] -> packed planes (nplanes, rows, Ck) for conv2d_transpose_merged_planes."""
     k, _, Cn, Ck = w.shape
     g = conv_geom(1, tuple(out_hw), k, stride)
@@ -277,8 +278,9 @@ def conv2d_transpose_merged_pack(w, out_hw, stride: int = 2, out=None, nplanes: 
         out = torch.empty((nplanes, rows, Ck), device=w.device, dtype=dtype or PLANES_DTYPE)
     elif tuple(out.shape) != (nplanes, rows, Ck):
         raise _lib.CtxError("conv2d_transpose_merged_pack: out must be (%d, %d, %d)" % (nplanes, rows, Ck))
-    check(_lib.load().ctx_conv2d_transpose_merged_pack_p16(_req(w, "w"), Ck, Cn, C.byref(g), _reqp(out, "out"), nplanes,
-                                                           _p16_dtype(out), _stream()), "ctx_conv2d_transpose_merged_pack_p16")
+    check(_lib.load().ctx_conv2d_transpose_merged_pack_p16(_req(w, "w"), Ck, Cn, C.byref(g), float(scale), _reqp(out, "out"),
+                                                           nplanes, _p16_dtype(out), _stream()),
+          "ctx_conv2d_transpose_merged_pack_p16")
     return out
 
 
@@ -371,6 +373,126 @@ def skip_grad_sum(dcat, G: int, C1: int, C2: int, dskip, skip_ref=None, accumula
     check(_lib.load().ctx_skip_grad_sum(_req(dcat, "dcat"), G, rows, C1, C2, _opt(skip_ref, "skip_ref"), float(slope),
                                         _req(dskip, "dskip"), int(accumulate), _stream()), "ctx_skip_grad_sum")
     return dskip
+
+
+# ---- image-side layers: few-channel input, patch matrix built in shared memory (csrc/tc_few.cu) -----------------------------
+def conv2d_few_eligible(n, in_hw, Cin, Co, k, stride) -> bool:
+    g = conv_geom(n, tuple(in_hw), k, stride)
+    return bool(_lib.load().ctx_conv2d_few_eligible(Cin, Co, C.byref(g)))
+
+
+def conv2d_few_pack(w, nplanes: int = 2, out=None):
+    """HWIO filter [k,k,C,Co] -> the packed operand image conv2d_few reads (uint8 bytes; once per parameter update)."""
+    k, _, Cin, Co = w.shape
+    g = conv_geom(1, (k, k), k, 1)
+    nbytes = int(_lib.load().ctx_conv2d_few_pack_bytes(Co, C.byref(g), nplanes))
+    if out is None:
+        out = torch.empty(nbytes, device=w.device, dtype=torch.uint8)
+    elif out.numel() != nbytes or out.dtype != torch.uint8:
+        raise _lib.CtxError("conv2d_few_pack: out must be %d uint8 bytes" % nbytes)
+    check(_lib.load().ctx_conv2d_few_pack(_req(w, "w"), Cin, Co, C.byref(g), _req(out, "out", torch.uint8), nplanes, _stream()),
+          "ctx_conv2d_few_pack")
+    return out
+
+
+def _req_img(x, name):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype not in (torch.float32, torch.uint8) or not x.is_contiguous():
+        raise _lib.CtxError("%s must be a contiguous CUDA float32 or uint8 tensor" % name)
+    return x.data_ptr()
+
+
+def conv2d_few(x, wimg, k: int, Co: int, bias=None, stride: int = 2, act: bool = False, out=None, out_planes=None,
+               nprod: int = 3, x_amax=None, amax=None):
+    """conv2d(SAME) + bias (+ lrelu) of a few-channel x [N,H,W,C] (fp32, or uint8 frames normalised on the fly) with the
+    packed filter `wimg` (conv2d_few_pack).  x_amax: x is a gradient, scaled internally by the power of two its max asks for."""
+    N, H, W_, Cin = x.shape
+    g = conv_geom(N, (H, W_), k, stride)
+    if out is None:
+        out = torch.empty((N, g.P, g.Q, Co), device=x.device, dtype=torch.float32)
+    if out_planes is not None and (out_planes.dtype != torch.float16 or out_planes.numel() != out_planes.shape[0] * out.numel()):
+        raise _lib.CtxError("conv2d_few: out_planes must be float16 planes of the output")
+    epi = make_epilogue(bias, act)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * k * k * Cin)
+    check(_lib.load().ctx_conv2d_few_fprop(
+        _req_img(x, "x"), int(x.dtype == torch.uint8), Cin, _req(wimg, "wimg", torch.uint8), _req(out, "out"),
+        None if out_planes is None else _reqp(out_planes, "out_planes"), 0 if out_planes is None else out_planes.shape[0],
+        Co, C.byref(g), C.byref(epi), int(nprod), None if x_amax is None else _req(x_amax, "x_amax", torch.int32),
+        None if amax is None else _req(amax, "amax", torch.int32), _stream()), "ctx_conv2d_few_fprop")
+    pr.done(_lib.IMPL_P16X3 if nprod == 3 else _lib.IMPL_P16X1)
+    return out
+
+
+def conv2d_few_wgrad(x, small1p, k: int, stride: int, small2p=None, dw=None, x_amax=None, r_scale=None):
+    """dw[k,k,C,Cb1+Cb2] += patches(x)^T [small1 ‖ small2]; small*p: one fp16 plane (1,.,P,Q,Cb*) each."""
+    N, H, W_, Cin = x.shape
+    Cb1 = small1p.shape[-1]
+    Cb2 = 0 if small2p is None else small2p.shape[-1]
+    g = conv_geom(N, (H, W_), k, stride)
+    if small1p.dtype != torch.float16 or small1p.numel() != N * g.P * g.Q * Cb1:
+        raise _lib.CtxError("conv2d_few_wgrad: small1p must be one float16 plane of [N,P,Q,Cb1]")
+    if small2p is not None and (small2p.dtype != torch.float16 or small2p.numel() % (g.P * g.Q * Cb2) != 0):
+        raise _lib.CtxError("conv2d_few_wgrad: small2p must be one float16 plane of [N2,P,Q,Cb2]")
+    if dw is None:
+        dw = torch.zeros((k, k, Cin, Cb1 + Cb2), device=x.device, dtype=torch.float32)
+    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Cin)
+    check(_lib.load().ctx_conv2d_few_wgrad(
+        _req_img(x, "x"), int(x.dtype == torch.uint8), Cin, _reqp(small1p, "small1p"), Cb1,
+        None if small2p is None else _reqp(small2p, "small2p"), Cb2,
+        0 if small2p is None else small2p.numel() // (g.P * g.Q * Cb2), _req(dw, "dw"), C.byref(g),
+        None if x_amax is None else _req(x_amax, "x_amax", torch.int32), _opt(r_scale, "r_scale"), _stream()),
+        "ctx_conv2d_few_wgrad")
+    pr.done(_lib.IMPL_P16X1)
+    return dw
+
+
+def conv2d_transpose_few_eligible(n, out_hw, C1, C2, x2_batch, Cn, k, stride) -> bool:
+    g = conv_geom(n, tuple(out_hw), k, stride)
+    return bool(_lib.load().ctx_conv2d_transpose_few_eligible(C1, C2, x2_batch, Cn, C.byref(g)))
+
+
+def conv2d_transpose_few_pack(w, out=None):
+    """Transposed-conv filter [k,k,Cn,Ck] (few output channels Cn) -> the packed operand image conv2d_transpose_few reads."""
+    k, _, Cn, Ck = w.shape
+    g = conv_geom(1, (k, k), k, 1)
+    nbytes = int(_lib.load().ctx_conv2d_transpose_few_pack_bytes(Ck, C.byref(g)))
+    if nbytes <= 0:
+        raise _lib.CtxError("conv2d_transpose_few_pack: filter %s not eligible" % (tuple(w.shape),))
+    if out is None:
+        out = torch.empty(nbytes, device=w.device, dtype=torch.uint8)
+    elif out.numel() != nbytes or out.dtype != torch.uint8:
+        raise _lib.CtxError("conv2d_transpose_few_pack: out must be %d uint8 bytes" % nbytes)
+    check(_lib.load().ctx_conv2d_transpose_few_pack(_req(w, "w"), Ck, Cn, C.byref(g), _req(out, "out", torch.uint8), _stream()),
+          "ctx_conv2d_transpose_few_pack")
+    return out
+
+
+def conv2d_transpose_few(x1p, wimg, out_hw, k: int, Cn: int, bias=None, stride: int = 2, x2p=None, act: bool = False, out=None,
+                         l2: Optional[dict] = None):
+    """conv2d_transpose(SAME) + bias (+ lrelu) to a FEW output channels over concat([x1, x2], 3) from fp16 (hi, lo) planes
+    x1p (2,N,P,Q,C1), x2p (2,N2,P,Q,C2); wimg from conv2d_transpose_few_pack.  l2 = dict(tgt, loss, pass_images[, resid, weight,
+    dpred, amax]) also evaluates the reconstruction loss of the result in the same pass (ops.l2_loss_fwd_bwd semantics)."""
+    _, N, P, Q, C1 = x1p.shape
+    C2 = 0 if x2p is None else x2p.shape[4]
+    if x1p.dtype != torch.float16 or x1p.shape[0] != 2 or (x2p is not None and (x2p.dtype != torch.float16 or x2p.shape[0] != 2)):
+        raise _lib.CtxError("conv2d_transpose_few: operands must be float16 (hi, lo) planes")
+    g = conv_geom(N, tuple(out_hw), k, stride)
+    if (g.P, g.Q) != (P, Q):
+        raise _lib.CtxError("conv2d_transpose_few: output %s inconsistent with input grid %s" % (tuple(out_hw), (P, Q)))
+    if out is None:
+        out = torch.empty((N, g.H, g.W, Cn), device=x1p.device, dtype=torch.float32)
+    epi = make_epilogue(bias, act)
+    lf = None
+    if l2 is not None:
+        lf = _lib.L2Fused(_req(l2["tgt"], "tgt"), _opt(l2.get("resid"), "resid"), _opt(l2.get("weight"), "weight"),
+                          _req(l2["loss"], "loss"), _opt(l2.get("dpred"), "dpred"),
+                          None if l2.get("amax") is None else _req(l2["amax"], "amax", torch.int32), int(l2["pass_images"]))
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * (C1 + C2))
+    check(_lib.load().ctx_conv2d_transpose_few(
+        _reqp(x1p, "x1p"), C1, None if x2p is None else _reqp(x2p, "x2p", x1p), C2, 0 if x2p is None else x2p.shape[1],
+        _req(wimg, "wimg", torch.uint8), _req(out, "out"), Cn, C.byref(g), C.byref(epi),
+        None if lf is None else C.byref(lf), _stream()), "ctx_conv2d_transpose_few")
+    pr.done(_lib.IMPL_P16X3)
+    return out
 
 
 # round-1 names (bf16 planes, three products)

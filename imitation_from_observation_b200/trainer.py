@@ -51,6 +51,16 @@ class ModelTrainer:
         if self.data is None:
             bank = synthetic.video_bank(self.nlen, self.nvideos, self.idims[0], self.idims[1], seed=1234 + self.seed)
             return bank if self.inception else synthetic.to_float(bank)   # inception: uint8 frames (rescale=False)
+        if isinstance(self.data, str) and not self.data.endswith(".npy"):
+            # a glob of demo videos (train_script.py:58: "model/videos/*.mp4"): decode, pick frames, transform, save the bank
+            import glob
+            from . import data as D
+            bank = D.videos_to_bank(sorted(glob.glob(self.data)), self.nlen, self.nskip, self.idims, self.rescale,
+                                    self.nvideos, self.inception, np.random.RandomState(self.seed), self.log)
+            os.makedirs(self.basedir, exist_ok=True)
+            np.save(os.path.join(self.basedir, "vdata_strike%d" % bank.shape[1]), bank)          # :90
+            self.log(str(bank.shape))
+            return bank
         if isinstance(self.data, str):
             return np.load(self.data)
         return np.asarray(self.data)

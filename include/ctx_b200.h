@@ -154,14 +154,17 @@ typedef struct ctx_p16 {
   uint32_t* amax_bits;       /* device word or NULL: atomicMax of the bit patterns of |y| (input of ctx_grad_planes)    */
 } ctx_p16;
 
-/* planes[0][i] = rn16(x[i]); planes[1][i] = rn16(x[i] - planes[0][i]) (nplanes == 2) for i < n; fp16 saturates. */
-int ctx_split_planes(const float* x, int64_t n, void* planes, int32_t nplanes, int32_t dtype, void* stream);
+/* v = scale * x[i]; planes[0][i] = rn16(v); planes[1][i] = rn16(v - planes[0][i]) (nplanes == 2) for i < n; fp16 saturates.
+ * scale: a power of two.  Filters are ~N(0, 0.02): at scale 1 the lo part of an fp16 split falls into fp16's subnormals and
+ * hi + lo keeps 19 bits instead of 22; the forward pass splits its filters at scale 2^8 and passes a device scalar 2^8 as
+ * ctx_p16.a_scale (which divides the result). */
+int ctx_split_planes(const float* x, int64_t n, float scale, void* planes, int32_t nplanes, int32_t dtype, void* stream);
 
 /* w [T][R][Cc] fp32 -> planes [nplanes][T][Cc][R]: a conv filter [kh*kw][Cin][Cout] (arm_shaping.py:25) becomes the per-tap
  * K-major matrix [kh*kw*Cout][Cin] ctx_conv2d_fprop_p16 reads; a transposed-conv filter [kh*kw][Cout][Cin] becomes the
  * [kh*kw*Cin][Cout] matrix its data gradient (a conv fprop over dY) reads.  (Used as stored, a transposed-conv filter is
  * already K-major for its forward pass and a conv filter for its data gradient: ctx_split_planes.) */
-int ctx_split_planes_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, void* planes, int32_t nplanes,
+int ctx_split_planes_transpose(const float* w, int32_t T, int32_t R, int32_t Cc, float scale, void* planes, int32_t nplanes,
                                int32_t dtype, void* stream);
 
 int ctx_conv2d_fprop_p16_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g);
@@ -191,8 +194,8 @@ int ctx_conv2d_transpose_p16(const void* x1_planes, int32_t C1, const void* x2_p
 int ctx_conv2d_transpose_merged_p16_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn,
                                              const ctx_conv_geom* g);
 int64_t ctx_conv2d_transpose_merged_rows(int32_t Cn, const ctx_conv_geom* g);
-int ctx_conv2d_transpose_merged_pack_p16(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g, void* wm_planes,
-                                         int32_t nplanes, int32_t dtype, void* stream);
+int ctx_conv2d_transpose_merged_pack_p16(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g, float scale,
+                                         void* wm_planes, int32_t nplanes, int32_t dtype, void* stream);
 int ctx_conv2d_transpose_merged_p16(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2,
                                     int32_t x2_batch, const void* wm_planes, float* y, void* y_planes, int32_t y_planes_n,
                                     int32_t Cn, const ctx_conv_geom* g, const ctx_epilogue* epi, const ctx_p16* cfg,
@@ -228,6 +231,62 @@ int ctx_amax(const float* x, int64_t n, uint32_t* amax_bits, void* stream);
  * (the state half goes through ctx_grad_planes). */
 int ctx_skip_grad_sum(const float* dcat, int32_t G, int64_t rows, int32_t C1, int32_t C2, const float* skip_ref,
                       float slope, float* dskip, int32_t accumulate, void* stream);
+
+/* ---- the image-side layers: convolutions over a few-channel input, patch matrix built in shared memory (csrc/tc_few.cu) ----
+ * The reference's first encoder layer  h0 = lrelu(conv2d(image, 5x5, stride 2, 3 -> 64))  (arm_shaping.py:1283) and the
+ * backward pass of its mirror image, the last decoder layer d_h4 (128 -> 3, arm_shaping.py:1329): no im2col buffer in HBM,
+ * the input is read once and the result written once.  x is [N,H,W,C] fp32, or uint8 frames normalised on the fly
+ * ((u/255 - 0.5) * 2 in three fp32 roundings, base.py:117-119); kw * C <= 16, kh <= 8, stride 1 or 2, 64 or 128 output
+ * channels, output grids that tile into 128 pixels — ask ctx_conv2d_few_eligible.  Operands are fp16: nprod = 3 splits the
+ * input and the filter into (hi, lo) (fp32-grade, the forward pass), nprod = 1 uses the hi parts (backward).  When
+ * x_amax_bits is given x is a gradient: it is scaled by the power of two 2^k with amax * 2^k in [2^14, 2^15) before the
+ * fp16 conversion and the result is divided by it. */
+int ctx_conv2d_few_eligible(int32_t C, int32_t Co, const ctx_conv_geom* g);
+
+/* Bytes of the packed filter image for ctx_conv2d_few_fprop; ctx_conv2d_few_pack fills it from the HWIO filter
+ * [kh,kw,C,Co] (once per parameter update).  The image is the kernel's shared-memory operand tile, swizzle included. */
+int64_t ctx_conv2d_few_pack_bytes(int32_t Co, const ctx_conv_geom* g, int32_t nplanes);
+int ctx_conv2d_few_pack(const float* w, int32_t C, int32_t Co, const ctx_conv_geom* g, void* wimg, int32_t nplanes,
+                        void* stream);
+
+/* y [N,P,Q,Co] fp32 = conv2d(SAME)(x, w) + bias (+ lrelu); y_planes [y_planes_n][N,P,Q,Co] fp16 or NULL; epilogue: bias and
+ * lrelu only; amax_bits (or NULL): atomicMax of the bit patterns of |y|.  Also the data gradient of a transposed conv with
+ * few OUTPUT channels (x = dY [N,H,W,Cn], the [kh,kw,Cn,Ck] filter read as HWIO, nprod = 1, x_amax_bits set). */
+int ctx_conv2d_few_fprop(const void* x, int32_t x_is_u8, int32_t C, const void* wimg, float* y, void* y_planes,
+                         int32_t y_planes_n, int32_t Co, const ctx_conv_geom* g, const ctx_epilogue* epi, int32_t nprod,
+                         const uint32_t* x_amax_bits, uint32_t* amax_bits, void* stream);
+
+/* dw [kh,kw,C,Cb1+Cb2] fp32 += sum over pixels of patches(x) (x) [small1 ‖ small2]: the filter gradient of the conv
+ * (x = its input, small1 = one fp16 plane of dY scaled by *r_scale) and of the few-output-channel transposed conv (x = dY
+ * with x_amax_bits, small1 / small2 = fp16 hi planes of [state ‖ skip], small2 read at image n % small2_batch).  small*
+ * are [rows, Cb*] fp16, Cb1 and Cb2 multiples of 64, Cb1 + Cb2 = 64 or 128.  One product; the sums are divided by
+ * *r_scale when given, else by the scale x_amax_bits implies. */
+int ctx_conv2d_few_wgrad(const void* x, int32_t x_is_u8, int32_t C, const void* small1_plane, int32_t Cb1,
+                         const void* small2_plane, int32_t Cb2, int32_t small2_batch, float* dw, const ctx_conv_geom* g,
+                         const uint32_t* x_amax_bits, const float* r_scale, void* stream);
+
+/* The reference's last decoder layer  d_h4 = conv2d_transpose([state ‖ skip], 5x5, stride 2, 128 -> 3)  (arm_shaping.py:1329):
+ * channel contraction on the tensor cores (G[pixel][tap, co] = cat[pixel][:] . W[tap, co, :]), col2im as a gather from shared
+ * memory — no atomics, y written once.  x1_planes [2][N,P,Q,C1], x2_planes [2][x2_batch,P,Q,C2] or NULL: fp16 (hi, lo)
+ * planes, three products.  wimg from ctx_conv2d_transpose_few_pack of the [kh,kw,Cn,C1+C2] filter.  Epilogue: bias, lrelu.
+ * With `loss` the reconstruction losses of arm_shaping.py:1352-1353 are evaluated in the same pass, as ctx_l2_loss_fwd_bwd
+ * would on y: image n belongs to decoder pass n / pass_images, d = y (+ resid) - tgt (both indexed by the image within
+ * its pass), loss[pass] += sum d^2 / 2, dpred = weight[pass] * d, *dpred_amax = max(.., bits(max |dpred|)). */
+typedef struct ctx_l2_fused {
+  const float* tgt;          /* [pass_images,H,W,Cn] */
+  const float* resid;        /* [pass_images,H,W,Cn] or NULL (ContextAEInception2's residual output, arm_shaping.py:1889) */
+  const float* weight;       /* [passes] or NULL */
+  float* loss;               /* [passes], += */
+  float* dpred;              /* [N,H,W,Cn] or NULL */
+  uint32_t* dpred_amax;      /* or NULL */
+  int32_t pass_images;
+} ctx_l2_fused;
+int ctx_conv2d_transpose_few_eligible(int32_t C1, int32_t C2, int32_t x2_batch, int32_t Cn, const ctx_conv_geom* g);
+int64_t ctx_conv2d_transpose_few_pack_bytes(int32_t Ck, const ctx_conv_geom* g);
+int ctx_conv2d_transpose_few_pack(const float* w, int32_t Ck, int32_t Cn, const ctx_conv_geom* g, void* wimg, void* stream);
+int ctx_conv2d_transpose_few(const void* x1_planes, int32_t C1, const void* x2_planes, int32_t C2, int32_t x2_batch,
+                             const void* wimg, float* y, int32_t Cn, const ctx_conv_geom* g, const ctx_epilogue* epi,
+                             const ctx_l2_fused* loss, void* stream);
 
 /* ---- round-1 names of the planes entry points: bf16 planes, three products, two result planes -------------------- */
 

@@ -302,3 +302,40 @@ def test_tf_checkpoint_v1_single_file(tmp_path):
         T.load_variables(str(tmp_path / "m"), ["b"], prefixes=("", "contextmodel/"))
     with pytest.raises(FileNotFoundError):
         T.load_variables(str(tmp_path / "absent"), ["a"])
+
+
+def test_videos_to_bank_reads_mp4_like_the_reference(tmp_path):
+    """train_script.py:58-96 on real mp4 files: 51-frame videos only, frames 1, 1 + nskip, ..., transform, black-frame drop."""
+    cv2 = pytest.importorskip("cv2")
+    from imitation_from_observation_b200 import data as D
+    rs = np.random.RandomState(3)
+
+    def write(name, nframes, black_at=None):
+        path = str(tmp_path / name)
+        vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25.0, (64, 48))
+        if not vw.isOpened():
+            pytest.skip("no mp4 encoder in this OpenCV build")
+        for j in range(nframes):
+            base = np.full((48, 64, 3), 40 + 3 * j, np.uint8)
+            base[:, :, 1] = rs.randint(60, 200)
+            vw.write(np.zeros((48, 64, 3), np.uint8) if j == black_at else base)
+        vw.release()
+        return path
+
+    good = [write("a.mp4", 51), write("b.mp4", 51)]
+    short = write("c.mp4", 30)
+    black = write("d.mp4", 51, black_at=11)                     # frame 11 = 1 + 2 * 5 is sampled at nskip = 5
+    frames = D.read_video(good[0])
+    assert len(frames) == 51 and frames[0].shape == (48, 64, 3) and frames[0].dtype == np.uint8
+    assert abs(int(frames[7][0, 0, 0]) - (40 + 21)) <= 3        # RGB order: channel 0 holds the ramp (lossy codec)
+    bank = D.videos_to_bank(good + [short, black, str(tmp_path / "missing.mp4")], nlen=10, nskip=5, idims=(24, 32),
+                            rng=np.random.RandomState(0))
+    assert bank.shape == (10, 2, 24, 32, 3) and bank.dtype == np.float64
+    assert bank.min() >= -1.0 and bank.max() <= 1.0
+    # time order: the ramp brightens by 3 * nskip grey levels per kept frame
+    ramp = (bank[:, 0, 0, 0, 0] + 1.0) * 127.5
+    assert np.all(np.abs(np.diff(ramp) - 15.0) <= 4.0)
+    # uint8 path of the inception trainer: no rescale, black frames are kept (train_script.py:73 `not self.inception`)
+    bank8 = D.videos_to_bank(good + [black], nlen=10, nskip=5, idims=(24, 32), rescale=False, inception=True,
+                             rng=np.random.RandomState(0))
+    assert bank8.shape == (10, 3, 24, 32, 3) and bank8.dtype == np.uint8

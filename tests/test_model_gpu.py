@@ -309,7 +309,9 @@ def test_uint8_feeds_through_minimize_only_steps():
             sess.run(opt, {ph: feed})
         torch.cuda.synchronize()
         finals.append(m.net.flat_p.clone())
-    assert rel_l2(finals[0].cpu(), finals[1].cpu()) < 1e-5
+    # (split-K / bias-gradient atomics make the two runs differ in the last bits, and Adam's first steps are sign-like where a
+    # gradient is ~0: 1e-4-grade noise; a batch mixed up in the staging buffer moves the parameters by percents)
+    assert rel_l2(finals[0].cpu(), finals[1].cpu()) < 1e-3
 
 
 def test_saver_tf_checkpoint_round_trip_through_the_network(tmp_path):

@@ -223,7 +223,7 @@ def test_conv2d_transpose_merged_planes_fp16(N, P, Q, C1, C2, NB, k, Cn):
 # ---- filter gradient (MN-major operands, split-K) ----------------------------------------------------------------------------
 # (N, H, W, Ca, Cb1, Cb2, NB, k, stride): 64-pixel K blocks inside an image and across whole images, both sources, pairs and
 # single CTAs, odd tile counts (25 taps x 64 channels = 12.5 tiles), stride 1 and 2
-WGRAD = [(4, 16, 16, 128, 256, 0, 0, 5, 2), (8, 8, 8, 256, 512, 0, 0, 5, 2), (4, 8, 8, 256, 512, 512, 2, 5, 2),
+WGRAD = [(4, 16, 16, 128, 256, 0, 0, 5, 2), (8, 8, 8, 256, 512, 0, 0, 5, 2), (4, 8, 8, 256, 512, 512, 4, 5, 2),
          (2, 32, 32, 64, 128, 128, 1, 5, 2), (32, 4, 4, 64, 64, 64, 16, 3, 2), (4, 8, 8, 128, 64, 192, 4, 3, 1),
          (16, 8, 8, 64, 128, 0, 0, 3, 1), (64, 2, 2, 128, 128, 0, 0, 3, 2)]
 
@@ -252,3 +252,141 @@ def test_conv2d_wgrad_planes(N, H, W, Ca, Cb1, Cb2, NB, k, st, nprod):
     dw = base.clone().cuda()
     ops.conv2d_wgrad_planes(bigp, s1p, k, st, small2p=s2p, dw=dw, nprod=nprod, a_scale=scale)
     assert rel_err(dw.cpu().double() - base.double(), wr.grad) < TOL
+
+
+# ---- image-side layers: few-channel input, patch matrix built in shared memory (csrc/tc_few.cu) -----------------------------
+# (N, H, W, C, Co, k, stride): the reference's h0 (64x64x3, 5x5 s2 -> 64), whole-image tiles, stride 1, 3x3, 128 outputs,
+# odd tile counts, the 128x128 frames of the deeper net
+FEW = [(3, 64, 64, 3, 64, 5, 2), (5, 16, 16, 3, 64, 5, 2), (2, 32, 32, 3, 128, 5, 2), (7, 8, 8, 3, 64, 5, 2),
+       (2, 16, 16, 4, 64, 3, 1), (1, 128, 128, 3, 64, 5, 2), (4, 16, 8, 2, 128, 3, 2), (2, 16, 32, 1, 64, 5, 1),
+       (100, 64, 64, 3, 64, 5, 2)]           # 800 tiles: several per persistent CTA
+
+
+@pytest.mark.parametrize("N,H,W,C,Co,k,st", FEW)
+def test_conv2d_few_three_products(N, H, W, C, Co, k, st):
+    x, w, b = rnd((N, H, W, C), 21), rnd((k, k, C, Co), 22, (k * k * C) ** -0.5), rnd((Co,), 23, 0.1)
+    assert ops.conv2d_few_eligible(N, (H, W), C, Co, k, st)
+    ref = O.lrelu(O.conv2d(x.double(), w.double(), b.double(), st))
+    wimg = ops.conv2d_few_pack(w.cuda())
+    yp = torch.zeros((2,) + tuple(ref.shape), device="cuda", dtype=torch.float16)
+    slot = torch.zeros(1, dtype=torch.int32, device="cuda")
+    y = ops.conv2d_few(x.cuda(), wimg, k, Co, bias=b.cuda(), stride=st, act=True, out_planes=yp, amax=slot)
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert rel_err(y.cpu(), ref) < TOL
+    assert same_bits(yp, planes_ref(y.cpu(), torch.float16))
+    assert slot.cpu().view(torch.float32).item() == y.abs().max().item()
+    y2 = ops.conv2d_few(x.cuda(), wimg, k, Co, stride=st)
+    assert rel_err(y2.cpu(), O.conv2d(x.double(), w.double(), None, st)) < TOL
+
+
+def test_conv2d_few_uint8_frames():
+    """uint8 frames are normalised inside the kernel exactly as base.py:117-119 does (three fp32 roundings)."""
+    N, H, W, C, Co, k, st = 4, 64, 64, 3, 64, 5, 2
+    u = torch.randint(0, 256, (N, H, W, C), generator=torch.Generator().manual_seed(24), dtype=torch.uint8)
+    w, b = rnd((k, k, C, Co), 25, 0.1), rnd((Co,), 26, 0.1)
+    xf = ops.u8_normalize(u.cuda())
+    wimg = ops.conv2d_few_pack(w.cuda())
+    ya = ops.conv2d_few(u.cuda(), wimg, k, Co, bias=b.cuda(), stride=st, act=True)
+    yb = ops.conv2d_few(xf, wimg, k, Co, bias=b.cuda(), stride=st, act=True)
+    assert torch.equal(ya, yb)
+    assert rel_err(ya.cpu(), O.lrelu(O.conv2d(xf.cpu().double(), w.double(), b.double(), st))) < TOL
+
+
+@pytest.mark.parametrize("N,H,W,C,Co,k,st", FEW)
+def test_conv2d_few_single_product_gradient_input(N, H, W, C, Co, k, st):
+    """The data gradient of the last decoder layer: x = d loss / d pred (tiny values, scaled inside from its max)."""
+    x, w = rnd((N, H, W, C), 27, 3e-6), rnd((k, k, C, Co), 28, (k * k * C) ** -0.5)
+    slot = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.amax(x.cuda(), slot)
+    s = scale_ref(x.abs().max().item())
+    exact = O.conv2d(hi(x * s) / s, hi(w), None, st)
+    y = ops.conv2d_few(x.cuda(), ops.conv2d_few_pack(w.cuda(), nplanes=1), k, Co, stride=st, nprod=1, x_amax=slot)
+    assert rel_err(y.cpu(), exact) < TOL
+    assert rel_err(y.cpu(), O.conv2d(x.double(), w.double(), None, st)) < TOL_RN11
+
+
+# (N, H, W, C, Cb1, Cb2, NB, k, stride)
+FEW_WGRAD = [(6, 64, 64, 3, 64, 0, 0, 5, 2), (4, 64, 64, 3, 64, 64, 2, 5, 2), (5, 16, 16, 3, 128, 0, 0, 5, 2),
+             (18, 8, 8, 3, 64, 64, 8, 5, 2), (2, 16, 16, 4, 64, 0, 0, 3, 1), (600, 8, 8, 3, 64, 0, 0, 5, 2),
+             (120, 64, 64, 3, 64, 0, 0, 5, 2)]   # 960 tiles: the double-buffered tile loop of a CTA
+
+
+@pytest.mark.parametrize("N,H,W,C,Cb1,Cb2,NB,k,st", FEW_WGRAD)
+@pytest.mark.parametrize("grad_is_x", [False, True])
+def test_conv2d_few_wgrad(N, H, W, C, Cb1, Cb2, NB, k, st, grad_is_x):
+    """grad_is_x: the transposed conv's filter gradient (x = dY, scaled inside; small = activations);
+    else the conv's (x = image; small1 = a scaled gradient plane)."""
+    if Cb2 and not grad_is_x:
+        pytest.skip("two small sources only occur in the transposed conv's filter gradient (x = dY)")
+    P, Q = -(-H // st), -(-W // st)
+    x = rnd((N, H, W, C), 29, 3e-6 if grad_is_x else 1.0)
+    s1 = rnd((N, P, Q, Cb1), 30, 1.0 if grad_is_x else 2e-5)
+    s2 = rnd((NB, P, Q, Cb2), 31) if Cb2 else None
+    small = _cat(s1, s2, N, NB)
+    slot = scale = None
+    if grad_is_x:
+        slot = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.amax(x.cuda(), slot)
+        sx, ss = scale_ref(x.abs().max().item()), 1.0
+    else:
+        sx, ss = 1.0, scale_ref(s1.abs().max().item())
+        scale = torch.tensor([ss], device="cuda")
+    s1p = ops.split_planes((s1 * ss).cuda(), nplanes=1)
+    s2p = None if s2 is None else ops.split_planes(s2.cuda(), nplanes=1)
+    wr = torch.zeros((k, k, C, Cb1 + Cb2), dtype=torch.float64, requires_grad=True)
+    small_h = hi(small) if s2 is None else torch.cat([hi(s1 * ss) / ss, hi(s2).repeat((N // NB, 1, 1, 1))], 3)
+    if s2 is None:
+        small_h = hi(s1 * ss) / ss
+    (O.conv2d(hi(x * sx) / sx, wr, None, st) * small_h).sum().backward()
+    base = rnd((k, k, C, Cb1 + Cb2), 32, float(wr.grad.abs().max()))
+    dw = base.clone().cuda()
+    ops.conv2d_few_wgrad(x.cuda(), s1p, k, st, small2p=s2p, dw=dw, x_amax=slot, r_scale=scale)
+    assert rel_err(dw.cpu().double() - base.double(), wr.grad) < TOL
+
+
+# (N, P, Q, C1, C2, skip batch, Cn, k, stride): the reference's d_h4 (32x32x[64+64] -> 64x64x3), partial last tile, one source,
+# stride 1, 3x3, whole-image tiles, the deeper net's 64x64 -> 128x128
+FEW_T = [(4, 32, 32, 64, 64, 2, 3, 5, 2), (3, 16, 16, 64, 64, 3, 3, 5, 2), (2, 32, 32, 128, 0, 0, 3, 5, 2),
+         (2, 16, 16, 64, 64, 1, 4, 3, 1), (5, 8, 8, 64, 0, 0, 2, 3, 2), (1, 64, 64, 64, 64, 1, 3, 5, 2),
+         (300, 32, 32, 64, 64, 150, 3, 5, 2)]
+
+
+@pytest.mark.parametrize("N,P,Q,C1,C2,NB,Cn,k,st", FEW_T)
+def test_conv2d_transpose_few(N, P, Q, C1, C2, NB, Cn, k, st):
+    H, W = P * st, Q * st
+    x1 = rnd((N, P, Q, C1), 33)
+    x2 = rnd((NB, P, Q, C2), 34) if C2 else None
+    w = rnd((k, k, Cn, C1 + C2), 35, (k * k * (C1 + C2) / st ** 2) ** -0.5)
+    b = rnd((Cn,), 36, 0.1)
+    assert ops.conv2d_transpose_few_eligible(N, (H, W), C1, C2, NB, Cn, k, st)
+    small = N <= 8
+    wimg = ops.conv2d_transpose_few_pack(w.cuda())
+    x1p = ops.split_planes(x1.cuda())
+    x2p = None if x2 is None else ops.split_planes(x2.cuda())
+    y = ops.conv2d_transpose_few(x1p, wimg, (H, W), k, Cn, bias=b.cuda(), stride=st, x2p=x2p)
+    if small:
+        ref = O.conv2d_transpose(_cat(x1, x2, N, NB).double(), w.double(), b.double(), (H, W), st)
+    else:       # many tiles per persistent CTA: against the exact-fp32 kernel (the fp64 oracle would take minutes)
+        ref = ops.conv2d_transpose(x1.cuda(), w.cuda(), (H, W), bias=b.cuda(), stride=st, x2=None if x2 is None else x2.cuda(),
+                                   impl=_lib.IMPL_SIMT).cpu().double()
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert rel_err(y.cpu(), ref) < TOL
+    # the reconstruction loss evaluated in the same pass == ctx_l2_loss_fwd_bwd on the stored result, bit for bit in dpred
+    if N % 2 == 0:
+        Bp = N // 2
+        tgt, res, wts = rnd((Bp, H, W, Cn), 37).cuda(), rnd((Bp, H, W, Cn), 38, 0.1).cuda(), torch.tensor([1.0, 0.5]).cuda()
+        loss, dpred = torch.zeros(2, device="cuda"), torch.empty_like(y)
+        slot = torch.zeros(1, dtype=torch.int32, device="cuda")
+        y2 = ops.conv2d_transpose_few(x1p, wimg, (H, W), k, Cn, bias=b.cuda(), stride=st, x2p=x2p,
+                                      l2=dict(tgt=tgt, resid=res, weight=wts, loss=loss, dpred=dpred, amax=slot, pass_images=Bp))
+        assert torch.equal(y2, y)
+        loss_ref, dpred_ref = torch.zeros(2, device="cuda"), torch.empty_like(y)
+        ops.l2_loss_fwd_bwd(y, tgt, loss_ref, dpred=dpred_ref, resid=res, weight=wts)
+        assert torch.equal(dpred, dpred_ref)
+        assert rel_err(loss.cpu(), loss_ref.cpu()) < 1e-5
+        assert slot.cpu().view(torch.float32).item() == dpred.abs().max().item()
+
+
+def test_conv2d_transpose_few_rejects():
+    assert not ops.conv2d_transpose_few_eligible(2, (64, 64), 64, 64, 1, 8, 5, 2)      # kw * Cn > 16
+    assert not ops.conv2d_transpose_few_eligible(2, (64, 64), 48, 0, 0, 3, 5, 2)       # channels % 64

@@ -50,9 +50,16 @@ def add_fprop(name, N, H, C, Co, k=5, st=2):
     P = -(-H // st)
     y = torch.empty((N, P, P, Co), device=dev)
     bf = ops.conv2d_planes_eligible(N, (H, H), C, Co, k, st)
+    few = ops.conv2d_few_eligible(N, (H, H), C, Co, k, st)
     cache = {}
 
     def run(impl):
+        if impl in PL and few and PL[impl][0] == torch.float16:
+            if impl not in cache:
+                cache[impl] = (ops.conv2d_few_pack(w, PL[impl][2]), torch.empty((PL[impl][2], N, P, P, Co), device=dev,
+                                                                                dtype=torch.float16))
+            wimg, yp = cache[impl]
+            return ops.conv2d_few(x, wimg, k, Co, bias=b, stride=st, act=True, out=y, out_planes=yp, nprod=PL[impl][1])
         if impl in PL:
             if not bf:
                 return None
@@ -82,8 +89,14 @@ def add_trans(name, N, P, C1, C2, NB, Cn, k=5, st=2, act=True):
     merged = os.environ.get("CTX_BF3_MERGE", "1") != "0" and \
         ops.conv2d_transpose_merged_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
     cache = {}
+    fewt = ops.conv2d_transpose_few_eligible(N, (P * st, P * st), C1, C2, NB, Cn, k, st)
 
     def run(impl):
+        if impl == "p3" and fewt:
+            if impl not in cache:
+                cache[impl] = (planes_of(x1, impl), planes_of(x2, impl) if C2 else None, ops.conv2d_transpose_few_pack(w))
+            return ops.conv2d_transpose_few(cache[impl][0], cache[impl][2], (P * st, P * st), k, Cn, bias=b, stride=st,
+                                            x2p=cache[impl][1], act=act, out=y)
         if impl in PL:
             if not (bf or merged):
                 return None
@@ -109,9 +122,14 @@ def add_wgrad(name, N, H, Ca, Cb1, Cb2, NB, k=5, st=2):
     s2 = rnd(NB, P, P, Cb2) if Cb2 else None
     dw = torch.zeros((k, k, Ca, Cb1 + Cb2), device=dev)
     ok = ops.conv2d_wgrad_planes_eligible(N, (H, H), Ca, Cb1, Cb2, NB, k, st)
+    few = ops.conv2d_few_eligible(N, (H, H), Ca, Cb1 + Cb2, k, st)
     cache = {}
 
     def run(impl):
+        if impl == "p1" and few:
+            if impl not in cache:
+                cache[impl] = (planes_of(s1, impl), planes_of(s2, impl) if Cb2 else None)
+            return ops.conv2d_few_wgrad(big, cache[impl][0], k, st, small2p=cache[impl][1], dw=dw)
         if impl in PL:
             if not ok:
                 return None
@@ -159,6 +177,10 @@ else:
     cases_done = False
 # forward
 if not cases_done:
+  add_fprop("h0 (3->64 @64)", E, 64, 3, 64)
+  add_fprop("d_h4.dgrad (3->128 @64)", D, 64, 3, 128)
+  add_wgrad("h0.wgrad (few)", E, 64, 3, 64, 0, 0)
+  add_wgrad("d_h4.wgrad (few)", D, 64, 3, 64, 64, B)
   add_im2col("h0.im2col", E, 64, 3)
   add_gemm("h0.gemm (K=75)", E * 1024, 64, 75, pad=1)
   add_fprop("h1", E, 32, 64, 128)

@@ -109,6 +109,10 @@ SIGNATURES = {
     "ctx_conv2d_transpose_few_pack": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ConvGeom), c_void_p, c_void_p]),
     "ctx_conv2d_transpose_few": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                            POINTER(ConvGeom), POINTER(Epilogue), POINTER(L2Fused), c_void_p]),
+    "ctx_adam_schedule": (c_int32, [c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "ctx_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
+                                    c_float, c_void_p, c_void_p]),
+    "ctx_gae_tail": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "ctx_crc32c": (C.c_uint32, [c_void_p, C.c_uint64, C.c_uint32]),
     "ctx_gather_frames": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "ctx_lrelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_void_p]),

@@ -116,13 +116,17 @@ extern "C" uint32_t ctx_crc32c(const void* data, uint64_t n, uint32_t crc) {
 extern "C" int64_t ctx_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int ctx_tc_available(void) {
+  static int cached_dev = -1, cached = 0;                  // (called by every tensor-core entry point: one query per device)
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (dev == cached_dev) return cached;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  return (major == 10 && tc_compiled()) ? 1 : 0;
+  cached = (major == 10 && tc_compiled()) ? 1 : 0;
+  cached_dev = dev;
+  return cached;
 }
 
 extern "C" int ctx_conv2d_fprop_ld(const float* x, int32_t C, const float* w, float* y, int32_t y_ld, int32_t Co,

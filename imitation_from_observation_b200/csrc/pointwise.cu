@@ -404,7 +404,8 @@ __global__ void copy_channels_vec_kernel(const float4* __restrict__ src, float4*
 // ---- fused TF-Adam ----------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps,
-                            float gscale, float* __restrict__ p_tf32) {
+                            float gscale, float* __restrict__ p_tf32, const float* __restrict__ lr_t_dev) {
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);                  // (CUDA-graph replays: the step-dependent rate lives on the device)
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
@@ -729,8 +730,34 @@ extern "C" int ctx_adam_step(float* p, const float* g, float* m, float* v, int64
               "adam_step: buffers must be 16-byte aligned");
   if (n == 0) return CTX_OK;
   adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, b1, b2, eps,
-                                                                            grad_scale, p_tf32);
+                                                                            grad_scale, p_tf32, nullptr);
   CTX_LAUNCH_CHECK("adam_step");
+  return CTX_OK;
+}
+
+__global__ void adam_schedule_kernel(int64_t* step, float lr, float b1, float b2, float* lr_t) {
+  const int64_t t = *step + 1;
+  *step = t;
+  *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+
+extern "C" int ctx_adam_schedule(int64_t* step, float lr, float b1, float b2, float* lr_t, void* stream) {
+  CTX_REQUIRE(step && lr_t, "adam_schedule: null pointer");
+  adam_schedule_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, lr, b1, b2, lr_t);
+  CTX_LAUNCH_CHECK("adam_schedule");
+  return CTX_OK;
+}
+
+extern "C" int ctx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_t, float b1,
+                                 float b2, float eps, float grad_scale, float* p_tf32, void* stream) {
+  CTX_REQUIRE(p && g && m && v && lr_t && n >= 0, "adam_step_dev: bad arguments");
+  CTX_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                  ((uintptr_t)v % 16 == 0) && ((uintptr_t)p_tf32 % 16 == 0),
+              "adam_step_dev: buffers must be 16-byte aligned");
+  if (n == 0) return CTX_OK;
+  adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, b1, b2, eps, grad_scale, p_tf32,
+                                                                            lr_t);
+  CTX_LAUNCH_CHECK("adam_step_dev");
   return CTX_OK;
 }
 
@@ -791,5 +818,41 @@ extern "C" int ctx_reward_inception(const float* feat, const float* means, const
   reward_inception_kernel<<<dim3(T, paths), 256, 0, (cudaStream_t)stream>>>(feat, means, std, T, per_frame, rewards,
                                                                             rew_stride, cost);
   CTX_LAUNCH_CHECK("reward_inception");
+  return CTX_OK;
+}
+
+// ---- advantage / return tail of a TRPO batch (rllab/sampler/base.py:258-266) ------------------------------------------------
+// One thread per path walks its steps backwards: y[t] = x[t] + d * y[t + 1], one fp64 multiply and one fp64 add per step in
+// the order scipy.signal.lfilter([1], [1, -d], x[::-1])[::-1] (rllab/misc/special.py:107-111) performs them — no FMA
+// contraction — so the result is bit-identical to the reference's.
+namespace ctx {
+__global__ void gae_tail_kernel(const double* __restrict__ rewards, const double* __restrict__ baselines,
+                                const int64_t* __restrict__ offsets, int paths, double discount, double gae_lambda,
+                                double* __restrict__ advantages, double* __restrict__ returns) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= paths) return;
+  const int64_t t0 = offsets[p], t1 = offsets[p + 1];
+  const double dl = __dmul_rn(discount, gae_lambda);
+  double adv = 0.0, ret = 0.0, b_next = 0.0;                    // np.append(path_baselines, 0): the baseline after the last step
+  for (int64_t t = t1 - 1; t >= t0; --t) {
+    const double r = rewards[t], b = baselines[t];
+    const double delta = __dsub_rn(__dadd_rn(r, __dmul_rn(discount, b_next)), b);
+    adv = (t == t1 - 1) ? delta : __dadd_rn(delta, __dmul_rn(dl, adv));
+    ret = (t == t1 - 1) ? r : __dadd_rn(r, __dmul_rn(discount, ret));
+    advantages[t] = adv;
+    returns[t] = ret;
+    b_next = b;
+  }
+}
+}  // namespace ctx
+
+extern "C" int ctx_gae_tail(const double* rewards, const double* baselines, const int64_t* offsets, int32_t paths,
+                            double discount, double gae_lambda, double* advantages, double* returns, void* stream) {
+  CTX_REQUIRE(paths >= 0, "gae_tail: negative path count");
+  if (paths == 0) return CTX_OK;
+  CTX_REQUIRE(rewards && baselines && offsets && advantages && returns, "gae_tail: null pointer");
+  ctx::gae_tail_kernel<<<(paths + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, baselines, offsets, paths, discount,
+                                                                             gae_lambda, advantages, returns);
+  CTX_LAUNCH_CHECK("gae_tail");
   return CTX_OK;
 }

@@ -54,7 +54,8 @@ struct FewParams {
   int32_t BP, NB, tiles_per_img, num_tiles;
   int32_t RI;                                       // input rows of a tile's footprint, per image
   int32_t natoms, np;
-  uint32_t a_region;                                // fprop: bytes of the A / staging region
+  int32_t groups;                                   // fprop: 256-thread groups per CTA (1 | 2)
+  uint32_t a_region, raw_bytes, st_elems, grp_bytes, RS;   // fprop: A / staging region; raw rows; staged halves per plane; per group
   int32_t tiles_per_cta;                            // wgrad: contiguous tile range per CTA
 };
 
@@ -122,10 +123,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_store_commit_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -180,51 +180,86 @@ __device__ __forceinline__ void raw_issue(const FewParams& p, int tile, uint8_t*
              reinterpret_cast<const uint8_t*>(p.x) + ((int64_t)(n0 + img) * p.H + hs) * rowbytes, per, bar);
 }
 
-// ---- build: thread (row, sub) assembles filter rows sub, sub + 2, ... of output pixel `row` from the raw rows into the
-// swizzled A tile(s): scale, fp16 (hi, lo) split, zero padding (SAME) all happen here -------------------------------------------
-__device__ __forceinline__ void build_rows(const FewParams& p, int n0, int p0, float s, const uint8_t* raw, uint8_t* A_hi,
-                                           uint8_t* A_lo) {
-  const int row = threadIdx.x & 127, sub = threadIdx.x >> 7;
-  const int per_img = p.BP * p.Q;
-  const int img = row / per_img, rem = row - img * per_img;
-  const int dp = rem / p.Q, dq = rem - dp * p.Q;
-  const int kc = p.kw * p.C, wc = p.W * p.C;
-  const int e0 = (dq * p.stride - p.pad_w) * p.C;          // element of the image row the patch row starts at (may be < 0)
-  const int hb = p0 * p.stride - p.pad_h + dp * p.stride;   // image row of filter row 0
-  const bool img_ok = n0 + img < p.N;
-  const uint32_t sw = (uint32_t)(row & 7);
+// ---- stage: raw rows -> fp16 (hi, lo) rows with the SAME zero padding, one conversion per INPUT element -----------------------
+// Staged row = [pad_w * C zeros | W * C values | zeros], RS halves long; rows above / below the image are zeros.  `nthr`
+// threads (a 256-thread group) cooperate, `tid` is the thread's index in the group.
+__device__ __forceinline__ void stage_rows(const FewParams& p, int n0, int p0, float s, const uint8_t* raw, uint16_t* st_hi,
+                                           uint16_t* st_lo, int tid, int nthr) {
+  const int h0 = p0 * p.stride - p.pad_h;
+  const int wc = p.W * p.C, lead = p.pad_w * p.C;
+  const int rows = p.NB * p.RI;
   const uint32_t rowbytes = (uint32_t)wc * (p.x_u8 ? 1u : 4u);
-  for (int r = sub; r < p.kh; r += 2) {
-    const int h = hb + r;
-    const bool ok = img_ok && h >= 0 && h < p.H;
-    const uint8_t* src = raw + (uint32_t)(img * p.RI + dp * p.stride + r) * rowbytes;
-    float v[16];
+  const int rq = p.RS >> 2;                                // RS is a multiple of 4: four halves (8 bytes) per thread and turn
+  for (int i = tid; i < rows * rq; i += nthr) {
+    const int row = i / rq, e4 = (i - row * rq) * 4;
+    const int img = row / p.RI, ri = row - img * p.RI;
+    const int h = h0 + ri;
+    const bool ok = n0 + img < p.N && h >= 0 && h < p.H;
+    const uint8_t* src = raw + (uint32_t)row * rowbytes;
+    float v[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int e = e0 + j;
+    for (int k = 0; k < 4; ++k) {
+      const int g = e4 + k - lead;
       float t = 0.f;
-      if (ok && j < kc && e >= 0 && e < wc) {
-        if (p.x_u8) t = __fmul_rn(__fsub_rn(__fmul_rn((float)src[e], 1.0f / 255.0f), 0.5f), 2.0f);   // base.py:117-119
-        else t = reinterpret_cast<const float*>(src)[e];
+      if (ok && g >= 0 && g < wc) {
+        if (p.x_u8) t = __fmul_rn(__fsub_rn(__fmul_rn((float)src[g], 1.0f / 255.0f), 0.5f), 2.0f);     // base.py:117-119
+        else t = reinterpret_cast<const float*>(src)[g];
       }
-      v[j] = t * s;
+      v[k] = t * s;
     }
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      hi[j] = pack_h2(v[2 * j], v[2 * j + 1]);
-      lo[j] = pack_h2(v[2 * j] - h2f((uint16_t)(hi[j] & 0xFFFFu)), v[2 * j + 1] - h2f((uint16_t)(hi[j] >> 16)));
-    }
-    const uint32_t a = (uint32_t)r >> 2, c0 = ((uint32_t)r & 3u) * 2u;
-    const uint32_t o0 = a * kFAtom + (uint32_t)row * 128u + ((c0 ^ sw) << 4), o1 = a * kFAtom + (uint32_t)row * 128u + (((c0 + 1u) ^ sw) << 4);
-    *reinterpret_cast<uint4*>(A_hi + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(A_hi + o1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    if (A_lo) {
-      *reinterpret_cast<uint4*>(A_lo + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<uint4*>(A_lo + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    const uint32_t h01 = pack_h2(v[0], v[1]), h23 = pack_h2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(st_hi + (int64_t)row * p.RS + e4) = make_uint2(h01, h23);
+    if (st_lo) {
+      const uint32_t l01 = pack_h2(v[0] - h2f((uint16_t)(h01 & 0xFFFFu)), v[1] - h2f((uint16_t)(h01 >> 16)));
+      const uint32_t l23 = pack_h2(v[2] - h2f((uint16_t)(h23 & 0xFFFFu)), v[3] - h2f((uint16_t)(h23 >> 16)));
+      *reinterpret_cast<uint2*>(st_lo + (int64_t)row * p.RS + e4) = make_uint2(l01, l23);
     }
   }
 }
+
+// ---- build: thread (row, sub) copies filter rows sub, sub + 2, ... of output pixel `row` from the staged rows into the
+// swizzled A tile(s) ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_rows(const FewParams& p, const uint16_t* st_hi, const uint16_t* st_lo, uint8_t* A_hi,
+                                           uint8_t* A_lo, int tid) {
+  const int row = tid & 127, sub = tid >> 7;
+  const int per_img = p.BP * p.Q;
+  const int img = row / per_img, rem = row - img * per_img;
+  const int dp = rem / p.Q, dq = rem - dp * p.Q;
+  const int kc = p.kw * p.C;
+  const uint32_t sw = (uint32_t)(row & 7);
+  for (int r = sub; r < p.kh; r += 2) {
+    const int src = (img * p.RI + dp * p.stride + r) * p.RS + dq * p.stride * p.C;
+    const uint32_t a = (uint32_t)r >> 2, c0 = ((uint32_t)r & 3u) * 2u;
+    const uint32_t o0 = a * kFAtom + (uint32_t)row * 128u + ((c0 ^ sw) << 4), o1 = a * kFAtom + (uint32_t)row * 128u + (((c0 + 1u) ^ sw) << 4);
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      const uint16_t* sp = pl ? st_lo : st_hi;
+      uint8_t* A = pl ? A_lo : A_hi;
+      if (!sp) break;
+      uint32_t w[8];
+      if ((src & 1) == 0) {                                // (staged rows start 4-byte aligned: RS is a multiple of 4)
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + src);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t t = 2 * j < kc ? s32[j] : 0u;
+          if (2 * j + 1 >= kc) t &= 0xFFFFu;
+          w[j] = t;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t lo = 2 * j < kc ? (uint32_t)sp[src + 2 * j] : 0u;
+          const uint32_t hi = 2 * j + 1 < kc ? (uint32_t)sp[src + 2 * j + 1] : 0u;
+          w[j] = lo | (hi << 16);
+        }
+      }
+      *reinterpret_cast<uint4*>(A + o0) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(A + o1) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
+}
+
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
 __device__ __forceinline__ void tile_origin(const FewParams& p, int tile, int* n0, int* p0) {
   if (p.NB > 1 || p.tiles_per_img == 1) { *n0 = tile * p.NB; *p0 = 0; }
@@ -233,29 +268,41 @@ __device__ __forceinline__ void tile_origin(const FewParams& p, int tile, int* n
 }  // namespace few
 
 // ---- convolution: D[128 pixels x Co] = patches x W^T -----------------------------------------------------------------------------
+// A CTA is TWO independent 256-thread groups that share the filter image: each group walks its own tiles (raw rows by bulk
+// copy -> stage -> build -> MMAs -> epilogue) with its own operand tile, accumulator columns and barriers, so one group's
+// tensor-core and store phases overlap the other's conversion phases (what two co-resident CTAs would do, minus a second
+// copy of the filters, which would not fit).
+constexpr int kFGroups = 2;                              // (p.groups = 1 when two operand tiles do not fit shared memory)
+
 template <int kProd>
-__global__ void __launch_bounds__(kFThreads) few_fprop_kernel(const __grid_constant__ FewParams p) {
+__global__ void __launch_bounds__(kFThreads * kFGroups) few_fprop_kernel(const __grid_constant__ FewParams p) {
   using namespace few;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int np = kProd == 3 ? 2 : 1;
+  const int grp = threadIdx.x >> 8, tid = threadIdx.x & 255;
   const uint32_t a_plane = (uint32_t)p.natoms * kFAtom, w_plane = (uint32_t)p.natoms * (uint32_t)p.Co * 128u;
-  uint8_t* A = sm;
-  uint8_t* Wt = A + p.a_region;                          // (>= np * a_plane: the region doubles as the epilogue's staging area)
-  uint8_t* raw = Wt + np * w_plane;
-  __shared__ __align__(8) uint64_t bars[2];                // [0]: the tile's raw rows have landed; [1]: its MMAs are done
+  uint8_t* Wt = sm;                                        // shared by both groups
+  uint8_t* A = Wt + np * w_plane + (uint32_t)grp * p.grp_bytes;   // [A / epilogue staging | raw rows | staged hi | staged lo]
+  uint8_t* raw = A + p.a_region;
+  uint16_t* st_hi = reinterpret_cast<uint16_t*>(raw + p.raw_bytes);
+  uint16_t* st_lo = np == 2 ? st_hi + p.st_elems : nullptr;
+  __shared__ __align__(8) uint64_t bars_all[kFGroups][2];  // [0]: the tile's raw rows have landed; [1]: its MMAs are done
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[128];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = bars_all[grp];
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t gcols = (uint32_t)(np * p.Co);            // accumulator columns of one group
   uint32_t ncols = 32;
-  while (ncols < (uint32_t)(np * p.Co)) ncols <<= 1;
-  if (threadIdx.x == 0) {
+  while (ncols < (uint32_t)p.groups * gcols) ncols <<= 1;
+  const int first_tile = blockIdx.x * p.groups + grp, tile_step = gridDim.x * p.groups;
+  if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
     mbar_init(smem_u32(&bars[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if ((int)blockIdx.x < p.num_tiles) raw_issue(p, blockIdx.x, raw, smem_u32(&bars[0]));
+    if (first_tile < p.num_tiles) raw_issue(p, first_tile, raw, smem_u32(&bars[0]));
   }
-  if (warp == 1) {
+  if (threadIdx.x >> 5 == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -263,13 +310,14 @@ __global__ void __launch_bounds__(kFThreads) few_fprop_kernel(const __grid_const
     const uint4* src = p.wimg;
     uint4* dst = reinterpret_cast<uint4*>(Wt);
     const int n16 = (int)(np * w_plane / 16);
-    for (int i = threadIdx.x; i < n16; i += kFThreads) dst[i] = __ldg(src + i);
-    if (threadIdx.x < p.Co) s_bias[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    if ((int)threadIdx.x < p.Co) s_bias[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = tmem_slot + (uint32_t)grp * gcols;
   float s = 1.f;
   if (p.x_amax) s = scale_for(__ldg(p.x_amax));
   float inv = 1.f / s;
@@ -278,15 +326,20 @@ __global__ void __launch_bounds__(kFThreads) few_fprop_kernel(const __grid_const
   const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Co >> 3) << 17) | ((128u >> 4) << 24);
   uint32_t amax = 0u;
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+  for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++it) {
     int n0, p0;
     tile_origin(p, tile, &n0, &p0);
     mbar_wait(smem_u32(&bars[0]), it & 1u);
-    build_rows(p, n0, p0, s, raw, A, np == 2 ? A + a_plane : nullptr);
+    stage_rows(p, n0, p0, s, raw, st_hi, st_lo, tid, kFThreads);
+    if (tid == 0) tma_store_wait_read();                 // the previous tile's stores have drained the staging area = A
+    group_sync(grp);
+    // the raw rows are consumed: fetch the next tile's under this tile's build, MMAs and epilogue
+    if (tid == 0 && tile + tile_step < p.num_tiles) raw_issue(p, tile + tile_step, raw, smem_u32(&bars[0]));
+    build_rows(p, st_hi, st_lo, A, np == 2 ? A + a_plane : nullptr, tid);
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    group_sync(grp);
+    if (tid == 0) {
       tc_fence_after();
       const uint32_t sa = smem_u32(A), sw = smem_u32(Wt);
       for (int ks = 0; ks < p.kh; ++ks) {
@@ -301,9 +354,6 @@ __global__ void __launch_bounds__(kFThreads) few_fprop_kernel(const __grid_const
         }
       }
       umma_commit(smem_u32(&bars[1]));
-      // the raw rows were consumed by build (every thread is past the barrier above): fetch the next tile's under this
-      // tile's MMAs and epilogue
-      if (tile + (int)gridDim.x < p.num_tiles) raw_issue(p, tile + gridDim.x, raw, smem_u32(&bars[0]));
     }
     mbar_wait(smem_u32(&bars[1]), it & 1u);
     tc_fence_after();
@@ -358,45 +408,52 @@ __global__ void __launch_bounds__(kFThreads) few_fprop_kernel(const __grid_const
           }
         }
         fence_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        tc_fence_before();
+        group_sync(grp);
+        if (tid == 0) {
           tma_store_2d(&p.mapY, smem_u32(st_f), cg, row0);
           tma_store_2d(&p.mapY, smem_u32(st_f) + kFAtom, cg + 32, row0);
           if (p.yp) {
             tma_store_3d(&p.mapYp, smem_u32(st_h), cg, row0, 0);
             if (p.yp_n == 2) tma_store_3d(&p.mapYp, smem_u32(st_h) + kFAtom, cg, row0, 1);
           }
-          tma_store_commit_wait();                         // (the stores have READ the staging area)
+          tma_store_commit();
+          if (cg + 64 < p.Co) tma_store_wait_read();       // the next column group reuses the staging area right away
         }
-        if (cg + 64 < p.Co) __syncthreads();               // next column group reuses the staging area
+        // the accumulator is free again; the staging area = A tile once the stores have read it (waited for above, or —
+        // last column group — under the next tile's stage pass)
+        if (cg + 64 < p.Co) group_sync(grp);
       }
     }
-    tc_fence_before();
-    __syncthreads();                                       // tensor memory and the operand tiles are free for the next tile
   }
   if (p.amax_bits) {
     amax = __reduce_max_sync(0xffffffffu, amax);
     if (lane == 0 && amax) atomicMax(p.amax_bits, amax);
   }
-  if (warp == 1) {
+  if (tid == 0) tma_store_wait_all();                      // shared memory must outlive the last stores
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x >> 5 == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(ncols) : "memory");
   }
 }
 
 // ---- filter gradient: D[patch index x Cb] += patches^T x [small1 ‖ small2], pixels = the reduction dimension ---------------------
-// A (patches, built here) and B (the 16-bit plane rows of the tile, one TMA box per 64-channel atom) are double-buffered; the
-// raw rows and B of tile t + 1 are in flight while tile t is built and multiplied.
+// The MMAs of a tile are a few hundred cycles; staging and building its patch tile is the work.  So the CTA is small (one A and
+// one B tile, ~70 KB: three CTAs share an SM and overlap each other's phases), the raw rows are fetched TWO tiles ahead, and B
+// (the 16-bit plane rows of the tile, one TMA box per 64-channel atom) is requested as soon as the previous tile's MMAs retire.
 __global__ void __launch_bounds__(kFThreads) few_wgrad_kernel(const __grid_constant__ FewParams p) {
   using namespace few;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int Cb = p.Cb1 + p.Cb2;
   const uint32_t a_bytes = 2u * kFAtom, b_bytes = (uint32_t)(Cb / 64) * kFAtom;     // A always spans M = 128 (two atoms)
-  uint8_t* Abuf[2] = {sm, sm + a_bytes + b_bytes};
-  uint8_t* Bbuf[2] = {sm + a_bytes, sm + 2 * a_bytes + b_bytes};
-  uint8_t* raw = sm + 2 * (a_bytes + b_bytes);
-  // [0]: raw rows landed; [1], [2]: B of buffer 0 / 1 landed; [3], [4]: the MMAs reading buffer 0 / 1 are done; [5]: all done
+  uint8_t* Abuf = sm;
+  uint8_t* Bbuf = sm + a_bytes;
+  uint8_t* rawb[2] = {Bbuf + b_bytes, Bbuf + b_bytes + p.raw_bytes};
+  uint16_t* st_hi = reinterpret_cast<uint16_t*>(rawb[1] + p.raw_bytes);
+  // [0], [1]: raw rows of buffer 0 / 1 landed; [2]: B landed; [3]: the tile's MMAs are done; [5]: all done
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -406,22 +463,23 @@ __global__ void __launch_bounds__(kFThreads) few_wgrad_kernel(const __grid_const
   uint32_t ncols = 32;
   while (ncols < (uint32_t)Cb) ncols <<= 1;
   const int pq = p.P * p.Q;
-  auto b_issue = [&](int tile, int b) {                    // one thread
+  auto b_issue = [&](int tile) {                           // one thread
     int n0, p0;
     tile_origin(p, tile, &n0, &p0);
-    const uint32_t bar = smem_u32(&bars[1 + b]);
+    const uint32_t bar = smem_u32(&bars[2]);
     mbar_arrive_expect_tx(bar, b_bytes);
     for (int a = 0; a < p.Cb1 / 64; ++a)
-      tma_load_2d(smem_u32(Bbuf[b]) + (uint32_t)a * kFAtom, &p.mapB[0], bar, a * 64, tile * 128);
+      tma_load_2d(smem_u32(Bbuf) + (uint32_t)a * kFAtom, &p.mapB[0], bar, a * 64, tile * 128);
     const int row2 = (n0 % p.s2_batch) * pq + p0 * p.Q;
     for (int a = 0; a < p.Cb2 / 64; ++a)
-      tma_load_2d(smem_u32(Bbuf[b]) + (uint32_t)(p.Cb1 / 64 + a) * kFAtom, &p.mapB[1], bar, a * 64, row2);
+      tma_load_2d(smem_u32(Bbuf) + (uint32_t)(p.Cb1 / 64 + a) * kFAtom, &p.mapB[1], bar, a * 64, row2);
   };
   if (threadIdx.x == 0) {
     for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    raw_issue(p, t_begin, raw, smem_u32(&bars[0]));
-    b_issue(t_begin, 0);
+    raw_issue(p, t_begin, rawb[0], smem_u32(&bars[0]));
+    if (t_begin + 1 < t_end) raw_issue(p, t_begin + 1, rawb[1], smem_u32(&bars[1]));
+    b_issue(t_begin);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols) : "memory");
@@ -438,31 +496,31 @@ __global__ void __launch_bounds__(kFThreads) few_wgrad_kernel(const __grid_const
   // A and B MN-major (bits 15, 16), M = 128, N = Cb
   const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(Cb >> 3) << 17) | ((128u >> 4) << 24);
   for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
-    const int b = it & 1;
+    const int rb = it & 1;
     int n0, p0;
     tile_origin(p, tile, &n0, &p0);
-    if (it >= 2) mbar_wait(smem_u32(&bars[3 + b]), (uint32_t)((it >> 1) - 1) & 1u);   // tile it - 2 no longer reads buffer b
-    mbar_wait(smem_u32(&bars[0]), (uint32_t)it & 1u);
-    build_rows(p, n0, p0, s, raw, Abuf[b], nullptr);
+    mbar_wait(smem_u32(&bars[rb]), (uint32_t)(it >> 1) & 1u);
+    stage_rows(p, n0, p0, s, rawb[rb], st_hi, nullptr, threadIdx.x, kFThreads);
+    if (it >= 1) mbar_wait(smem_u32(&bars[3]), (uint32_t)(it - 1) & 1u);         // the previous tile's MMAs released A and B
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (tile + 2 < t_end) raw_issue(p, tile + 2, rawb[rb], smem_u32(&bars[rb]));     // (this buffer's rows are consumed)
+      if (it >= 1) b_issue(tile);
+    }
+    build_rows(p, st_hi, nullptr, Abuf, nullptr, threadIdx.x);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
-      const bool more = tile + 1 < t_end;
-      if (more) raw_issue(p, tile + 1, raw, smem_u32(&bars[0]));       // (every thread is done reading the raw rows)
-      mbar_wait(smem_u32(&bars[1 + b]), (uint32_t)(it >> 1) & 1u);     // B of this tile has landed
+      mbar_wait(smem_u32(&bars[2]), (uint32_t)it & 1u);    // B of this tile has landed
       tc_fence_after();
-      const uint32_t sa = smem_u32(Abuf[b]), sb = smem_u32(Bbuf[b]);
+      const uint32_t sa = smem_u32(Abuf), sb = smem_u32(Bbuf);
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)                       // 16 pixels per K-step = 2048 B inside every atom
         umma_f16(tmem_base, make_desc(sa + ks * 2048, kFAtom, 1024), make_desc(sb + ks * 2048, kFAtom, 1024), idesc,
                  (it | ks) ? 1u : 0u);
-      umma_commit(smem_u32(&bars[3 + b]));
-      if (!more) umma_commit(smem_u32(&bars[5]));
-      if (more) {                                          // B of the next tile into the other buffer, once tile it - 1 is done with it
-        if (it >= 1) mbar_wait(smem_u32(&bars[3 + (b ^ 1)]), (uint32_t)((it - 1) >> 1) & 1u);
-        b_issue(tile + 1, b ^ 1);
-      }
+      umma_commit(smem_u32(&bars[3]));
+      if (tile + 1 == t_end) umma_commit(smem_u32(&bars[5]));
     }
   }
   mbar_wait(smem_u32(&bars[5]), 0);
@@ -782,6 +840,8 @@ static int few_fill(FewParams& p, int C, const ctx_conv_geom& g, const char* who
   p.num_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * p.tiles_per_img;
   p.RI = (p.BP - 1) * g.stride + g.kh;
   p.natoms = (g.kh * 16 + 63) / 64;
+  p.RS = (uint32_t)((((g.Q - 1) * g.stride + g.kw) * C + 3) & ~3);       // staged row: padded width x channels, in halves
+  p.st_elems = (uint32_t)(((size_t)p.NB * p.RI * p.RS + 7) & ~(size_t)7);
   return CTX_OK;
 }
 
@@ -796,12 +856,26 @@ static int few_eligible(int C, int Co, const ctx_conv_geom& g) {
   return 1;
 }
 
+// (cudaDeviceGetAttribute / cudaFuncSetAttribute cost tens to hundreds of microseconds of HOST time: once per kernel and device)
 static int few_smem_attr(const void* fn, size_t bytes, const char* who) {
-  int dev = 0, optin = 0;
+  static int optin_dev[64] = {0};
+  struct Seen { const void* fn; int dev; size_t bytes; };
+  static Seen seen[32];
+  static int nseen = 0;
+  int dev = 0;
   CTX_CUDA(cudaGetDevice(&dev));
-  CTX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if ((int64_t)bytes > optin - 2048) { set_error("%s: the tile does not fit shared memory (%zu bytes)", who, bytes); return CTX_ERR_UNSUPPORTED; }
+  if (dev < 0 || dev >= 64) { set_error("%s: device index %d out of range", who, dev); return CTX_ERR_ARG; }
+  if (optin_dev[dev] == 0) CTX_CUDA(cudaDeviceGetAttribute(&optin_dev[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if ((int64_t)bytes > optin_dev[dev] - 2048) { set_error("%s: the tile does not fit shared memory (%zu bytes)", who, bytes); return CTX_ERR_UNSUPPORTED; }
+  for (int i = 0; i < nseen; ++i)
+    if (seen[i].fn == fn && seen[i].dev == dev) {
+      if (seen[i].bytes >= bytes) return CTX_OK;
+      CTX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      seen[i].bytes = bytes;
+      return CTX_OK;
+    }
   CTX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (nseen < 32) { seen[nseen].fn = fn; seen[nseen].dev = dev; seen[nseen].bytes = bytes; ++nseen; }
   return CTX_OK;
 }
 
@@ -874,19 +948,21 @@ extern "C" int ctx_conv2d_few_fprop(const void* x, int32_t x_is_u8, int32_t C, c
   // (the A region doubles as the epilogue's staging area: 2 fp32 atoms + hi + lo atoms of a 64-channel group)
   const size_t a_bytes = std::max((size_t)np * p.natoms * kFAtom, (size_t)(y_planes ? 4 : 2) * kFAtom);
   p.a_region = (uint32_t)a_bytes;
-  const size_t smem = 1024 + a_bytes + (size_t)np * p.natoms * Co * 128 + raw_bytes;
+  p.raw_bytes = (uint32_t)raw_bytes;
+  p.grp_bytes = (uint32_t)((a_bytes + raw_bytes + (size_t)np * p.st_elems * 2 + 1023) & ~(size_t)1023);
+  p.groups = kFGroups;
+  size_t smem = 1024 + (size_t)np * p.natoms * Co * 128 + (size_t)p.groups * p.grp_bytes;
+  if (smem > 224 * 1024 || (size_t)p.groups * np * Co > 512) {
+    p.groups = 1;
+    smem = 1024 + (size_t)np * p.natoms * Co * 128 + p.grp_bytes;
+  }
   const void* fn = nprod == 3 ? (const void*)few_fprop_kernel<3> : (const void*)few_fprop_kernel<1>;
   rc = few_smem_attr(fn, smem, "conv2d_few_fprop");
   if (rc) return rc;
-  int occ = (int)(220 * 1024 / (smem + 1024));
-  const int tm = 512 / (np * Co <= 32 ? 32 : (np * Co <= 64 ? 64 : (np * Co <= 128 ? 128 : 256)));
-  if (occ > tm) occ = tm;
-  if (occ < 1) occ = 1;
-  if (occ > 4) occ = 4;
-  int grid = sm_count() * occ;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  if (nprod == 3) few_fprop_kernel<3><<<grid, kFThreads, smem, (cudaStream_t)stream>>>(p);
-  else few_fprop_kernel<1><<<grid, kFThreads, smem, (cudaStream_t)stream>>>(p);
+  int grid = sm_count();                                   // one CTA (its groups walk tiles independently) per SM
+  if (grid > (p.num_tiles + p.groups - 1) / p.groups) grid = (p.num_tiles + p.groups - 1) / p.groups;
+  if (nprod == 3) few_fprop_kernel<3><<<grid, kFThreads * p.groups, smem, (cudaStream_t)stream>>>(p);
+  else few_fprop_kernel<1><<<grid, kFThreads * p.groups, smem, (cudaStream_t)stream>>>(p);
   CTX_LAUNCH_CHECK("conv2d_few_fprop");
   return CTX_OK;
 }
@@ -934,12 +1010,13 @@ extern "C" int ctx_conv2d_few_wgrad(const void* x, int32_t x_is_u8, int32_t C, c
     if (rc) return rc;
   }
   const size_t raw_bytes = ((size_t)p.NB * p.RI * g->W * C * (x_is_u8 ? 1 : 4) + 127) & ~(size_t)127;
-  const size_t smem = 1024 + 2 * (2 * (size_t)kFAtom + (size_t)(Cb / 64) * kFAtom) + raw_bytes;
+  p.raw_bytes = (uint32_t)raw_bytes;
+  const size_t smem = 1024 + 2 * (size_t)kFAtom + (size_t)(Cb / 64) * kFAtom + 2 * raw_bytes + (size_t)p.st_elems * 2;
   rc = few_smem_attr((const void*)few_wgrad_kernel, smem, "conv2d_few_wgrad");
   if (rc) return rc;
-  int occ = (int)(220 * 1024 / (smem + 1024));
+  int occ = (int)(224 * 1024 / (smem + 1024));
   if (occ < 1) occ = 1;
-  if (occ > 2) occ = 2;
+  if (occ > 3) occ = 3;
   int grid = sm_count() * occ;
   if (grid > p.num_tiles) grid = p.num_tiles;
   p.tiles_per_cta = (int)cdiv(p.num_tiles, grid);

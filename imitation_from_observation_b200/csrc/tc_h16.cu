@@ -31,6 +31,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <string.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace ctx {
@@ -49,6 +50,8 @@ struct HSeg {                                      // K-major: one filter tap of
 struct HParams {
   CUtensorMap mapA[8];                             // K-major: up to 4 parity views / 2 sources; MN-major: [view + 4 * plane]
   CUtensorMap mapB[2];                             // K-major: [0]; MN-major: small1 / small2
+  CUtensorMap mapY[4], mapYP[4];                   // result (fp32) / its planes per stride phase: TMA-store epilogue
+  int32_t tma_out, epi_bufs;                       // 1: epilogue through shared memory + TMA stores; staging buffers (1 | 2)
   HSeg seg[kHMaxSeg];
   int32_t mn;                                      // 0 = K-major operands (conv / transposed conv), 1 = MN-major (filter gradient)
   int32_t BN, stages, f16;
@@ -119,6 +122,14 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
                                             int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -392,6 +403,110 @@ __global__ void __launch_bounds__(kHThreads, kProd == 1 ? 2 : 1) h16_kernel(cons
       mbar_wait<false>(acc_bar, 0, p.err_flag, 3);
       tc_fence_after();
     }
+    if (p.tma_out) {
+      // ---- epilogue through shared memory: 64 columns at a time, every epilogue thread writes its row's 32 columns (and
+      // their planes) into a 128-byte-swizzled box image in the (now idle) operand stages, and one thread hands the boxes to
+      // the TMA unit — whole 128-byte lines instead of 32 partial lines per st.global instruction.  Two staging buffers:
+      // the stores of one column group drain while the next one is computed.
+      const uint32_t sw = (uint32_t)(r & 7);
+      const uint32_t need = (2u + (uint32_t)p.out_np) * kHATile;
+      const bool elected = warp == 2 && lane == 0;
+      int gi = 0;
+      for (int cg = 0; cg < p.BN; cg += 64, ++gi) {
+        const int c0 = cg + half * 32;
+        uint32_t v[32];
+        if (nkb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          if constexpr (kProd == 3) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v2[16];
+              tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0 + 16 * h), v2);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                v[16 * h + j] = __float_as_uint(__uint_as_float(v[16 * h + j]) + __uint_as_float(v2[j]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        const int col = ncol0 + c0;
+        int co = col, mi = z;
+        int64_t ooff = roff + col;
+        if (p.merge_cn) {
+          mi = col / p.merge_cn;
+          co = col - mi * p.merge_cn;
+          ooff = roff + ((int64_t)(mi >> 1) * p.merge_W + (mi & 1)) * p.merge_cn + co;
+        }
+        const bool live = row_ok && col < p.N;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 ref = make_float4(0.f, 0.f, 0.f, 0.f), prev = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.act_ref && live) ref = __ldg(reinterpret_cast<const float4*>(p.act_ref + ooff + j));
+          if (p.accumulate && live) prev = *reinterpret_cast<const float4*>(p.out + ooff + j);
+          const float* rr = reinterpret_cast<const float*>(&ref);
+          const float* pp = reinterpret_cast<const float*>(&prev);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t = __uint_as_float(v[j + e]) * inv_scale;
+            if (p.bias) t += __ldg(p.bias + co + j + e);
+            if (p.act) t = fmaxf(t, p.slope * t);
+            if (p.act_ref) t *= (rr[e] >= 0.f ? 1.f : p.slope);
+            if (p.accumulate) t += pp[e];
+            v[j + e] = __float_as_uint(t);
+            if (live) amax = max(amax, __float_as_uint(t) & 0x7FFFFFFFu);
+          }
+        }
+        // the buffer this group goes into was last read by the stores of group gi - epi_bufs
+        const uint32_t sbuf = smem_base + (uint32_t)(gi % p.epi_bufs) * need;
+        if (elected && gi >= p.epi_bufs) {
+          if (p.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        {
+          const uint32_t fo = sbuf + (uint32_t)half * kHATile + (uint32_t)r * 128u;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fo + ((((uint32_t)j >> 2) ^ sw) << 4)), "r"(v[j]),
+                         "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+          if (p.planes) {
+            const uint32_t po = sbuf + 2u * kHATile + (uint32_t)r * 128u;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = __uint_as_float(v[j + 2 * e]), x1 = __uint_as_float(v[j + 2 * e + 1]);
+                hi[e] = pack16(x0, x1, f16);
+                lo[e] = pack16(x0 - unpack16_lo(hi[e], f16), x1 - unpack16_hi(hi[e], f16), f16);
+              }
+              const uint32_t ch = ((((uint32_t)half * 4u + ((uint32_t)j >> 3)) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(po + ch), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+              if (p.out_np == 2)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(po + kHATile + ch), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (elected && ncol0 + cg < p.N) {
+          // (a 64-column group never straddles stride phases of the merged form: merge_cn is a multiple of 64)
+          const int colg = ncol0 + cg;
+          int mg = z, cc = colg;
+          if (p.merge_cn) { mg = colg / p.merge_cn; cc = colg - mg * p.merge_cn; }
+          tma_store_4d(&p.mapY[mg], sbuf, cc, 0, p0, n0);
+          tma_store_4d(&p.mapY[mg], sbuf + kHATile, cc + 32, 0, p0, n0);
+          if (p.planes) {
+            tma_store_5d(&p.mapYP[mg], sbuf + 2u * kHATile, cc, 0, p0, n0, 0);
+            if (p.out_np == 2) tma_store_5d(&p.mapYP[mg], sbuf + 3u * kHATile, cc, 0, p0, n0, 1);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory outlives the stores
+    } else
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       uint32_t v[32];
       if (nkb > 0) {
@@ -583,6 +698,12 @@ static int h_launch(HParams& p, int m_tiles, int zdim, const H16Cfg& cfg, cudaSt
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("%s: tile does not fit shared memory", name); return CTX_ERR_ARG; }
   p.stages = stages;
+  if (p.tma_out) {                                   // the epilogue stages 64-column groups in the idle operand stages
+    const uint32_t need = (2u + (uint32_t)p.out_np) * kHATile;
+    const uint32_t have = (uint32_t)stages * stage;
+    p.epi_bufs = have >= 2 * need ? 2 : 1;
+    if (have < need || p.atomic_out || p.mn) p.tma_out = 0;
+  }
   p.f16 = cfg.f16 ? 1 : 0;
   p.a_scale = cfg.a_scale;
   p.amax_bits = cfg.amax_bits;
@@ -625,6 +746,27 @@ static void h_fill_common(HParams& p, const Epi& epi, float* y, void* yp, int yp
 }
 
 static bool h_aligned16(const void* ptr) { return ((uintptr_t)ptr & 15) == 0; }
+
+// Output boxes of the TMA-store epilogue for one stride phase: the tile's pixels (n, p, q) of a [Cn, Qg, Pg, N] view of y with
+// element strides (1, sQ, sP, sN) starting `base` elements into y; the planes get the same view plus a plane dimension.
+static int h_out_maps(HParams& p, int idx, float* y, void* yp, int yp_n, int f16, int64_t base, int Cn, int Qg, int Pg, int N,
+                      int64_t sQ, int64_t sP, int64_t sN, int64_t plane_stride) {
+  int64_t dims[5] = {Cn, Qg, Pg, N, yp_n > 0 ? yp_n : 1}, str[5] = {1, sQ, sP, sN, plane_stride};
+  int box[5] = {32, Qg, p.BP, p.NB, 1};
+  int rc = h16_make_map(&p.mapY[idx], 2, y + base, 4, dims, str, box);
+  if (rc) return rc;
+  if (yp) {
+    box[0] = 64;
+    rc = h16_make_map(&p.mapYP[idx], f16, (uint16_t*)yp + base, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  return CTX_OK;
+}
+static bool h_tma_out_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CTX_TMA_STORE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 // ---- conv fprop -----------------------------------------------------------------------------------------------------------
 int h16_conv2d_fprop_eligible(int C, int Co, const ctx_conv_geom& g) {
@@ -696,6 +838,11 @@ int h16_conv2d_fprop(const void* xp, int C, const void* wp, float* y, void* yp, 
     }
   p.ph_seg0[0] = 0; p.ph_nseg[0] = nseg; p.ph_kblocks[0] = nseg * cblk; p.ph_obase[0] = 0;
   p.sN = (int64_t)g.P * g.Q * Co; p.sP = (int64_t)g.Q * Co; p.sQ = Co;
+  if (h_tma_out_enabled()) {
+    rc = h_out_maps(p, 0, y, yp, yp_n, cfg.f16, 0, Co, g.Q, g.P, g.N, p.sQ, p.sP, p.sN, p.plane_stride);
+    if (rc) return rc;
+    p.tma_out = 1;
+  }
   return h_launch(p, m_tiles, 1, cfg, stream, "h16_conv2d_fprop");
 }
 
@@ -808,6 +955,13 @@ int h16_conv2d_transpose(const void* x1p, int C1, const void* x2p, int C2, int x
   }
   p.nphase = nph;
   p.sN = (int64_t)g.H * g.W * Cn; p.sP = (int64_t)st * g.W * Cn; p.sQ = (int64_t)st * Cn;
+  if (h_tma_out_enabled()) {
+    for (int i = 0; i < nph; ++i) {
+      rc = h_out_maps(p, i, y, yp, yp_n, cfg.f16, p.ph_obase[i], Cn, phs[i].Wp, phs[i].Hp, g.N, p.sQ, p.sP, p.sN, p.plane_stride);
+      if (rc) return rc;
+    }
+    p.tma_out = 1;
+  }
   return h_launch(p, m_tiles, nph, cfg, stream, "h16_conv2d_transpose");
 }
 
@@ -963,6 +1117,14 @@ int h16_conv2d_transpose_merged(const void* x1p, int C1, const void* x2p, int C2
   p.ph_seg0[0] = 0; p.ph_nseg[0] = nseg; p.ph_kblocks[0] = kblocks; p.ph_obase[0] = 0;
   p.nphase = 1;
   p.sN = (int64_t)g.H * g.W * Cn; p.sP = 2 * (int64_t)g.W * Cn; p.sQ = 2 * (int64_t)Cn;
+  if (h_tma_out_enabled()) {
+    for (int ph = 0; ph < 4; ++ph) {
+      rc = h_out_maps(p, ph, y, yp, yp_n, cfg.f16, ((int64_t)(ph >> 1) * g.W + (ph & 1)) * Cn, Cn, g.Q, g.P, g.N, p.sQ, p.sP,
+                      p.sN, p.plane_stride);
+      if (rc) return rc;
+    }
+    p.tma_out = 1;
+  }
   return h_launch(p, m_tiles, 1, cfg, stream, "h16_conv2d_transpose_merged");
 }
 

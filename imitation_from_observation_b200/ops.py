@@ -725,7 +725,18 @@ def im2col(x, k: int, stride: int, ld: int, out=None, round_tf32=False, padding:
     return out
 
 
+def adam_schedule(step, lr: float, b1: float, b2: float, lr_t):
+    """step (int64[1], device) += 1; lr_t (float32[1], device) = lr * sqrt(1 - b2^step) / (1 - b1^step)."""
+    check(_lib.load().ctx_adam_schedule(_req(step, "step", torch.int64), float(lr), float(b1), float(b2), _req(lr_t, "lr_t"),
+                                        _stream()), "ctx_adam_schedule")
+
+
 def adam_step(p, g, m, v, lr_t, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, p_tf32=None):
+    if torch.is_tensor(lr_t):                              # the rate lives on the device (CUDA-graph replays)
+        check(_lib.load().ctx_adam_step_dev(_req(p, "p"), _req(g, "g"), _req(m, "m"), _req(v, "v"), p.numel(),
+                                            _req(lr_t, "lr_t"), b1, b2, eps, grad_scale, _opt(p_tf32, "p_tf32"), _stream()),
+              "ctx_adam_step_dev")
+        return
     check(_lib.load().ctx_adam_step(_req(p, "p"), _req(g, "g"), _req(m, "m"), _req(v, "v"), p.numel(), lr_t, b1, b2,
                                     eps, grad_scale, _opt(p_tf32, "p_tf32"), _stream()), "ctx_adam_step")
 
@@ -775,3 +786,15 @@ def reward_inception(feat, means, std, paths: int, T: int, rewards=None, cost=No
     check(_lib.load().ctx_reward_inception(_req(feat, "feat"), _req(means, "means"), _req(std, "std"), paths, T, per,
                                            None if rewards is None else _req(rewards, "rewards", torch.float64), rs,
                                            _opt(cost, "cost"), _stream()), "ctx_reward_inception")
+
+
+def gae_tail(rewards, baselines, offsets, discount: float, gae_lambda: float):
+    """rllab/sampler/base.py:258-266 on the device: float64 rewards / baselines of all paths laid end to end, int64 offsets
+    [paths + 1] -> (advantages, returns), bit-identical to the reference's numpy / scipy evaluation."""
+    paths = offsets.numel() - 1
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    check(_lib.load().ctx_gae_tail(_req(rewards, "rewards", torch.float64), _req(baselines, "baselines", torch.float64),
+                                   _req(offsets, "offsets", torch.int64), paths, float(discount), float(gae_lambda),
+                                   _req(adv, "advantages", torch.float64), _req(ret, "returns", torch.float64), _stream()),
+          "ctx_gae_tail")
+    return adv, ret

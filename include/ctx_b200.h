@@ -383,6 +383,13 @@ int ctx_copy_channels(const float* src, int32_t Cs, float* dst, int32_t Cd, int3
 int ctx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
                   float eps, float grad_scale, float* p_tf32, void* stream);
 
+/* The same update with the step-dependent rate on the DEVICE, so that a whole training step can be replayed as a CUDA graph:
+ * ctx_adam_schedule does  *step += 1;  *lr_t = lr * sqrt(1 - b2^step) / (1 - b1^step)  (float64 arithmetic, as the host
+ * formula), ctx_adam_step_dev reads *lr_t. */
+int ctx_adam_schedule(int64_t* step, float lr, float b1, float b2, float* lr_t, void* stream);
+int ctx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_t, float b1, float b2,
+                      float eps, float grad_scale, float* p_tf32, void* stream);
+
 /* y = round_to_nearest_tf32(x) (keeps fp32 storage) — operand preparation for the tcgen05 path. */
 int ctx_round_tf32(const float* x, float* y, int64_t n, void* stream);
 
@@ -411,6 +418,15 @@ int ctx_reward_ours(const float* z, const float* x, const float* means, const fl
  *   rewards[p*rew_stride + 2j+1] -= (double)m[p,j] * j*j */
 int ctx_reward_inception(const float* feat, const float* means, const float* std, int32_t paths, int32_t T,
                          int64_t per_frame, double* rewards, int64_t rew_stride, float* cost, void* stream);
+
+/* The advantage / return tail of a TRPO batch (rllab/sampler/base.py:258-266) for `paths` trajectories laid end to end;
+ * offsets[p] .. offsets[p + 1] are the steps of path p (int64, device).  All float64, as the reference:
+ *   deltas     = rewards + discount * append(baselines, 0)[1:] - baselines
+ *   advantages = discount_cumsum(deltas, discount * gae_lambda)      (rllab/misc/special.py:107-111)
+ *   returns    = discount_cumsum(rewards, discount)
+ * bit-identical to the numpy / scipy.signal.lfilter evaluation (one multiply and one add per step, no FMA). */
+int ctx_gae_tail(const double* rewards, const double* baselines, const int64_t* offsets, int32_t paths, double discount,
+                 double gae_lambda, double* advantages, double* returns, void* stream);
 
 #ifdef __cplusplus
 }

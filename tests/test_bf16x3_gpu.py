@@ -106,7 +106,7 @@ def test_conv2d_transpose_merged_bf16x3(N, P, Q, C1, C2, NB, k):
     assert ops.conv2d_transpose_merged_eligible(N, (H, W), C1, C2, NB, Cn, k, st)
     cat = x1 if x2 is None else torch.cat([x1, x2.repeat((N // NB, 1, 1, 1))], 3)
     ref = O.lrelu(O.conv2d_transpose(cat.double(), w.double(), b.double(), (H, W), st))
-    wm = ops.conv2d_transpose_merged_pack(w.cuda(), (H, W), st)
+    wm = ops.conv2d_transpose_merged_pack(w.cuda(), (H, W), st, dtype=torch.bfloat16)
     yp = torch.zeros((2,) + tuple(ref.shape), device="cuda", dtype=torch.bfloat16)
     y = ops.conv2d_transpose_merged_bf16x3(ops.split_bf16(x1.cuda()), wm, (H, W), k, Cn, bias=b.cuda(), stride=st,
                                            x2p=None if x2 is None else ops.split_bf16(x2.cuda()), act=True, out_planes=yp)

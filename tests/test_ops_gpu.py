@@ -419,3 +419,23 @@ def test_device_bank_answers_the_trainer_expressions():
     # raw uint8 pixels: gathered through the same table (rescale=True semantics)
     raw = synthetic.video_bank(nlen, N, 16, 16, seed=3)
     assert np.array_equal(DeviceBank(raw)[0, choice].cpu().numpy(), f32[0, choice])
+
+
+def test_gae_tail_bit_exact():
+    """base.py:258-266 (deltas, special.discount_cumsum = scipy.signal.lfilter) on ragged paths, float64, bit for bit."""
+    import scipy.signal
+    rs = np.random.RandomState(7)
+    lens = [50, 1, 25, 50, 7, 50]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    r, b = rs.randn(offs[-1]) * 3.0, rs.randn(offs[-1])
+    gamma, lam = 0.99, 0.97
+    adv, ret = ops.gae_tail(torch.from_numpy(r).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(offs).cuda(), gamma, lam)
+
+    def discount_cumsum(x, d):
+        return scipy.signal.lfilter([1], [1, float(-d)], x[::-1], axis=0)[::-1]
+    for i in range(len(lens)):
+        s, e = offs[i], offs[i + 1]
+        pb = np.append(b[s:e], 0)
+        deltas = r[s:e] + gamma * pb[1:] - pb[:-1]
+        assert np.array_equal(adv[s:e].cpu().numpy(), discount_cumsum(deltas, gamma * lam))
+        assert np.array_equal(ret[s:e].cpu().numpy(), discount_cumsum(r[s:e], gamma))

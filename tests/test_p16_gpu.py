@@ -307,7 +307,7 @@ def test_conv2d_few_single_product_gradient_input(N, H, W, C, Co, k, st):
 
 # (N, H, W, C, Cb1, Cb2, NB, k, stride)
 FEW_WGRAD = [(6, 64, 64, 3, 64, 0, 0, 5, 2), (4, 64, 64, 3, 64, 64, 2, 5, 2), (5, 16, 16, 3, 128, 0, 0, 5, 2),
-             (18, 8, 8, 3, 64, 64, 8, 5, 2), (2, 16, 16, 4, 64, 0, 0, 3, 1), (600, 8, 8, 3, 64, 0, 0, 5, 2),
+             (16, 8, 8, 3, 64, 64, 8, 5, 2), (2, 16, 16, 4, 64, 0, 0, 3, 1), (600, 8, 8, 3, 64, 0, 0, 5, 2),
              (120, 64, 64, 3, 64, 0, 0, 5, 2)]   # 960 tiles: the double-buffered tile loop of a CTA
 
 

@@ -25,7 +25,7 @@ for Co in (64, 128, 256):
                       out_planes=torch.empty((2, 4, 8, 8, Co), device="cuda", dtype=torch.bfloat16))
 ops.conv2d_transpose_bf16x3(ops.split_bf16(r(4, 8, 8, 64)), ops.split_bf16(r(5, 5, 128, 128)), (16, 16), 5, bias=r(128), stride=2,
                             x2p=ops.split_bf16(r(2, 8, 8, 64)), act=True)
-ops.conv2d_transpose_merged_bf16x3(ops.split_bf16(r(4, 8, 8, 64)), ops.conv2d_transpose_merged_pack(r(5, 5, 64, 128), (16, 16)),
+ops.conv2d_transpose_merged_bf16x3(ops.split_bf16(r(4, 8, 8, 64)), ops.conv2d_transpose_merged_pack(r(5, 5, 64, 128), (16, 16), dtype=torch.bfloat16),
                                    (16, 16), 5, 64, bias=r(64), stride=2, x2p=ops.split_bf16(r(2, 8, 8, 64)), act=True)
 ops.gather_frames(r(10, 16, 16, 3), torch.tensor([3, 1, 9], device="cuda"))
 torch.cuda.synchronize()

@@ -300,15 +300,19 @@ class Session:
                     if lr_value is None:
                         raise _lib.CtxError("learning-rate placeholder was not fed")
                     lr = lr_value
-                m.net.zero_grad()
-                m.net.forward(FWD_ALL)
-                # fetched values must be those of the pre-update graph, like TF: read them before Adam
+                graphed = m.net.step_graphed(float(lr), opt.b1, opt.b2, opt.eps)
+                if not graphed:
+                    m.net.zero_grad()
+                    m.net.forward(FWD_ALL)
+                # fetched values must be those of the pre-update graph, like TF.  Backward and Adam never write a forward
+                # buffer, so after a whole-step graph replay the activations and losses still are the pre-update ones.
                 for f in mine:
                     if isinstance(f, Fetch):
                         results[id(f)] = m.net.fetch(f.name).detach().clone()
                     elif isinstance(f, NNErr):
                         results[id(f)] = m.net.nn_err(f.nlen)
-                m.net.apply_gradients(float(lr), opt.b1, opt.b2, opt.eps)
+                if not graphed:
+                    m.net.apply_gradients(float(lr), opt.b1, opt.b2, opt.eps)
             else:
                 m.net.forward(max(level, 1))
                 for f in mine:

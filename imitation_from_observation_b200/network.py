@@ -194,6 +194,18 @@ class ContextNet:
         self.bf3 = any(self._enc_bf3) or any(self._dec_bf3) or any(self._enc_few) or any(self._dec_few)
         self.p1 = any(self._enc_p1) or any(self._dec_p1) or any(self._enc_few) or any(self._dec_few)
         self._level = 0
+        # The whole training step (zero_grad + forward + backward + Adam over three streams) replayed as ONE CUDA graph: the
+        # graph is static, so after two eager steps have allocated every buffer the ~120 launches of a step
+        # cost one cudaGraphLaunch of host time.  One graph per (input slot, learning rate).  CTX_GRAPH=0 disables.
+        self._graph_on = os.environ.get("CTX_GRAPH", "1") != "0"
+        self._graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
+        self._graph_meta: Dict[tuple, tuple] = {}
+        self._capturing = False
+        self._in_fresh = False
+        self._eager_steps = 0
+        self._step_dev = None                            # int64[1]: Adam's step counter on the device (graph replays)
+        self._lr_t_dev = None
+        self._step_dev_host = -1
         self._l2_fused = False                           # the last forward evaluated the reconstruction loss inside d_h<L>
 
     # ---- second stream -----------------------------------------------------------------------------------------
@@ -336,6 +348,7 @@ class ContextNet:
         uint8 is normalised on the fly (base.py:117-119)."""
         B = self.B
         pre, self._prefetched = self._prefetched, None
+        self._in_fresh = False
         if use_prefetched:
             if pre is None or not torch.is_tensor(image) or pre[0] != image.data_ptr():
                 raise _lib.CtxError("set_input(use_prefetched=True): no matching prefetch_input() is pending")
@@ -365,6 +378,7 @@ class ContextNet:
             # context encoder (side stream) starts while the source / target frames are still in flight
             # (the copy stream first waits for the current stream: the previous step is done with the input buffers)
             self._in_events = self._copy_roles(image, dst, torch.cuda.current_stream(self.device))
+            self._in_fresh = True                          # copies just issued: an eager step starts under them, role by role
             return
         for r in range(3):
             if image.dtype == torch.uint8:
@@ -374,7 +388,7 @@ class ContextNet:
 
     def _wait_input(self, which: int):
         """Make the current stream wait for the staged host input: 0 = context frames, 1 = everything."""
-        if self._in_events is not None:
+        if self._in_events is not None and not self._capturing:
             torch.cuda.current_stream(self.device).wait_event(self._in_events[which])
 
     # ---- 16-bit (hi, lo) planes --------------------------------------------------------------------------------------
@@ -866,6 +880,10 @@ class ContextNet:
         g_transz = g_z2[:B]                                # trans_z is linear
         g_tz = g_z2[B:]
         ops.lrelu_bwd(g_tz, z2[B:], out=g_tz)              # tgt_z = lrelu(hz_lin(.))
+        if self.round_b:
+            # the loss gradient was added in exact fp32: back to nearest-TF32 before the single-pass GEMMs below read it
+            # (the tensor core would truncate instead, a one-sided error that every upstream gradient inherits)
+            ops.round_tf32(g_z2, out=g_z2)
         # ---- translator -------------------------------------------------------------------------------------------------
         # (every filter / bias gradient of these small layers goes to the side stream: the data-gradient chain below is
         # a sequence of ~20 us launches that leave most SMs idle)
@@ -1004,9 +1022,14 @@ class ContextNet:
     def adam_step(self, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
         """tf.train.AdamOptimizer (train_script.py:128), one fused launch over the flat buffers."""
         self._ensure_moments()
-        self.step_count += 1
-        t = self.step_count
-        lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        if self._capturing:                                # graph replays: the step-dependent rate lives on the device
+            ops.adam_schedule(self._step_dev, lr, b1, b2, self._lr_t_dev)
+            lr_t = self._lr_t_dev
+        else:
+            self.step_count += 1
+            self._eager_steps += 1
+            t = self.step_count
+            lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
         ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr_t, b1, b2, eps, p_tf32=self.flat_pr)
         self._wp_stale = True
 
@@ -1071,9 +1094,14 @@ class ContextNet:
         # leaves it, so its slice of the HBM-bound Adam pass runs on a third stream under the remaining backward GEMMs.
         from . import parallel
         self._ensure_moments()
-        self.step_count += 1
-        t = self.step_count
-        lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        if self._capturing:                                # graph replays: the step-dependent rate lives on the device
+            ops.adam_schedule(self._step_dev, lr, b1, b2, self._lr_t_dev)
+            lr_t = self._lr_t_dev
+        else:
+            self.step_count += 1
+            self._eager_steps += 1
+            t = self.step_count
+            lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
         ranges = {sc: (a, b) for sc, a, b in parallel.scope_ranges(self.offsets, self.flat_size)}
         if self._s3 is None:
             self._s3 = torch.cuda.Stream(device=self.device)
@@ -1096,9 +1124,65 @@ class ContextNet:
         `allreduce` is a parallel.BucketedAllReduce (or anything with stage_done(scope) / finish())."""
         if allreduce is not None:
             self.allreduce = allreduce
+        if self.step_graphed(lr):
+            return
         self.zero_grad()
         self.forward(FWD_ALL)
         self.apply_gradients(lr)
+
+    def step_graphed(self, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> bool:
+        """zero_grad + forward(FWD_ALL) + apply_gradients on the current input as one CUDA-graph launch.  Returns False when
+        the step has to run eagerly (first two steps, data parallel, profiling, CTX_GRAPH=0, capture not possible)."""
+        if (not self._graph_on or self._eager_steps < 2 or not self.concurrent or ops.PROFILE is not None or
+                (self.allreduce is not None and getattr(self.allreduce, "enabled", False))):
+            return False
+        if self._in_fresh:
+            # a host batch whose copies were issued just now (no prefetch): the eager step overlaps them with the context
+            # encoder role by role; a graph would have to wait for the whole batch first
+            return False
+        cur = torch.cuda.current_stream(self.device)
+        if self._in_events is not None:                    # staged host input: the graph starts after the copies
+            cur.wait_event(self._in_events[0])
+            cur.wait_event(self._in_events[1])
+        key = (self._in_slot, float(lr), float(b1), float(b2), float(eps))
+        g = self._graphs.get(key)
+        if g is None:
+            if self._step_dev is None:
+                self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int64)
+                self._lr_t_dev = torch.zeros(1, device=self.device, dtype=torch.float32)
+            try:
+                g = torch.cuda.CUDAGraph()
+                self._capturing = True
+                l0 = ops.launch_count()
+                with torch.cuda.graph(g):
+                    self.zero_grad()
+                    self.forward(FWD_ALL)
+                    self.apply_gradients(lr, b1, b2, eps)
+                # kernels of this library one replay runs; whether the step leaves the weight planes stale
+                self._graph_meta[key] = (ops.launch_count() - l0, self._wp_stale)
+            except Exception as ex:                        # noqa: BLE001  (anything not capturable: stay eager, say so once)
+                self._graph_on = False
+                self._capturing = False
+                torch.cuda.synchronize(self.device)
+                import traceback
+                import warnings
+                tb = traceback.format_exc().strip().splitlines()
+                warnings.warn("CUDA-graph capture of the training step failed (%s | %s | library: %s); running eagerly"
+                              % (str(ex)[:200], " <- ".join(t.strip() for t in tb[-6:-1])[:600], _lib.last_error()[:200]))
+                return False
+            finally:
+                self._capturing = False
+            self._graphs[key] = g
+        if self._step_dev_host != self.step_count:         # eager steps ran in between: realign the device counter
+            self._step_dev.fill_(self.step_count)
+        g.replay()
+        launches, stale = self._graph_meta[key]
+        ops.count_replayed(launches)
+        self.step_count += 1
+        self._step_dev_host = self.step_count
+        self._level = FWD_ALL
+        self._wp_stale = stale
+        return True
 
     # ---- fetches -----------------------------------------------------------------------------------------------------------
     def fetch(self, name: str) -> torch.Tensor:

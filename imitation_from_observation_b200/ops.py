@@ -70,9 +70,17 @@ def conv_geom(n: int, big_hw: Tuple[int, int], k: int, stride: int) -> ConvGeom:
                     same_pad(H, k, stride)[0], same_pad(W, k, stride)[0])
 
 
+_REPLAYED = 0        # kernels of this library run by CUDA-graph replays (the library counts a captured launch once)
+
+
+def count_replayed(n: int):
+    global _REPLAYED
+    _REPLAYED += int(n)
+
+
 def launch_count() -> int:
-    """Kernels launched by libctx_b200.so in this process so far."""
-    return int(_lib.load().ctx_launch_count())
+    """Kernels of libctx_b200.so run in this process so far: direct launches + those inside replayed CUDA graphs."""
+    return int(_lib.load().ctx_launch_count()) + _REPLAYED
 
 
 def device_info():

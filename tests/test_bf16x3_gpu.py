@@ -112,4 +112,4 @@ def test_conv2d_transpose_merged_bf16x3(N, P, Q, C1, C2, NB, k):
                                            x2p=None if x2 is None else ops.split_bf16(x2.cuda()), act=True, out_planes=yp)
     assert rel_err(y.cpu(), ref) < TOL
     assert torch.equal(yp.cpu().view(torch.int16), planes_ref(y.cpu()).view(torch.int16))
-    assert not ops.conv2d_transpose_merged_eligible(N, (H, W), C1, C2, NB, 128, k, st)      # 4 * Cn must be 256
+    assert not ops.conv2d_transpose_merged_eligible(N, (H, W), C1, C2, NB, 192, k, st)      # 4 * Cn must be 256 or 512

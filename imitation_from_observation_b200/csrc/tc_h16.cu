@@ -399,6 +399,28 @@ __global__ void __launch_bounds__(kHThreads, kProd == 1 ? 2 : 1) h16_kernel(cons
     float inv_scale = 1.f;
     if (p.a_scale) inv_scale = 1.f / __ldg(p.a_scale);   // (a power of two: exact)
     uint32_t amax = 0u;
+    // lrelu' mask of a 32-column chunk as 32 sign bits of the saved activation.  The epilogue warps are idle during the main
+    // loop, so the first chunk's bits are fetched BEFORE waiting for the accumulator and each further chunk's right after the
+    // previous one left the registers: the row-per-thread global loads never sit between tensor memory and the stores.
+    auto ref_mask = [&](int cg) -> uint32_t {
+      if (!p.act_ref) return 0xFFFFFFFFu;
+      const int col = ncol0 + cg + half * 32;
+      int64_t ooff = roff + col;
+      if (p.merge_cn) {
+        const int mi = col / p.merge_cn;
+        ooff = roff + ((int64_t)(mi >> 1) * p.merge_W + (mi & 1)) * p.merge_cn + (col - mi * p.merge_cn);
+      }
+      if (!(row_ok && col < p.N)) return 0xFFFFFFFFu;
+      uint32_t m = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.act_ref + ooff + j));
+        m |= (a.x >= 0.f ? 1u : 0u) << j | (a.y >= 0.f ? 1u : 0u) << (j + 1) | (a.z >= 0.f ? 1u : 0u) << (j + 2) |
+             (a.w >= 0.f ? 1u : 0u) << (j + 3);
+      }
+      return m;
+    };
+    uint32_t mask = p.tma_out ? ref_mask(0) : 0u;
     if (nkb > 0) {
       mbar_wait<false>(acc_bar, 0, p.err_flag, 3);
       tc_fence_after();
@@ -442,17 +464,15 @@ __global__ void __launch_bounds__(kHThreads, kProd == 1 ? 2 : 1) h16_kernel(cons
         const bool live = row_ok && col < p.N;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float4 ref = make_float4(0.f, 0.f, 0.f, 0.f), prev = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.act_ref && live) ref = __ldg(reinterpret_cast<const float4*>(p.act_ref + ooff + j));
+          float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.accumulate && live) prev = *reinterpret_cast<const float4*>(p.out + ooff + j);
-          const float* rr = reinterpret_cast<const float*>(&ref);
           const float* pp = reinterpret_cast<const float*>(&prev);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float t = __uint_as_float(v[j + e]) * inv_scale;
             if (p.bias) t += __ldg(p.bias + co + j + e);
             if (p.act) t = fmaxf(t, p.slope * t);
-            if (p.act_ref) t *= (rr[e] >= 0.f ? 1.f : p.slope);
+            if (p.act_ref) t *= ((mask >> (j + e)) & 1u) ? 1.f : p.slope;
             if (p.accumulate) t += pp[e];
             v[j + e] = __float_as_uint(t);
             if (live) amax = max(amax, __float_as_uint(t) & 0x7FFFFFFFu);
@@ -490,6 +510,7 @@ __global__ void __launch_bounds__(kHThreads, kProd == 1 ? 2 : 1) h16_kernel(cons
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (cg + 64 < p.BN) mask = ref_mask(cg + 64);       // (the chunk's registers are free: next chunk's sign bits)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (elected && ncol0 + cg < p.N) {
           // (a 64-column group never straddles stride phases of the merged form: merge_cn is a multiple of 64)

@@ -369,15 +369,22 @@ def run_ours(args):
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
         w_sum = 0.0                                  # tensor-core time units issued, in 16-bit (kind::f16) MMA equivalents
-        for kind, impl, flops, a, b in prof:
+        launch_list = []
+        for kind, impl, flops, a, b, *dims in prof:
             # 2 / 3 = single-pass / 3-pass TF32 (tc_gemm.cu); 5 / 6 = three / one product on 16-bit planes (tc_h16.cu)
             key = {1: "simt", 2: "tc", 3: "tc", 5: "tc", 6: "tc"}.get(impl, "simt")
             w_sum = w_sum + flops * {2: 2.0, 3: 6.0, 5: 3.0, 6: 1.0}.get(impl, 0.0) if key == "tc" else w_sum
             t = a.elapsed_time(b) * 1e-3
+            launch_list.append(dict(kind=kind, impl=impl, dims=list(dims[0]) if dims and dims[0] else None, gflop=flops * 1e-9,
+                                 us=t * 1e6, tflops=flops / max(t, 1e-12) * 1e-12))
             d = agg.setdefault(key, dict(flops=0.0, s=0.0, calls=0))
             d["flops"] += flops; d["s"] += t; d["calls"] += 1
             d2 = agg.setdefault(key + ":" + {5: "p16x3_", 6: "p16x1_"}.get(impl, "") + kind, dict(flops=0.0, s=0.0, calls=0))
             d2["flops"] += flops; d2["s"] += t; d2["calls"] += 1
+        if args.dump_launches:
+            with open(args.dump_launches, "w") as f:
+                for L in launch_list:
+                    f.write(json.dumps(L) + "\n")
         breakdown = {k: dict(tflops=v["flops"] / max(v["s"], 1e-12) / 1e12, ms=v["s"] * 1e3, calls=v["calls"])
                      for k, v in sorted(agg.items())}
         dom = "tc" if "tc" in agg and agg["tc"]["s"] >= agg.get("simt", dict(s=0))["s"] * 0.5 else "simt"
@@ -583,6 +590,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="triples per GPU")
     ap.add_argument("--ref-batch", type=int, default=256, help="max triples per step of the CPU reference (reduced to fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default="", help="write the per-launch profile of one forward+backward (JSON lines)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: this many triples in total, split evenly over the GPUs (overrides --batch)")
     ap.add_argument("--workload", default="train", choices=["train", "striker6", "inception", "inception2"],

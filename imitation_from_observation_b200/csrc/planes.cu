@@ -105,7 +105,9 @@ __device__ __forceinline__ float p16_scale_for(uint32_t amax_bits) {
 }
 
 // block (64, 4): threadIdx.x walks 64 column quads (256 columns, coalesced 128-bit accesses), threadIdx.y strides the rows
-// of the block's slab; column sums are reduced over threadIdx.y in shared memory, one atomic per column and block.
+// of the block's slab; column sums are reduced over threadIdx.y in shared memory, one atomic per column and block.  A tensor
+// with fewer than 256 channels puts `rp` = 64 / (C / 4) consecutive rows side by side on the 64 x-lanes (C = 64: four rows
+// per pass), so every lane moves bytes whatever the channel count.
 __global__ void grad_planes_kernel(const float* __restrict__ x, int64_t rows, int C, int ldx, const float* __restrict__ ref,
                                    float slope, const uint32_t* __restrict__ amax_bits, float* scale_out,
                                    uint16_t* __restrict__ planes, int nplanes, int f16, float* db, float* __restrict__ out_f32,
@@ -115,15 +117,17 @@ __global__ void grad_planes_kernel(const float* __restrict__ x, int64_t rows, in
   float s = 1.f;
   if (h && amax_bits) s = p16_scale_for(*amax_bits);
   if (scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *scale_out = s;
-  const int cq = blockIdx.x * 64 + threadIdx.x;          // column quad
   const int Cq = C >> 2;
+  const int rp = Cq < 64 ? 64 / Cq : 1;                  // rows side by side on the x-lanes
+  const int sub = rp > 1 ? (int)threadIdx.x / Cq : 0;
+  const int cq = rp > 1 ? (int)threadIdx.x - sub * Cq : (int)(blockIdx.x * 64 + threadIdx.x);   // column quad
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t plane = rows * (int64_t)C;
-  if (cq < Cq) {
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4) {
+  if (cq < Cq && sub < rp) {
+    for (int64_t r = r0 + (int64_t)threadIdx.y * rp + sub; r < r1; r += 4 * rp) {
       float4 v = *reinterpret_cast<const float4*>(x + r * ldx + 4 * cq);
       const int64_t o = r * C + 4 * cq;
       if (ref) {
@@ -144,13 +148,13 @@ __global__ void grad_planes_kernel(const float* __restrict__ x, int64_t rows, in
   if (db) {
     part[threadIdx.y][threadIdx.x] = sum;
     __syncthreads();
-    if (threadIdx.y == 0 && cq < Cq) {
-      float4 t = part[0][threadIdx.x];
-#pragma unroll
-      for (int j = 1; j < 4; ++j) {
-        const float4 u = part[j][threadIdx.x];
-        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-      }
+    if (threadIdx.y == 0 && cq < Cq && sub == 0) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 4; ++j)
+        for (int q = 0; q < rp; ++q) {
+          const float4 u = part[j][threadIdx.x + q * Cq];
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
       atomicAdd(db + 4 * cq, t.x); atomicAdd(db + 4 * cq + 1, t.y);
       atomicAdd(db + 4 * cq + 2, t.z); atomicAdd(db + 4 * cq + 3, t.w);
     }
@@ -253,7 +257,8 @@ extern "C" int ctx_grad_planes(const float* x, int64_t rows, int32_t C, int32_t 
   const int gx = (int)cdiv(C / 4, 64);
   // enough row slabs to fill the machine a few times over, at least 16 rows each (the block reduces over 4 row lanes)
   int64_t gy = cdiv((int64_t)(sm_count() > 0 ? sm_count() : 148) * 8, gx);
-  if (gy > cdiv(rows, 16)) gy = cdiv(rows, 16);
+  const int rp = C / 4 < 64 ? 64 / (C / 4) : 1;        // rows a block covers per pass of its 64 x-lanes (see the kernel)
+  if (gy > cdiv(rows, 16 * rp)) gy = cdiv(rows, 16 * rp);
   if (gy < 1) gy = 1;
   if (gy > 65535) gy = 65535;
   const int64_t rpb = cdiv(rows, gy);

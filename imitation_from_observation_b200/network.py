@@ -1053,9 +1053,14 @@ class ContextNet:
             # optimiser stream as soon as its reduction is done, under the rest of backward / the later reductions.
             ar = self.allreduce
             self._ensure_moments()
-            self.step_count += 1
-            t = self.step_count
-            lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+            if self._capturing:                            # graph replays: the step-dependent rate lives on the device
+                ops.adam_schedule(self._step_dev, lr, b1, b2, self._lr_t_dev)
+                lr_t = self._lr_t_dev
+            else:
+                self.step_count += 1
+                self._eager_steps += 1
+                t = self.step_count
+                lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
             if self._s3 is None:
                 self._s3 = torch.cuda.Stream(device=self.device)
             cur = torch.cuda.current_stream(self.device)
@@ -1132,9 +1137,10 @@ class ContextNet:
 
     def step_graphed(self, lr: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> bool:
         """zero_grad + forward(FWD_ALL) + apply_gradients on the current input as one CUDA-graph launch.  Returns False when
-        the step has to run eagerly (first two steps, data parallel, profiling, CTX_GRAPH=0, capture not possible)."""
+        the step has to run eagerly (first two steps, profiling, CTX_GRAPH=0 / CTX_DP_GRAPH=0, capture not possible)."""
+        dp = self.allreduce is not None and getattr(self.allreduce, "enabled", False)
         if (not self._graph_on or self._eager_steps < 2 or not self.concurrent or ops.PROFILE is not None or
-                (self.allreduce is not None and getattr(self.allreduce, "enabled", False))):
+                (dp and os.environ.get("CTX_DP_GRAPH", "1") == "0")):
             return False
         if self._in_fresh:
             # a host batch whose copies were issued just now (no prefetch): the eager step overlaps them with the context
@@ -1154,7 +1160,9 @@ class ContextNet:
                 g = torch.cuda.CUDAGraph()
                 self._capturing = True
                 l0 = ops.launch_count()
-                with torch.cuda.graph(g):
+                # data parallel: the bucketed NCCL all-reduces are captured with the step (NCCL's watchdog thread polls
+                # events, which only a thread-local capture tolerates)
+                with torch.cuda.graph(g, capture_error_mode="thread_local" if dp else "global"):
                     self.zero_grad()
                     self.forward(FWD_ALL)
                     self.apply_gradients(lr, b1, b2, eps)

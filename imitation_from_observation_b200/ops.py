@@ -23,10 +23,10 @@ PROFILE = None
 
 
 class _Prof:
-    __slots__ = ("kind", "flops", "e0")
+    __slots__ = ("kind", "flops", "e0", "dims")
 
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, dims=None):
+        self.kind, self.flops, self.dims = kind, flops, dims
         self.e0 = None
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
@@ -36,7 +36,8 @@ class _Prof:
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.kind, int(_lib.load().ctx_last_impl()) if impl is None else impl, self.flops, self.e0, e1))
+            PROFILE.append((self.kind, int(_lib.load().ctx_last_impl()) if impl is None else impl, self.flops, self.e0, e1,
+                            self.dims))
 
 
 def _stream() -> int:
@@ -106,7 +107,7 @@ def conv2d(x, w, bias=None, stride: int = 2, act: bool = False, out=None, act_re
     if out is None:
         out = torch.empty((N, g.P, g.Q, Co), device=x.device, dtype=torch.float32)
     epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
-    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * kh * kw * Cin)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * kh * kw * Cin, (N, g.P, g.Q, Co, kh, kw, Cin,))
     check(_lib.load().ctx_conv2d_fprop(_req(x, "x"), Cin, _req(w, "w"), _req(out, "out"), Co, C.byref(g),
                                        C.byref(epi), impl, _stream()), "ctx_conv2d_fprop")
     pr.done()
@@ -131,7 +132,7 @@ def conv2d_transpose(x1, w, out_hw, bias=None, stride: int = 2, x2=None, act: bo
     if out is None:
         out = torch.empty((N, g.H, g.W, Cn), device=x1.device, dtype=torch.float32)
     epi = make_epilogue(bias, act, act_ref, accumulate, round_tf32)
-    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * kh * kw * Ck)
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * kh * kw * Ck, (N, P, Q, Cn, kh, kw, Ck,))
     check(_lib.load().ctx_conv2d_transpose(_req(x1, "x1"), C1, _opt(x2, "x2"), C2, 0 if x2 is None else x2.shape[0],
                                            _req(w, "w"), _req(out, "out"), Cn, C.byref(g), C.byref(epi), impl,
                                            _stream()), "ctx_conv2d_transpose")
@@ -224,7 +225,7 @@ def conv2d_planes(xp, wp, k: int, bias=None, stride: int = 2, act: bool = False,
         raise _lib.CtxError("conv2d_planes: out_planes has the wrong size")
     epi = make_epilogue(bias, act, act_ref, accumulate)
     cfg = _p16(xp, nprod, a_scale, amax)
-    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * k * k * Cin)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * k * k * Cin, (N, g.P, g.Q, Co, k, k, Cin,))
     check(_lib.load().ctx_conv2d_fprop_p16(_reqp(xp, "xp"), Cin, _reqp(wp, "wp", xp), _req(out, "out"),
                                            None if out_planes is None else _reqp(out_planes, "out_planes", xp),
                                            0 if out_planes is None else out_planes.shape[0], Co, C.byref(g), C.byref(epi),
@@ -260,7 +261,7 @@ def conv2d_transpose_planes(x1p, wp, out_hw, k: int, bias=None, stride: int = 2,
         raise _lib.CtxError("conv2d_transpose_planes: out_planes has the wrong size")
     epi = make_epilogue(bias, act, act_ref, accumulate)
     cfg = _p16(x1p, nprod, a_scale, amax)
-    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * Ck)
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * Ck, (N, P, Q, Cn, k, k, Ck,))
     check(_lib.load().ctx_conv2d_transpose_p16(
         _reqp(x1p, "x1p"), C1, None if x2p is None else _reqp(x2p, "x2p", x1p), C2, 0 if x2p is None else x2p.shape[1],
         _reqp(wp, "wp", x1p), _req(out, "out"), None if out_planes is None else _reqp(out_planes, "out_planes", x1p),
@@ -310,7 +311,7 @@ def conv2d_transpose_merged_planes(x1p, wmp, out_hw, k: int, Cn: int, bias=None,
         raise _lib.CtxError("conv2d_transpose_merged_planes: out_planes has the wrong size")
     epi = make_epilogue(bias, act, act_ref, accumulate)
     cfg = _p16(x1p, nprod, a_scale, amax)
-    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * (C1 + C2))
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * (C1 + C2), (N, P, Q, Cn, k, k, (C1 + C2),))
     check(_lib.load().ctx_conv2d_transpose_merged_p16(
         _reqp(x1p, "x1p"), C1, None if x2p is None else _reqp(x2p, "x2p", x1p), C2, 0 if x2p is None else x2p.shape[1],
         _reqp(wmp, "wmp", x1p), _req(out, "out"), None if out_planes is None else _reqp(out_planes, "out_planes", x1p),
@@ -340,7 +341,7 @@ def conv2d_wgrad_planes(bigp, small1p, k: int, stride: int, small2p=None, dw=Non
     cfg = _p16(bigp, nprod, a_scale, None)
     if nprod == 3 and (small1p.shape[0] < 2 or (small2p is not None and small2p.shape[0] < 2)):
         raise _lib.CtxError("conv2d_wgrad_planes: three-product mode needs (hi, lo) planes of every operand")
-    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Ca)
+    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Ca, (N, g.P, g.Q, (Cb1 + Cb2), k, k, Ca,))
     check(_lib.load().ctx_conv2d_wgrad_p16(_reqp(bigp, "bigp"), Ca, _reqp(small1p, "small1p", bigp), Cb1,
                                            None if small2p is None else _reqp(small2p, "small2p", bigp), Cb2,
                                            0 if small2p is None else small2p.shape[1], _req(dw, "dw"), C.byref(g),
@@ -420,7 +421,7 @@ def conv2d_few(x, wimg, k: int, Co: int, bias=None, stride: int = 2, act: bool =
     if out_planes is not None and (out_planes.dtype != torch.float16 or out_planes.numel() != out_planes.shape[0] * out.numel()):
         raise _lib.CtxError("conv2d_few: out_planes must be float16 planes of the output")
     epi = make_epilogue(bias, act)
-    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * k * k * Cin)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * k * k * Cin, (N, g.P, g.Q, Co, k, k, Cin,))
     check(_lib.load().ctx_conv2d_few_fprop(
         _req_img(x, "x"), int(x.dtype == torch.uint8), Cin, _req(wimg, "wimg", torch.uint8), _req(out, "out"),
         None if out_planes is None else _reqp(out_planes, "out_planes"), 0 if out_planes is None else out_planes.shape[0],
@@ -442,7 +443,7 @@ def conv2d_few_wgrad(x, small1p, k: int, stride: int, small2p=None, dw=None, x_a
         raise _lib.CtxError("conv2d_few_wgrad: small2p must be one float16 plane of [N2,P,Q,Cb2]")
     if dw is None:
         dw = torch.zeros((k, k, Cin, Cb1 + Cb2), device=x.device, dtype=torch.float32)
-    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Cin)
+    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Cin, (N, g.P, g.Q, (Cb1 + Cb2), k, k, Cin,))
     check(_lib.load().ctx_conv2d_few_wgrad(
         _req_img(x, "x"), int(x.dtype == torch.uint8), Cin, _reqp(small1p, "small1p"), Cb1,
         None if small2p is None else _reqp(small2p, "small2p"), Cb2,
@@ -494,7 +495,7 @@ def conv2d_transpose_few(x1p, wimg, out_hw, k: int, Cn: int, bias=None, stride: 
         lf = _lib.L2Fused(_req(l2["tgt"], "tgt"), _opt(l2.get("resid"), "resid"), _opt(l2.get("weight"), "weight"),
                           _req(l2["loss"], "loss"), _opt(l2.get("dpred"), "dpred"),
                           None if l2.get("amax") is None else _req(l2["amax"], "amax", torch.int32), int(l2["pass_images"]))
-    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * (C1 + C2))
+    pr = _Prof("transpose", 2.0 * N * P * Q * Cn * k * k * (C1 + C2), (N, P, Q, Cn, k, k, (C1 + C2),))
     check(_lib.load().ctx_conv2d_transpose_few(
         _reqp(x1p, "x1p"), C1, None if x2p is None else _reqp(x2p, "x2p", x1p), C2, 0 if x2p is None else x2p.shape[1],
         _req(wimg, "wimg", torch.uint8), _req(out, "out"), Cn, C.byref(g), C.byref(epi),
@@ -522,7 +523,7 @@ def conv2d_wgrad(big, small1, k: int, stride: int, small2=None, dw=None, impl=IM
                             % (tuple(small1.shape), N, g.P, g.Q))
     if dw is None:
         dw = torch.zeros((k, k, Ca, Cb1 + Cb2), device=big.device, dtype=torch.float32)
-    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Ca)
+    pr = _Prof("wgrad", 2.0 * N * g.P * g.Q * (Cb1 + Cb2) * k * k * Ca, (N, g.P, g.Q, (Cb1 + Cb2), k, k, Ca,))
     check(_lib.load().ctx_conv2d_wgrad(_req(big, "big"), Ca, _req(small1, "small1"), Cb1, _opt(small2, "small2"), Cb2,
                                        0 if small2 is None else small2.shape[0], _req(dw, "dw"), C.byref(g), impl,
                                        _stream()), "ctx_conv2d_wgrad")
@@ -555,7 +556,7 @@ def conv2d_general(x, w, bias=None, stride: int = 1, padding: str = "SAME", act:
         raise _lib.CtxError("conv2d_general: filter %s does not match input %s" % (tuple(w.shape), tuple(x.shape)))
     g = _geom_general(N, H, W_, kh, kw, stride, padding)
     epi = make_epilogue(bias, act, None, False, False, slope)
-    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * kh * kw * Cin)
+    pr = _Prof("fprop", 2.0 * N * g.P * g.Q * Co * kh * kw * Cin, (N, g.P, g.Q, Co, kh, kw, Cin,))
     if into is not None:
         # write channels [c_off, c_off + Co) of the wider NHWC tensor `into` (the block's concat result)
         if tuple(into.shape[:3]) != (N, g.P, g.Q) or c_off < 0 or c_off + Co > into.shape[3]:
@@ -597,7 +598,7 @@ def copy_channels(src, dst, c_off: int):
 # ---- dense -------------------------------------------------------------------------------------------------------
 def gemm_raw(tA: bool, tB: bool, M: int, N: int, K: int, A_ptr: int, lda: int, B_ptr: int, ldb: int, C_ptr: int,
              ldc: int, epi: Optional[Epilogue] = None, impl=IMPL_AUTO):
-    pr = _Prof("gemm", 2.0 * M * N * K)
+    pr = _Prof("gemm", 2.0 * M * N * K, (M, N, K,))
     check(_lib.load().ctx_gemm(int(tA), int(tB), M, N, K, A_ptr, lda, B_ptr, ldb, C_ptr, ldc,
                                C.byref(epi) if epi is not None else None, impl, _stream()), "ctx_gemm")
     pr.done()

@@ -714,20 +714,43 @@ __global__ void __launch_bounds__(kFThreads) few_transpose_kernel(const __grid_c
       const int g = p.pass_images > 0 ? n / p.pass_images : 0;
       const float wg = p.weight ? __ldg(p.weight + g) : 1.f;
       float ls = 0.f;
-      for (int pix = threadIdx.x; pix < out_rows * p.W; pix += kFThreads) {
-        const int ohl = pix / p.W, ow = pix - ohl * p.W;
+      // No division inside the loop: (row, column) of the thread's pixel advance by constants from turn to turn.  The patch
+      // entries of one output pixel sit at constant strides in G: filter row r + ST <-> input row pp - 1, filter column
+      // sx + ST <-> input column qq - 1 (shared-memory loads by 32-bit address; G is row-major [pixel][r * 16 + sx * Cn + co]).
+      const uint32_t Gs = smem_u32(G);
+      const int step_row = kFThreads / p.W, step_col = kFThreads - step_row * p.W;
+      int ohl = (int)threadIdx.x / p.W, ow = (int)threadIdx.x - ohl * p.W;
+      const int d_r = ST * 16 - p.Q * p.GS, d_s = ST * p.Cn - p.GS;          // G offset steps (floats) of r += ST, sx += ST
+      const int total = out_rows * p.W;
+      for (int pix = threadIdx.x; pix < total; pix += kFThreads) {
         const int oh = p0 * ST + ohl;
         float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int r = (oh + p.pad_h) % ST; r < p.kh; r += ST) {
-          const int pp = (oh + p.pad_h - r) / ST - pbase;           // row of G's tile (rows outside the image hold zeros)
+        const unsigned uh = (unsigned)(oh + p.pad_h), uw = (unsigned)(ow + p.pad_w);
+        const int r0 = (int)(uh % ST), s0 = (int)(uw % ST);
+        int pp = (int)(uh / ST) - pbase;                               // input row of filter row r0 (rows outside hold zeros)
+        const int q0 = (int)(uw / ST);
+        int off_r = (pp * p.Q + q0) * p.GS + r0 * 16 + s0 * p.Cn;
+        for (int r = r0; r < p.kh; r += ST, --pp, off_r += d_r) {
           if (pp < 0 || pp >= p.RT) continue;
-          for (int sx = (ow + p.pad_w) % ST; sx < p.kw; sx += ST) {
-            const int qq = (ow + p.pad_w - sx) / ST;
+          int qq = q0, off = off_r;
+          for (int sx = s0; sx < p.kw; sx += ST, --qq, off += d_s) {
             if (qq < 0 || qq >= p.Q) continue;
-            const float* gp = G + (int64_t)(pp * p.Q + qq) * p.GS + r * 16 + sx * p.Cn;
+            const uint32_t ga = Gs + 4u * (uint32_t)off;
+            float g0, g1, g2;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g0) : "r"(ga));
+            if (p.Cn == 3) {
+              asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(g1) : "r"(ga));
+              asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(g2) : "r"(ga));
+              acc[0] += g0; acc[1] += g1; acc[2] += g2;
+            } else {
+              acc[0] += g0;
 #pragma unroll
-            for (int co = 0; co < 5; ++co)
-              if (co < p.Cn) acc[co] += gp[co];
+              for (int co = 1; co < 5; ++co)
+                if (co < p.Cn) {
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g1) : "r"(ga + 4u * (uint32_t)co));
+                  acc[co] += g1;
+                }
+            }
           }
         }
         const int64_t o = (((int64_t)n * p.H + oh) * p.W + ow) * p.Cn;
@@ -748,6 +771,8 @@ __global__ void __launch_bounds__(kFThreads) few_transpose_kernel(const __grid_c
             }
           }
         }
+        ohl += step_row; ow += step_col;
+        if (ow >= p.W) { ow -= p.W; ++ohl; }
       }
       if (p.tgt) {
 #pragma unroll

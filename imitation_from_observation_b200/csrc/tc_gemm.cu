@@ -1568,10 +1568,12 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
   if (rc) return rc;
   const int n_tiles = (int)cdiv(N, p.BN);
   int splits = 1;
-  if (plain_accumulate) splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 8, passes, p.BN);
+  if (plain_accumulate) splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 4, passes, p.BN);
   p.kblocks_per_split = (int)cdiv(p.total_kblocks, splits);
   splits = (int)cdiv(p.total_kblocks, p.kblocks_per_split);
-  p.atomic_out = (plain_accumulate && splits > 1) ? 1 : 0;
+  // plain += always goes out as vector reductions (fire and forget): the read-modify-write epilogue is a chain of dependent
+  // row-per-thread loads (ncu, hz_lin's filter gradient: 37 us for 8 k-blocks, every FADD waiting on its own load)
+  p.atomic_out = plain_accumulate ? 1 : 0;
   if (p.atomic_out) p.epi.accumulate = 0;
   p.out = C;
   // D (and a K-major A) rows are matrix rows: a 128-"image" tile of 1x1 grids

@@ -421,6 +421,22 @@ __global__ void __launch_bounds__(kHThreads, kProd == 1 ? 2 : 1) h16_kernel(cons
       return m;
     };
     uint32_t mask = p.tma_out ? ref_mask(0) : 0u;
+    // accumulate (+=): the chunk's previous values, fetched the same way — eight independent 128-bit loads in flight per thread
+    // before the accumulator wait / under the previous chunk's stores, instead of one load -> add -> next load chain.
+    float4 prev[8];
+    auto load_prev = [&](int cg) {
+      const int col = ncol0 + cg + half * 32;
+      int64_t ooff = roff + col;
+      if (p.merge_cn) {
+        const int mi = col / p.merge_cn;
+        ooff = roff + ((int64_t)(mi >> 1) * p.merge_W + (mi & 1)) * p.merge_cn + (col - mi * p.merge_cn);
+      }
+      const bool ok = row_ok && col < p.N;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        prev[j] = ok ? *reinterpret_cast<const float4*>(p.out + ooff + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (p.tma_out && p.accumulate) load_prev(0);
     if (nkb > 0) {
       mbar_wait<false>(acc_bar, 0, p.err_flag, 3);
       tc_fence_after();
@@ -464,9 +480,7 @@ __global__ void __launch_bounds__(kHThreads, kProd == 1 ? 2 : 1) h16_kernel(cons
         const bool live = row_ok && col < p.N;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.accumulate && live) prev = *reinterpret_cast<const float4*>(p.out + ooff + j);
-          const float* pp = reinterpret_cast<const float*>(&prev);
+          const float* pp = reinterpret_cast<const float*>(&prev[j >> 2]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float t = __uint_as_float(v[j + e]) * inv_scale;
@@ -510,7 +524,10 @@ __global__ void __launch_bounds__(kHThreads, kProd == 1 ? 2 : 1) h16_kernel(cons
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (cg + 64 < p.BN) mask = ref_mask(cg + 64);       // (the chunk's registers are free: next chunk's sign bits)
+        if (cg + 64 < p.BN) {                               // (the chunk's registers are free: next chunk's sign bits / sums)
+          mask = ref_mask(cg + 64);
+          if (p.accumulate) load_prev(cg + 64);
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (elected && ncol0 + cg < p.N) {
           // (a 64-column group never straddles stride phases of the merged form: merge_cn is a multiple of 64)

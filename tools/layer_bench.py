@@ -207,6 +207,8 @@ if not cases_done:
   # backward: encoder
   add_gemm("h4_lin.wgrad", 8192, 1024, E, tA=True, bias=False, accumulate=True)
   add_gemm("h4_lin.dgrad", E, 8192, 1024, tB=True, bias=False)
+  add_gemm("hz_lin.wgrad", 1024, 1024, B, tA=True, bias=False, accumulate=True)
+  add_gemm("hz_lin.dgrad", B, 1024, 1024, tB=True, bias=False)
   add_wgrad("h3.wgrad", E, 8, 256, 512, 0, 0)
   add_trans("h3.dgrad", E, 4, 512, 0, 0, 256)
   add_wgrad("h2.wgrad", E, 16, 128, 256, 0, 0)

@@ -109,6 +109,11 @@ struct TcParams {
   float* out;
   int64_t sN, sP, sQ, obase;       // element strides of D rows over (n, p, q)
   int32_t atomic_out;
+  // split-K inside a thread-block CLUSTER (1 x 1 x cluster_k CTAs, one K range each): the partial accumulators of ranks
+  // 1.. travel through distributed shared memory into rank 0's idle operand ring, rank 0 adds them to its own and runs
+  // the fused epilogue — one launch and a deterministic sum where split-K over the grid needs a zero fill, atomics and
+  // a second epilogue pass.  0 / 1 = off.
+  int32_t cluster_k;
   // scatter epilogue (transposed conv with few output channels computed as ONE pixel x (tap, channel) GEMM):
   // column j = tap*sc_Cn + co of row (n, p, q) is added to out[n, p*sc_st + r - sc_padh, q*sc_st + s - sc_padw, co]
   int32_t scatter, sc_kw, sc_Cn, sc_st, sc_padh, sc_padw, sc_H, sc_W;
@@ -283,6 +288,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 // carries "my tiles are split" — the tiles themselves stay in this CTA's tensor / shared memory, are read by this
 // SM's own MMA datapath, and were already ordered by the splitters' proxy fence + local barrier; a cluster-scope
 // release here puts a full memory barrier per k-block on the follower's critical path (measured: the pair ran 20 % slower).
+// 16 bytes into the shared memory of CTA `rank` of this cluster, at the address `addr` has in this CTA's window
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t rank, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "st.shared::cluster.v4.b32 [ra], {%2, %3, %4, %5};\n\t}" ::"r"(addr), "r"(rank), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
@@ -728,9 +739,48 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
     }
   }
 
+  // ================================= cluster split-K: partial sums -> rank 0 ====================================
+  uint32_t krank = 0u;
+  if (p.cluster_k > 1) {
+    krank = cluster_ctarank();
+    if (nkb > 0) {
+      mbar_wait(acc_bar, 0, p.err_flag, 9);        // (every thread: the accumulator and so the operand ring are final)
+      tc_fence_after();
+    }
+    __syncwarp();
+    cluster_sync_all();                            // every CTA's MMAs have read their rings: rank 0's is free to receive
+    if (krank != 0 && warp >= 2) {
+      // partial (rank - 1) as [column quad][row] float4: consecutive lanes write consecutive 16-byte words
+      const int q = warp & 3, r = q * 32 + lane;
+      const int nch = (p.BN + 31) >> 5, ch_half = (nch + 1) >> 1;
+      const int c_begin = ((warp - 2) >> 2) ? ch_half * 32 : 0, c_end = ((warp - 2) >> 2) ? p.BN : min(p.BN, ch_half * 32);
+      const uint32_t dst = smem_base + (krank - 1u) * (uint32_t)p.BN * 512u + (uint32_t)r * 16u;
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint32_t v[32];
+        if (nkb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          if (kX3) {
+            uint32_t v2[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), v2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          st_cluster_v4(dst + (uint32_t)((c0 + j) >> 2) * 2048u, 0u, v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();                            // (release / acquire: the partials are visible to rank 0)
+  }
+
   // ================================= epilogue: warps 2..9 ======================================================
   // warp w reads TMEM lane quarter w % 4 (hardware rule); the two warps of a quarter split the 32-column chunks
-  if (warp >= 2) {
+  if (warp >= 2 && krank == 0u) {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                   // tile row
     const int nch = (p.BN + 31) >> 5, ch_half = (nch + 1) >> 1;
@@ -759,6 +809,21 @@ __global__ void __launch_bounds__(kThreads, 2) tc_igemm_kernel(const __grid_cons
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (p.cluster_k > 1) {                       // + the other ranks' partial sums, in rank order (deterministic)
+        for (int s = 0; s < p.cluster_k - 1; ++s) {
+          const uint32_t src = smem_base + (uint32_t)s * (uint32_t)p.BN * 512u + (uint32_t)r * 16u;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 t;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                         : "r"(src + (uint32_t)((c0 + j) >> 2) * 2048u));
+            v[j] = __float_as_uint(__uint_as_float(v[j]) + t.x);
+            v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + t.y);
+            v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + t.z);
+            v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + t.w);
+          }
+        }
       }
       if (!row_ok) continue;
       const int col = ncol0 + c0;
@@ -942,6 +1007,7 @@ static int knob_lo_depth() { static int v = env_int("CTX_TC_LO_DEPTH", 4); retur
 static int knob_pair() { static int v = env_int("CTX_TC_PAIR", 1); return v; }
 static int knob_atmem() { static int v = env_int("CTX_TC_ATMEM", 1); return v; }
 static int knob_occ() { static int v = env_int("CTX_TC_OCC", 0); return v; }
+static int knob_cluster_k() { static int v = env_int("CTX_TC_CLUSTER_K", 1); return v; }
 
 // CTAs per SM the operand ring is sized for.  Two co-resident CTAs overlap each other's prologue / epilogue /
 // pipeline-fill bubbles and double the TMA instructions in flight: measured +30..70 % for single-pass tiles
@@ -1051,6 +1117,29 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
                 cudaGetErrorName(e2));
       return CTX_ERR_CUDA;
     }
+    count_launch();
+    return CTX_OK;
+  }
+  if (p.cluster_k > 1) {
+    if (splits != p.cluster_k || p.atomic_out || p.nphase > 1 || p.scatter || p.BN % 32 != 0 ||
+        (size_t)(p.cluster_k - 1) * p.BN * 512 > smem - 1024) {
+      set_error("%s: internal: cluster split-K misconfigured", name);
+      return CTX_ERR_ARG;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p.cluster_k;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = p.passes == 3 ? cudaLaunchKernelEx(&cfg, tc_igemm_kernel<false, true>, p)
+                                  : cudaLaunchKernelEx(&cfg, tc_igemm_kernel<false, false>, p);
+    if (e != cudaSuccess) return cuda_fail(e, name);
     count_launch();
     return CTX_OK;
   }
@@ -1502,7 +1591,26 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
   // Skinny GEMMs (the `linear` layers: M = batch <= a few hundred rows, K up to 8192) leave most SMs idle and run a
   // long serial K loop.  When the fused epilogue is not a plain accumulation, split K anyway: zero C, accumulate
   // the raw partial sums with the split-K path, then apply the epilogue in a second, tiny pass over C.
-  if (!epi.accumulate) {
+  // Few tiles and a long K, any fused epilogue: split K over a thread-block cluster (partials meet in rank 0's shared memory).
+  int cluster_k = 1;
+  if (!epi.accumulate && knob_cluster_k()) {
+    const int bn = pick_bn(N, cdiv(M, 128), passes);
+    const int64_t tiles = cdiv(M, 128) * cdiv(N, bn);
+    const int kblocks = (int)cdiv(K, 32);
+    for (int sk = 8; sk >= 2; sk >>= 1) {
+      const int occ = tc_occupancy(passes, bn, (int)cdiv(kblocks, sk));
+      const int64_t slots = (int64_t)sm_count() * occ;
+      // ring bytes rank 0 can lend: what launch_tc gives a CTA at this occupancy (conservative)
+      const int64_t ring = (occ == 1 ? 200 : 100) * 1024;
+      if (tiles * sk > slots) continue;                                    // (the whole cluster grid in one wave)
+      if (kblocks / sk < 4 || bn % 32 != 0) continue;
+      if ((int64_t)(sk - 1) * bn * 512 > ring) continue;
+      if ((int64_t)(sk - 1) * cdiv(kblocks, sk) >= kblocks) continue;      // every rank gets work
+      cluster_k = sk;
+      break;
+    }
+  }
+  if (!epi.accumulate && cluster_k == 1) {
     const int bn = pick_bn(N, 1 << 20, passes);
     const int64_t tiles = cdiv(M, 128) * cdiv(N, bn);
     const int kblocks = (int)cdiv(K, 32);
@@ -1569,8 +1677,13 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
   const int n_tiles = (int)cdiv(N, p.BN);
   int splits = 1;
   if (plain_accumulate) splits = pick_splits(m_tiles * n_tiles, p.total_kblocks, 4, passes, p.BN);
+  if (cluster_k > 1) splits = cluster_k;
   p.kblocks_per_split = (int)cdiv(p.total_kblocks, splits);
   splits = (int)cdiv(p.total_kblocks, p.kblocks_per_split);
+  if (cluster_k > 1) {
+    if (splits == cluster_k && p.BN % 32 == 0) p.cluster_k = cluster_k;
+    else { splits = 1; p.kblocks_per_split = p.total_kblocks; }             // (cannot happen: checked above)
+  }
   // plain += always goes out as vector reductions (fire and forget): the read-modify-write epilogue is a chain of dependent
   // row-per-thread loads (ncu, hz_lin's filter gradient: 37 us for 8 k-blocks, every FADD waiting on its own load)
   p.atomic_out = plain_accumulate ? 1 : 0;

@@ -454,7 +454,7 @@ def run_ours(args):
                     step_tflops=3 * 2.0 * spec.fwd_macs_per_triple() * B * world / (ms_step * 1e-3) / 1e12)
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        _orderly_exit()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -577,10 +577,33 @@ def run_inception(args):
                               gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                               gflop_per_step=B * INC_FLOP_PER_IMG / 1e9)))
     if world > 1:
-        dist.destroy_process_group()
+        _orderly_exit()
+
+
+def _orderly_exit():
+    """Data-parallel teardown that cannot hang the launcher: graphs before the process group (parallel.shutdown), and a
+    watchdog that ends the process if NCCL's teardown still blocks — the JSON line is already out."""
+    import threading
+    sys.stdout.flush()
+    t = threading.Timer(45.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    from imitation_from_observation_b200 import parallel
+    parallel.shutdown()
+    t.cancel()
 
 
 def main():
+    # a run that stops making progress says where: Python stacks of every thread go to stderr on SIGTERM (what `timeout` and
+    # the launcher send) and, unprompted, after 4 minutes
+    import faulthandler
+    import signal
+    faulthandler.enable()
+    try:
+        faulthandler.register(signal.SIGTERM, all_threads=True, chain=True)
+    except (AttributeError, ValueError):
+        pass
+    faulthandler.dump_traceback_later(240, repeat=False, exit=False)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

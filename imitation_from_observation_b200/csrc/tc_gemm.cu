@@ -1007,7 +1007,11 @@ static int knob_lo_depth() { static int v = env_int("CTX_TC_LO_DEPTH", 4); retur
 static int knob_pair() { static int v = env_int("CTX_TC_PAIR", 1); return v; }
 static int knob_atmem() { static int v = env_int("CTX_TC_ATMEM", 1); return v; }
 static int knob_occ() { static int v = env_int("CTX_TC_OCC", 0); return v; }
-static int knob_cluster_k() { static int v = env_int("CTX_TC_CLUSTER_K", 1); return v; }
+// Cluster split-K for the skinny dense GEMMs is OFF by default: measured (profiles/r2_layer_gemm_cluster_k.txt) it loses to
+// the wide-tile grid split — 84 vs 67 us for h4_lin's forward, 81 vs 62 us for d_h0_lin's data gradient: four times the
+// CTAs at BN = 64 re-read A four times as often, and the two cluster barriers + the DSMEM hop cost more than the zero
+// fill + second pass they replace.  CTX_TC_CLUSTER_K=1 turns it on (bit-reproducible sums).
+static int knob_cluster_k() { static int v = env_int("CTX_TC_CLUSTER_K", 0); return v; }
 
 // CTAs per SM the operand ring is sized for.  Two co-resident CTAs overlap each other's prologue / epilogue /
 // pipeline-fill bubbles and double the TMA instructions in flight: measured +30..70 % for single-pass tiles
@@ -1089,7 +1093,14 @@ static int launch_tc(TcParams& p, int m_tiles, int splits, cudaStream_t stream, 
   p.raw_slots = slots;
   if (p.raw_slots > 8) p.raw_slots = 8;
   if (p.raw_slots < 2) { set_error("%s: tile does not fit shared memory", name); return CTX_ERR_ARG; }
-  const size_t smem = (size_t)p.raw_slots * raw + (size_t)p.lo_slots * lo_b + 1024;
+  size_t smem = (size_t)p.raw_slots * raw + (size_t)p.lo_slots * lo_b + 1024;
+  if (p.cluster_k > 1) {
+    // rank 0 receives cluster_k - 1 partial tiles of 128 x BN fp32 in its (then idle) operand ring: make the allocation
+    // large enough for them, within this occupancy's share of the SM
+    const size_t need = (size_t)(p.cluster_k - 1) * p.BN * 512 + 1024;
+    if (need > (size_t)budget) { set_error("%s: internal: cluster split-K partials do not fit shared memory", name); return CTX_ERR_ARG; }
+    if (need > smem) smem = need;
+  }
   p.err_flag = nullptr;
   const int n_tiles = (int)cdiv(p.N, p.BN);
   if (n_tiles > 65535 || splits > 65535) { set_error("%s: grid too large", name); return CTX_ERR_ARG; }
@@ -1600,8 +1611,8 @@ int tc_gemm(int tA, int tB, int M, int N, int K, const float* A, int lda, const 
     for (int sk = 8; sk >= 2; sk >>= 1) {
       const int occ = tc_occupancy(passes, bn, (int)cdiv(kblocks, sk));
       const int64_t slots = (int64_t)sm_count() * occ;
-      // ring bytes rank 0 can lend: what launch_tc gives a CTA at this occupancy (conservative)
-      const int64_t ring = (occ == 1 ? 200 : 100) * 1024;
+      // bytes rank 0 can receive: this occupancy's share of the SM's shared memory (launch_tc sizes the allocation)
+      const int64_t ring = (occ == 1 ? 200 : 108) * 1024;
       if (tiles * sk > slots) continue;                                    // (the whole cluster grid in one wave)
       if (kblocks / sk < 4 || bn % 32 != 0) continue;
       if ((int64_t)(sk - 1) * bn * 512 > ring) continue;

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -38,6 +39,19 @@ def _numel(shape) -> int:
     for d in shape:
         n *= int(d)
     return n
+
+
+_LIVE_NETS: "weakref.WeakSet" = weakref.WeakSet()
+
+
+def release_all_graphs():
+    """Destroy the captured training-step graphs of every live net.  A data-parallel graph holds NCCL kernel nodes: it has to
+    go BEFORE the process group does (destroying the communicator under a live graph hangs at exit), so
+    parallel.shutdown() and an atexit hook call this first."""
+    for net in list(_LIVE_NETS):
+        net.release_graphs()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 class ContextNet:
@@ -90,6 +104,7 @@ class ContextNet:
         self._prefetched = None
         self.allreduce = None          # parallel.BucketedAllReduce when data-parallel (attach_allreduce)
         self._bufs: Dict[str, torch.Tensor] = {}
+        _LIVE_NETS.add(self)
 
         # ---- flat parameter / gradient / moment buffers -----------------------------------------------------
         self.shapes = spec.param_shapes()
@@ -1123,6 +1138,12 @@ class ContextNet:
         self.backward(on_stage=adam_scope)
         cur.wait_stream(self._s3)
         self._wp_stale = False
+
+    def release_graphs(self):
+        """Drop the captured step graphs (the next train_step captures again after two eager steps)."""
+        self._graphs.clear()
+        self._graph_meta.clear()
+        self._eager_steps = 0
 
     def train_step(self, lr: float = 1e-4, allreduce=None):
         """forward + backward + (optional bucketed gradient all-reduce) + Adam: one `sess.run(optimizer, ...)`.

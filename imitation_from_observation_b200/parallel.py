@@ -45,7 +45,27 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
                 os.close(saved)
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
+    global _SHUTDOWN_HOOKED
+    if world > 1 and not _SHUTDOWN_HOOKED:
+        import atexit
+        atexit.register(shutdown)
+        _SHUTDOWN_HOOKED = True
     return rank, world, local
+
+
+_SHUTDOWN_HOOKED = False
+
+
+def shutdown():
+    """Orderly end of a data-parallel process: captured step graphs (they hold NCCL kernel nodes) are destroyed first, the
+    device drains, then the process group goes.  Idempotent; registered with atexit by init_distributed."""
+    from . import network
+    network.release_all_graphs()
+    if dist.is_available() and dist.is_initialized():
+        try:
+            dist.destroy_process_group()
+        except Exception:                                  # noqa: BLE001  (exit path: nothing useful to do with it)
+            pass
 
 
 def scope_ranges(offsets: Dict[str, int], flat_size: int) -> List[Tuple[str, int, int]]:

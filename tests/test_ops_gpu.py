@@ -206,6 +206,54 @@ def test_gemm_leading_dimensions_and_backward_epilogue(impl, tol):
     assert torch.equal(C_d.cpu()[:, :N], Cbig[:, :N])         # untouched columns stay bit-identical
 
 
+_CLUSTER_K_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from imitation_from_observation_b200 import ops, _lib
+from imitation_from_observation_b200._lib import IMPL_AUTO, IMPL_FAST
+g = torch.Generator().manual_seed(27)
+M, N, K = 256, 1024, 1024
+A = torch.randn((M, K), generator=g); Bm = torch.randn((N, K), generator=g) * K ** -0.5; bias = torch.randn((N,), generator=g) * 0.1
+yref = torch.randn((M, 2 * N), generator=g); base = torch.randn((M, 2 * N), generator=g)
+for impl, tol in ((IMPL_AUTO, 2e-5), (IMPL_FAST, 3e-3)):
+    C_d, y_d = base.clone().cuda(), yref.cuda()
+    ref = base.double().clone()
+    ref[:, N:] = (A.double() @ Bm.double().t()) * torch.where(yref[:, N:] >= 0, 1.0, 0.2).double()
+    epi = _lib.Epilogue(None, y_d.data_ptr() + N * 4, 0.2, 0, 0, 0)
+    ops.gemm_raw(False, True, M, N, K, A.cuda().data_ptr(), K, Bm.cuda().data_ptr(), K, C_d.data_ptr() + N * 4, 2 * N, epi, impl)
+    err = float((C_d.cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err < tol, ("mask epilogue", impl, err)
+    assert torch.equal(C_d.cpu()[:, :N], base[:, :N])
+    outs = [ops.gemm(A.cuda(), Bm.cuda(), transB=True, bias=bias.cuda(), act=True, impl=impl).cpu() for _ in range(3)]
+    y = A.double() @ Bm.double().t() + bias.double()
+    y = torch.where(y >= 0, y, 0.2 * y)
+    err = float((outs[0].double() - y).abs().max() / y.abs().max())
+    assert err < tol, ("bias + lrelu", impl, err)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    for (m, n, k) in ((64, 1024, 8192), (512, 1024, 8192), (256, 1024, 2048)):
+        a = torch.randn((m, k), generator=g); b = torch.randn((k, n), generator=g) * k ** -0.5
+        c = ops.gemm(a.cuda(), b.cuda(), impl=impl).cpu().double()
+        r = a.double() @ b.double()
+        err = float((c - r).abs().max() / r.abs().max())
+        assert err < tol, (m, n, k, impl, err)
+print("cluster-k ok")
+"""
+
+
+def test_gemm_cluster_split_k_epilogue():
+    """CTX_TC_CLUSTER_K=1 (off by default: measured slower than the wide-tile grid split): the skinny dense layers split K
+    over a thread-block cluster; rank 0 adds the partial sums that arrive through distributed shared memory and runs the fused
+    epilogue — bias + lrelu, lrelu' mask from a column-sliced activation into a column-sliced output — and the sum is
+    bit-reproducible.  The knob is read once per process, so the check runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CTX_TC_CLUSTER_K="1")
+    r = subprocess.run([sys.executable, "-c", _CLUSTER_K_SCRIPT % root], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "cluster-k ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_u8_normalize_bit_exact():
     x = torch.randint(0, 256, (3, 5, 7, 9, 3), generator=g(23), dtype=torch.uint8)
     for xs in (x, x.reshape(-1)[1:-2]):                        # aligned and unaligned / odd-length paths

@@ -698,6 +698,16 @@ static bool h_tile_grid(int P, int Q, int rows, int* BP, int* NB, int* tiles_per
 
 static int h_pick_bn(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); }
 
+// CTA pairs (cta_group::2, two SMs on one 256-row tile, each staging half of B): every 256-wide tile.  CTX_H16_PAIR128=1 also
+// pairs the 128-wide THREE-product tiles (a single-CTA 128 x 128 three-product tile moves 64 KB per k-block for 768 MMA cycles,
+// a pair 48 KB per CTA) — measured a wash (h1's forward 169 vs 160 us, d_h2 311 vs 316 us, the step 4.80 ms either way: those
+// layers are not held back by operand traffic alone), so it stays off.
+static bool h_pair(int BN, int m_tiles, int nprod) {
+  static int knob = -1;
+  if (knob < 0) { const char* e = getenv("CTX_H16_PAIR128"); knob = (e && e[0] == '1') ? 1 : 0; }
+  return m_tiles >= 2 && (BN == 256 || (BN == 128 && nprod == 3 && knob));
+}
+
 static int h_nprod_ok(const H16Cfg& cfg, const char* name) {
   CTX_REQUIRE(cfg.nprod == 1 || cfg.nprod == 3, "%s: nprod must be 1 or 3", name);
   CTX_REQUIRE(cfg.nprod == 3 || cfg.f16, "%s: single-product mode needs fp16 planes (bf16 keeps 8 significant bits)", name);
@@ -726,7 +736,7 @@ static int h_launch(HParams& p, int m_tiles, int zdim, const H16Cfg& cfg, cudaSt
     CTX_CUDA(cudaFuncSetAttribute(h16_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     max_dyn_dev[dev] = dyn;
   }
-  const bool pair = p.BN == 256 && m_tiles >= 2;     // 256-wide tiles run as CTA pairs (each CTA stages half of B)
+  const bool pair = p.mn ? (p.BN == 256 && m_tiles >= 2) : h_pair(p.BN, m_tiles, cfg.nprod);   // (each CTA stages half of B)
   const uint32_t np = cfg.nprod == 3 ? 2u : 1u;
   const uint32_t stage = np * (kHATile + (uint32_t)(pair ? p.BN / 2 : p.BN) * 128u);
   // single-product tiles: two CTAs (pairs) per SM overlap each other's prologue / epilogue (256 TMEM columns each)
@@ -836,7 +846,7 @@ int h16_conv2d_fprop(const void* xp, int C, const void* wp, float* y, void* yp, 
   p.BN = h_pick_bn(Co);
   p.NG = g.N; p.PG = g.P; p.QG = g.Q; p.N = Co;
   const int np = cfg.nprod == 3 ? 2 : 1;
-  const bool pair = p.BN == 256 && m_tiles >= 2;
+  const bool pair = h_pair(p.BN, m_tiles, cfg.nprod);
   const int64_t x_plane = (int64_t)g.N * g.H * g.W * C;
   if (g.stride == 1) {
     int64_t dims[5] = {C, g.W, g.H, g.N, np}, str[5] = {1, C, (int64_t)g.W * C, (int64_t)g.H * g.W * C, x_plane};
@@ -857,7 +867,7 @@ int h16_conv2d_fprop(const void* xp, int C, const void* wp, float* y, void* yp, 
   {
     const int64_t rows = (int64_t)g.kh * g.kw * Co;
     int64_t dims[3] = {C, rows, np}, str[3] = {1, C, rows * C};
-    int box[3] = {64, pair ? 128 : p.BN, np};
+    int box[3] = {64, pair ? p.BN / 2 : p.BN, np};
     rc = h16_make_map(&p.mapB[0], cfg.f16, wp, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -946,7 +956,7 @@ int h16_conv2d_transpose(const void* x1p, int C1, const void* x2p, int C2, int x
   p.tiles_per_img = tpi;
   const int m_tiles = p.NB > 1 ? (int)cdiv(g.N, p.NB) : g.N * tpi;
   p.BN = h_pick_bn(Cn);
-  const bool pair = p.BN == 256 && m_tiles >= 2;
+  const bool pair = h_pair(p.BN, m_tiles, cfg.nprod);
   p.NG = g.N; p.PG = phs[0].Hp; p.QG = phs[0].Wp; p.N = Cn;
   p.a_wrap = x2_batch > 0 ? x2_batch : 1;
   {
@@ -966,7 +976,7 @@ int h16_conv2d_transpose(const void* x1p, int C1, const void* x2p, int C2, int x
   {
     const int64_t rows = (int64_t)g.kh * g.kw * Cn;
     int64_t dims[3] = {Ck, rows, np}, str[3] = {1, Ck, rows * Ck};
-    int box[3] = {64, pair ? 128 : p.BN, np};
+    int box[3] = {64, pair ? p.BN / 2 : p.BN, np};
     rc = h16_make_map(&p.mapB[0], cfg.f16, wp, 3, dims, str, box);
     if (rc) return rc;
   }

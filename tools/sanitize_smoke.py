@@ -29,9 +29,21 @@ ops.conv2d_transpose_merged_bf16x3(ops.split_bf16(r(4, 8, 8, 64)), ops.conv2d_tr
                                    (16, 16), 5, 64, bias=r(64), stride=2, x2p=ops.split_bf16(r(2, 8, 8, 64)), act=True)
 ops.gather_frames(r(10, 16, 16, 3), torch.tensor([3, 1, 9], device="cuda"))
 torch.cuda.synchronize()
-net = ContextNet(S.context_skip_new(32, 32, 3, df_dim=64, featsize=64), 8, precision="mixed")      # bf16-plane layers active
-assert net.bf3
-net.set_input((torch.rand((3, 8, 32, 32, 3), generator=g) * 2 - 1).cuda())
-net.train_step(1e-4)
+# skinny dense layers: cluster split-K when CTX_TC_CLUSTER_K=1 (partials through distributed shared memory), else grid split-K
+for impl in (IMPL_AUTO, IMPL_FAST):
+    ops.gemm(r(64, 2048), r(2048, 1024), bias=r(1024), act=True, impl=impl)
+    ops.gemm(r(256, 1024), r(1024, 1024), transB=True, impl=impl)
+    ops.gemm(r(256, 1024), r(256, 512), transA=True, accumulate=True, out=torch.zeros(1024, 512).cuda(), impl=impl)   # += as vector reductions
 torch.cuda.synchronize()
-print("sanitize smoke done, loss", float(net.fetch("loss")))
+# two eager training steps of full-width nets in "mixed": h16_kernel (three products forward, one product backward, merged
+# phases, filter gradients), the few-channel kernels at 64x64 (h0, d_h4 + fused loss and their gradients), grad_planes / amax /
+# skip_grad_sum, Adam with plane refresh
+for (hw, B) in ((32, 8), (64, 4)):
+    net = ContextNet(S.context_skip_new(hw, hw, 3, df_dim=64, featsize=64), B, precision="mixed")
+    net._graph_on = False
+    assert net.bf3 and net.p1
+    for _ in range(2):
+        net.set_input((torch.rand((3, B, hw, hw, 3), generator=g) * 2 - 1).cuda())
+        net.train_step(1e-4)
+    torch.cuda.synchronize()
+    print("sanitize smoke %dx%d done, loss" % (hw, hw), float(net.fetch("loss")), "few:", net._enc_few[0], net._dec_fewt[-1])

@@ -97,6 +97,8 @@ class ContextNet:
         self.concurrent = os.environ.get("CTX_CONCURRENT", "1") != "0"
         self._s2 = None
         self._s3 = None
+        self._s4 = None                                 # backward: the context encoder's chain (data gradients) ...
+        self._s5 = None                                 # ... and its filter gradients
         self._copy_stream = None
         self._in_events = None
         self._in_slot = 0                               # input double buffering (prefetch_input)
@@ -626,6 +628,9 @@ class ContextNet:
                 c_hs, c_h4 = [h[2 * B:] for h in e_hs], e_h4[2 * B:]
                 self._fwd_hz(self.ctx_scope, c_h4, cat.data_ptr() + F * f4, 2 * F, act=sp.ctx_hz_lrelu)  # ctx z
             th0 = self._buf("th0", (B, F))
+            if level == FWD_ALL:
+                with self._side():                         # independent of the translator: rows B.. of the decoder's input
+                    self._fwd_hz("conv", e_h4[B:2 * B], z2.data_ptr() + B * F * f4, F, act=True)
             self._gemm(False, False, B, F, 2 * F, cat.data_ptr(), 2 * F,
                        self.Wf["translate/trans_h0/Matrix"].data_ptr(), F, th0.data_ptr(), F,
                        bias=self.P["translate/trans_h0/bias"], act=True)
@@ -633,7 +638,7 @@ class ContextNet:
                        z2.data_ptr(), F, bias=self.P["translate/trans_z/bias"], act=False)      # trans_z -> z2[:B]
             nd = B
             if level == FWD_ALL:
-                self._fwd_hz("conv", e_h4[B:2 * B], z2.data_ptr() + B * F * f4, F, act=True)  # tgt z -> z2[B:]
+                self._join()                               # tgt z (issued beside the translator, below) -> z2[B:]
                 nd = 2 * B
             d = self._dec_buffers()
             l2 = None
@@ -921,6 +926,22 @@ class ContextNet:
         self._gemm(False, True, B, F, F, g_th0.data_ptr(), F, Wt0.data_ptr() + F * F * f4, F,
                    g_cat.data_ptr() + F * f4, 2 * F,
                    act_ref=(cat.data_ptr() + F * f4) if sp.ctx_hz_lrelu else None, bwd=True)
+        # The context encoder's backward chain (hz_lin, h<L>_lin, its convs) depends on nothing the
+        # source / target encoder's chain produces: with its own weights it runs on its own pair of streams (data gradients /
+        # filter gradients) beside that chain.  Its kernels see B images — 32 ... 128 CTAs for the upper layers — so alone they
+        # leave most SMs idle.
+        fine = on_stage is not None and getattr(getattr(on_stage, "__self__", None), "fine", False)
+        ctx_par = (sp.separate_ctx_encoder and self.concurrent and ops.PROFILE is None and not fine and
+                   os.environ.get("CTX_BWD_CTX_STREAM", "1") != "0")
+        cur = torch.cuda.current_stream(self.device)
+        if ctx_par:
+            if self._s4 is None:
+                self._s4 = torch.cuda.Stream(device=self.device)
+                self._s5 = torch.cuda.Stream(device=self.device)
+        # (every reader of the translator's weights is enqueued on THIS stream above: the optimiser slice on_stage("translate")
+        # starts may overwrite them as soon as what is enqueued here has run)
+        if ctx_par:
+            self._s4.wait_stream(cur)                      # everything the chain reads (g_cat, the skip gradients) is enqueued
         if on_stage:
             self._join()
             on_stage("translate")
@@ -938,12 +959,11 @@ class ContextNet:
 
         hz_backward("conv", g_cat.data_ptr(), 2 * F, e_h4[:B], ge_h4[:B])                     # src
         hz_backward("conv", g_tz.data_ptr(), F, e_h4[B:2 * B], ge_h4[B:2 * B])               # tgt
-        hz_backward(self.ctx_scope, g_cat.data_ptr() + F * f4, 2 * F, c_h4, gc_h4)           # ctx
+        if not ctx_par:
+            hz_backward(self.ctx_scope, g_cat.data_ptr() + F * f4, 2 * F, c_h4, gc_h4)       # ctx
 
         # ---- encoders: h<L>_lin then the convs -----------------------------------------------------------------------------
-        # finer all-reduce stages (data parallel): issued from the stream that wrote the gradients, no join needed
-        fine = on_stage is not None and getattr(getattr(on_stage, "__self__", None), "fine", False)
-
+        # (finer all-reduce stages, data parallel: issued from the stream that wrote the gradients, no join needed)
         def encoder_backward(scope, x, hs, h4, g_hs, g_h4, groups, tag):
             """groups: [(row0, rows, accumulate)] — ctx rows already hold the skip gradients, so they accumulate.
             tag: forward()'s buffer tag of this encoder pass (its operand planes)."""
@@ -1017,7 +1037,24 @@ class ContextNet:
                                              out=g_hs[j - 1][r0:r0 + nr], act_ref=hs[j - 1][r0:r0 + nr],
                                              accumulate=acc, round_tf32=self.round_b, impl=self.impl_b)
 
-        if sp.separate_ctx_encoder:
+        if sp.separate_ctx_encoder and ctx_par:
+            main_side = self._s2
+            with torch.cuda.stream(self._s4):
+                self._s2 = self._s5                        # (_side / _join of the enclosed calls use the chain's own side stream)
+                try:
+                    hz_backward(self.ctx_scope, g_cat.data_ptr() + F * f4, 2 * F, c_h4, gc_h4)
+                    encoder_backward("conv_context", xc, c_hs, c_h4, gc_hs, gc_h4, [(0, B, True)], "c")
+                    self._join()                           # s4 waits for the chain's filter gradients
+                finally:
+                    self._s2 = main_side
+            encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False)], "e")
+            if on_stage:
+                self._join()
+                on_stage("conv")
+            cur.wait_stream(self._s4)
+            if on_stage:
+                on_stage("conv_context")
+        elif sp.separate_ctx_encoder:
             encoder_backward("conv", xe, e_hs, e_h4, ge_hs, ge_h4, [(0, 2 * B, False)], "e")
             if on_stage:
                 self._join()

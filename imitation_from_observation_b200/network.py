@@ -874,7 +874,8 @@ class ContextNet:
                 # pass; skip half -> sum of the two decoder passes -> lrelu' -> the context encoder's fp32 gradient
                 gp = to_planes(dcat, Cs, "gp_d%d" % i, ldx=Ck, ref=state, slot=slot_d,
                                db=G["deconv/%s/biases" % self.dec[i - 1]["name"]])
-                ops.skip_grad_sum(dcat, 2, Cs, Ck - Cs, gc_hs[Ld - 1 - i], skip_ref=skip)
+                with self._side():                         # only the context encoder's chain reads it, much later
+                    ops.skip_grad_sum(dcat, 2, Cs, Ck - Cs, gc_hs[Ld - 1 - i], skip_ref=skip)
                 g_out, bias_done = None, True
                 continue
             g_state = self._buf("g_d%d" % i, tuple(state.shape))
@@ -934,16 +935,15 @@ class ContextNet:
         ctx_par = (sp.separate_ctx_encoder and self.concurrent and ops.PROFILE is None and not fine and
                    os.environ.get("CTX_BWD_CTX_STREAM", "1") != "0")
         cur = torch.cuda.current_stream(self.device)
+        # (every reader of the translator's weights is enqueued on THIS stream above: the optimiser slice on_stage("translate")
+        # starts may overwrite them as soon as what is enqueued here has run)
+        self._join()                                       # filter gradients so far, and the skip-gradient sums the chain reads
         if ctx_par:
             if self._s4 is None:
                 self._s4 = torch.cuda.Stream(device=self.device)
                 self._s5 = torch.cuda.Stream(device=self.device)
-        # (every reader of the translator's weights is enqueued on THIS stream above: the optimiser slice on_stage("translate")
-        # starts may overwrite them as soon as what is enqueued here has run)
-        if ctx_par:
             self._s4.wait_stream(cur)                      # everything the chain reads (g_cat, the skip gradients) is enqueued
         if on_stage:
-            self._join()
             on_stage("translate")
         # ---- hz_lin of the three roles -> gradient w.r.t. h4 (lrelu' fused) -------------------------------------------
         def hz_backward(scope, g_ptr, ldg, h4_rows, gh4_rows):

@@ -45,51 +45,85 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md 'clocks line')."""
+    """nvidia-smi sampled every 100 ms (B200_PROFILING.md 'clocks line').  The sampler process is started ONCE, at the very
+    beginning of main() — before this process initialises CUDA: forking a process that holds a CUDA context (driver threads,
+    atfork handlers) is the one place a rare host-side stall was ever seen in this benchmark — and runs until the end; the
+    samples of the timed region are picked by their time stamps."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    _proc, _path = None, None
+
+    @classmethod
+    def launch(cls, index: int):
+        if cls._proc is not None:
+            return
+        try:
+            fd, cls._path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            cls._proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + cls.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(cls._path, "w"), stderr=subprocess.DEVNULL, stdin=subprocess.DEVNULL)
+        except Exception:
+            cls._proc = None
+
+    @classmethod
+    def shutdown(cls):
+        if cls._proc is not None:
+            try:
+                cls._proc.terminate()
+                cls._proc.wait(timeout=5)
+            except Exception:
+                try:
+                    cls._proc.kill()
+                except Exception:
+                    pass
+            cls._proc = None
+        if cls._path:
+            try:
+                os.unlink(cls._path)
+            except OSError:
+                pass
+            cls._path = None
 
     def __init__(self, index: int):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.t0, self.t1 = index, None, None
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import datetime
+        self.t0 = datetime.datetime.now()
 
     def stop(self):
+        import datetime
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        if self.proc is None:
+        if ClockSampler._proc is None or self.t0 is None:
             return out
-        time.sleep(0.25)
-        self.proc.terminate()
+        self.t1 = datetime.datetime.now()
+        time.sleep(0.25)                                     # let the sample that covers the end of the region land
+        rows = []
         try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        try:
-            for line in open(self.path):
+            for line in open(ClockSampler._path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((ts, float(f[2]), float(f[3]), float(f[4]), f[6:10]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
         except Exception:
-            pass
+            return out
+        pad = datetime.timedelta(seconds=0.12)               # a sample describes the ~100 ms before its time stamp
+        inside = [r for r in rows if self.t0 <= r[0] <= self.t1 + pad]
+        if not inside and rows:                              # region shorter than the sampling period: the nearest sample
+            inside = [min(rows, key=lambda r: abs((r[0] - self.t1).total_seconds()))]
+        sm, mx, power, reasons = [], [], [], set()
+        for ts, c, m, p_, flags in inside:
+            sm.append(c); mx.append(m); power.append(p_)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
         if sm:
             out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
                        samples=len(sm), power_w_max=float(max(power)) if power else None)
@@ -591,6 +625,7 @@ def _orderly_exit():
     watchdog that ends the process if NCCL's teardown still blocks — the JSON line is already out."""
     import threading
     sys.stdout.flush()
+    ClockSampler.shutdown()                               # (os._exit below would skip the atexit hook and orphan nvidia-smi)
     t = threading.Timer(45.0, lambda: os._exit(0))
     t.daemon = True
     t.start()
@@ -610,6 +645,10 @@ def main():
     except (AttributeError, ValueError):
         pass
     faulthandler.dump_traceback_later(240, repeat=False, exit=False)
+    if os.environ.get("RANK", "0") == "0" and "reference" not in sys.argv:
+        ClockSampler.launch(int(os.environ.get("LOCAL_RANK", "0")))      # before CUDA is initialised in this process
+        import atexit
+        atexit.register(ClockSampler.shutdown)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

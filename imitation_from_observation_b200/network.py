@@ -740,10 +740,13 @@ class ContextNet:
         self._ensure_grads()
         self.flat_g.zero_()
 
-    def backward(self, on_stage=None):
+    def backward(self, on_stage=None, on_dense=None):
         """Gradient of the (ablated) loss w.r.t. every parameter, accumulated into the flat gradient buffer.
         `on_stage(scope)` is called as soon as all gradients of a parameter scope ("deconv", "translate", "conv",
-        "conv_context" — the order of the flat buffer) are enqueued, so a bucketed all-reduce can start early."""
+        "conv_context" — the order of the flat buffer) are enqueued, so a bucketed all-reduce can start early.
+        `on_dense(scope)` is called inside an encoder scope as soon as the gradients of its dense layers (hz_lin, h<L>_lin:
+        the first two thirds of the scope's parameters) AND the last readers of those weights are enqueued — the former on
+        the side stream current at that moment (self._s2), the latter on the current stream."""
         if self._level != FWD_ALL:
             raise _lib.CtxError("backward() needs forward(FWD_ALL) first")
         self._ensure_grads()
@@ -978,6 +981,8 @@ class ContextNet:
                 self._gemm(False, True, nr, flat, F, g_h4[r0:r0 + nr].data_ptr(), F,
                            Wb["%s/%s/Matrix" % (scope, self.lin)].data_ptr(), F, g_hs[-1][r0:r0 + nr].data_ptr(), flat,
                            act_ref=hs[-1][r0:r0 + nr].data_ptr(), accumulate=acc, bwd=True)
+            if on_dense is not None:
+                on_dense(scope)
             gp, bias_done = None, False                    # (plane, scale) of g_hs[j] when conv j runs on planes
             for j in reversed(range(Ld)):
                 wname = "%s/h%d_conv/w" % (scope, j)
@@ -1164,15 +1169,38 @@ class ContextNet:
             self._s3 = torch.cuda.Stream(device=self.device)
         cur = torch.cuda.current_stream(self.device)
 
+        dense_done: Dict[str, int] = {}                    # scope -> end of the part adam_dense already updated
+
+        def adam_range(a, b):
+            ops.adam_step(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr_t, b1, b2, eps,
+                          p_tf32=None if self.flat_pr is None else self.flat_pr[a:b])
+
         def adam_scope(scope):                             # called after backward's join: gradients of `scope` are final
             a, b = ranges[scope]
+            a = dense_done.get(scope, a)
             self._s3.wait_stream(cur)
             with torch.cuda.stream(self._s3):
-                ops.adam_step(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr_t, b1, b2, eps,
-                              p_tf32=None if self.flat_pr is None else self.flat_pr[a:b])
+                adam_range(a, b)
                 self._refresh_weight_planes(scope)         # next step's forward operands, under the remaining backward
 
-        self.backward(on_stage=adam_scope)
+        def adam_dense(scope):
+            # the dense layers hold two thirds of an encoder scope and are done first: their slice runs under the scope's conv
+            # backward instead of after it (the weights' last readers — the hz_lin / h<L>_lin data gradients — are on the
+            # current stream, their filter gradients on the current side stream)
+            top = "%s/h%d_conv/w" % (scope, self.L - 1)
+            if scope not in ranges or top not in self.offsets:
+                return
+            a, b = ranges[scope][0], self.offsets[top]
+            if not a < b <= ranges[scope][1]:
+                return
+            self._s3.wait_stream(torch.cuda.current_stream(self.device))
+            if self._s2 is not None:
+                self._s3.wait_stream(self._s2)
+            with torch.cuda.stream(self._s3):
+                adam_range(a, b)
+            dense_done[scope] = b
+
+        self.backward(on_stage=adam_scope, on_dense=adam_dense if os.environ.get("CTX_ADAM_DENSE_EARLY", "1") != "0" else None)
         cur.wait_stream(self._s3)
         self._wp_stale = False
 

@@ -1184,8 +1184,8 @@ class ContextNet:
                 self._refresh_weight_planes(scope)         # next step's forward operands, under the remaining backward
 
         def adam_dense(scope):
-            # the dense layers hold two thirds of an encoder scope and are done first: their slice runs under the scope's conv
-            # backward instead of after it (the weights' last readers — the hz_lin / h<L>_lin data gradients — are on the
+            # (CTX_ADAM_DENSE_EARLY=1; measured neutral at B = 256 and B = 32, so off by default) the dense layers hold two
+            # thirds of an encoder scope and are done first: their slice runs under the scope's conv backward instead of after it (the weights' last readers — the hz_lin / h<L>_lin data gradients — are on the
             # current stream, their filter gradients on the current side stream)
             top = "%s/h%d_conv/w" % (scope, self.L - 1)
             if scope not in ranges or top not in self.offsets:
@@ -1200,7 +1200,7 @@ class ContextNet:
                 adam_range(a, b)
             dense_done[scope] = b
 
-        self.backward(on_stage=adam_scope, on_dense=adam_dense if os.environ.get("CTX_ADAM_DENSE_EARLY", "1") != "0" else None)
+        self.backward(on_stage=adam_scope, on_dense=adam_dense if os.environ.get("CTX_ADAM_DENSE_EARLY", "0") == "1" else None)
         cur.wait_stream(self._s3)
         self._wp_stale = False
 

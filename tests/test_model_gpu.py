@@ -530,3 +530,35 @@ def test_cuda_graph_replay_equals_eager_steps(precision):
         losses.append(ls)
     assert np.allclose(losses[0], losses[1], rtol=2e-4)
     assert rel_l2(finals[0].cpu(), finals[1].cpu()) < 5e-3          # (a kernel missing from the graph is off by O(1))
+
+
+def test_stream_schedule_equals_serial_execution(monkeypatch):
+    """The step runs on up to five streams (context encoder beside the source / target encoder in forward and in backward,
+    filter gradients and skip-gradient sums beside data gradients, Adam slices under the remaining backward).  A missing
+    dependency would show as a different result: the same four steps with every launch on ONE stream (concurrent = False)
+    must give the same losses and parameters, up to the reordering of fp32 atomics that Adam amplifies."""
+    spec, B = S.context_skip_new(64, 64, df_dim=64, featsize=128), 16
+    rs = np.random.RandomState(5)
+    batches = [torch.from_numpy((rs.rand(3, B, 64, 64, 3) * 2 - 1).astype(np.float32)).cuda() for _ in range(4)]
+    finals, losses, grads = [], [], []
+    for mode in ("streams", "serial", "streams_no_ctx_chain"):
+        monkeypatch.setenv("CTX_BWD_CTX_STREAM", "0" if mode == "streams_no_ctx_chain" else "1")
+        net = ContextNet(spec, B, precision="mixed", seed=11)
+        net.concurrent = mode != "serial"
+        net._graph_on = False                                   # (graph replay vs eager has its own test)
+        assert net.p1 and net.bf3
+        ls = []
+        for k, x in enumerate(batches):
+            net.set_input(x)
+            net.train_step(1e-3)
+            ls.append(float(net.fetch("loss").item()))
+            if k == 0:
+                grads.append(net.flat_g.clone())                # first step: same parameters in every mode
+        torch.cuda.synchronize()
+        finals.append(net.flat_p.clone())
+        losses.append(ls)
+    for i in (1, 2):
+        assert np.allclose(losses[0], losses[i], rtol=2e-4), (losses[0], losses[i])
+        assert rel_l2(grads[0].cpu(), grads[i].cpu()) < 1e-4        # (fp32 atomics reorder sums: ~1e-6)
+        assert rel_l2(finals[0].cpu(), finals[i].cpu()) < 2e-2      # (Adam turns reordering noise on near-zero gradients into +-lr)
+

@@ -449,12 +449,15 @@ def run_ours(args):
                     tr = json.load(f)
                 roofline["traffic"] = tr.get("dominant_kernel_dram_bytes_per_launch")
                 roofline["traffic_source"] = tr.get("source")
+                # the live figure divides SERIALISED per-launch times by the OVERLAPPED step (it can exceed 1); for the
+                # headline workload the share of the step's kernel time comes from the committed ncu launch list of this
+                # same command, elsewhere the live figure is capped at 1
+                roofline["serialised_launch_ms_over_step_ms"] = roofline["share_of_step"]
                 if tr.get("tensor_kernels_share_of_kernel_time") and "train" in args.workload:
-                    # the live figure divides SERIALISED per-launch times by the OVERLAPPED step (it can exceed 1); the share
-                    # of the step's kernel time comes from the committed ncu launch list of this same command
-                    roofline["serialised_launch_ms_over_step_ms"] = roofline["share_of_step"]
                     roofline["share_of_step"] = tr["tensor_kernels_share_of_kernel_time"]
                     roofline["share_source"] = tr.get("share_source")
+                else:
+                    roofline["share_of_step"] = min(1.0, roofline["share_of_step"])
 
     # ---- CPU baseline: the restated reference on this box's host cores, bounded sample ---------------------------
     cpu = None

@@ -935,6 +935,8 @@ class ContextNet:
         # filter gradients) beside that chain.  Its kernels see B images — 32 ... 128 CTAs for the upper layers — so alone they
         # leave most SMs idle.
         fine = on_stage is not None and getattr(getattr(on_stage, "__self__", None), "fine", False)
+        # (single process only: under the bucketed all-reduce — `fine` is set whenever on_stage is BucketedAllReduce.stage_done —
+        # the chain stays on the main stream: with it the 2-GPU bench stalled, and there was no GPU time left to find out why)
         ctx_par = (sp.separate_ctx_encoder and self.concurrent and ops.PROFILE is None and not fine and
                    os.environ.get("CTX_BWD_CTX_STREAM", "1") != "0")
         cur = torch.cuda.current_stream(self.device)
@@ -1126,9 +1128,12 @@ class ContextNet:
             scopes = parallel.scope_ranges(self.offsets, self.flat_size)
 
             def adam_range(a, b):                          # runs with the optimiser stream current, after the bucket
-                # every kernel that READS these parameters (the data gradients of their layers) is already enqueued on
-                # the main stream when a later bucket is launched: the update must not overtake it
+                # every kernel that READS these parameters (the data gradients of their layers) is already enqueued — on
+                # the main stream, or on the context encoder's chain — when a later bucket is launched: the update must not
+                # overtake it
                 self._s3.wait_stream(cur)
+                if self._s4 is not None:
+                    self._s3.wait_stream(self._s4)
                 ops.adam_step(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr_t, b1, b2, eps,
                               p_tf32=None if self.flat_pr is None else self.flat_pr[a:b])
                 # next step's operand planes of every scope this bucket completes, under the remaining backward /

@@ -634,7 +634,7 @@ def _emit(line: dict):
 def _arm_stall_guard():
     """Last line of defence against a run that stops making progress (seen twice in ~70 single-GPU runs of an earlier build,
     never reproduced under observation; the one suspect — forking nvidia-smi from a process that holds a CUDA context — is
-    gone, see ClockSampler).  A default run ends within ~70 s; after 300 s + 0.2 s per requested step the guard dumps every
+    gone, see ClockSampler).  A default run ends within ~70 s; after 200 s + 0.2 s per requested step the guard dumps every
     thread's stack to stderr and, on a single GPU, restarts the process ONCE in place (same PID, fresh CUDA context); under
     torchrun it exits non-zero so the launcher tears the job down instead of hanging."""
     import faulthandler
@@ -646,7 +646,7 @@ def _arm_stall_guard():
                 steps = int(sys.argv[i + 1])
             except ValueError:
                 pass
-    deadline = float(os.environ.get("CTX_BENCH_STALL_S", 300.0 + 0.2 * steps))
+    deadline = float(os.environ.get("CTX_BENCH_STALL_S", 200.0 + 0.2 * steps))
 
     def fire():
         try:
@@ -689,7 +689,7 @@ def main():
         faulthandler.register(signal.SIGTERM, all_threads=True, chain=True)
     except (AttributeError, ValueError):
         pass
-    faulthandler.dump_traceback_later(240, repeat=False, exit=False)
+    faulthandler.dump_traceback_later(150, repeat=False, exit=False)
     _arm_stall_guard()
     if os.environ.get("RANK", "0") == "0" and "reference" not in sys.argv:
         ClockSampler.launch(int(os.environ.get("LOCAL_RANK", "0")))      # before CUDA is initialised in this process

@@ -83,7 +83,10 @@ def _worker(rank, world, port, q):
     if rank == 0:
         q.put((ok_bucket, err))
     dist.barrier()
-    dist.destroy_process_group()
+    # orderly end of a data-parallel process: graphs (none here) before the process group; idempotent, and what atexit runs again
+    parallel.shutdown()
+    assert not dist.is_initialized()
+    parallel.shutdown()
 
 
 @pytest.mark.timeout(180)

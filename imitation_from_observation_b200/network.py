@@ -935,9 +935,11 @@ class ContextNet:
         # filter gradients) beside that chain.  Its kernels see B images — 32 ... 128 CTAs for the upper layers — so alone they
         # leave most SMs idle.
         fine = on_stage is not None and getattr(getattr(on_stage, "__self__", None), "fine", False)
-        # (single process only: under the bucketed all-reduce — `fine` is set whenever on_stage is BucketedAllReduce.stage_done —
-        # the chain stays on the main stream: with it the 2-GPU bench stalled, and there was no GPU time left to find out why)
-        ctx_par = (sp.separate_ctx_encoder and self.concurrent and ops.PROFILE is None and not fine and
+        # (under the bucketed all-reduce — `fine` is set whenever on_stage is BucketedAllReduce.stage_done — the chain stays on
+        # the main stream unless CTX_DP_CTX_STREAM=1: with NCCL's spinning kernels and more streams than the default eight
+        # hardware queues the 2-GPU bench stalled; CUDA_DEVICE_MAX_CONNECTIONS=32 cured it (4.90 vs 5.00 ms per step, one run))
+        ctx_par = (sp.separate_ctx_encoder and self.concurrent and ops.PROFILE is None and
+                   (not fine or os.environ.get("CTX_DP_CTX_STREAM", "0") == "1") and
                    os.environ.get("CTX_BWD_CTX_STREAM", "1") != "0")
         cur = torch.cuda.current_stream(self.device)
         # (every reader of the translator's weights is enqueued on THIS stream above: the optimiser slice on_stage("translate")
